@@ -1,0 +1,147 @@
+/* ls_b200.h -- C ABI of the B200-native laser_slam hot path (libls_b200.so).
+ *
+ * Plain C, plain pointers and sizes; no torch / CUDA types cross this boundary.  Each entry point
+ * names the reference interface it replaces (paths relative to the reference repo root).
+ *
+ * Conventions
+ *   - Clouds use the libpointmatcher DataPoints memory layout the reference passes around
+ *     (laser_slam/include/laser_slam/common.hpp:14-15,113-120): `features` is a column-major
+ *     4xN float matrix, i.e. N consecutive {x, y, z, 1} quadruples; a `normals` descriptor is read
+ *     through (pointer, stride-in-floats) so a DxN descriptor block can be passed without copying.
+ *   - 4x4 transforms are 16 floats, column-major (PointMatcher::TransformationParameters::data()).
+ *   - Host buffers are owned by the caller and only read/written during the call.  Device memory
+ *     is owned by the library (ls_ctx / ls_map) and freed by the matching *_destroy.
+ *   - Return value: 0 ok; > 0 algorithmic condition (LS_ERR_CONVERGENCE maps to
+ *     PointMatcher::ConvergenceError, which laser_slam/src/laser_track.cpp:495-502 catches and
+ *     turns into "keep the initial guess"; laser_slam/src/incremental_estimator.cpp:108 lets it
+ *     propagate); < 0 argument / CUDA / resource error.  There is no CPU fallback: without a usable
+ *     CUDA device ls_b200_init fails with LS_ERR_CUDA.
+ *   - Calls on one ls_ctx are serialised by the caller (the reference holds
+ *     full_laser_track_mutex_ / full_class_mutex_ around them); distinct contexts are independent
+ *     (own stream, own buffers).  Calls are synchronous: results are on the host at return.
+ */
+#ifndef LS_B200_H_
+#define LS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LS_OK 0
+#define LS_ERR_CONVERGENCE 1 /* no point to minimise / NaN  -> PointMatcher::ConvergenceError */
+#define LS_ERR_ARG (-1)
+#define LS_ERR_CUDA (-2)
+#define LS_ERR_NOMEM (-3)
+#define LS_ERR_STATE (-4)
+#define LS_ERR_NCCL (-5)
+
+typedef struct ls_ctx ls_ctx;
+typedef struct ls_map ls_map;
+
+/* ICP chain parameters = the subset of laser_slam/configurations/icp_default.yaml the path uses. */
+typedef struct ls_icp_params {
+  int max_iterations;   /* CounterTransformationChecker.maxIterationCount      yaml:22-23 */
+  float trim_ratio;     /* TrimmedDistOutlierFilter.ratio                      yaml:14-16 */
+  int use_differential; /* DifferentialTransformationChecker present           yaml:24-27 */
+  float min_diff_rot;   /* minDiffRotErr [rad] */
+  float min_diff_trans; /* minDiffTransErr [m] */
+  int smooth_length;    /* smoothLength (<= 15) */
+  /* spatial-hash tuning (no reference counterpart; results do not depend on these) */
+  float cell_size;      /* level-0 cell edge [m]; <= 0 -> 1.0 */
+  int leaf_split;       /* subdivide cells holding more points; <= 0 -> 32 (min 16) */
+  int max_cells;        /* cap on level-0 cells; <= 0 -> 4194304 */
+} ls_icp_params;
+
+typedef struct ls_icp_stats {
+  int iterations;       /* ICP iterations executed */
+  int converged;        /* stopped by the differential checker */
+  int max_iter_reached; /* stopped by the counter (flag, not an error) */
+  int last_kept;        /* matches with weight 1 in the last iteration */
+  float last_limit;     /* trimmed squared-distance limit of the last iteration */
+  float used_ratio;     /* last_kept / n (libpointmatcher pointUsedRatio) */
+  float device_ms;      /* CUDA-event time of the device work of this call */
+  float build_ms;       /* of which: sub-map assembly + spatial-hash build */
+  int grid_cells;       /* level-0 cells */
+  int grid_tables;      /* level-1 + level-2 tables */
+  int grid_overflow;    /* 1 if a table pool overflowed (slower, still exact) */
+} ls_icp_stats;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int ls_b200_init(int device, ls_ctx** out);
+void ls_b200_destroy(ls_ctx* ctx);
+const char* ls_b200_last_error(const ls_ctx* ctx); /* text of the last failure on this context */
+int ls_b200_version(void);
+/* Number of this library's kernel launches issued on the context so far (bench "gpu_launches"). */
+uint64_t ls_b200_launch_count(const ls_ctx* ctx);
+
+/* icp_.setDefault()-like defaults, but with the values of icp_default.yaml:9-27
+ * (replaces PointMatcher::ICP::loadFromYaml at laser_slam/src/laser_track.cpp:14-21). */
+void ls_icp_default_params(ls_icp_params* p);
+/* Parse the keys of icp_default.yaml this path honours out of a YAML text; unknown modules are
+ * ignored, unsupported matcher / minimiser names return LS_ERR_ARG. */
+int ls_icp_params_from_yaml(const char* yaml_text, ls_icp_params* p);
+
+/* ---- one-shot registration ----------------------------------------------------------------------
+ * Replaces PointMatcher::ICP::compute(reading, reference, T0) at
+ *   laser_slam/src/laser_track.cpp:496              (scan -> sub-map)
+ *   laser_slam/src/incremental_estimator.cpp:108    (sub-map b -> sub-map a on loop closure)
+ * reading: 4xN features; reference: 4xM features + normals.  T_out = T_ref<-reading.
+ * On LS_ERR_CONVERGENCE T_out == T0.  opt_ids / opt_d2 (may be NULL, length n) receive the
+ * correspondence indices (into the reference, -1 = none) and squared distances of the LAST
+ * iteration; opt_T_iter_hist (may be NULL, max_iterations*16 floats) the accumulated T_iter after
+ * every iteration (centred frame). */
+int ls_icp_register(ls_ctx* ctx, const ls_icp_params* prm, const float* reading4, int n,
+                    const float* ref4, const float* ref_normals, int normals_stride, int m,
+                    const float T0[16], float T_out[16], ls_icp_stats* stats, int32_t* opt_ids,
+                    float* opt_d2, float* opt_T_iter_hist);
+
+/* KDTreeMatcher-level entry (icp_default.yaml:9-12): nearest reference point of T0*reading for
+ * every reading point, with the reference centred exactly as ICP::compute does.  ids index the
+ * reference as given; d2 are squared float32 distances. */
+int ls_nn_query(ls_ctx* ctx, const ls_icp_params* prm, const float* reading4, int n, const float* ref4,
+                int m, const float T0[16], int32_t* ids, float* d2);
+
+/* RigidTransformation::compute (laser_slam/src/laser_track.cpp:265,485,508,511,630,643):
+ * out = T * features, normals rotated by the 3x3 block.  normals/out_normals may be NULL. */
+int ls_transform_cloud(ls_ctx* ctx, const float T[16], const float* in4, const float* normals,
+                       int normals_stride, int n, float* out4, float* out_normals3);
+/* RigidTransformation::checkParameters / correctParameters as used by
+ * correctTransformationMatrix (laser_slam/include/laser_slam/common.hpp:136-149).  Host-side. */
+int ls_check_rigid(const float T[16]);
+void ls_correct_rigid(const float T_in[16], float T_out[16]);
+
+/* ---- device-resident rolling map ------------------------------------------------------------------
+ * Replaces LaserTrack::laser_scans_ + the per-scan copy/transform/concatenate loop of
+ * LaserTrack::localScanToSubMap (laser_slam/src/laser_track.cpp:466-486) and
+ * LaserTrack::buildSubMapAroundTime (laser_track.cpp:602-651): scans are uploaded once, kept in
+ * their own sensor frame, and sub-maps are assembled on the device. */
+int ls_map_create(ls_ctx* ctx, int capacity_scans, int max_pts_per_scan, ls_map** out);
+void ls_map_destroy(ls_map* map);
+/* Upload one scan; returns its id through *scan_id (ids grow monotonically; the scan stays
+ * addressable until `capacity_scans` newer scans have been pushed). */
+int ls_map_push_scan(ls_map* map, const float* features4, const float* normals, int normals_stride, int n,
+                     uint64_t* scan_id);
+int ls_map_scan_size(const ls_map* map, uint64_t scan_id); /* points, or <0 if evicted/unknown */
+
+/* Scan -> sub-map registration on resident data.  The reference is the concatenation, in order,
+ * of scans part_ids[0..n_parts) each transformed by T_parts[16*p..] (float32, already passed
+ * through correctTransformationMatrix by the caller; an exact identity matrix copies the scan
+ * verbatim as laser_track.cpp:476 does).  Reading = scan reading_id, untransformed.
+ * Correspondence ids index that concatenation. */
+int ls_icp_register_submap(ls_ctx* ctx, const ls_icp_params* prm, const ls_map* map, uint64_t reading_id,
+                           int n_parts, const uint64_t* part_ids, const float* T_parts, const float T0[16],
+                           float T_out[16], ls_icp_stats* stats, int32_t* opt_ids, float* opt_d2,
+                           float* opt_T_iter_hist);
+
+/* Assemble a sub-map and download it (LaserTrack::buildSubMapAroundTime,
+ * LaserTrack::getLocalCloudInWorldFrame laser_track.cpp:247-266).  out4: 4*M floats,
+ * out_normals3: 3*M floats (may be NULL); returns M through *m_out. */
+int ls_map_assemble(ls_ctx* ctx, const ls_map* map, int n_parts, const uint64_t* part_ids,
+                    const float* T_parts, float* out4, float* out_normals3, int* m_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LS_B200_H_ */

@@ -1,0 +1,296 @@
+"""laser_slam_b200 -- B200-native scan-to-local-map ICP + pose-graph hot path of ethz-asl/laser_slam.
+
+This package is a thin ctypes front-end over the C ABI in include/ls_b200.h (libls_b200.so, built by
+laser_slam_b200/csrc/Makefile for sm_100a).  The compute path is the CUDA library; there is NO CPU
+fallback: loading fails loudly when the shared library is missing and ls_b200_init fails when no
+CUDA device is usable.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_build", "libls_b200.so")
+_lib = None
+
+LS_OK, LS_ERR_CONVERGENCE = 0, 1
+
+
+class ConvergenceError(RuntimeError):
+    """Mirror of PointMatcher::ConvergenceError (reference laser_slam/src/laser_track.cpp:499)."""
+
+
+class LsError(RuntimeError):
+    pass
+
+
+class IcpParams(ctypes.Structure):
+    _fields_ = [("max_iterations", ctypes.c_int), ("trim_ratio", ctypes.c_float),
+                ("use_differential", ctypes.c_int), ("min_diff_rot", ctypes.c_float),
+                ("min_diff_trans", ctypes.c_float), ("smooth_length", ctypes.c_int),
+                ("cell_size", ctypes.c_float), ("leaf_split", ctypes.c_int), ("max_cells", ctypes.c_int)]
+
+
+class IcpStats(ctypes.Structure):
+    _fields_ = [("iterations", ctypes.c_int), ("converged", ctypes.c_int), ("max_iter_reached", ctypes.c_int),
+                ("last_kept", ctypes.c_int), ("last_limit", ctypes.c_float), ("used_ratio", ctypes.c_float),
+                ("device_ms", ctypes.c_float), ("build_ms", ctypes.c_float), ("grid_cells", ctypes.c_int),
+                ("grid_tables", ctypes.c_int), ("grid_overflow", ctypes.c_int)]
+
+
+def build(force=False):
+    """Compile libls_b200.so in-tree (nvcc cross-compiles sm_100a without a GPU)."""
+    src_dir = os.path.join(_HERE, "csrc")
+    srcs = [os.path.join(src_dir, f) for f in os.listdir(src_dir)] + [os.path.join(_HERE, "..", "include", "ls_b200.h")]
+    stale = (not os.path.exists(LIB_PATH)) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(s) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-C", src_dir, "-s"])
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LsError(f"{LIB_PATH} is missing: build it with laser_slam_b200.build() "
+                          "(there is no CPU fallback for this path)")
+        L = ctypes.CDLL(LIB_PATH)
+        vp, ci, u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64
+        PP, PS = ctypes.POINTER(IcpParams), ctypes.POINTER(IcpStats)
+        L.ls_b200_init.argtypes = [ci, ctypes.POINTER(vp)]
+        L.ls_b200_destroy.argtypes = [vp]
+        L.ls_b200_destroy.restype = None
+        L.ls_b200_last_error.argtypes = [vp]
+        L.ls_b200_last_error.restype = ctypes.c_char_p
+        L.ls_b200_launch_count.argtypes = [vp]
+        L.ls_b200_launch_count.restype = u64
+        L.ls_icp_default_params.argtypes = [PP]
+        L.ls_icp_default_params.restype = None
+        L.ls_icp_params_from_yaml.argtypes = [ctypes.c_char_p, PP]
+        L.ls_icp_register.argtypes = [vp, PP, vp, ci, vp, vp, ci, ci, vp, vp, PS, vp, vp, vp]
+        L.ls_nn_query.argtypes = [vp, PP, vp, ci, vp, ci, vp, vp, vp]
+        L.ls_transform_cloud.argtypes = [vp, vp, vp, vp, ci, ci, vp, vp]
+        L.ls_check_rigid.argtypes = [vp]
+        L.ls_correct_rigid.argtypes = [vp, vp]
+        L.ls_correct_rigid.restype = None
+        L.ls_map_create.argtypes = [vp, ci, ci, ctypes.POINTER(vp)]
+        L.ls_map_destroy.argtypes = [vp]
+        L.ls_map_destroy.restype = None
+        L.ls_map_push_scan.argtypes = [vp, vp, vp, ci, ci, ctypes.POINTER(u64)]
+        L.ls_map_scan_size.argtypes = [vp, u64]
+        L.ls_icp_register_submap.argtypes = [vp, PP, vp, u64, ci, vp, vp, vp, vp, PS, vp, vp, vp]
+        L.ls_map_assemble.argtypes = [vp, vp, ci, vp, vp, vp, vp, ctypes.POINTER(ci)]
+        _lib = L
+    return _lib
+
+
+def default_params(**kw):
+    p = IcpParams()
+    lib().ls_icp_default_params(ctypes.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def params_from_yaml(text):
+    p = IcpParams()
+    rc = lib().ls_icp_params_from_yaml(text.encode(), ctypes.byref(p))
+    if rc != 0:
+        raise LsError(f"unsupported ICP chain configuration (rc={rc})")
+    return p
+
+
+def colmajor(T):
+    return np.ascontiguousarray(np.asarray(T, np.float32).T).ravel()
+
+
+def from_colmajor(t16):
+    return np.asarray(t16).reshape(4, 4).T.copy()
+
+
+def _ptr(a):
+    return a.ctypes.data if a is not None else None
+
+
+def _f32c(a, cols):
+    a = np.asarray(a)
+    if a.dtype != np.float32 or not a.flags.c_contiguous:
+        a = np.ascontiguousarray(a, np.float32)
+    assert a.ndim == 2 and a.shape[1] == cols, f"expected (N,{cols}) float32"
+    return a
+
+
+class Context:
+    """One ls_ctx: one CUDA device, one stream; calls are synchronous (results on the host at return)."""
+
+    def __init__(self, device=0):
+        self._h = ctypes.c_void_p()
+        rc = lib().ls_b200_init(device, ctypes.byref(self._h))
+        if rc != 0:
+            raise LsError(f"ls_b200_init(device={device}) failed with {rc}: no usable CUDA device "
+                          "(this path has no CPU fallback)")
+
+    def close(self):
+        if self._h:
+            lib().ls_b200_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc == LS_ERR_CONVERGENCE:
+            raise ConvergenceError(lib().ls_b200_last_error(self._h).decode())
+        if rc != 0:
+            raise LsError(f"rc={rc}: {lib().ls_b200_last_error(self._h).decode()}")
+
+    @property
+    def launch_count(self):
+        return int(lib().ls_b200_launch_count(self._h))
+
+    def icp_register(self, reading4, ref4, ref_normals3, T0, params=None, want_ids=False, want_hist=False,
+                     raise_on_convergence=True):
+        """PointMatcher::ICP::compute(reading, reference, T0).  Returns dict(T, stats, rc[, ids, d2, T_iter_hist])."""
+        reading4, ref4 = _f32c(reading4, 4), _f32c(ref4, 4)
+        nrm = np.asarray(ref_normals3)
+        if nrm.dtype != np.float32 or not nrm.flags.c_contiguous:
+            nrm = np.ascontiguousarray(nrm, np.float32)
+        stride = nrm.shape[1]
+        p = params or default_params()
+        n, m = reading4.shape[0], ref4.shape[0]
+        t0 = colmajor(T0)
+        tout = np.empty(16, np.float32)
+        st = IcpStats()
+        ids = np.empty(max(n, 1), np.int32) if want_ids else None
+        d2 = np.empty(max(n, 1), np.float32) if want_ids else None
+        hist = np.zeros((p.max_iterations, 16), np.float32) if want_hist else None
+        rc = lib().ls_icp_register(self._h, ctypes.byref(p), reading4.ctypes.data, n, ref4.ctypes.data, nrm.ctypes.data,
+                                   stride, m, t0.ctypes.data, tout.ctypes.data, ctypes.byref(st), _ptr(ids), _ptr(d2),
+                                   _ptr(hist))
+        if rc != LS_ERR_CONVERGENCE or raise_on_convergence:
+            self._check(rc)
+        out = dict(T=from_colmajor(tout), stats=st, rc=rc)
+        if want_ids:
+            out["ids"], out["d2"] = ids[:n], d2[:n]
+        if want_hist:
+            out["T_iter_hist"] = hist[:st.iterations].reshape(-1, 4, 4).transpose(0, 2, 1).copy()
+        return out
+
+    def nn_query(self, reading4, ref4, T0=None, params=None):
+        reading4, ref4 = _f32c(reading4, 4), _f32c(ref4, 4)
+        p = params or default_params()
+        n = reading4.shape[0]
+        t0 = colmajor(np.eye(4) if T0 is None else T0)
+        ids = np.empty(max(n, 1), np.int32)
+        d2 = np.empty(max(n, 1), np.float32)
+        self._check(lib().ls_nn_query(self._h, ctypes.byref(p), reading4.ctypes.data, n, ref4.ctypes.data,
+                                      ref4.shape[0], t0.ctypes.data, ids.ctypes.data, d2.ctypes.data))
+        return ids[:n], d2[:n]
+
+    def transform_cloud(self, T, pts4, normals3=None):
+        pts4 = _f32c(pts4, 4)
+        n = pts4.shape[0]
+        out = np.empty_like(pts4)
+        nrm = nout = None
+        if normals3 is not None:
+            nrm = _f32c(normals3, 3)
+            nout = np.empty_like(nrm)
+        t = colmajor(T)
+        self._check(lib().ls_transform_cloud(self._h, t.ctypes.data, pts4.ctypes.data, _ptr(nrm), 3, n, out.ctypes.data,
+                                             _ptr(nout)))
+        return (out, nout) if normals3 is not None else out
+
+    def create_map(self, capacity_scans, max_pts_per_scan):
+        return Map(self, capacity_scans, max_pts_per_scan)
+
+
+class Map:
+    """Device-resident ring of the last `capacity_scans` scans (LaserTrack::laser_scans_ on the GPU)."""
+
+    def __init__(self, ctx, capacity_scans, max_pts_per_scan):
+        self.ctx = ctx
+        self._h = ctypes.c_void_p()
+        ctx._check(lib().ls_map_create(ctx._h, capacity_scans, max_pts_per_scan, ctypes.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().ls_map_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def push_scan(self, features4, normals3):
+        f = _f32c(features4, 4)
+        nrm = np.asarray(normals3)
+        if nrm.dtype != np.float32 or not nrm.flags.c_contiguous:
+            nrm = np.ascontiguousarray(nrm, np.float32)
+        sid = ctypes.c_uint64(0)
+        self.ctx._check(lib().ls_map_push_scan(self._h, f.ctypes.data, nrm.ctypes.data, nrm.shape[1], f.shape[0],
+                                               ctypes.byref(sid)))
+        return sid.value
+
+    def push_scan_raw(self, feat_ptr, nrm_ptr, nrm_stride, n):
+        """Pointer form (e.g. torch pinned tensors' data_ptr()) -- no numpy conversion on the way."""
+        sid = ctypes.c_uint64(0)
+        self.ctx._check(lib().ls_map_push_scan(self._h, feat_ptr, nrm_ptr, nrm_stride, n, ctypes.byref(sid)))
+        return sid.value
+
+    def scan_size(self, scan_id):
+        return int(lib().ls_map_scan_size(self._h, scan_id))
+
+    def register(self, reading_id, part_ids, T_parts, T0, params=None, want_ids=False, want_hist=False,
+                 raise_on_convergence=True):
+        """Scan -> sub-map ICP on resident scans (LaserTrack::localScanToSubMap, reference laser_track.cpp:466-519)."""
+        p = params or default_params()
+        ids_arr = np.ascontiguousarray(part_ids, np.uint64)
+        tp = np.ascontiguousarray(np.stack([colmajor(T) for T in T_parts]), np.float32)
+        t0 = colmajor(T0)
+        tout = np.empty(16, np.float32)
+        st = IcpStats()
+        n = self.scan_size(reading_id)
+        ids = np.empty(max(n, 1), np.int32) if want_ids else None
+        d2 = np.empty(max(n, 1), np.float32) if want_ids else None
+        hist = np.zeros((p.max_iterations, 16), np.float32) if want_hist else None
+        rc = lib().ls_icp_register_submap(self.ctx._h, ctypes.byref(p), self._h, reading_id, len(ids_arr),
+                                          ids_arr.ctypes.data, tp.ctypes.data, t0.ctypes.data, tout.ctypes.data,
+                                          ctypes.byref(st), _ptr(ids), _ptr(d2), _ptr(hist))
+        if rc != LS_ERR_CONVERGENCE or raise_on_convergence:
+            self.ctx._check(rc)
+        out = dict(T=from_colmajor(tout), stats=st, rc=rc)
+        if want_ids:
+            out["ids"], out["d2"] = ids[:n], d2[:n]
+        if want_hist:
+            out["T_iter_hist"] = hist[:st.iterations].reshape(-1, 4, 4).transpose(0, 2, 1).copy()
+        return out
+
+    def assemble(self, part_ids, T_parts, want_normals=True):
+        ids_arr = np.ascontiguousarray(part_ids, np.uint64)
+        tp = np.ascontiguousarray(np.stack([colmajor(T) for T in T_parts]), np.float32)
+        m = sum(self.scan_size(int(i)) for i in ids_arr)
+        out = np.empty((max(m, 1), 4), np.float32)
+        nout = np.empty((max(m, 1), 3), np.float32) if want_normals else None
+        mo = ctypes.c_int(0)
+        self.ctx._check(lib().ls_map_assemble(self.ctx._h, self._h, len(ids_arr), ids_arr.ctypes.data, tp.ctypes.data,
+                                              out.ctypes.data, _ptr(nout), ctypes.byref(mo)))
+        return out[:mo.value], (nout[:mo.value] if want_normals else None)
+
+
+def check_rigid(T):
+    t = colmajor(T)
+    return bool(lib().ls_check_rigid(t.ctypes.data))
+
+
+def correct_rigid(T):
+    t = colmajor(T)
+    o = np.empty(16, np.float32)
+    lib().ls_correct_rigid(t.ctypes.data, o.ctypes.data)
+    return from_colmajor(o)

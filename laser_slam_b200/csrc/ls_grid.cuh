@@ -1,0 +1,358 @@
+// GPU-resident spatial hash of the local map and the exact nearest-neighbour query over it.
+//
+// Replaces libnabo's kd-tree behind libpointmatcher's KDTreeMatcher{knn 1, epsilon 0} (reference
+// laser_slam/configurations/icp_default.yaml:9-12, executed inside icp_.compute at reference
+// laser_slam/src/laser_track.cpp:496).  Result contract (oracle/icp_oracle.cpp):
+//   id  = argmin_j (d2(q, p_j), j) lexicographic  -> lowest reference index wins exact ties
+//   d2  = fl(fl(fl(dx*dx) + fl(dy*dy)) + fl(dz*dz)), float32, no FMA
+//
+// Structure: a three-level sparse voxel grid.  The hash of a point is its lattice cell -- a perfect
+// hash over the map's bounding box, so a lookup is one indexed load, never a probe sequence:
+//   level 0  dense array of cells of edge H0 over the bounding box        (Entry top[nx*ny*nz])
+//   level 1  cells holding more than `leaf_split` points get a 4x4x4 table of H0/4 sub-cells
+//   level 2  level-1 cells holding more than `leaf_split` points get a 4x4x4 table of H0/16 cells
+// Points are stored sorted by (level-0 cell, level-1 sub-cell, level-2 sub-cell), x fastest, as
+// float4 {x, y, z, original index bits}, so every cell at every level is one contiguous range and
+// a row of x-adjacent level-2 cells is one contiguous candidate run.  Lidar density varies by
+// ~1000x between the near ground rings and the far field; three levels keep a leaf at tens of
+// points in both regimes.
+//
+// Exactness: the query is a ball query around a real candidate (the previous iteration's match, or
+// a seed found by descending the grid), with radius sqrt(best).  Loop bounds come from the same
+// monotone float cell-coordinate function that binned the points, so they are a superset of the
+// cells a closer point could be in; per-cell pruning uses a geometric lower bound widened by
+// `margin` and is only taken when strictly greater than the current best, so ties are never pruned.
+//
+// This header is also compiled for the host by tests/sim (CPU simulation of the query against
+// brute force).  The product never runs it on the CPU.
+#pragma once
+#include <cfloat>
+#include <climits>
+#include <cstring>
+
+#include <vector_types.h>
+
+#include "ls_math.cuh"
+
+namespace ls {
+
+struct Entry {
+  uint32_t start;  // first sorted position of the cell's points
+  int32_t meta;    // >= 0: leaf holding `meta` points;  < 0: internal, child table index = ~meta
+};
+
+struct Grid {
+  float org[3];  // lower corner of the level-0 lattice, centred coordinates
+  float H0, H1, H2;
+  float inv0, inv1, inv2;
+  int dim[3];
+  int n_cells0;
+  float margin;     // absolute slack (metres) covering float rounding of cell boundaries
+  float mu[3];      // reference mean (float32) subtracted from the map
+  int m;            // number of map points
+  int leaf_split;   // a cell with more points than this is subdivided
+  int n_tab1, n_tab2;
+  int overflow;     // set if a table pool was exhausted (cells then stay leaves: slower, still exact)
+};
+
+struct GridView {
+  const Entry* top;
+  const Entry* tab1;
+  const Entry* tab2;
+  const float4* pts;  // sorted {x,y,z,idx}
+};
+
+struct Best {
+  float d2;
+  int idx;  // original reference index
+  int pos;  // sorted position
+};
+
+// tests/sim instruments the query (candidates examined, table entries loaded) to tune H0/leaf_split
+#if defined(LS_SIM_COUNTERS) && !defined(__CUDA_ARCH__)
+extern thread_local long long ls_sim_cand, ls_sim_entries;
+#define LS_CNT_CAND() (++ls_sim_cand)
+#define LS_CNT_ENTRY() (++ls_sim_entries)
+#else
+#define LS_CNT_CAND() ((void)0)
+#define LS_CNT_ENTRY() ((void)0)
+#endif
+
+#if defined(__CUDA_ARCH__)
+LS_HD float4 ld_pt(const float4* p) { return __ldg(p); }
+LS_HD Entry ld_entry(const Entry* e) {
+  const int2 v = __ldg(reinterpret_cast<const int2*>(e));
+  Entry r;
+  r.start = (uint32_t)v.x;
+  r.meta = v.y;
+  return r;
+}
+LS_HD int f2i(float f) { return __float_as_int(f); }
+LS_HD float i2f(int i) { return __int_as_float(i); }
+#else
+LS_HD float4 ld_pt(const float4* p) { LS_CNT_CAND(); return *p; }
+LS_HD Entry ld_entry(const Entry* e) { LS_CNT_ENTRY(); return *e; }
+LS_HD int f2i(float f) { int i; std::memcpy(&i, &f, 4); return i; }
+LS_HD float i2f(int i) { float f; std::memcpy(&f, &i, 4); return f; }
+#endif
+
+// Monotone (non-decreasing in v) cell coordinate functions; the SAME functions bin the map points
+// at build time and bound the query loops.
+LS_HD int coord_top(float v, float o, float inv, int n) {
+  float t = floorf((v - o) * inv);
+  t = fminf(fmaxf(t, 0.0f), (float)(n - 1));
+  return (int)t;
+}
+LS_HD int coord_sub(float v, float lo, float inv) {
+  float t = floorf((v - lo) * inv);
+  t = fminf(fmaxf(t, 0.0f), 3.0f);
+  return (int)t;
+}
+LS_HD float cell_lo(float o, int c, float H) { return o + (float)c * H; }
+
+// distance from q to the slab [lo - m, hi + m] (0 inside)
+LS_HD float gap(float q, float lo, float hi, float m) {
+  const float a = (lo - m) - q;
+  const float b = q - (hi + m);
+  return fmaxf(0.0f, fmaxf(a, b));
+}
+
+// prune iff lower_bound * kShrink > best: kShrink absorbs the relative rounding of the bound itself
+#define LS_SHRINK 0.999999f
+
+LS_HD float ball_radius(float best_d2, float margin) { return sqrtf(best_d2) * 1.000001f + margin; }
+
+LS_HD void consider(const float4* pts, int pos, float qx, float qy, float qz, Best& b) {
+  const float4 p = ld_pt(pts + pos);
+  const float d = dist2(qx, qy, qz, p.x, p.y, p.z);
+  const int idx = f2i(p.w);
+  if (d < b.d2 || (d == b.d2 && idx < b.idx)) {
+    b.d2 = d;
+    b.idx = idx;
+    b.pos = pos;
+  }
+}
+
+LS_HD void scan_range(const float4* pts, uint32_t a, uint32_t e, float qx, float qy, float qz, Best& b) {
+  for (uint32_t pos = a; pos < e; ++pos) consider(pts, (int)pos, qx, qy, qz, b);
+}
+
+// ---- ball query, level 2 table (all entries are leaves; x-runs are contiguous) -------------------
+LS_HD void visit_l2(const Grid& g, const Entry* tab, float lox, float loy, float loz, const float4* pts,
+                    float qx, float qy, float qz, Best& b) {
+  const float R = ball_radius(b.d2, g.margin);
+  const int x0 = coord_sub(qx - R, lox, g.inv2), x1 = coord_sub(qx + R, lox, g.inv2);
+  const int y0 = coord_sub(qy - R, loy, g.inv2), y1 = coord_sub(qy + R, loy, g.inv2);
+  const int z0 = coord_sub(qz - R, loz, g.inv2), z1 = coord_sub(qz + R, loz, g.inv2);
+  for (int z = z0; z <= z1; ++z) {
+    const float gz = gap(qz, cell_lo(loz, z, g.H2), cell_lo(loz, z + 1, g.H2), g.margin);
+    const float gz2 = gz * gz;
+    if (gz2 * LS_SHRINK > b.d2) continue;
+    for (int y = y0; y <= y1; ++y) {
+      const float gy = gap(qy, cell_lo(loy, y, g.H2), cell_lo(loy, y + 1, g.H2), g.margin);
+      const float lb = gy * gy + gz2;
+      if (lb * LS_SHRINK > b.d2) continue;
+      const Entry e0 = ld_entry(tab + (z * 4 + y) * 4 + x0);
+      const Entry e1 = ld_entry(tab + (z * 4 + y) * 4 + x1);
+      scan_range(pts, e0.start, e1.start + (uint32_t)e1.meta, qx, qy, qz, b);
+    }
+  }
+}
+
+// ---- ball query, level 1 table -----------------------------------------------------------------
+LS_HD void visit_l1(const Grid& g, const Entry* tab, const Entry* tab2, float lox, float loy, float loz,
+                    const float4* pts, float qx, float qy, float qz, Best& b) {
+  const float R = ball_radius(b.d2, g.margin);
+  const int x0 = coord_sub(qx - R, lox, g.inv1), x1 = coord_sub(qx + R, lox, g.inv1);
+  const int y0 = coord_sub(qy - R, loy, g.inv1), y1 = coord_sub(qy + R, loy, g.inv1);
+  const int z0 = coord_sub(qz - R, loz, g.inv1), z1 = coord_sub(qz + R, loz, g.inv1);
+  for (int z = z0; z <= z1; ++z) {
+    const float cz = cell_lo(loz, z, g.H1);
+    const float gz = gap(qz, cz, cell_lo(loz, z + 1, g.H1), g.margin);
+    const float gz2 = gz * gz;
+    if (gz2 * LS_SHRINK > b.d2) continue;
+    for (int y = y0; y <= y1; ++y) {
+      const float cy = cell_lo(loy, y, g.H1);
+      const float gy = gap(qy, cy, cell_lo(loy, y + 1, g.H1), g.margin);
+      const float lbyz = gy * gy + gz2;
+      if (lbyz * LS_SHRINK > b.d2) continue;
+      for (int x = x0; x <= x1; ++x) {
+        const float cx = cell_lo(lox, x, g.H1);
+        const float gx = gap(qx, cx, cell_lo(lox, x + 1, g.H1), g.margin);
+        const float lb = gx * gx + lbyz;
+        if (lb * LS_SHRINK > b.d2) continue;
+        const Entry e = ld_entry(tab + (z * 4 + y) * 4 + x);
+        if (e.meta > 0) {
+          scan_range(pts, e.start, e.start + (uint32_t)e.meta, qx, qy, qz, b);
+        } else if (e.meta < 0) {
+          visit_l2(g, tab2 + (size_t)(~e.meta) * 64, cx, cy, cz, pts, qx, qy, qz, b);
+        }
+      }
+    }
+  }
+}
+
+// ---- ball query, level 0 -----------------------------------------------------------------------
+LS_HD void ball_query(const Grid& g, const GridView& v, float qx, float qy, float qz, Best& b) {
+  const float R = ball_radius(b.d2, g.margin);
+  const int x0 = coord_top(qx - R, g.org[0], g.inv0, g.dim[0]), x1 = coord_top(qx + R, g.org[0], g.inv0, g.dim[0]);
+  const int y0 = coord_top(qy - R, g.org[1], g.inv0, g.dim[1]), y1 = coord_top(qy + R, g.org[1], g.inv0, g.dim[1]);
+  const int z0 = coord_top(qz - R, g.org[2], g.inv0, g.dim[2]), z1 = coord_top(qz + R, g.org[2], g.inv0, g.dim[2]);
+  for (int z = z0; z <= z1; ++z) {
+    const float cz = cell_lo(g.org[2], z, g.H0);
+    const float gz = gap(qz, cz, cell_lo(g.org[2], z + 1, g.H0), g.margin);
+    const float gz2 = gz * gz;
+    if (gz2 * LS_SHRINK > b.d2) continue;
+    for (int y = y0; y <= y1; ++y) {
+      const float cy = cell_lo(g.org[1], y, g.H0);
+      const float gy = gap(qy, cy, cell_lo(g.org[1], y + 1, g.H0), g.margin);
+      const float lbyz = gy * gy + gz2;
+      if (lbyz * LS_SHRINK > b.d2) continue;
+      const Entry* row = v.top + ((size_t)z * g.dim[1] + y) * g.dim[0];
+      for (int x = x0; x <= x1; ++x) {
+        const float cx = cell_lo(g.org[0], x, g.H0);
+        const float gx = gap(qx, cx, cell_lo(g.org[0], x + 1, g.H0), g.margin);
+        const float lb = gx * gx + lbyz;
+        if (lb * LS_SHRINK > b.d2) continue;
+        const Entry e = ld_entry(row + x);
+        if (e.meta > 0) {
+          scan_range(v.pts, e.start, e.start + (uint32_t)e.meta, qx, qy, qz, b);
+        } else if (e.meta < 0) {
+          visit_l1(g, v.tab1 + (size_t)(~e.meta) * 64, v.tab2, cx, cy, cz, v.pts, qx, qy, qz, b);
+        }
+      }
+    }
+  }
+}
+
+// ---- seed: any real candidate close to q (first iteration only; later iterations warm-start) -----
+LS_HDN void seed_query(const Grid& g, const GridView& v, float qx, float qy, float qz, Best& b) {
+  const int cx = coord_top(qx, g.org[0], g.inv0, g.dim[0]);
+  const int cy = coord_top(qy, g.org[1], g.inv0, g.dim[1]);
+  const int cz = coord_top(qz, g.org[2], g.inv0, g.dim[2]);
+  const Entry e = ld_entry(v.top + ((size_t)cz * g.dim[1] + cy) * g.dim[0] + cx);
+  if (e.meta == 0) {
+    // empty level-0 cell: first point of every occupied cell of the nearest occupied Chebyshev shell
+    int rmax = g.dim[0] > g.dim[1] ? g.dim[0] : g.dim[1];
+    rmax = rmax > g.dim[2] ? rmax : g.dim[2];
+    for (int r = 1; r <= rmax; ++r) {
+      bool any = false;
+      const int za = cz - r < 0 ? 0 : cz - r, zb = cz + r >= g.dim[2] ? g.dim[2] - 1 : cz + r;
+      const int ya = cy - r < 0 ? 0 : cy - r, yb = cy + r >= g.dim[1] ? g.dim[1] - 1 : cy + r;
+      for (int z = za; z <= zb; ++z)
+        for (int y = ya; y <= yb; ++y) {
+          const Entry* row = v.top + ((size_t)z * g.dim[1] + y) * g.dim[0];
+          const bool face = (z == cz - r) || (z == cz + r) || (y == cy - r) || (y == cy + r);
+          if (face) {
+            const int xa = cx - r < 0 ? 0 : cx - r, xb = cx + r >= g.dim[0] ? g.dim[0] - 1 : cx + r;
+            for (int x = xa; x <= xb; ++x) {
+              const Entry s = ld_entry(row + x);
+              if (s.meta != 0) { consider(v.pts, (int)s.start, qx, qy, qz, b); any = true; }
+            }
+          } else {
+            if (cx - r >= 0) {
+              const Entry s = ld_entry(row + cx - r);
+              if (s.meta != 0) { consider(v.pts, (int)s.start, qx, qy, qz, b); any = true; }
+            }
+            if (cx + r < g.dim[0]) {
+              const Entry s = ld_entry(row + cx + r);
+              if (s.meta != 0) { consider(v.pts, (int)s.start, qx, qy, qz, b); any = true; }
+            }
+          }
+        }
+      if (any) break;
+    }
+    return;
+  }
+  if (e.meta > 0) { scan_range(v.pts, e.start, e.start + (uint32_t)e.meta, qx, qy, qz, b); return; }
+  const float lox = cell_lo(g.org[0], cx, g.H0), loy = cell_lo(g.org[1], cy, g.H0), loz = cell_lo(g.org[2], cz, g.H0);
+  const int fx = coord_sub(qx, lox, g.inv1), fy = coord_sub(qy, loy, g.inv1), fz = coord_sub(qz, loz, g.inv1);
+  const Entry e1 = ld_entry(v.tab1 + (size_t)(~e.meta) * 64 + (fz * 4 + fy) * 4 + fx);
+  if (e1.meta == 0) { consider(v.pts, (int)e.start, qx, qy, qz, b); return; }
+  if (e1.meta > 0) { scan_range(v.pts, e1.start, e1.start + (uint32_t)e1.meta, qx, qy, qz, b); return; }
+  const float l1x = cell_lo(lox, fx, g.H1), l1y = cell_lo(loy, fy, g.H1), l1z = cell_lo(loz, fz, g.H1);
+  const int hx = coord_sub(qx, l1x, g.inv2), hy = coord_sub(qy, l1y, g.inv2), hz = coord_sub(qz, l1z, g.inv2);
+  const Entry e2 = ld_entry(v.tab2 + (size_t)(~e1.meta) * 64 + (hz * 4 + hy) * 4 + hx);
+  if (e2.meta == 0) { consider(v.pts, (int)e1.start, qx, qy, qz, b); return; }
+  scan_range(v.pts, e2.start, e2.start + (uint32_t)e2.meta, qx, qy, qz, b);
+}
+
+// Exact 1-NN.  warm_pos: sorted position of the previous iteration's match, or -1.
+LS_HD Best nn_search(const Grid& g, const GridView& v, float qx, float qy, float qz, int warm_pos) {
+  Best b;
+  b.d2 = INFINITY;
+  b.idx = INT_MAX;
+  b.pos = -1;
+  if (g.m <= 0) { b.idx = -1; return b; }
+  if (warm_pos >= 0) consider(v.pts, warm_pos, qx, qy, qz, b);
+  else seed_query(g, v, qx, qy, qz, b);
+  ball_query(g, v, qx, qy, qz, b);
+  return b;
+}
+
+// Cell keys used by the build (same functions => same membership as the query assumes).
+LS_HD int top_index(const Grid& g, float x, float y, float z) {
+  const int cx = coord_top(x, g.org[0], g.inv0, g.dim[0]);
+  const int cy = coord_top(y, g.org[1], g.inv0, g.dim[1]);
+  const int cz = coord_top(z, g.org[2], g.inv0, g.dim[2]);
+  return (cz * g.dim[1] + cy) * g.dim[0] + cx;
+}
+LS_HD void top_origin(const Grid& g, int c0, float& lox, float& loy, float& loz) {
+  const int cx = c0 % g.dim[0];
+  const int cy = (c0 / g.dim[0]) % g.dim[1];
+  const int cz = c0 / (g.dim[0] * g.dim[1]);
+  lox = cell_lo(g.org[0], cx, g.H0);
+  loy = cell_lo(g.org[1], cy, g.H0);
+  loz = cell_lo(g.org[2], cz, g.H0);
+}
+LS_HD int sub_index(float x, float y, float z, float lox, float loy, float loz, float inv) {
+  return (coord_sub(z, loz, inv) * 4 + coord_sub(y, loy, inv)) * 4 + coord_sub(x, lox, inv);
+}
+LS_HD void sub_origin(int f, float lox, float loy, float loz, float H, float& ox, float& oy, float& oz) {
+  ox = cell_lo(lox, f & 3, H);
+  oy = cell_lo(loy, (f >> 2) & 3, H);
+  oz = cell_lo(loz, f >> 4, H);
+}
+
+// Grid geometry from the centred bounding box (single thread on the device; host in tests/sim).
+LS_HDN void grid_setup(Grid& g, const float* lo, const float* hi, float cell_size, int max_cells, int leaf_split,
+                       int m) {
+  float H = cell_size > 0.f ? cell_size : 2.0f;
+  float ext[3], emax = 0.f, oabs = 0.f;
+  for (int a = 0; a < 3; ++a) {
+    ext[a] = hi[a] - lo[a];
+    if (!(ext[a] >= 0.f)) ext[a] = 0.f;
+    emax = fmaxf(emax, ext[a]);
+    oabs = fmaxf(oabs, fmaxf(fabsf(lo[a]), fabsf(hi[a])));
+  }
+  // grow H (powers of two) until the dense level-0 array fits the budget
+  for (int it = 0; it < 40; ++it) {
+    double cells = 1.0;
+    for (int a = 0; a < 3; ++a) cells *= floor((double)ext[a] / (double)H) + 1.0;
+    if (cells <= (double)max_cells) break;
+    H = H * 2.0f;
+  }
+  g.H0 = H;
+  g.H1 = H * 0.25f;
+  g.H2 = H * 0.0625f;
+  g.inv0 = 1.0f / g.H0;
+  g.inv1 = 1.0f / g.H1;
+  g.inv2 = 1.0f / g.H2;
+  int n = 1;
+  for (int a = 0; a < 3; ++a) {
+    g.org[a] = lo[a];
+    int d = (int)floorf(ext[a] * g.inv0) + 1;
+    if (d < 1) d = 1;
+    g.dim[a] = d;
+    n *= d;
+  }
+  g.n_cells0 = n;
+  g.margin = (oabs + emax + H) * 1.9073486328125e-06f;  // 2^-19 of the coordinate magnitude
+  g.m = m;
+  g.leaf_split = leaf_split > 0 ? leaf_split : 32;
+  g.n_tab1 = 0;
+  g.n_tab2 = 0;
+  g.overflow = 0;
+}
+
+}  // namespace ls

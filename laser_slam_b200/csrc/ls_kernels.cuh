@@ -1,0 +1,788 @@
+// CUDA kernels of the registration hot path (sm_100a).  No tensor cores: there is no dense
+// contraction on this path; every kernel is an HBM/L2-bound gather, scatter, histogram or reduction.
+//
+//   K0  assemble_kernel      sub-map = concat_p( T_p * scan_p ), exact mean sums, bounding box
+//                            (LaserTrack::localScanToSubMap, reference laser_slam/src/laser_track.cpp:476-486)
+//   K1  setup/count/scan/table/scatter kernels: three-level spatial hash build (counting sort)
+//                            (matcher->init(reference) inside ICP::compute, laser_track.cpp:496)
+//   K2..K4 icp_kernel        ONE persistent cooperative kernel for the whole ICP loop: per iteration
+//                            NN query (K2) -> exact trimmed-quantile radix select (K3) -> point-to-plane
+//                            normal equations, order-independent int64 reduction, 6x6 solve (K4),
+//                            transformation checkers; grid-wide barriers between phases.
+//                            (KDTreeMatcher / TrimmedDistOutlierFilter / PointToPlaneErrorMinimizer /
+//                            Counter+Differential checkers, icp_default.yaml:9-27)
+#pragma once
+#include <cuda_runtime.h>
+#include <cooperative_groups.h>
+
+#include "ls_grid.cuh"
+
+namespace ls {
+
+constexpr int kMaxParts = 16;
+constexpr int kScanTile = 4096;       // level-0 cells per scan block
+constexpr int kScanThreads = 512;
+constexpr int kIcpThreads = 512;
+constexpr int kMaxSmooth = 15;
+constexpr uint32_t kTag1 = 1u << 30, kTag2 = 2u << 30, kKeyMask = (1u << 30) - 1u;
+
+struct Parts {
+  int n_parts;
+  int offset[kMaxParts + 1];
+  const float4* pts[kMaxParts];
+  const float4* nrm[kMaxParts];
+  float T[kMaxParts][16];
+  int identity[kMaxParts];
+};
+
+struct BuildState {
+  unsigned long long sum[3];         // exact fixed-point (2^-24 m) coordinate sums
+  unsigned int minkey[3], maxkey[3];  // order-preserving integer images of float min/max
+  Grid grid;
+  float T_pre[16];                    // T_refMean_dataIn = [R0 | t0 - mu]
+  unsigned int tile_sums[1024];
+};
+
+struct BuildArrays {
+  float4* sub_pts;   // assembled (then centred) sub-map, original order
+  float4* sub_nrm;
+  float4* srt_pts;   // sorted {x,y,z,idx}
+  float4* srt_nrm;
+  uint32_t* pkey;    // per point: tag | deepest cell key found so far
+  Entry* top;
+  uint32_t* cnt0;
+  Entry* tab1;
+  uint32_t* cnt1;
+  uint32_t* tab1_cell;   // level-0 cell of each level-1 table
+  Entry* tab2;
+  uint32_t* cnt2;
+  uint32_t* tab2_key1;   // level-1 key (table*64+sub) of each level-2 table
+  int tab_cap;
+};
+
+struct IcpParamsDev {
+  int max_iterations;
+  float trim_ratio;
+  int use_differential;
+  float min_diff_rot, min_diff_trans;
+  int smooth_length;
+};
+
+struct IcpWork {
+  unsigned int barrier;
+  unsigned int pad0[31];
+  unsigned int hist[2][3][2048];
+  unsigned long long acc[2][32];
+  float T_out[16];
+  int status, iterations, converged, max_iter_reached, last_kept;
+  float last_limit;
+  int fail_code;       // 1 no finite match, 2 nothing kept, 3 non-finite solve, 4 NaN in checker, 5 non-finite T
+  unsigned int dbg_total, dbg_bin[3], dbg_rem[3];
+  double dbg_A[6], dbg_x[6];
+};
+
+struct IcpProblem {
+  const BuildState* bs;
+  GridView view;
+  const float4* nrm;  // sorted normals
+  const float4* rd;   // pre-transformed reading
+  int n;
+  int* pos;
+  float* d2;
+  int* ids;
+  IcpWork* work;
+  float* T_hist;  // max_iterations*16 floats or null
+  float T0[16];
+};
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int float_order_key(float f) {
+  const unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float float_from_order_key(unsigned int k) {
+  const unsigned int u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(u);
+}
+
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+  // 3 x 21-bit limbs through the integer warp-reduce unit (REDUX); exact, order independent
+  unsigned int lo = (unsigned int)(v & 0x1FFFFF);
+  unsigned int mid = (unsigned int)((v >> 21) & 0x1FFFFF);
+  int hi = (int)(v >> 42);
+  lo = __reduce_add_sync(0xffffffffu, lo);
+  mid = __reduce_add_sync(0xffffffffu, mid);
+  hi = __reduce_add_sync(0xffffffffu, hi);
+  return ((long long)hi << 42) + ((long long)mid << 21) + (long long)lo;
+}
+
+// ---- K0: assemble + statistics -------------------------------------------------------------------
+__global__ void __launch_bounds__(256) assemble_kernel(const __grid_constant__ Parts parts, float4* __restrict__ sub_pts,
+                                                       float4* __restrict__ sub_nrm, BuildState* bs) {
+  const int total = parts.offset[parts.n_parts];
+  long long s0 = 0, s1 = 0, s2 = 0;
+  float mn0 = INFINITY, mn1 = INFINITY, mn2 = INFINITY, mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY;
+  int p = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    while (i >= parts.offset[p + 1]) ++p;
+    const int j = i - parts.offset[p];
+    float4 a = __ldg(parts.pts[p] + j);
+    float4 nn = __ldg(parts.nrm[p] + j);
+    if (!parts.identity[p]) {
+      float x, y, z;
+      xform_point(parts.T[p], a.x, a.y, a.z, x, y, z);
+      a.x = x; a.y = y; a.z = z;
+      rotate_vec(parts.T[p], nn.x, nn.y, nn.z, x, y, z);
+      nn.x = x; nn.y = y; nn.z = z;
+    }
+    sub_pts[i] = a;
+    sub_nrm[i] = nn;
+    s0 += __double2ll_rn((double)a.x * 16777216.0);
+    s1 += __double2ll_rn((double)a.y * 16777216.0);
+    s2 += __double2ll_rn((double)a.z * 16777216.0);
+    mn0 = fminf(mn0, a.x); mx0 = fmaxf(mx0, a.x);
+    mn1 = fminf(mn1, a.y); mx1 = fmaxf(mx1, a.y);
+    mn2 = fminf(mn2, a.z); mx2 = fmaxf(mx2, a.z);
+  }
+  s0 = warp_sum_ll(s0); s1 = warp_sum_ll(s1); s2 = warp_sum_ll(s2);
+  for (int o = 16; o > 0; o >>= 1) {
+    mn0 = fminf(mn0, __shfl_xor_sync(0xffffffffu, mn0, o)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, o));
+    mn1 = fminf(mn1, __shfl_xor_sync(0xffffffffu, mn1, o)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, o));
+    mn2 = fminf(mn2, __shfl_xor_sync(0xffffffffu, mn2, o)); mx2 = fmaxf(mx2, __shfl_xor_sync(0xffffffffu, mx2, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&bs->sum[0], (unsigned long long)s0);
+    atomicAdd(&bs->sum[1], (unsigned long long)s1);
+    atomicAdd(&bs->sum[2], (unsigned long long)s2);
+    atomicMin(&bs->minkey[0], float_order_key(mn0)); atomicMax(&bs->maxkey[0], float_order_key(mx0));
+    atomicMin(&bs->minkey[1], float_order_key(mn1)); atomicMax(&bs->maxkey[1], float_order_key(mx1));
+    atomicMin(&bs->minkey[2], float_order_key(mn2)); atomicMax(&bs->maxkey[2], float_order_key(mx2));
+  }
+}
+
+// normals descriptor (stride floats per point) -> float4
+__global__ void expand_normals_kernel(const float* __restrict__ raw, int stride, int n, float4* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float* r = raw + (size_t)i * stride;
+    out[i] = make_float4(r[0], r[1], r[2], 0.f);
+  }
+}
+
+__global__ void reset_build_kernel(BuildState* bs) {
+  const int t = threadIdx.x;
+  if (t < 3) {
+    bs->sum[t] = 0ull;
+    bs->minkey[t] = 0xffffffffu;
+    bs->maxkey[t] = 0u;
+  }
+}
+
+// ---- K1a: mean, bounding box, grid geometry, T_pre -------------------------------------------------
+__global__ void setup_kernel(BuildState* bs, int m, float cell_size, int max_cells, int leaf_split,
+                             const float* __restrict__ T0 /* 16 floats, device */) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float mu[3], lo[3], hi[3];
+  for (int a = 0; a < 3; ++a) {
+    const long long s = (long long)bs->sum[a];
+    mu[a] = (float)((double)s / ((double)m * 16777216.0));
+    // min over fl(x - mu) == fl(min x - mu): rounding is monotone
+    lo[a] = float_from_order_key(bs->minkey[a]) - mu[a];
+    hi[a] = float_from_order_key(bs->maxkey[a]) - mu[a];
+  }
+  Grid g;
+  grid_setup(g, lo, hi, cell_size, max_cells, leaf_split, m);
+  for (int a = 0; a < 3; ++a) g.mu[a] = mu[a];
+  bs->grid = g;
+  for (int i = 0; i < 16; ++i) bs->T_pre[i] = T0[i];
+  for (int a = 0; a < 3; ++a) bs->T_pre[12 + a] = T0[12 + a] - mu[a];
+}
+
+// ---- K1b: centre + level-0 histogram --------------------------------------------------------------
+__global__ void __launch_bounds__(256) count0_kernel(const BuildState* __restrict__ bs, BuildArrays A, int m) {
+  __shared__ Grid g;
+  if (threadIdx.x == 0) g = bs->grid;
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+    float4 p = A.sub_pts[i];
+    p.x = p.x - g.mu[0];
+    p.y = p.y - g.mu[1];
+    p.z = p.z - g.mu[2];
+    A.sub_pts[i] = p;
+    const int c0 = top_index(g, p.x, p.y, p.z);
+    atomicAdd(&A.cnt0[c0], 1u);
+    A.pkey[i] = (uint32_t)c0;
+  }
+}
+
+// ---- K1c: exclusive scan of the level-0 histogram (two kernels, no spin-waits) ----------------------
+__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(BuildState* bs, const uint32_t* __restrict__ cnt0) {
+  const int n = bs->grid.n_cells0;
+  const int base = blockIdx.x * kScanTile;
+  if (base >= n) return;
+  unsigned int s = 0;
+  for (int k = threadIdx.x; k < kScanTile; k += kScanThreads) {
+    const int c = base + k;
+    if (c < n) s += cnt0[c];
+  }
+  s = __reduce_add_sync(0xffffffffu, s);
+  __shared__ unsigned int ws[kScanThreads / 32];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = 0;
+    for (int w = 0; w < kScanThreads / 32; ++w) t += ws[w];
+    bs->tile_sums[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(BuildState* bs, BuildArrays A) {
+  const int n = bs->grid.n_cells0;
+  const int base = blockIdx.x * kScanTile;
+  if (base >= n) return;
+  const int split = bs->grid.leaf_split;
+  __shared__ unsigned int ws[kScanThreads / 32];
+  __shared__ unsigned int tile_off;
+  // offset of this tile = sum of the previous tile sums
+  unsigned int s = 0;
+  for (int u = threadIdx.x; u < (int)blockIdx.x; u += kScanThreads) s += bs->tile_sums[u];
+  s = __reduce_add_sync(0xffffffffu, s);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = 0;
+    for (int w = 0; w < kScanThreads / 32; ++w) t += ws[w];
+    tile_off = t;
+  }
+  __syncthreads();
+  // each thread owns 8 consecutive cells
+  constexpr int per = kScanTile / kScanThreads;
+  unsigned int c[per], loc = 0;
+  const int first = base + threadIdx.x * per;
+#pragma unroll
+  for (int k = 0; k < per; ++k) {
+    c[k] = (first + k < n) ? A.cnt0[first + k] : 0u;
+    loc += c[k];
+  }
+  unsigned int incl = loc;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  __syncthreads();
+  if (lane == 31) ws[warp] = incl;
+  __syncthreads();
+  unsigned int woff = 0;
+  for (int w = 0; w < warp; ++w) woff += ws[w];
+  unsigned int run = tile_off + woff + incl - loc;
+#pragma unroll
+  for (int k = 0; k < per; ++k) {
+    const int cell = first + k;
+    if (cell < n) {
+      Entry e;
+      e.start = run;
+      e.meta = (int)c[k];
+      if ((int)c[k] > split) {
+        const int t = atomicAdd(&bs->grid.n_tab1, 1);
+        if (t < A.tab_cap) {
+          e.meta = ~t;
+          A.tab1_cell[t] = (uint32_t)cell;
+          A.cnt0[cell] = 0u;  // not a scatter cursor; leave the array clean for the next build
+        } else {
+          bs->grid.overflow = 1;
+        }
+      }
+      A.top[cell] = e;
+    }
+    run += c[k];
+  }
+}
+
+// ---- K1d: level-1 histogram -------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) count1_kernel(const BuildState* __restrict__ bs, BuildArrays A, int m) {
+  __shared__ Grid g;
+  if (threadIdx.x == 0) g = bs->grid;
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+    const uint32_t c0 = A.pkey[i];
+    const Entry e = A.top[c0];
+    if (e.meta >= 0) continue;
+    const float4 p = A.sub_pts[i];
+    float lx, ly, lz;
+    top_origin(g, (int)c0, lx, ly, lz);
+    const uint32_t key = (uint32_t)(~e.meta) * 64u + (uint32_t)sub_index(p.x, p.y, p.z, lx, ly, lz, g.inv1);
+    atomicAdd(&A.cnt1[key], 1u);
+    A.pkey[i] = kTag1 | key;
+  }
+}
+
+// one warp per table: exclusive scan of 64 counts, allocate child tables for heavy sub-cells
+template <int LEVEL>
+__global__ void __launch_bounds__(256) tables_kernel(BuildState* bs, BuildArrays A) {
+  const int n_tab = LEVEL == 1 ? min(bs->grid.n_tab1, A.tab_cap) : min(bs->grid.n_tab2, A.tab_cap);
+  const int split = bs->grid.leaf_split;
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_tab; t += warps) {
+    uint32_t* cnt = (LEVEL == 1 ? A.cnt1 : A.cnt2) + (size_t)t * 64;
+    Entry* tab = (LEVEL == 1 ? A.tab1 : A.tab2) + (size_t)t * 64;
+    uint32_t base;
+    if (LEVEL == 1) {
+      base = A.top[A.tab1_cell[t]].start;
+    } else {
+      base = A.tab1[A.tab2_key1[t]].start;
+    }
+    const unsigned int c0 = cnt[2 * lane], c1 = cnt[2 * lane + 1];
+    const unsigned int loc = c0 + c1;
+    unsigned int incl = loc;
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const unsigned int ex = base + incl - loc;
+    Entry e0, e1;
+    e0.start = ex; e0.meta = (int)c0;
+    e1.start = ex + c0; e1.meta = (int)c1;
+    if (LEVEL == 1) {
+      if ((int)c0 > split) {
+        const int t2 = atomicAdd(&bs->grid.n_tab2, 1);
+        if (t2 < A.tab_cap) { e0.meta = ~t2; A.tab2_key1[t2] = (uint32_t)t * 64u + 2u * lane; cnt[2 * lane] = 0u; }
+        else bs->grid.overflow = 1;
+      }
+      if ((int)c1 > split) {
+        const int t2 = atomicAdd(&bs->grid.n_tab2, 1);
+        if (t2 < A.tab_cap) { e1.meta = ~t2; A.tab2_key1[t2] = (uint32_t)t * 64u + 2u * lane + 1u; cnt[2 * lane + 1] = 0u; }
+        else bs->grid.overflow = 1;
+      }
+    }
+    tab[2 * lane] = e0;
+    tab[2 * lane + 1] = e1;
+  }
+}
+
+// ---- K1e: level-2 histogram -------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) count2_kernel(const BuildState* __restrict__ bs, BuildArrays A, int m) {
+  __shared__ Grid g;
+  if (threadIdx.x == 0) g = bs->grid;
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+    const uint32_t k = A.pkey[i];
+    if ((k & ~kKeyMask) != kTag1) continue;
+    const uint32_t key1 = k & kKeyMask;
+    const Entry e1 = A.tab1[key1];
+    if (e1.meta >= 0) continue;
+    const float4 p = A.sub_pts[i];
+    float lx, ly, lz, mx, my, mz;
+    top_origin(g, (int)A.tab1_cell[key1 >> 6], lx, ly, lz);
+    sub_origin((int)(key1 & 63u), lx, ly, lz, g.H1, mx, my, mz);
+    const uint32_t key2 = (uint32_t)(~e1.meta) * 64u + (uint32_t)sub_index(p.x, p.y, p.z, mx, my, mz, g.inv2);
+    atomicAdd(&A.cnt2[key2], 1u);
+    A.pkey[i] = kTag2 | key2;
+  }
+}
+
+// ---- K1f: scatter into sorted order (the leaf histograms double as cursors and end at zero) ---------
+__global__ void __launch_bounds__(256) scatter_kernel(BuildArrays A, int m) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+    const uint32_t k = A.pkey[i];
+    const uint32_t tag = k & ~kKeyMask, key = k & kKeyMask;
+    uint32_t pos;
+    if (tag == kTag2) pos = A.tab2[key].start + atomicSub(&A.cnt2[key], 1u) - 1u;
+    else if (tag == kTag1) pos = A.tab1[key].start + atomicSub(&A.cnt1[key], 1u) - 1u;
+    else pos = A.top[key].start + atomicSub(&A.cnt0[key], 1u) - 1u;
+    float4 p = A.sub_pts[i];
+    p.w = __int_as_float(i);
+    A.srt_pts[pos] = p;
+    A.srt_nrm[pos] = A.sub_nrm[i];
+  }
+}
+
+// ---- reading pre-transform: R' = T_refMean_dataIn * R ----------------------------------------------
+__global__ void __launch_bounds__(256) reading_kernel(const BuildState* __restrict__ bs, const float4* __restrict__ in,
+                                                      int n, float4* __restrict__ out) {
+  __shared__ float T[16];
+  if (threadIdx.x < 16) T[threadIdx.x] = bs->T_pre[threadIdx.x];
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 a = __ldg(in + i);
+    float4 o;
+    xform_point(T, a.x, a.y, a.z, o.x, o.y, o.z);
+    o.w = a.w;
+    out[i] = o;
+  }
+}
+
+// plain RigidTransformation::compute on a cloud
+__global__ void __launch_bounds__(256) transform_kernel(const float* __restrict__ Tg, const float4* __restrict__ in,
+                                                        const float4* __restrict__ nin, int n, float4* __restrict__ out,
+                                                        float4* __restrict__ nout) {
+  __shared__ float T[16];
+  if (threadIdx.x < 16) T[threadIdx.x] = Tg[threadIdx.x];
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 a = __ldg(in + i);
+    float4 o;
+    xform_point(T, a.x, a.y, a.z, o.x, o.y, o.z);
+    o.w = a.w;
+    out[i] = o;
+    if (nin) {
+      const float4 b = __ldg(nin + i);
+      float4 r;
+      rotate_vec(T, b.x, b.y, b.z, r.x, r.y, r.z);
+      r.w = 0.f;
+      nout[i] = r;
+    }
+  }
+}
+
+// float4 normals -> packed 3 floats (download helper)
+__global__ void pack_normals_kernel(const float4* __restrict__ in, int n, float* __restrict__ out3) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 a = in[i];
+    out3[3 * (size_t)i] = a.x;
+    out3[3 * (size_t)i + 1] = a.y;
+    out3[3 * (size_t)i + 2] = a.z;
+  }
+}
+
+// un-centre an assembled sub-map is never needed: ls_map_assemble downloads before centring.
+
+// ---- matcher-only kernel (ls_nn_query): cold exact NN for every pre-transformed reading point -------
+__global__ void __launch_bounds__(256) nn_query_kernel(const BuildState* __restrict__ bs, GridView view,
+                                                       const float4* __restrict__ rd, int n, int* __restrict__ ids,
+                                                       float* __restrict__ d2) {
+  __shared__ Grid g;
+  if (threadIdx.x == 0) g = bs->grid;
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 q = __ldg(rd + i);
+    const Best b = nn_search(g, view, q.x, q.y, q.z, -1);
+    ids[i] = b.idx;
+    d2[i] = b.d2;
+  }
+}
+
+// ================================================================================================
+// Persistent ICP kernel
+// ================================================================================================
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// All CTAs of one problem.  `epoch` is the number of arrivals expected so far (kept in a register).
+__device__ __forceinline__ void problem_barrier(unsigned int* ctr, unsigned int n_ctas, unsigned int& epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    epoch += n_ctas;
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    while (ld_acquire_u32(ctr) < epoch) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+struct SelectOut {
+  unsigned int bin, rem, total;
+};
+
+// Block-wide: find the histogram bin holding the element of 0-based rank k.
+// If `first` the rank is derived from the total: k = (unsigned)((float)total * ratio), clamped.
+__device__ __forceinline__ void block_select(const unsigned int* ghist, int nbins, unsigned int k, bool first,
+                                             float ratio, SelectOut* out, unsigned int* ws) {
+  const int per = nbins / kIcpThreads;  // 2 or 4
+  unsigned int c[4], loc = 0;
+  for (int j = 0; j < per; ++j) {
+    c[j] = __ldcg(ghist + threadIdx.x * per + j);
+    loc += c[j];
+  }
+  unsigned int incl = loc;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  __syncthreads();  // ws reuse
+  if (lane == 31) ws[warp] = incl;
+  __syncthreads();
+  unsigned int woff = 0, total = 0;
+  for (int w = 0; w < kIcpThreads / 32; ++w) {
+    const unsigned int v = ws[w];
+    if (w < warp) woff += v;
+    total += v;
+  }
+  if (first) {
+    k = (unsigned int)((float)total * ratio);
+    if (total > 0 && k >= total) k = total - 1;
+  }
+  unsigned int run = woff + incl - loc;
+  for (int j = 0; j < per; ++j) {
+    if (k >= run && k < run + c[j]) {
+      out->bin = threadIdx.x * per + j;
+      out->rem = k - run;
+    }
+    run += c[j];
+  }
+  if (threadIdx.x == 0) out->total = total;
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kIcpThreads, 2)
+icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParamsDev prm) {
+  const int pi = blockIdx.x / ctas_per_problem;
+  const int cta = blockIdx.x - pi * ctas_per_problem;
+  const IcpProblem& P = probs[pi];
+  IcpWork* W = P.work;
+  const unsigned int G = (unsigned int)ctas_per_problem;
+  const int tid = threadIdx.x, lane = tid & 31;
+
+  __shared__ Grid g;
+  __shared__ float T_iter[16];
+  __shared__ unsigned int hist_s[2048];
+  __shared__ unsigned long long acc_s[28];
+  __shared__ SelectOut sel;
+  __shared__ unsigned int ws[kIcpThreads / 32];
+  __shared__ double qh[kMaxSmooth + 2][4];
+  __shared__ double th[kMaxSmooth + 2][3];
+  __shared__ int flag_stop, flag_status;
+
+  if (tid == 0) {
+    g = P.bs->grid;
+    for (int i = 0; i < 16; ++i) T_iter[i] = (i % 5 == 0) ? 1.f : 0.f;
+    quat_from_T(T_iter, qh[0]);
+    th[0][0] = th[0][1] = th[0][2] = 0.0;
+    flag_stop = 0;
+    flag_status = 0;
+  }
+  __syncthreads();
+
+  // contiguous chunk of queries per CTA (spatially compact, coalesced)
+  const int n = P.n;
+  int chunk = (n + (int)G - 1) / (int)G;
+  chunk = (chunk + 31) & ~31;
+  const int q_begin = min(n, cta * chunk), q_end = min(n, q_begin + chunk);
+
+  unsigned int epoch = 0;
+  int hist_count = 1;  // entries in qh/th
+  int iter = 0, converged = 0, max_reached = 0, last_kept = 0;
+  float last_limit = 0.f;
+
+  for (;;) {
+    const int par = iter & 1;
+    // ---------------- phase A: K2 nearest neighbour + level-1 histogram ----------------
+    for (int k = tid; k < 2048; k += kIcpThreads) hist_s[k] = 0u;
+    __syncthreads();
+    for (int i = q_begin + tid; i < q_end; i += kIcpThreads) {
+      const float4 r = __ldg(P.rd + i);
+      float sx, sy, sz;
+      xform_point(T_iter, r.x, r.y, r.z, sx, sy, sz);
+      const int warm = iter > 0 ? P.pos[i] : -1;
+      const Best b = nn_search(g, P.view, sx, sy, sz, warm);
+      P.pos[i] = b.pos;
+      P.d2[i] = b.d2;
+      P.ids[i] = b.idx;
+      const unsigned int key = __float_as_uint(b.d2);
+      if (key < 0x7f800000u) atomicAdd(&hist_s[key >> 21], 1u);  // finite, non-negative
+    }
+    __syncthreads();
+    for (int k = tid; k < 1024; k += kIcpThreads) {
+      const unsigned int v = hist_s[k];
+      if (v) atomicAdd(&W->hist[par][0][k], v);
+    }
+    problem_barrier(&W->barrier, G, epoch);
+
+    // ---------------- phase B: K3 select level 1, build level-2 histogram ----------------
+    block_select(W->hist[par][0], 1024, 0u, true, prm.trim_ratio, &sel, ws);
+    if (sel.total == 0u) {  // no finite match at all -> ConvergenceError
+      if (tid == 0) { flag_status = 1; if (cta == 0) W->fail_code = 1; }
+      __syncthreads();
+      break;
+    }
+    const unsigned int bin1 = sel.bin, rem1 = sel.rem;
+    if (cta == 0) {  // clear the other parity's scratch for the next iteration
+      unsigned int* h = &W->hist[par ^ 1][0][0];
+      for (int k = tid; k < 3 * 2048; k += kIcpThreads) h[k] = 0u;
+      if (tid < 32) W->acc[par ^ 1][tid] = 0ull;
+    }
+    for (int k = tid; k < 2048; k += kIcpThreads) hist_s[k] = 0u;
+    __syncthreads();
+    for (int i = q_begin + tid; i < q_end; i += kIcpThreads) {
+      const unsigned int key = __float_as_uint(P.d2[i]);
+      if (key < 0x7f800000u && (key >> 21) == bin1) atomicAdd(&hist_s[(key >> 10) & 2047u], 1u);
+    }
+    __syncthreads();
+    for (int k = tid; k < 2048; k += kIcpThreads) {
+      const unsigned int v = hist_s[k];
+      if (v) atomicAdd(&W->hist[par][1][k], v);
+    }
+    problem_barrier(&W->barrier, G, epoch);
+
+    // ---------------- phase C: select level 2, build level-3 histogram ----------------
+    block_select(W->hist[par][1], 2048, rem1, false, 0.f, &sel, ws);
+    const unsigned int bin2 = sel.bin, rem2 = sel.rem;
+    for (int k = tid; k < 1024; k += kIcpThreads) hist_s[k] = 0u;
+    __syncthreads();
+    const unsigned int prefix12 = (bin1 << 11) | bin2;
+    for (int i = q_begin + tid; i < q_end; i += kIcpThreads) {
+      const unsigned int key = __float_as_uint(P.d2[i]);
+      if (key < 0x7f800000u && (key >> 10) == prefix12) atomicAdd(&hist_s[key & 1023u], 1u);
+    }
+    __syncthreads();
+    for (int k = tid; k < 1024; k += kIcpThreads) {
+      const unsigned int v = hist_s[k];
+      if (v) atomicAdd(&W->hist[par][2][k], v);
+    }
+    problem_barrier(&W->barrier, G, epoch);
+
+    // ---------------- phase D: K4 normal equations over matches with d2 <= limit ----------------
+    block_select(W->hist[par][2], 1024, rem2, false, 0.f, &sel, ws);
+    const float limit = __uint_as_float((prefix12 << 10) | sel.bin);
+    if (tid < 28) acc_s[tid] = 0ull;
+    __syncthreads();
+    long long a[27];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) a[k] = 0;
+    int kept = 0;
+    for (int i = q_begin + tid; i < q_end; i += kIcpThreads) {
+      const float d = P.d2[i];
+      if (!(d <= limit)) continue;
+      const int pos = P.pos[i];
+      if (pos < 0) continue;
+      ++kept;
+      const float4 r = __ldg(P.rd + i);
+      float sx, sy, sz;
+      xform_point(T_iter, r.x, r.y, r.z, sx, sy, sz);
+      const float4 q = __ldg(P.view.pts + pos);
+      const float4 nn = __ldg(P.nrm + pos);
+      float f[6];
+      {
+        float u = sy * nn.z, v = sz * nn.y;
+        f[0] = u - v;
+        u = sz * nn.x; v = sx * nn.z;
+        f[1] = u - v;
+        u = sx * nn.y; v = sy * nn.x;
+        f[2] = u - v;
+      }
+      f[3] = nn.x; f[4] = nn.y; f[5] = nn.z;
+      const float dx = sx - q.x, dy = sy - q.y, dz = sz - q.z;
+      float e = dx * nn.x;
+      float t = dy * nn.y;
+      e = e + t;
+      t = dz * nn.z;
+      e = e + t;
+      int k = 0;
+#pragma unroll
+      for (int rr = 0; rr < 6; ++rr)
+#pragma unroll
+        for (int cc = rr; cc < 6; ++cc, ++k) a[k] += __float2ll_rn((f[rr] * f[cc]) * 4194304.0f);
+#pragma unroll
+      for (int rr = 0; rr < 6; ++rr) a[21 + rr] += __float2ll_rn((f[rr] * e) * 4194304.0f);
+    }
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+      const long long s = warp_sum_ll(a[k]);
+      if (lane == 0 && s != 0) atomicAdd(&acc_s[k], (unsigned long long)s);
+    }
+    {
+      const int ks = __reduce_add_sync(0xffffffffu, kept);
+      if (lane == 0 && ks) atomicAdd(&acc_s[27], (unsigned long long)ks);
+    }
+    __syncthreads();
+    if (tid < 28 && acc_s[tid] != 0ull) atomicAdd(&W->acc[par][tid], acc_s[tid]);
+    problem_barrier(&W->barrier, G, epoch);
+
+    // ---------------- phase E: solve, update, checkers (every CTA, identically) ----------------
+    if (tid == 0) {
+      double A[36], b[6], x[6];
+      int k = 0;
+      for (int rr = 0; rr < 6; ++rr)
+        for (int cc = rr; cc < 6; ++cc, ++k) {
+          const double v = (double)(long long)__ldcg(&W->acc[par][k]) / 4194304.0;
+          A[rr * 6 + cc] = v;
+          A[cc * 6 + rr] = v;
+        }
+      for (int rr = 0; rr < 6; ++rr) b[rr] = -((double)(long long)__ldcg(&W->acc[par][21 + rr]) / 4194304.0);
+      last_kept = (int)__ldcg(&W->acc[par][27]);
+      last_limit = limit;
+      int status = 0, stop = 0;
+      if (last_kept == 0) {
+        status = 1;
+        if (cta == 0) W->fail_code = 2;
+      } else {
+        if (!chol6(A, b, x)) jacobi_pinv_solve6(A, b, x);
+        for (int i = 0; i < 6; ++i)
+          if (!is_finite_d(x[i])) status = 1;
+        if (status && cta == 0) W->fail_code = 3;
+      }
+      if (cta == 0) {
+        W->dbg_total = sel.total; W->dbg_bin[0] = bin1; W->dbg_bin[1] = bin2; W->dbg_bin[2] = sel.bin;
+        W->dbg_rem[0] = rem1; W->dbg_rem[1] = rem2; W->dbg_rem[2] = sel.rem;
+        for (int i = 0; i < 6; ++i) { W->dbg_A[i] = A[i * 6 + i]; W->dbg_x[i] = x[i]; }
+      }
+      if (!status) {
+        float T_step[16];
+        step_matrix(x, T_step);
+        mat4_mul(T_step, T_iter, T_iter);
+        if (P.T_hist && cta == 0)
+          for (int i = 0; i < 16; ++i) P.T_hist[iter * 16 + i] = T_iter[i];
+        if (iter + 1 >= prm.max_iterations) { stop = 1; max_reached = 1; }
+        if (prm.use_differential) {
+          const int L = prm.smooth_length;
+          // ring buffer of the last L+1 (quaternion, translation) samples
+          if (hist_count == L + 1) {
+            for (int i = 0; i < L; ++i) {
+              for (int c = 0; c < 4; ++c) qh[i][c] = qh[i + 1][c];
+              for (int c = 0; c < 3; ++c) th[i][c] = th[i + 1][c];
+            }
+            --hist_count;
+          }
+          quat_from_T(T_iter, qh[hist_count]);
+          th[hist_count][0] = (double)T_iter[12];
+          th[hist_count][1] = (double)T_iter[13];
+          th[hist_count][2] = (double)T_iter[14];
+          ++hist_count;
+          if (hist_count > L) {
+            double mr = 0.0, mt = 0.0;
+            for (int i = hist_count - 1; i >= hist_count - L; --i) {
+              mr += fabs(quat_angular_distance(qh[i], qh[i - 1]));
+              const double ddx = th[i][0] - th[i - 1][0], ddy = th[i][1] - th[i - 1][1], ddz = th[i][2] - th[i - 1][2];
+              mt += sqrt(ddx * ddx + ddy * ddy + ddz * ddz);
+            }
+            mr /= (double)L;
+            mt /= (double)L;
+            if (mr != mr || mt != mt) { status = 1; if (cta == 0) W->fail_code = 4; }
+            else if (mr < (double)prm.min_diff_rot && mt < (double)prm.min_diff_trans) { stop = 1; converged = 1; }
+          }
+        }
+      }
+      flag_status = status;
+      flag_stop = stop | status;
+    }
+    __syncthreads();
+    if (!flag_status) ++iter;  // every thread tracks the iteration count (parity, warm start)
+    if (flag_stop) break;
+  }
+
+  if (cta == 0 && tid == 0) {
+    int status = flag_status;
+    float T_mean[16], tmp[16], T_fin[16];
+    for (int i = 0; i < 16; ++i) T_mean[i] = (i % 5 == 0) ? 1.f : 0.f;
+    T_mean[12] = g.mu[0]; T_mean[13] = g.mu[1]; T_mean[14] = g.mu[2];
+    mat4_mul(T_mean, T_iter, tmp);
+    mat4_mul(tmp, P.bs->T_pre, T_fin);
+    for (int i = 0; i < 16; ++i)
+      if (!is_finite_f(T_fin[i])) { status = 1; W->fail_code = 5; }
+    for (int i = 0; i < 16; ++i) W->T_out[i] = status ? P.T0[i] : T_fin[i];
+    W->status = status;
+    W->iterations = iter;
+    W->converged = converged;
+    W->max_iter_reached = max_reached;
+    W->last_kept = last_kept;
+    W->last_limit = last_limit;
+  }
+}
+
+}  // namespace ls

@@ -1,0 +1,202 @@
+"""ORACLE — test infrastructure only.  ctypes bindings of oracle/icp_oracle.cpp.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this package; the product (laser_slam_b200/) never does.  PARITY UNPINNED — see icp_oracle.cpp.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_build", "libls_oracle.so")
+_lib = None
+
+
+class IcpParams(ctypes.Structure):
+    _fields_ = [("max_iterations", ctypes.c_int), ("trim_ratio", ctypes.c_float),
+                ("use_differential", ctypes.c_int), ("min_diff_rot", ctypes.c_float),
+                ("min_diff_trans", ctypes.c_float), ("smooth_length", ctypes.c_int),
+                ("num_threads", ctypes.c_int)]
+
+
+class IcpStats(ctypes.Structure):
+    _fields_ = [("iterations", ctypes.c_int), ("converged", ctypes.c_int), ("max_iter_reached", ctypes.c_int),
+                ("last_kept", ctypes.c_int), ("last_limit", ctypes.c_float), ("used_ratio", ctypes.c_float)]
+
+
+def build(force=False):
+    srcs = [os.path.join(_HERE, f) for f in ("icp_oracle.cpp", "icp_oracle.h", "Makefile")]
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(s) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(LIB_PATH)
+        vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+        L.lso_default_params.argtypes = [ctypes.POINTER(IcpParams)]
+        L.lso_mean.argtypes = [vp, ci, vp]
+        L.lso_nn_brute.argtypes = [vp, ci, vp, ci, vp, vp]
+        L.lso_nn_kdtree.argtypes = [vp, ci, vp, ci, vp, vp, ci]
+        L.lso_trim_limit.argtypes = [vp, ci, cf, vp]
+        L.lso_trim_limit.restype = cf
+        L.lso_transform_points.argtypes = [vp, vp, ci, vp]
+        L.lso_transform_cloud.argtypes = [vp, vp, vp, ci, ci, vp, vp]
+        L.lso_check_rigid.argtypes = [vp]
+        L.lso_check_rigid.restype = ci
+        L.lso_correct_rigid.argtypes = [vp, vp]
+        L.lso_normal_equations.argtypes = [vp, ci, vp, vp, ci, vp, vp, cf, vp, vp, vp, vp, vp]
+        L.lso_solve_step.argtypes = [vp, vp, vp, vp]
+        L.lso_solve_step.restype = ci
+        L.lso_mat4_mul.argtypes = [vp, vp, vp]
+        L.lso_sincos.argtypes = [ctypes.c_double, vp, vp]
+        L.lso_icp.argtypes = [vp, ci, vp, vp, ci, ci, vp, ctypes.POINTER(IcpParams), vp,
+                              ctypes.POINTER(IcpStats), vp, vp, vp]
+        L.lso_icp.restype = ci
+        _lib = L
+    return _lib
+
+
+def default_params(**kw):
+    p = IcpParams()
+    lib().lso_default_params(ctypes.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, np.float32)
+
+
+def colmajor(T):
+    """4x4 (row, col) array -> 16 floats column-major (Eigen / TransformationParameters::data())."""
+    return np.ascontiguousarray(np.asarray(T, np.float32).T).ravel()
+
+
+def from_colmajor(t16):
+    return np.asarray(t16).reshape(4, 4).T.copy()
+
+
+def mean(ref4):
+    ref4 = _f32(ref4)
+    mu = np.empty(3, np.float32)
+    lib().lso_mean(ref4.ctypes.data, ref4.shape[0], mu.ctypes.data)
+    return mu
+
+
+def nn_brute(q3, ref3):
+    q3, ref3 = _f32(q3), _f32(ref3)
+    ids = np.empty(q3.shape[0], np.int32)
+    d2 = np.empty(q3.shape[0], np.float32)
+    lib().lso_nn_brute(q3.ctypes.data, q3.shape[0], ref3.ctypes.data, ref3.shape[0], ids.ctypes.data, d2.ctypes.data)
+    return ids, d2
+
+
+def nn_kdtree(q3, ref3, num_threads=1):
+    q3, ref3 = _f32(q3), _f32(ref3)
+    ids = np.empty(q3.shape[0], np.int32)
+    d2 = np.empty(q3.shape[0], np.float32)
+    lib().lso_nn_kdtree(q3.ctypes.data, q3.shape[0], ref3.ctypes.data, ref3.shape[0], ids.ctypes.data,
+                        d2.ctypes.data, num_threads)
+    return ids, d2
+
+
+def trim_limit(d2, ratio):
+    d2 = _f32(d2)
+    nf = ctypes.c_int(0)
+    lim = lib().lso_trim_limit(d2.ctypes.data, d2.shape[0], ratio, ctypes.addressof(nf))
+    return float(lim), nf.value
+
+
+def transform_points(T, pts4):
+    pts4 = _f32(pts4)
+    out = np.empty_like(pts4)
+    t = colmajor(T)
+    lib().lso_transform_points(t.ctypes.data, pts4.ctypes.data, pts4.shape[0], out.ctypes.data)
+    return out
+
+
+def transform_cloud(T, pts4, nrm3):
+    pts4, nrm3 = _f32(pts4), _f32(nrm3)
+    out = np.empty_like(pts4)
+    nout = np.empty_like(nrm3)
+    t = colmajor(T)
+    lib().lso_transform_cloud(t.ctypes.data, pts4.ctypes.data, nrm3.ctypes.data, 3, pts4.shape[0],
+                              out.ctypes.data, nout.ctypes.data)
+    return out, nout
+
+
+def check_rigid(T):
+    t = colmajor(T)
+    return bool(lib().lso_check_rigid(t.ctypes.data))
+
+
+def correct_rigid(T):
+    t = colmajor(T)
+    o = np.empty(16, np.float32)
+    lib().lso_correct_rigid(t.ctypes.data, o.ctypes.data)
+    return from_colmajor(o)
+
+
+def normal_equations(step4, refc3, nrm3, ids, d2, limit):
+    step4, refc3, nrm3, d2 = _f32(step4), _f32(refc3), _f32(nrm3), _f32(d2)
+    ids = np.ascontiguousarray(ids, np.int32)
+    A = np.empty((6, 6))
+    b = np.empty(6)
+    Ad = np.empty((6, 6))
+    bd = np.empty(6)
+    kept = ctypes.c_int(0)
+    lib().lso_normal_equations(step4.ctypes.data, step4.shape[0], refc3.ctypes.data, nrm3.ctypes.data, 3,
+                               ids.ctypes.data, d2.ctypes.data, limit, A.ctypes.data, b.ctypes.data,
+                               ctypes.addressof(kept), Ad.ctypes.data, bd.ctypes.data)
+    return A, b, kept.value, Ad, bd
+
+
+def solve_step(A, b):
+    A = np.ascontiguousarray(A, np.float64)
+    b = np.ascontiguousarray(b, np.float64)
+    T = np.empty(16, np.float32)
+    x = np.empty(6)
+    rc = lib().lso_solve_step(A.ctypes.data, b.ctypes.data, T.ctypes.data, x.ctypes.data)
+    return rc, from_colmajor(T), x
+
+
+def mat4_mul(A, B):
+    a, b = colmajor(A), colmajor(B)
+    c = np.empty(16, np.float32)
+    lib().lso_mat4_mul(a.ctypes.data, b.ctypes.data, c.ctypes.data)
+    return from_colmajor(c)
+
+
+def sincos(x):
+    s = ctypes.c_double()
+    c = ctypes.c_double()
+    lib().lso_sincos(x, ctypes.addressof(s), ctypes.addressof(c))
+    return s.value, c.value
+
+
+def icp(reading4, ref4, ref_normals3, T0, params=None, want_hist=False):
+    """Returns dict(rc, T (4x4 f32), stats, ids_hist (iters,n) or None, d2_last, T_iter_hist)."""
+    reading4, ref4, ref_normals3 = _f32(reading4), _f32(ref4), _f32(ref_normals3)
+    n, m = reading4.shape[0], ref4.shape[0]
+    p = params or default_params()
+    t0 = colmajor(T0)
+    tout = np.empty(16, np.float32)
+    st = IcpStats()
+    ids_hist = np.full((p.max_iterations, max(n, 1)), -2, np.int32) if want_hist else None
+    t_hist = np.zeros((p.max_iterations, 16), np.float32) if want_hist else None
+    d2_last = np.empty(max(n, 1), np.float32)
+    rc = lib().lso_icp(reading4.ctypes.data, n, ref4.ctypes.data, ref_normals3.ctypes.data, 3, m, t0.ctypes.data,
+                       ctypes.byref(p), tout.ctypes.data, ctypes.byref(st),
+                       ids_hist.ctypes.data if want_hist else None, d2_last.ctypes.data,
+                       t_hist.ctypes.data if want_hist else None)
+    return dict(rc=rc, T=from_colmajor(tout), stats=st,
+                ids_hist=ids_hist[:st.iterations, :n] if want_hist else None, d2_last=d2_last[:n],
+                T_iter_hist=(t_hist[:st.iterations].reshape(-1, 4, 4).transpose(0, 2, 1).copy()
+                             if want_hist else None))
