@@ -37,6 +37,7 @@ struct ls_ctx {
   IcpWork* work = nullptr;
   IcpProblem* prob = nullptr;
   float* T_hist = nullptr;
+  unsigned long long* phase_ns = nullptr;  // debug (LS_PHASE_TIMING=1)
   float* T0_dev = nullptr;
   // pinned host mirror for small results
   IcpWork* h_work = nullptr;  // only the tail (results) is read
@@ -137,6 +138,7 @@ int ensure_capacity(ls_ctx* ctx, int n, int m, int max_cells, int max_iter) {
     int rc;
     if ((rc = dev_alloc(ctx, &ctx->A.top, (size_t)max_cells + 1))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->A.cnt0, (size_t)max_cells + 1))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->A.pyr, (size_t)max_cells / 2 + 4096))) return rc;
     CU(cudaMemsetAsync(ctx->A.cnt0, 0, ((size_t)max_cells + 1) * sizeof(uint32_t), ctx->stream));
     ctx->cells_cap = max_cells;
   }
@@ -191,6 +193,10 @@ int enqueue_build(ls_ctx* ctx, const Parts& parts, const Resolved& r, const floa
   LAUNCH_CHECK();
   scan_apply_kernel<<<tiles, kScanThreads, 0, ctx->stream>>>(ctx->bs, ctx->A);
   LAUNCH_CHECK();
+  pyramid1_kernel<<<blocks_for(r.max_cells / 16 + 1, 256, ctx->sm_count * 4), 256, 0, ctx->stream>>>(ctx->bs, ctx->A);
+  LAUNCH_CHECK();
+  pyramid_up_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->bs, ctx->A);
+  LAUNCH_CHECK();
   count1_kernel<<<pb, 256, 0, ctx->stream>>>(ctx->bs, ctx->A, m);
   LAUNCH_CHECK();
   const int tb = ctx->sm_count * 4;
@@ -238,6 +244,7 @@ int run_icp(ls_ctx* ctx, const ls_icp_params* prm, const float4* reading_dev, in
   hp.view.tab1 = ctx->A.tab1;
   hp.view.tab2 = ctx->A.tab2;
   hp.view.pts = ctx->A.srt_pts;
+  hp.view.pyr = ctx->A.pyr;
   hp.nrm = ctx->A.srt_nrm;
   hp.rd = ctx->rd;
   hp.n = n;
@@ -246,6 +253,13 @@ int run_icp(ls_ctx* ctx, const ls_icp_params* prm, const float4* reading_dev, in
   hp.ids = ctx->ids;
   hp.work = ctx->work;
   hp.T_hist = opt_T_hist ? ctx->T_hist : nullptr;
+  const bool want_phase = getenv("LS_PHASE_TIMING") != nullptr;
+  if (want_phase) {
+    if (ctx->phase_ns) cudaFree(ctx->phase_ns);
+    CU(cudaMalloc((void**)&ctx->phase_ns, (size_t)prm->max_iterations * 6 * sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(ctx->phase_ns, 0, (size_t)prm->max_iterations * 6 * sizeof(unsigned long long), ctx->stream));
+  }
+  hp.phase_ns = want_phase ? ctx->phase_ns : nullptr;
   std::memcpy(hp.T0, T0, sizeof(hp.T0));
   CU(cudaMemcpyAsync(ctx->prob, &hp, sizeof(hp), cudaMemcpyHostToDevice, ctx->stream));
   IcpParamsDev dp;
@@ -273,6 +287,16 @@ int run_icp(ls_ctx* ctx, const ls_icp_params* prm, const float4* reading_dev, in
                        ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   const IcpWork& w = *ctx->h_work;
+  if (want_phase) {
+    std::vector<unsigned long long> ph((size_t)prm->max_iterations * 6);
+    cudaMemcpy(ph.data(), ctx->phase_ns, ph.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[ls] phase us per iteration: A(nn) B(sel1) C(sel2) D(sel3+acc) E(solve) | total\n");
+    for (int it = 0; it < w.iterations && it < prm->max_iterations; ++it) {
+      const unsigned long long* q = &ph[(size_t)it * 6];
+      fprintf(stderr, "[ls] it %2d: %8.1f %8.1f %8.1f %8.1f %8.1f | %8.1f\n", it, (q[1] - q[0]) * 1e-3, (q[2] - q[1]) * 1e-3,
+              (q[3] - q[2]) * 1e-3, (q[4] - q[3]) * 1e-3, (q[5] - q[4]) * 1e-3, (q[5] - q[0]) * 1e-3);
+    }
+  }
   std::memcpy(T_out, w.T_out, 16 * sizeof(float));
   if (stats) {
     std::memset(stats, 0, sizeof(*stats));
@@ -386,7 +410,7 @@ void ls_b200_destroy(ls_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   void* bufs[] = {ctx->A.sub_pts, ctx->A.sub_nrm, ctx->A.srt_pts, ctx->A.srt_nrm, ctx->A.pkey, ctx->A.top, ctx->A.cnt0,
-                  ctx->A.tab1, ctx->A.cnt1, ctx->A.tab1_cell, ctx->A.tab2, ctx->A.cnt2, ctx->A.tab2_key1, ctx->bs,
+                  ctx->A.tab1, ctx->A.cnt1, ctx->A.tab1_cell, ctx->A.tab2, ctx->A.cnt2, ctx->A.tab2_key1, ctx->A.pyr, ctx->bs,
                   ctx->reading, ctx->rd, ctx->ref_stage, ctx->ref_nrm_stage, ctx->nrm_raw, ctx->pos, ctx->d2, ctx->ids,
                   ctx->work, ctx->prob, ctx->T_hist, ctx->T0_dev};
   for (void* b : bufs)
@@ -476,7 +500,7 @@ int ls_nn_query(ls_ctx* ctx, const ls_icp_params* prm, const float* reading4, in
   if ((rc = enqueue_build(ctx, parts, r, T0))) return rc;
   reading_kernel<<<blocks_for(n, 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(ctx->bs, ctx->reading, n, ctx->rd);
   LAUNCH_CHECK();
-  GridView v{ctx->A.top, ctx->A.tab1, ctx->A.tab2, ctx->A.srt_pts};
+  GridView v{ctx->A.top, ctx->A.tab1, ctx->A.tab2, ctx->A.srt_pts, ctx->A.pyr};
   nn_query_kernel<<<blocks_for(n, 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(ctx->bs, v, ctx->rd, n, ctx->ids, ctx->d2);
   LAUNCH_CHECK();
   CU(cudaMemcpyAsync(ids, ctx->ids, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

@@ -53,6 +53,12 @@ struct Grid {
   int leaf_split;   // a cell with more points than this is subdivided
   int n_tab1, n_tab2;
   int overflow;     // set if a table pool was exhausted (cells then stay leaves: slower, still exact)
+  // occupancy pyramid above level 0: level l (1..n_pyr) has cells of edge H0*4^l, each a 64-bit mask
+  // of its non-empty 4x4x4 children; the top level is a single cell.
+  int n_pyr;
+  int pdim[8][3];   // pdim[0] == dim
+  int poff[8];      // offset of level l's masks in GridView::pyr (poff[0] unused)
+  int n_pyr_cells;
 };
 
 struct GridView {
@@ -60,6 +66,7 @@ struct GridView {
   const Entry* tab1;
   const Entry* tab2;
   const float4* pts;  // sorted {x,y,z,idx}
+  const unsigned long long* pyr;  // occupancy masks, levels 1..n_pyr
 };
 
 struct Best {
@@ -89,11 +96,15 @@ LS_HD Entry ld_entry(const Entry* e) {
 }
 LS_HD int f2i(float f) { return __float_as_int(f); }
 LS_HD float i2f(int i) { return __int_as_float(i); }
+LS_HD unsigned long long ld_mask(const unsigned long long* p) { return __ldg(p); }
+LS_HD int ctz64(unsigned long long m) { return __ffsll((long long)m) - 1; }
 #else
 LS_HD float4 ld_pt(const float4* p) { LS_CNT_CAND(); return *p; }
 LS_HD Entry ld_entry(const Entry* e) { LS_CNT_ENTRY(); return *e; }
 LS_HD int f2i(float f) { int i; std::memcpy(&i, &f, 4); return i; }
 LS_HD float i2f(int i) { float f; std::memcpy(&f, &i, 4); return f; }
+LS_HD unsigned long long ld_mask(const unsigned long long* p) { LS_CNT_ENTRY(); return *p; }
+LS_HD int ctz64(unsigned long long m) { return __builtin_ctzll(m); }
 #endif
 
 // Monotone (non-decreasing in v) cell coordinate functions; the SAME functions bin the map points
@@ -133,8 +144,27 @@ LS_HD void consider(const float4* pts, int pos, float qx, float qy, float qz, Be
   }
 }
 
+LS_HD void consider_pt(const float4 p, int pos, float qx, float qy, float qz, Best& b) {
+  const float d = dist2(qx, qy, qz, p.x, p.y, p.z);
+  const int idx = f2i(p.w);
+  if (d < b.d2 || (d == b.d2 && idx < b.idx)) {
+    b.d2 = d;
+    b.idx = idx;
+    b.pos = pos;
+  }
+}
+
+// candidates are independent loads: issue four before touching any (memory-level parallelism)
 LS_HD void scan_range(const float4* pts, uint32_t a, uint32_t e, float qx, float qy, float qz, Best& b) {
-  for (uint32_t pos = a; pos < e; ++pos) consider(pts, (int)pos, qx, qy, qz, b);
+  uint32_t pos = a;
+  for (; pos + 4 <= e; pos += 4) {
+    const float4 p0 = ld_pt(pts + pos), p1 = ld_pt(pts + pos + 1), p2 = ld_pt(pts + pos + 2), p3 = ld_pt(pts + pos + 3);
+    consider_pt(p0, (int)pos, qx, qy, qz, b);
+    consider_pt(p1, (int)pos + 1, qx, qy, qz, b);
+    consider_pt(p2, (int)pos + 2, qx, qy, qz, b);
+    consider_pt(p3, (int)pos + 3, qx, qy, qz, b);
+  }
+  for (; pos < e; ++pos) consider(pts, (int)pos, qx, qy, qz, b);
 }
 
 // ---- ball query, level 2 table (all entries are leaves; x-runs are contiguous) -------------------
@@ -144,11 +174,19 @@ LS_HD void visit_l2(const Grid& g, const Entry* tab, float lox, float loy, float
   const int x0 = coord_sub(qx - R, lox, g.inv2), x1 = coord_sub(qx + R, lox, g.inv2);
   const int y0 = coord_sub(qy - R, loy, g.inv2), y1 = coord_sub(qy + R, loy, g.inv2);
   const int z0 = coord_sub(qz - R, loz, g.inv2), z1 = coord_sub(qz + R, loz, g.inv2);
+  // home row first: the nearest candidates shrink the ball before the other rows are tested
+  const int hy = coord_sub(qy, loy, g.inv2), hz = coord_sub(qz, loz, g.inv2);
+  {
+    const Entry e0 = ld_entry(tab + (hz * 4 + hy) * 4 + x0);
+    const Entry e1 = ld_entry(tab + (hz * 4 + hy) * 4 + x1);
+    scan_range(pts, e0.start, e1.start + (uint32_t)e1.meta, qx, qy, qz, b);
+  }
   for (int z = z0; z <= z1; ++z) {
     const float gz = gap(qz, cell_lo(loz, z, g.H2), cell_lo(loz, z + 1, g.H2), g.margin);
     const float gz2 = gz * gz;
     if (gz2 * LS_SHRINK > b.d2) continue;
     for (int y = y0; y <= y1; ++y) {
+      if (y == hy && z == hz) continue;
       const float gy = gap(qy, cell_lo(loy, y, g.H2), cell_lo(loy, y + 1, g.H2), g.margin);
       const float lb = gy * gy + gz2;
       if (lb * LS_SHRINK > b.d2) continue;
@@ -166,6 +204,16 @@ LS_HD void visit_l1(const Grid& g, const Entry* tab, const Entry* tab2, float lo
   const int x0 = coord_sub(qx - R, lox, g.inv1), x1 = coord_sub(qx + R, lox, g.inv1);
   const int y0 = coord_sub(qy - R, loy, g.inv1), y1 = coord_sub(qy + R, loy, g.inv1);
   const int z0 = coord_sub(qz - R, loz, g.inv1), z1 = coord_sub(qz + R, loz, g.inv1);
+  const int hx = coord_sub(qx, lox, g.inv1), hy = coord_sub(qy, loy, g.inv1), hz = coord_sub(qz, loz, g.inv1);
+  {
+    const Entry e = ld_entry(tab + (hz * 4 + hy) * 4 + hx);
+    if (e.meta > 0) {
+      scan_range(pts, e.start, e.start + (uint32_t)e.meta, qx, qy, qz, b);
+    } else if (e.meta < 0) {
+      visit_l2(g, tab2 + (size_t)(~e.meta) * 64, cell_lo(lox, hx, g.H1), cell_lo(loy, hy, g.H1), cell_lo(loz, hz, g.H1), pts,
+               qx, qy, qz, b);
+    }
+  }
   for (int z = z0; z <= z1; ++z) {
     const float cz = cell_lo(loz, z, g.H1);
     const float gz = gap(qz, cz, cell_lo(loz, z + 1, g.H1), g.margin);
@@ -177,6 +225,7 @@ LS_HD void visit_l1(const Grid& g, const Entry* tab, const Entry* tab2, float lo
       const float lbyz = gy * gy + gz2;
       if (lbyz * LS_SHRINK > b.d2) continue;
       for (int x = x0; x <= x1; ++x) {
+        if (x == hx && y == hy && z == hz) continue;
         const float cx = cell_lo(lox, x, g.H1);
         const float gx = gap(qx, cx, cell_lo(lox, x + 1, g.H1), g.margin);
         const float lb = gx * gx + lbyz;
@@ -192,12 +241,64 @@ LS_HD void visit_l1(const Grid& g, const Entry* tab, const Entry* tab2, float lo
   }
 }
 
+// one level-0 cell (leaf scan or descent)
+LS_HD void visit_top_cell(const Grid& g, const GridView& v, int x, int y, int z, float cx, float cy, float cz, float qx,
+                          float qy, float qz, Best& b) {
+  const Entry e = ld_entry(v.top + ((size_t)z * g.dim[1] + y) * g.dim[0] + x);
+  if (e.meta > 0) {
+    scan_range(v.pts, e.start, e.start + (uint32_t)e.meta, qx, qy, qz, b);
+  } else if (e.meta < 0) {
+    visit_l1(g, v.tab1 + (size_t)(~e.meta) * 64, v.tab2, cx, cy, cz, v.pts, qx, qy, qz, b);
+  }
+}
+
+// ---- large balls: depth-first walk of the occupancy pyramid (empty space costs one mask load per
+// 64 cells instead of one entry load per cell) -------------------------------------------------------
+LS_HDN void pyramid_query(const Grid& g, const GridView& v, float qx, float qy, float qz, Best& b) {
+  int lvl[8], bx[8], by[8], bz[8];
+  unsigned long long mk[8];
+  int sp = 0;
+  lvl[0] = g.n_pyr;
+  bx[0] = by[0] = bz[0] = 0;
+  mk[0] = ld_mask(v.pyr + g.poff[g.n_pyr]);
+  while (sp >= 0) {
+    if (mk[sp] == 0ull) { --sp; continue; }
+    const int bit = ctz64(mk[sp]);
+    mk[sp] &= mk[sp] - 1ull;
+    const int cl = lvl[sp] - 1;  // level of the child cell
+    const int cx = bx[sp] + (bit & 3), cy = by[sp] + ((bit >> 2) & 3), cz = bz[sp] + (bit >> 4);
+    const float Hc = g.H0 * (float)(1 << (2 * cl));
+    const float lx = cell_lo(g.org[0], cx, Hc), ly = cell_lo(g.org[1], cy, Hc), lz = cell_lo(g.org[2], cz, Hc);
+    const float gx = gap(qx, lx, cell_lo(g.org[0], cx + 1, Hc), g.margin);
+    const float gy = gap(qy, ly, cell_lo(g.org[1], cy + 1, Hc), g.margin);
+    const float gz = gap(qz, lz, cell_lo(g.org[2], cz + 1, Hc), g.margin);
+    const float lb = gx * gx + (gy * gy + gz * gz);
+    if (lb * LS_SHRINK > b.d2) continue;
+    if (cl == 0) {
+      visit_top_cell(g, v, cx, cy, cz, lx, ly, lz, qx, qy, qz, b);
+    } else {
+      ++sp;
+      lvl[sp] = cl;
+      bx[sp] = cx * 4; by[sp] = cy * 4; bz[sp] = cz * 4;
+      mk[sp] = ld_mask(v.pyr + g.poff[cl] + ((size_t)cz * g.pdim[cl][1] + cy) * g.pdim[cl][0] + cx);
+    }
+  }
+}
+
 // ---- ball query, level 0 -----------------------------------------------------------------------
 LS_HD void ball_query(const Grid& g, const GridView& v, float qx, float qy, float qz, Best& b) {
   const float R = ball_radius(b.d2, g.margin);
   const int x0 = coord_top(qx - R, g.org[0], g.inv0, g.dim[0]), x1 = coord_top(qx + R, g.org[0], g.inv0, g.dim[0]);
   const int y0 = coord_top(qy - R, g.org[1], g.inv0, g.dim[1]), y1 = coord_top(qy + R, g.org[1], g.inv0, g.dim[1]);
   const int z0 = coord_top(qz - R, g.org[2], g.inv0, g.dim[2]), z1 = coord_top(qz + R, g.org[2], g.inv0, g.dim[2]);
+  if ((x1 - x0 + 1) * (y1 - y0 + 1) * (z1 - z0 + 1) > 27 && g.n_pyr > 0) {
+    pyramid_query(g, v, qx, qy, qz, b);
+    return;
+  }
+  const int hx = coord_top(qx, g.org[0], g.inv0, g.dim[0]), hy = coord_top(qy, g.org[1], g.inv0, g.dim[1]),
+            hz = coord_top(qz, g.org[2], g.inv0, g.dim[2]);
+  visit_top_cell(g, v, hx, hy, hz, cell_lo(g.org[0], hx, g.H0), cell_lo(g.org[1], hy, g.H0), cell_lo(g.org[2], hz, g.H0),
+                 qx, qy, qz, b);
   for (int z = z0; z <= z1; ++z) {
     const float cz = cell_lo(g.org[2], z, g.H0);
     const float gz = gap(qz, cz, cell_lo(g.org[2], z + 1, g.H0), g.margin);
@@ -208,18 +309,13 @@ LS_HD void ball_query(const Grid& g, const GridView& v, float qx, float qy, floa
       const float gy = gap(qy, cy, cell_lo(g.org[1], y + 1, g.H0), g.margin);
       const float lbyz = gy * gy + gz2;
       if (lbyz * LS_SHRINK > b.d2) continue;
-      const Entry* row = v.top + ((size_t)z * g.dim[1] + y) * g.dim[0];
       for (int x = x0; x <= x1; ++x) {
+        if (x == hx && y == hy && z == hz) continue;
         const float cx = cell_lo(g.org[0], x, g.H0);
         const float gx = gap(qx, cx, cell_lo(g.org[0], x + 1, g.H0), g.margin);
         const float lb = gx * gx + lbyz;
         if (lb * LS_SHRINK > b.d2) continue;
-        const Entry e = ld_entry(row + x);
-        if (e.meta > 0) {
-          scan_range(v.pts, e.start, e.start + (uint32_t)e.meta, qx, qy, qz, b);
-        } else if (e.meta < 0) {
-          visit_l1(g, v.tab1 + (size_t)(~e.meta) * 64, v.tab2, cx, cy, cz, v.pts, qx, qy, qz, b);
-        }
+        visit_top_cell(g, v, x, y, z, cx, cy, cz, qx, qy, qz, b);
       }
     }
   }
@@ -232,36 +328,31 @@ LS_HDN void seed_query(const Grid& g, const GridView& v, float qx, float qy, flo
   const int cz = coord_top(qz, g.org[2], g.inv0, g.dim[2]);
   const Entry e = ld_entry(v.top + ((size_t)cz * g.dim[1] + cy) * g.dim[0] + cx);
   if (e.meta == 0) {
-    // empty level-0 cell: first point of every occupied cell of the nearest occupied Chebyshev shell
-    int rmax = g.dim[0] > g.dim[1] ? g.dim[0] : g.dim[1];
-    rmax = rmax > g.dim[2] ? rmax : g.dim[2];
-    for (int r = 1; r <= rmax; ++r) {
-      bool any = false;
-      const int za = cz - r < 0 ? 0 : cz - r, zb = cz + r >= g.dim[2] ? g.dim[2] - 1 : cz + r;
-      const int ya = cy - r < 0 ? 0 : cy - r, yb = cy + r >= g.dim[1] ? g.dim[1] - 1 : cy + r;
-      for (int z = za; z <= zb; ++z)
-        for (int y = ya; y <= yb; ++y) {
-          const Entry* row = v.top + ((size_t)z * g.dim[1] + y) * g.dim[0];
-          const bool face = (z == cz - r) || (z == cz + r) || (y == cy - r) || (y == cy + r);
-          if (face) {
-            const int xa = cx - r < 0 ? 0 : cx - r, xb = cx + r >= g.dim[0] ? g.dim[0] - 1 : cx + r;
-            for (int x = xa; x <= xb; ++x) {
-              const Entry s = ld_entry(row + x);
-              if (s.meta != 0) { consider(v.pts, (int)s.start, qx, qy, qz, b); any = true; }
-            }
-          } else {
-            if (cx - r >= 0) {
-              const Entry s = ld_entry(row + cx - r);
-              if (s.meta != 0) { consider(v.pts, (int)s.start, qx, qy, qz, b); any = true; }
-            }
-            if (cx + r < g.dim[0]) {
-              const Entry s = ld_entry(row + cx + r);
-              if (s.meta != 0) { consider(v.pts, (int)s.start, qx, qy, qz, b); any = true; }
-            }
-          }
-        }
-      if (any) break;
+    // empty level-0 cell: greedy descent of the occupancy pyramid towards the nearest occupied child
+    // at every level; the first point of the level-0 cell reached is a real (if loose) candidate.
+    int X = 0, Y = 0, Z = 0;
+    for (int l = g.n_pyr; l >= 1; --l) {
+      unsigned long long mask = ld_mask(v.pyr + g.poff[l] + ((size_t)Z * g.pdim[l][1] + Y) * g.pdim[l][0] + X);
+      const float Hc = g.H0 * (float)(1 << (2 * (l - 1)));
+      float best_lb = INFINITY;
+      int best_bit = -1;
+      while (mask) {
+        const int bit = ctz64(mask);
+        mask &= mask - 1ull;
+        const int ccx = X * 4 + (bit & 3), ccy = Y * 4 + ((bit >> 2) & 3), ccz = Z * 4 + (bit >> 4);
+        const float gx = gap(qx, cell_lo(g.org[0], ccx, Hc), cell_lo(g.org[0], ccx + 1, Hc), 0.f);
+        const float gy = gap(qy, cell_lo(g.org[1], ccy, Hc), cell_lo(g.org[1], ccy + 1, Hc), 0.f);
+        const float gz = gap(qz, cell_lo(g.org[2], ccz, Hc), cell_lo(g.org[2], ccz + 1, Hc), 0.f);
+        const float lb = gx * gx + (gy * gy + gz * gz);
+        if (lb < best_lb) { best_lb = lb; best_bit = bit; }
+      }
+      if (best_bit < 0) return;  // empty map
+      X = X * 4 + (best_bit & 3);
+      Y = Y * 4 + ((best_bit >> 2) & 3);
+      Z = Z * 4 + (best_bit >> 4);
     }
+    const Entry s0 = ld_entry(v.top + ((size_t)Z * g.dim[1] + Y) * g.dim[0] + X);
+    if (s0.meta != 0) consider(v.pts, (int)s0.start, qx, qy, qz, b);
     return;
   }
   if (e.meta > 0) { scan_range(v.pts, e.start, e.start + (uint32_t)e.meta, qx, qy, qz, b); return; }
@@ -353,6 +444,17 @@ LS_HDN void grid_setup(Grid& g, const float* lo, const float* hi, float cell_siz
   g.n_tab1 = 0;
   g.n_tab2 = 0;
   g.overflow = 0;
+  for (int a = 0; a < 3; ++a) g.pdim[0][a] = g.dim[a];
+  g.poff[0] = 0;
+  int off = 0, l = 0;
+  do {
+    ++l;
+    for (int a = 0; a < 3; ++a) g.pdim[l][a] = (g.pdim[l - 1][a] + 3) / 4;
+    g.poff[l] = off;
+    off += g.pdim[l][0] * g.pdim[l][1] * g.pdim[l][2];
+  } while ((g.pdim[l][0] > 1 || g.pdim[l][1] > 1 || g.pdim[l][2] > 1) && l < 7);
+  g.n_pyr = l;
+  g.n_pyr_cells = off;
 }
 
 }  // namespace ls

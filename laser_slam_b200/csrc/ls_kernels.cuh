@@ -58,6 +58,7 @@ struct BuildArrays {
   uint32_t* cnt2;
   uint32_t* tab2_key1;   // level-1 key (table*64+sub) of each level-2 table
   int tab_cap;
+  unsigned long long* pyr;  // occupancy pyramid masks
 };
 
 struct IcpParamsDev {
@@ -92,6 +93,7 @@ struct IcpProblem {
   int* ids;
   IcpWork* work;
   float* T_hist;  // max_iterations*16 floats or null
+  unsigned long long* phase_ns;  // debug: max_iterations*6 globaltimer stamps (CTA 0) or null
   float T0[16];
 };
 
@@ -298,6 +300,57 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(BuildState* bs
   }
 }
 
+// ---- K1c': occupancy pyramid (level 1 from the level-0 entries, upper levels by one CTA) -------------
+__device__ __forceinline__ unsigned long long pyramid_mask(const Grid& g, int l, int x, int y, int z, const Entry* top,
+                                                           const unsigned long long* pyr) {
+  const int* cd = g.pdim[l - 1];
+  unsigned long long mask = 0ull;
+  for (int k = 0; k < 4; ++k) {
+    const int cz = 4 * z + k;
+    if (cz >= cd[2]) break;
+    for (int j = 0; j < 4; ++j) {
+      const int cy = 4 * y + j;
+      if (cy >= cd[1]) break;
+      for (int i = 0; i < 4; ++i) {
+        const int cx = 4 * x + i;
+        if (cx >= cd[0]) break;
+        const size_t ci = ((size_t)cz * cd[1] + cy) * cd[0] + cx;
+        const bool occ = (l == 1) ? (top[ci].meta != 0) : (pyr[g.poff[l - 1] + ci] != 0ull);
+        if (occ) mask |= 1ull << ((k * 4 + j) * 4 + i);
+      }
+    }
+  }
+  return mask;
+}
+
+__global__ void __launch_bounds__(256) pyramid1_kernel(const BuildState* __restrict__ bs, BuildArrays A) {
+  __shared__ Grid g;
+  if (threadIdx.x == 0) g = bs->grid;
+  __syncthreads();
+  const int* pd = g.pdim[1];
+  const int n = pd[0] * pd[1] * pd[2];
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+    const int x = c % pd[0], y = (c / pd[0]) % pd[1], z = c / (pd[0] * pd[1]);
+    A.pyr[g.poff[1] + c] = pyramid_mask(g, 1, x, y, z, A.top, A.pyr);
+  }
+}
+
+__global__ void __launch_bounds__(1024) pyramid_up_kernel(const BuildState* __restrict__ bs, BuildArrays A) {
+  __shared__ Grid g;
+  if (threadIdx.x == 0) g = bs->grid;
+  __syncthreads();
+  for (int l = 2; l <= g.n_pyr; ++l) {
+    const int* pd = g.pdim[l];
+    const int n = pd[0] * pd[1] * pd[2];
+    for (int c = threadIdx.x; c < n; c += blockDim.x) {
+      const int x = c % pd[0], y = (c / pd[0]) % pd[1], z = c / (pd[0] * pd[1]);
+      A.pyr[g.poff[l] + c] = pyramid_mask(g, l, x, y, z, A.top, A.pyr);
+    }
+    __threadfence_block();
+    __syncthreads();
+  }
+}
+
 // ---- K1d: level-1 histogram -------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) count1_kernel(const BuildState* __restrict__ bs, BuildArrays A, int m) {
   __shared__ Grid g;
@@ -465,6 +518,16 @@ __global__ void __launch_bounds__(256) nn_query_kernel(const BuildState* __restr
 // ================================================================================================
 // Persistent ICP kernel
 // ================================================================================================
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define LS_STAMP(slot)                                                                   \
+  do {                                                                                   \
+    if (P.phase_ns && cta == 0 && tid == 0) P.phase_ns[iter * 6 + (slot)] = globaltimer_ns(); \
+  } while (0)
+
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   unsigned int v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -572,6 +635,7 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
 
   for (;;) {
     const int par = iter & 1;
+    LS_STAMP(0);
     // ---------------- phase A: K2 nearest neighbour + level-1 histogram ----------------
     for (int k = tid; k < 2048; k += kIcpThreads) hist_s[k] = 0u;
     __syncthreads();
@@ -593,6 +657,7 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
       if (v) atomicAdd(&W->hist[par][0][k], v);
     }
     problem_barrier(&W->barrier, G, epoch);
+    LS_STAMP(1);
 
     // ---------------- phase B: K3 select level 1, build level-2 histogram ----------------
     block_select(W->hist[par][0], 1024, 0u, true, prm.trim_ratio, &sel, ws);
@@ -619,6 +684,7 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
       if (v) atomicAdd(&W->hist[par][1][k], v);
     }
     problem_barrier(&W->barrier, G, epoch);
+    LS_STAMP(2);
 
     // ---------------- phase C: select level 2, build level-3 histogram ----------------
     block_select(W->hist[par][1], 2048, rem1, false, 0.f, &sel, ws);
@@ -636,6 +702,7 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
       if (v) atomicAdd(&W->hist[par][2][k], v);
     }
     problem_barrier(&W->barrier, G, epoch);
+    LS_STAMP(3);
 
     // ---------------- phase D: K4 normal equations over matches with d2 <= limit ----------------
     block_select(W->hist[par][2], 1024, rem2, false, 0.f, &sel, ws);
@@ -693,6 +760,7 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
     __syncthreads();
     if (tid < 28 && acc_s[tid] != 0ull) atomicAdd(&W->acc[par][tid], acc_s[tid]);
     problem_barrier(&W->barrier, G, epoch);
+    LS_STAMP(4);
 
     // ---------------- phase E: solve, update, checkers (every CTA, identically) ----------------
     if (tid == 0) {
@@ -760,6 +828,7 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
       }
       flag_status = status;
       flag_stop = stop | status;
+      LS_STAMP(5);
     }
     __syncthreads();
     if (!flag_status) ++iter;  // every thread tracks the iteration count (parity, warm start)

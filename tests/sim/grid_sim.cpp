@@ -19,6 +19,7 @@ struct SimGrid {
   ls::Grid g;
   std::vector<ls::Entry> top, tab1, tab2;
   std::vector<float4> pts;
+  std::vector<unsigned long long> pyr;
 };
 
 void build(SimGrid& S, const float* refc3, int m, float cell, int max_cells, int split) {
@@ -111,6 +112,25 @@ void build(SimGrid& S, const float* refc3, int m, float cell, int max_cells, int
   }
   S.g.n_tab1 = n1;
   S.g.n_tab2 = n2;
+  // occupancy pyramid
+  S.pyr.assign(g.n_pyr_cells, 0ull);
+  for (int l = 1; l <= g.n_pyr; ++l) {
+    const int* pd = g.pdim[l];
+    const int* cd = g.pdim[l - 1];
+    for (int z = 0; z < pd[2]; ++z)
+      for (int y = 0; y < pd[1]; ++y)
+        for (int x = 0; x < pd[0]; ++x) {
+          unsigned long long mask = 0;
+          for (int bit = 0; bit < 64; ++bit) {
+            const int cx = 4 * x + (bit & 3), cy = 4 * y + ((bit >> 2) & 3), cz = 4 * z + (bit >> 4);
+            if (cx >= cd[0] || cy >= cd[1] || cz >= cd[2]) continue;
+            const size_t ci = ((size_t)cz * cd[1] + cy) * cd[0] + cx;
+            const bool occ = (l == 1) ? (S.top[ci].meta != 0) : (S.pyr[g.poff[l - 1] + ci] != 0ull);
+            if (occ) mask |= 1ull << bit;
+          }
+          S.pyr[g.poff[l] + ((size_t)z * pd[1] + y) * pd[0] + x] = mask;
+        }
+  }
 }
 }  // namespace
 
@@ -119,12 +139,13 @@ extern "C" {
 // match ORIGINAL indices (-1 = cold).  stats (optional, 4 doubles): mean candidates, mean entry
 // loads, max candidates, #level-1 tables + 1e-6 * #level-2 tables.
 void sim_nn(const float* q3, int n, const float* refc3, int m, float cell, int max_cells, int split,
-            const int32_t* warm_ids, int32_t* ids, float* d2, double* stats) {
+            const int32_t* warm_ids, int32_t* ids, float* d2, double* stats, int32_t* per_query_cand,
+            int32_t* per_query_entries) {
   SimGrid S;
   build(S, refc3, m, cell, max_cells, split);
   std::vector<int> pos_of(m);
   for (int i = 0; i < m; ++i) pos_of[ls::f2i(S.pts[i].w)] = i;
-  ls::GridView v{S.top.data(), S.tab1.data(), S.tab2.data(), S.pts.data()};
+  ls::GridView v{S.top.data(), S.tab1.data(), S.tab2.data(), S.pts.data(), S.pyr.data()};
   long long cand = 0, ent = 0, cmax = 0;
   for (int i = 0; i < n; ++i) {
     ls::ls_sim_cand = 0;
@@ -133,6 +154,8 @@ void sim_nn(const float* q3, int n, const float* refc3, int m, float cell, int m
     const ls::Best b = ls::nn_search(S.g, v, q3[3 * i], q3[3 * i + 1], q3[3 * i + 2], warm);
     ids[i] = b.idx;
     d2[i] = b.d2;
+    if (per_query_cand) per_query_cand[i] = (int32_t)ls::ls_sim_cand;
+    if (per_query_entries) per_query_entries[i] = (int32_t)ls::ls_sim_entries;
     cand += ls::ls_sim_cand;
     ent += ls::ls_sim_entries;
     cmax = std::max(cmax, ls::ls_sim_cand);

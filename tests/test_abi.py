@@ -1,0 +1,117 @@
+"""The C-ABI library loads and exports every symbol include/ls_b200.h declares; host-only logic
+(YAML chain reader, rigid-matrix check) works; and the product refuses to run without a GPU
+(no CPU fallback).  No compute entry point is called here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def ls():
+    import laser_slam_b200 as m
+    m.build()
+    return m
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "ls_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ls_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(ls):
+    lib = ctypes.CDLL(ls.LIB_PATH)
+    syms = declared_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/ls_b200.h but not exported"
+
+
+def test_yaml_chain_reader(ls):
+    ref_yaml = """
+readingDataPointsFilters:
+  - RandomSamplingDataPointsFilter:
+      prob: 0.5
+referenceDataPointsFilters:
+  - SamplingSurfaceNormalDataPointsFilter:
+      knn: 10
+matcher:
+  KDTreeMatcher:
+    knn: 1
+    epsilon: 0
+outlierFilters:
+  - TrimmedDistOutlierFilter:
+      ratio: 0.75
+errorMinimizer:
+  PointToPlaneErrorMinimizer
+transformationCheckers:
+  - CounterTransformationChecker:
+      maxIterationCount: 40
+  - DifferentialTransformationChecker:
+      minDiffRotErr: 0.001
+      minDiffTransErr: 0.01
+      smoothLength: 4
+#inspector:
+#  NullInspector
+inspector:
+ VTKFileInspector:
+     baseFileName: pointmatcher-run1
+logger:
+  NullLogger
+"""
+    p = ls.params_from_yaml(ref_yaml)
+    assert (p.max_iterations, p.use_differential, p.smooth_length) == (40, 1, 4)
+    assert abs(p.trim_ratio - 0.75) < 1e-7 and abs(p.min_diff_rot - 1e-3) < 1e-9 and abs(p.min_diff_trans - 1e-2) < 1e-9
+    p2 = ls.params_from_yaml(ref_yaml.replace("maxIterationCount: 40", "maxIterationCount: 7").replace("ratio: 0.75", "ratio: 0.9"))
+    assert p2.max_iterations == 7 and abs(p2.trim_ratio - 0.9) < 1e-7
+    p3 = ls.params_from_yaml("matcher:\n  KDTreeMatcher:\n    knn: 1\ntransformationCheckers:\n  - CounterTransformationChecker:\n      maxIterationCount: 30\n")
+    assert p3.use_differential == 0 and p3.max_iterations == 30 and p3.trim_ratio == 1.0
+    for bad in ("matcher:\n  KDTreeMatcher:\n    knn: 3\n", "matcher:\n  KDTreeMatcher:\n    epsilon: 0.5\n",
+                "errorMinimizer:\n  PointToPointErrorMinimizer\n", "outlierFilters:\n  - MaxDistOutlierFilter:\n      maxDist: 1\n"):
+        with pytest.raises(ls.LsError):
+            ls.params_from_yaml(bad)
+
+
+def test_reference_default_yaml_is_accepted(ls):
+    """The reference's own chain file must parse (laser_slam/configurations/icp_default.yaml); only read when
+    the reference tree is mounted (never on the GPU box)."""
+    path = "/root/reference/laser_slam/configurations/icp_default.yaml"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not mounted")
+    p = ls.params_from_yaml(open(path).read())
+    assert p.max_iterations == 40 and p.use_differential == 1 and abs(p.trim_ratio - 0.75) < 1e-7
+
+
+def test_rigid_helpers_match_oracle(ls, oracle_mod):
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        T = np.eye(4, dtype=np.float32)
+        T[:3, :3] += rng.normal(scale=0.02, size=(3, 3)).astype(np.float32)
+        T[:3, 3] = rng.normal(size=3)
+        assert ls.check_rigid(T) == oracle_mod.check_rigid(T)
+        assert np.array_equal(ls.correct_rigid(T), oracle_mod.correct_rigid(T))
+
+
+def test_no_gpu_means_loud_failure(ls):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(ls.LsError, match="no usable CUDA device"):
+        ls.Context(0)
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under laser_slam_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "laser_slam_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", text, flags=re.M), f
+                assert not re.search(r"#\s*include\s*[\"<][^\">]*oracle", text), f
+                assert "libls_oracle" not in text and "lso_" not in text, f

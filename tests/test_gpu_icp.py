@@ -1,0 +1,254 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle -- the tests proper.
+
+Bar (BASELINE.json north_star): correspondence indices bit-exact under the lowest-index tie-break,
+poses within 1e-4 m / 1e-5 rad.  Because every reduction on the device is order independent
+(int64 fixed point) and every float op is individually rounded, the observed difference is ZERO:
+the tests assert bit equality of the final transform and of T_iter after every iteration, which
+implies the tolerance."""
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+POS_TOL, ROT_TOL = 1e-4, 1e-5
+
+
+def rot_angle(Ra, Rb):
+    """Angle of Ra^T Rb from its skew part (well conditioned near zero, unlike arccos of the trace)."""
+    D = Ra.T @ Rb
+    v = 0.5 * np.array([D[2, 1] - D[1, 2], D[0, 2] - D[2, 0], D[1, 0] - D[0, 1]])
+    return float(np.arcsin(min(1.0, np.linalg.norm(v))))
+
+
+def assert_pose_close(Tg, To):
+    assert np.abs(Tg[:3, 3] - To[:3, 3]).max() < POS_TOL
+    assert rot_angle(Tg[:3, :3].astype(np.float64), To[:3, :3].astype(np.float64)) < ROT_TOL
+
+
+def test_extension_is_the_cuda_library(gpu_ctx):
+    import laser_slam_b200 as ls
+    assert os.path.exists(ls.LIB_PATH)
+    assert any("libls_b200.so" in line for line in open("/proc/self/maps"))
+
+
+def test_nn_matches_oracle_small(gpu_ctx, oracle_mod, small_pair):
+    o = oracle_mod
+    mu = o.mean(small_pair["ref"])
+    refc = (small_pair["ref"][:, :3] - mu).astype(np.float32)
+    Tpre = small_pair["T0"].copy()
+    Tpre[:3, 3] -= mu
+    q = o.transform_points(Tpre, small_pair["reading"])[:, :3].copy()
+    ib, db = o.nn_brute(q, refc)
+    ig, dg = gpu_ctx.nn_query(small_pair["reading"], small_pair["ref"], small_pair["T0"])
+    assert np.array_equal(ib, ig) and np.array_equal(db, dg)
+
+
+@pytest.mark.parametrize("cell,split", [(0.0, 0), (2.0, 16), (0.5, 64), (4.0, 32)])
+def test_nn_independent_of_grid_tuning(gpu_ctx, oracle_mod, small_pair, cell, split):
+    import laser_slam_b200 as ls
+    ig0, dg0 = gpu_ctx.nn_query(small_pair["reading"], small_pair["ref"], small_pair["T0"])
+    ig, dg = gpu_ctx.nn_query(small_pair["reading"], small_pair["ref"], small_pair["T0"],
+                              ls.default_params(cell_size=cell, leaf_split=split))
+    assert np.array_equal(ig0, ig) and np.array_equal(dg0, dg)
+
+
+def test_nn_ties_and_edge_cases(gpu_ctx, oracle_mod):
+    rng = np.random.default_rng(2)
+    g = np.stack(np.meshgrid(np.arange(12), np.arange(12), np.arange(6), indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    ref3 = np.concatenate([g, g[rng.permutation(len(g))[:300]]])
+    q3 = np.concatenate([g + 0.5, g, rng.uniform(-3, 15, (500, 3)).astype(np.float32)]).astype(np.float32)
+
+    def run(q3, ref3):
+        ref4 = np.concatenate([ref3, np.ones((len(ref3), 1), np.float32)], 1)
+        q4 = np.concatenate([q3, np.ones((len(q3), 1), np.float32)], 1)
+        mu = oracle_mod.mean(ref4)
+        refc = (ref3 - mu).astype(np.float32)
+        T = np.eye(4, dtype=np.float32)
+        T[:3, 3] = -mu
+        qc = oracle_mod.transform_points(T, q4)[:, :3].copy()
+        ib, db = oracle_mod.nn_brute(qc, refc)
+        ig, dg = gpu_ctx.nn_query(q4, ref4)
+        assert np.array_equal(ib, ig) and np.array_equal(db, dg)
+
+    run(q3, ref3)                                                                   # lattice: massive exact ties
+    run(rng.normal(scale=10, size=(64, 3)).astype(np.float32), np.array([[1.5, -2.0, 0.25]], np.float32))  # 1 point
+    run(rng.normal(scale=10, size=(64, 3)).astype(np.float32), np.repeat(np.array([[1.5, -2, 0.25]], np.float32), 500, 0))
+    line = np.zeros((2000, 3), np.float32)
+    line[:, 0] = np.linspace(-400, 400, 2000)
+    run(rng.normal(scale=10, size=(64, 3)).astype(np.float32), line)
+    run((rng.normal(size=(200, 3)) * [500, 500, 50]).astype(np.float32), rng.normal(scale=3, size=(5000, 3)).astype(np.float32))
+    run(rng.normal(scale=0.02, size=(300, 3)).astype(np.float32), rng.normal(scale=0.01, size=(20000, 3)).astype(np.float32))
+    ids, d2 = gpu_ctx.nn_query(np.ones((5, 4), np.float32), np.zeros((0, 4), np.float32))  # empty map
+    assert (ids == -1).all() and np.isinf(d2).all()
+
+
+def test_icp_default_chain_bit_exact_small(gpu_ctx, oracle_mod, small_pair):
+    """icp_default.yaml chain (40 iterations max + differential checker, trim 0.75)."""
+    r = oracle_mod.icp(small_pair["reading"], small_pair["ref"], small_pair["ref_normals"], small_pair["T0"], want_hist=True)
+    g = gpu_ctx.icp_register(small_pair["reading"], small_pair["ref"], small_pair["ref_normals"], small_pair["T0"],
+                             want_ids=True, want_hist=True)
+    assert r["rc"] == 0 and g["rc"] == 0
+    assert g["stats"].iterations == r["stats"].iterations and g["stats"].converged == r["stats"].converged
+    assert np.array_equal(g["T_iter_hist"], r["T_iter_hist"])
+    assert np.array_equal(g["ids"], r["ids_hist"][-1]) and np.array_equal(g["d2"], r["d2_last"])
+    assert g["stats"].last_kept == r["stats"].last_kept and g["stats"].last_limit == r["stats"].last_limit
+    assert np.array_equal(g["T"], r["T"])
+    assert_pose_close(g["T"], r["T"])
+
+
+def test_icp_indices_bit_exact_every_iteration(gpu_ctx, oracle_mod, small_pair):
+    """Iteration-capped runs expose the correspondences of EVERY iteration (the path is deterministic)."""
+    import laser_slam_b200 as ls
+    K = 6
+    r = oracle_mod.icp(small_pair["reading"], small_pair["ref"], small_pair["ref_normals"], small_pair["T0"],
+                       oracle_mod.default_params(max_iterations=K, use_differential=0), want_hist=True)
+    for k in range(1, K + 1):
+        g = gpu_ctx.icp_register(small_pair["reading"], small_pair["ref"], small_pair["ref_normals"], small_pair["T0"],
+                                 ls.default_params(max_iterations=k, use_differential=0), want_ids=True)
+        assert np.array_equal(g["ids"], r["ids_hist"][k - 1]), f"iteration {k}"
+
+
+def test_icp_matches_committed_golden(gpu_ctx):
+    g = np.load(os.path.join(GOLDEN, "icp_small.npz"))
+    import laser_slam_b200 as ls
+    out = gpu_ctx.icp_register(g["reading"], g["ref"], g["ref_normals"], g["T0"],
+                               ls.default_params(max_iterations=int(g["max_iterations"]), use_differential=int(g["use_differential"])),
+                               want_ids=True, want_hist=True)
+    assert np.array_equal(out["T"], g["T"]) and np.array_equal(out["ids"], g["ids_last"])
+    assert np.array_equal(out["T_iter_hist"], g["T_iter_hist"]) and np.array_equal(out["d2"], g["d2_last"])
+    assert zlib.crc32(np.ascontiguousarray(out["ids"]).tobytes()) == int(g["ids_crc"][-1])
+
+
+def test_config1_scan_to_scan_full(gpu_ctx, oracle_mod, scans, traj):
+    """BASELINE.json configs[0]: two full HDL-64 clouds, perturbed truth as T0, default chain."""
+    truth, _ = traj
+    T0 = (np.linalg.inv(truth[0]) @ truth[1])
+    d = np.deg2rad([0.3, -0.2, 0.8])
+    Rp = np.array([[1, -d[2], d[1]], [d[2], 1, -d[0]], [-d[1], d[0], 1]])
+    T0[:3, :3] = T0[:3, :3] @ Rp
+    T0[:3, 3] += [0.10, -0.05, 0.02]
+    T0 = T0.astype(np.float32)
+    po = oracle_mod.default_params(num_threads=os.cpu_count() or 1)
+    r = oracle_mod.icp(scans[1][0], scans[0][0], scans[0][1], T0, po, want_hist=True)
+    g = gpu_ctx.icp_register(scans[1][0], scans[0][0], scans[0][1], T0, want_ids=True, want_hist=True)
+    assert g["stats"].iterations == r["stats"].iterations
+    assert np.array_equal(g["T_iter_hist"], r["T_iter_hist"]) and np.array_equal(g["ids"], r["ids_hist"][-1])
+    assert np.array_equal(g["T"], r["T"])
+    assert np.abs(g["T"][:3, 3] - (np.linalg.inv(truth[0]) @ truth[1])[:3, 3]).max() < 0.02
+
+
+def test_config2_scan_to_map_full(gpu_ctx, oracle_mod, config2):
+    """BASELINE.json configs[1]: 131072-point scan vs 524288-point map, 30 fixed iterations."""
+    import laser_slam_b200 as ls
+    po = oracle_mod.default_params(max_iterations=30, use_differential=0, num_threads=os.cpu_count() or 1)
+    r = oracle_mod.icp(config2["reading"], config2["ref"], config2["ref_normals"], config2["T0"], po, want_hist=True)
+    g = gpu_ctx.icp_register(config2["reading"], config2["ref"], config2["ref_normals"], config2["T0"],
+                             ls.default_params(max_iterations=30, use_differential=0), want_ids=True, want_hist=True)
+    assert g["stats"].iterations == 30 and g["stats"].max_iter_reached == 1
+    assert np.array_equal(g["T_iter_hist"], r["T_iter_hist"])
+    assert np.array_equal(g["ids"], r["ids_hist"][-1]) and np.array_equal(g["d2"], r["d2_last"])
+    assert np.array_equal(g["T"], r["T"])
+    assert_pose_close(g["T"], r["T"])
+    assert np.abs(g["T"][:3, 3] - config2["truth"][:3, 3]).max() < 5e-3
+
+
+def test_resident_submap_path_equals_one_shot(gpu_ctx, oracle_mod, scans, traj, config2):
+    """ls_map_* + ls_icp_register_submap (LaserTrack::localScanToSubMap on the device) gives the same bits."""
+    import laser_slam_b200 as ls
+    truth, _ = traj
+    mp = gpu_ctx.create_map(8, 131072)
+    sid = [mp.push_scan(*scans[k]) for k in range(5)]
+    Tparts = [np.eye(4, dtype=np.float32) if k == 3 else (np.linalg.inv(truth[3]) @ truth[k]).astype(np.float32)
+              for k in [3, 2, 1, 0]]
+    p = ls.default_params(max_iterations=8, use_differential=0)
+    g1 = gpu_ctx.icp_register(config2["reading"], config2["ref"], config2["ref_normals"], config2["T0"], p, want_ids=True)
+    g2 = mp.register(sid[4], [sid[3], sid[2], sid[1], sid[0]], Tparts, config2["T0"], p, want_ids=True)
+    assert np.array_equal(g1["T"], g2["T"]) and np.array_equal(g1["ids"], g2["ids"])
+    # assembled sub-map == oracle's transform + concatenate
+    pts, nrm = mp.assemble([sid[3], sid[2], sid[1], sid[0]], Tparts)
+    assert np.array_equal(pts, config2["ref"]) and np.array_equal(nrm, config2["ref_normals"])
+    # ring eviction
+    for k in range(8):
+        mp.push_scan(*scans[k % 5])
+    assert mp.scan_size(sid[0]) < 0
+    with pytest.raises(ls.LsError):
+        mp.register(sid[0], [sid[1]], [np.eye(4, dtype=np.float32)], config2["T0"], p)
+    mp.close()
+
+
+def test_transform_cloud_matches_oracle(gpu_ctx, oracle_mod, scans, traj):
+    truth, _ = traj
+    T = (np.linalg.inv(truth[3]) @ truth[1]).astype(np.float32)
+    po, no = oracle_mod.transform_cloud(T, *scans[1])
+    pg, ng = gpu_ctx.transform_cloud(T, scans[1][0], scans[1][1])
+    assert np.array_equal(po, pg) and np.array_equal(no, ng)
+    assert np.array_equal(gpu_ctx.transform_cloud(T, scans[1][0]), po)
+
+
+def test_error_paths(gpu_ctx, small_pair):
+    import laser_slam_b200 as ls
+    empty4, empty3 = np.zeros((0, 4), np.float32), np.zeros((0, 3), np.float32)
+    with pytest.raises(ls.ConvergenceError):
+        gpu_ctx.icp_register(empty4, small_pair["ref"], small_pair["ref_normals"], small_pair["T0"])
+    out = gpu_ctx.icp_register(small_pair["reading"], empty4, empty3, small_pair["T0"], raise_on_convergence=False)
+    assert out["rc"] == ls.LS_ERR_CONVERGENCE and np.array_equal(out["T"], small_pair["T0"])  # "keep the initial guess"
+    with pytest.raises(ls.LsError):
+        gpu_ctx.icp_register(small_pair["reading"], small_pair["ref"], small_pair["ref_normals"], small_pair["T0"],
+                             ls.default_params(max_iterations=0))
+    with pytest.raises(ls.LsError):
+        gpu_ctx.icp_register(small_pair["reading"], small_pair["ref"], small_pair["ref_normals"], small_pair["T0"],
+                             ls.default_params(trim_ratio=1.5))
+
+
+def test_special_inputs(gpu_ctx, oracle_mod, small_pair):
+    import laser_slam_b200 as ls
+    ref, nrm = small_pair["ref"], small_pair["ref_normals"]
+    I = np.eye(4, dtype=np.float32)
+    # identical clouds: theta == 0 -> rotation := identity guard of the minimiser
+    r = oracle_mod.icp(ref, ref, nrm, I)
+    g = gpu_ctx.icp_register(ref, ref, nrm, I)
+    assert np.array_equal(g["T"], r["T"]) and g["stats"].iterations == r["stats"].iterations
+    # no outlier filter (ratio 1), tiny and ragged sizes, degenerate (single plane) geometry -> min-norm solve
+    for n, m, ratio in [(1, 50, 0.75), (33, 1000, 1.0), (1000, 37, 0.5), (4097, 8192, 0.9)]:
+        po = oracle_mod.default_params(max_iterations=5, use_differential=0, trim_ratio=ratio)
+        pg = ls.default_params(max_iterations=5, use_differential=0, trim_ratio=ratio)
+        r = oracle_mod.icp(small_pair["reading"][:n], ref[:m], nrm[:m], small_pair["T0"], po, want_hist=True)
+        g = gpu_ctx.icp_register(small_pair["reading"][:n], ref[:m], nrm[:m], small_pair["T0"], pg, want_ids=True,
+                                 raise_on_convergence=False)
+        assert g["rc"] == r["rc"]
+        assert np.array_equal(g["T"], r["T"]), (n, m, ratio)
+        if r["rc"] == 0:
+            assert np.array_equal(g["ids"], r["ids_hist"][-1])
+    rng = np.random.default_rng(7)
+    plane = np.ones((3000, 4), np.float32)
+    plane[:, :2] = rng.uniform(-20, 20, (3000, 2))
+    plane[:, 2] = 0
+    pn = np.tile(np.array([0, 0, 1], np.float32), (3000, 1))
+    rd = plane.copy()
+    rd[:, 2] += 0.05
+    po = oracle_mod.default_params(max_iterations=4, use_differential=0)
+    pg = ls.default_params(max_iterations=4, use_differential=0)
+    r = oracle_mod.icp(rd, plane, pn, I, po)
+    g = gpu_ctx.icp_register(rd, plane, pn, I, pg)
+    assert r["rc"] == 0 and np.array_equal(g["T"], r["T"]) and abs(g["T"][2, 3] + 0.05) < 1e-4
+
+
+def test_full_size_properties(gpu_ctx, config2):
+    """Size-independent properties at BASELINE.json's full size (no oracle involved)."""
+    import laser_slam_b200 as ls
+    p = ls.default_params(max_iterations=30, use_differential=0)
+    a = gpu_ctx.icp_register(config2["reading"], config2["ref"], config2["ref_normals"], config2["T0"], p, want_ids=True)
+    b = gpu_ctx.icp_register(config2["reading"], config2["ref"], config2["ref_normals"], config2["T0"], p, want_ids=True)
+    assert np.array_equal(a["T"], b["T"]) and np.array_equal(a["ids"], b["ids"])          # run-to-run determinism
+    perm = np.random.default_rng(0).permutation(len(config2["reading"]))
+    c = gpu_ctx.icp_register(config2["reading"][perm], config2["ref"], config2["ref_normals"], config2["T0"], p, want_ids=True)
+    assert np.array_equal(a["T"], c["T"]) and np.array_equal(a["ids"][perm], c["ids"])    # reading order is irrelevant
+    # restarting from the solution stays at the solution
+    d = gpu_ctx.icp_register(config2["reading"], config2["ref"], config2["ref_normals"], a["T"], p)
+    assert np.abs(d["T"][:3, 3] - a["T"][:3, 3]).max() < 1e-3
+    assert a["stats"].last_kept == int(np.float32(len(config2["reading"])) * np.float32(0.75)) + 1 or a["stats"].last_kept >= 98304
+    assert (a["ids"] >= 0).all() and (a["ids"] < len(config2["ref"])).all()

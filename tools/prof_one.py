@@ -1,0 +1,23 @@
+"""Config-2 registration on resident scans, a few repetitions (profiling / phase-timing driver)."""
+import sys, os, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import laser_slam_b200 as ls
+from laser_slam_b200 import synth
+
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+ctx = ls.Context(0)
+truth, odom = synth.trajectory(0, 8)
+scans = [synth.scan(truth[k], 0, k) for k in range(5)]
+mp = ctx.create_map(8, 131072)
+sid = [mp.push_scan(*scans[k]) for k in range(5)]
+Tparts = [np.eye(4, dtype=np.float32) if k == 3 else (np.linalg.inv(truth[3]) @ truth[k]).astype(np.float32) for k in [3, 2, 1, 0]]
+T0 = (np.linalg.inv(truth[3]) @ odom[4]).astype(np.float32)
+p = ls.default_params(max_iterations=iters, use_differential=0)
+for k in ("cell_size", "leaf_split"):
+    if os.environ.get("LS_" + k.upper()):
+        setattr(p, k, type(getattr(p, k))(float(os.environ["LS_" + k.upper()])))
+for rep in range(reps):
+    g = mp.register(sid[4], [sid[3], sid[2], sid[1], sid[0]], Tparts, T0, p)
+    print(f"rep {rep}: device {g['stats'].device_ms:.3f} ms build {g['stats'].build_ms:.3f} ms iters {g['stats'].iterations}")
