@@ -105,22 +105,20 @@ def usable_threads():
     return n
 
 
-def best_thread_count(oracle):
+def best_thread_count(oracle, reading, refp, refn, T0):
     """The kd-tree query loop does not scale to every core count (memory bound; oversubscription under a
-    quota): calibrate on one NN pass and keep the fastest count -- the strongest CPU baseline."""
+    quota): calibrate with 6 ICP iterations of the real workload and keep the fastest count -- the
+    strongest CPU baseline this host can give."""
     nmax = usable_threads()
     cands = sorted({c for c in (1, 2, 4, 8, 16, 32, 64, nmax) if c <= nmax})
-    rng = np.random.default_rng(0)
-    ref = rng.normal(scale=20, size=(200000, 3)).astype(np.float32)
-    q = rng.normal(scale=20, size=(100000, 3)).astype(np.float32)
-    best, best_t = 1, float("inf")
-    for c in cands:
-        t0 = time.perf_counter()
-        oracle.nn_kdtree(q, ref, c)
-        dt = time.perf_counter() - t0
-        if dt < best_t:
-            best, best_t = c, dt
-    return best
+    t1 = {}
+    for its in (2, 8):   # difference of two runs isolates the per-iteration (query) cost from the tree build
+        for c in cands:
+            po = oracle.default_params(max_iterations=its, use_differential=0, num_threads=c)
+            t0 = time.perf_counter()
+            oracle.icp(reading, refp, refn, T0, po)
+            t1[(its, c)] = time.perf_counter() - t0
+    return min(cands, key=lambda c: t1[(8, c)] - t1[(2, c)])
 
 
 def run_reference(args, rank):
@@ -128,10 +126,14 @@ def run_reference(args, rank):
     if rank != 0:
         return
     import oracle
-    threads = best_thread_count(oracle)
     truth, odom, scans = make_pool(0)
-    po = oracle.default_params(max_iterations=ITERS, use_differential=0, num_threads=threads)
     hist = [walk(s) for s in range(K_MAP + 1)]
+    ref0, ks0, Ts0 = submap_parts(truth, hist)
+    parts0 = [scans[k] if k == ref0 else oracle.transform_cloud(T, *scans[k]) for k, T in zip(ks0, Ts0)]
+    threads = best_thread_count(oracle, scans[hist[-1]][0], np.concatenate([p[0] for p in parts0]),
+                                np.concatenate([p[1] for p in parts0]),
+                                (np.linalg.inv(truth[ref0]) @ odom[hist[-1]]).astype(np.float32))
+    po = oracle.default_params(max_iterations=ITERS, use_differential=0, num_threads=threads)
 
     def step(s):
         idx = walk(s + K_MAP + 1)
@@ -174,7 +176,7 @@ def cpu_baseline_sample():
     refp = np.concatenate([p[0] for p in parts])
     refn = np.concatenate([p[1] for p in parts])
     T0 = (np.linalg.inv(truth[ref]) @ odom[4]).astype(np.float32)
-    threads = best_thread_count(oracle)
+    threads = best_thread_count(oracle, scans[4][0], refp, refn, T0)
     out = {}
     for th, reps in ((threads, 4), (1, 1)) if threads > 1 else ((1, 3),):
         po = oracle.default_params(max_iterations=ITERS, use_differential=0, num_threads=th)

@@ -253,6 +253,7 @@ int run_icp(ls_ctx* ctx, const ls_icp_params* prm, const float4* reading_dev, in
   hp.ids = ctx->ids;
   hp.work = ctx->work;
   hp.T_hist = opt_T_hist ? ctx->T_hist : nullptr;
+  hp.want_matches = (opt_ids || opt_d2) ? 1 : 0;
   const bool want_phase = getenv("LS_PHASE_TIMING") != nullptr;
   if (want_phase) {
     if (ctx->phase_ns) cudaFree(ctx->phase_ns);

@@ -368,16 +368,21 @@ LS_HDN void seed_query(const Grid& g, const GridView& v, float qx, float qy, flo
   scan_range(v.pts, e2.start, e2.start + (uint32_t)e2.meta, qx, qy, qz, b);
 }
 
-// Exact 1-NN.  warm_pos: sorted position of the previous iteration's match, or -1.
-LS_HD Best nn_search(const Grid& g, const GridView& v, float qx, float qy, float qz, int warm_pos) {
+// Exact 1-NN within a squared-distance cap.  warm_pos: sorted position of the previous iteration's
+// match, or -1.  cap_d2 = +inf gives the unbounded search of KDTreeMatcher{maxDist: inf}.  With a
+// finite cap the result is the exact nearest neighbour whenever its d2 <= cap_d2, and "not found"
+// (idx -1, pos -1, d2 +inf) otherwise -- callers use caps that provably do not change what the
+// trimmed outlier filter keeps (ls_kernels.cuh, phase A).
+LS_HD Best nn_search(const Grid& g, const GridView& v, float qx, float qy, float qz, int warm_pos, float cap_d2) {
   Best b;
-  b.d2 = INFINITY;
+  b.d2 = cap_d2;
   b.idx = INT_MAX;
   b.pos = -1;
-  if (g.m <= 0) { b.idx = -1; return b; }
+  if (g.m <= 0) { b.idx = -1; b.d2 = INFINITY; return b; }
   if (warm_pos >= 0) consider(v.pts, warm_pos, qx, qy, qz, b);
-  else seed_query(g, v, qx, qy, qz, b);
+  else if (!(cap_d2 < INFINITY)) seed_query(g, v, qx, qy, qz, b);
   ball_query(g, v, qx, qy, qz, b);
+  if (b.pos < 0) { b.idx = -1; b.d2 = INFINITY; }
   return b;
 }
 

@@ -93,6 +93,7 @@ struct IcpProblem {
   int* ids;
   IcpWork* work;
   float* T_hist;  // max_iterations*16 floats or null
+  int want_matches;  // 1: finish with an uncapped NN pass so ids/d2 hold every point's true match
   unsigned long long* phase_ns;  // debug: max_iterations*6 globaltimer stamps (CTA 0) or null
   float T0[16];
 };
@@ -509,7 +510,7 @@ __global__ void __launch_bounds__(256) nn_query_kernel(const BuildState* __restr
   __syncthreads();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float4 q = __ldg(rd + i);
-    const Best b = nn_search(g, view, q.x, q.y, q.z, -1);
+    const Best b = nn_search(g, view, q.x, q.y, q.z, -1, INFINITY);
     ids[i] = b.idx;
     d2[i] = b.d2;
   }
@@ -603,7 +604,7 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
   const int tid = threadIdx.x, lane = tid & 31;
 
   __shared__ Grid g;
-  __shared__ float T_iter[16];
+  __shared__ float T_iter[16], T_last[16];
   __shared__ unsigned int hist_s[2048];
   __shared__ unsigned long long acc_s[28];
   __shared__ SelectOut sel;
@@ -628,6 +629,14 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
   chunk = (chunk + 31) & ~31;
   const int q_begin = min(n, cta * chunk), q_end = min(n, q_begin + chunk);
 
+  for (int i = q_begin + tid; i < q_end; i += kIcpThreads) P.pos[i] = -1;
+
+  // Trim-aware search cap (squared metres).  TrimmedDistOutlierFilter keeps matches with d2 <= limit,
+  // so a match only has to be exact if d2 <= limit; searching inside a ball of radius sqrt(cap) with
+  // cap >= limit finds exactly those.  cap is a GUESS (first iteration: 1 m^2, then 2x the previous
+  // limit) that is VERIFIED every iteration: points without a match inside the cap are counted in the
+  // +inf histogram bin, and if the quantile lands in that bin the search is redone with a larger cap.
+  float cap = 1.0f;
   unsigned int epoch = 0;
   int hist_count = 1;  // entries in qh/th
   int iter = 0, converged = 0, max_reached = 0, last_kept = 0;
@@ -643,13 +652,13 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
       const float4 r = __ldg(P.rd + i);
       float sx, sy, sz;
       xform_point(T_iter, r.x, r.y, r.z, sx, sy, sz);
-      const int warm = iter > 0 ? P.pos[i] : -1;
-      const Best b = nn_search(g, P.view, sx, sy, sz, warm);
-      P.pos[i] = b.pos;
+      const int warm = P.pos[i];
+      const Best b = nn_search(g, P.view, sx, sy, sz, warm, cap);
+      if (b.pos >= 0) P.pos[i] = b.pos;  // keep the last real match as the next warm start
       P.d2[i] = b.d2;
       P.ids[i] = b.idx;
       const unsigned int key = __float_as_uint(b.d2);
-      if (key < 0x7f800000u) atomicAdd(&hist_s[key >> 21], 1u);  // finite, non-negative
+      if (key <= 0x7f800000u) atomicAdd(&hist_s[key >> 21], 1u);  // non-negative; +inf (no match in cap) -> bin 1020
     }
     __syncthreads();
     for (int k = tid; k < 1024; k += kIcpThreads) {
@@ -661,10 +670,24 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
 
     // ---------------- phase B: K3 select level 1, build level-2 histogram ----------------
     block_select(W->hist[par][0], 1024, 0u, true, prm.trim_ratio, &sel, ws);
-    if (sel.total == 0u) {  // no finite match at all -> ConvergenceError
+    if (sel.total == 0u) {  // no point at all -> ConvergenceError
       if (tid == 0) { flag_status = 1; if (cta == 0) W->fail_code = 1; }
       __syncthreads();
       break;
+    }
+    if (sel.bin >= 1020u) {
+      // the quantile fell among the points with no match inside the cap: the cap was too small.
+      if (!(cap < INFINITY)) {  // uncapped and still +inf: empty map
+        if (tid == 0) { flag_status = 1; if (cta == 0) W->fail_code = 1; }
+        __syncthreads();
+        break;
+      }
+      cap = cap < 64.0f ? cap * 16.0f : INFINITY;
+      problem_barrier(&W->barrier, G, epoch);  // everyone has read the histogram
+      if (cta == 0)
+        for (int k = tid; k < 2048; k += kIcpThreads) W->hist[par][0][k] = 0u;
+      problem_barrier(&W->barrier, G, epoch);
+      continue;  // redo phase A of this iteration with the larger cap
     }
     const unsigned int bin1 = sel.bin, rem1 = sel.rem;
     if (cta == 0) {  // clear the other parity's scratch for the next iteration
@@ -707,6 +730,7 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
     // ---------------- phase D: K4 normal equations over matches with d2 <= limit ----------------
     block_select(W->hist[par][2], 1024, rem2, false, 0.f, &sel, ws);
     const float limit = __uint_as_float((prefix12 << 10) | sel.bin);
+    cap = fmaxf(limit * 2.0f, 1e-12f);  // guess for the next iteration (verified there)
     if (tid < 28) acc_s[tid] = 0ull;
     __syncthreads();
     long long a[27];
@@ -793,6 +817,7 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
       if (!status) {
         float T_step[16];
         step_matrix(x, T_step);
+        for (int i = 0; i < 16; ++i) T_last[i] = T_iter[i];
         mat4_mul(T_step, T_iter, T_iter);
         if (P.T_hist && cta == 0)
           for (int i = 0; i < 16; ++i) P.T_hist[iter * 16 + i] = T_iter[i];
@@ -833,6 +858,19 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
     __syncthreads();
     if (!flag_status) ++iter;  // every thread tracks the iteration count (parity, warm start)
     if (flag_stop) break;
+  }
+
+  if (P.want_matches && !flag_status && iter > 0) {
+    // The loop ended right after the update of T_iter; the matches reported are those of the LAST
+    // iteration, i.e. of the reading under T_last.  Redo that query without a cap.
+    for (int i = q_begin + tid; i < q_end; i += kIcpThreads) {
+      const float4 r = __ldg(P.rd + i);
+      float sx, sy, sz;
+      xform_point(T_last, r.x, r.y, r.z, sx, sy, sz);
+      const Best b = nn_search(g, P.view, sx, sy, sz, P.pos[i], INFINITY);
+      P.d2[i] = b.d2;
+      P.ids[i] = b.idx;
+    }
   }
 
   if (cta == 0 && tid == 0) {

@@ -140,7 +140,7 @@ extern "C" {
 // loads, max candidates, #level-1 tables + 1e-6 * #level-2 tables.
 void sim_nn(const float* q3, int n, const float* refc3, int m, float cell, int max_cells, int split,
             const int32_t* warm_ids, int32_t* ids, float* d2, double* stats, int32_t* per_query_cand,
-            int32_t* per_query_entries) {
+            int32_t* per_query_entries, float cap_d2) {
   SimGrid S;
   build(S, refc3, m, cell, max_cells, split);
   std::vector<int> pos_of(m);
@@ -151,7 +151,7 @@ void sim_nn(const float* q3, int n, const float* refc3, int m, float cell, int m
     ls::ls_sim_cand = 0;
     ls::ls_sim_entries = 0;
     const int warm = (warm_ids && warm_ids[i] >= 0) ? pos_of[warm_ids[i]] : -1;
-    const ls::Best b = ls::nn_search(S.g, v, q3[3 * i], q3[3 * i + 1], q3[3 * i + 2], warm);
+    const ls::Best b = ls::nn_search(S.g, v, q3[3 * i], q3[3 * i + 1], q3[3 * i + 2], warm, cap_d2);
     ids[i] = b.idx;
     d2[i] = b.d2;
     if (per_query_cand) per_query_cand[i] = (int32_t)ls::ls_sim_cand;

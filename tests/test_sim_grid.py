@@ -22,16 +22,16 @@ def sim():
                                "-I/usr/local/cuda/include", "-o", SIM_LIB, SIM_SRC])
     L = ctypes.CDLL(SIM_LIB)
     vp = ctypes.c_void_p
-    L.sim_nn.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp]
+    L.sim_nn.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp, ctypes.c_float]
 
-    def run(q, ref, cell=1.0, max_cells=1 << 22, split=32, warm=None):
+    def run(q, ref, cell=1.0, max_cells=1 << 22, split=32, warm=None, cap=np.inf):
         q = np.ascontiguousarray(q, np.float32)
         ref = np.ascontiguousarray(ref, np.float32)
         ids = np.empty(max(len(q), 1), np.int32)
         d2 = np.empty(max(len(q), 1), np.float32)
         w = np.ascontiguousarray(warm, np.int32) if warm is not None else None
         L.sim_nn(q.ctypes.data, len(q), ref.ctypes.data, len(ref), cell, max_cells, split,
-                 w.ctypes.data if w is not None else None, ids.ctypes.data, d2.ctypes.data, None, None, None)
+                 w.ctypes.data if w is not None else None, ids.ctypes.data, d2.ctypes.data, None, None, None, cap)
         return ids[:len(q)], d2[:len(q)]
     return run
 
@@ -94,3 +94,16 @@ def test_sim_small_cell_budget_grows_cells(sim, oracle_mod, small_pair):
     refc = small_pair["ref"][:, :3].copy()
     q = small_pair["reading"][:2000, :3].copy()
     _check(sim, oracle_mod, q, refc, cell=0.25, max_cells=4096)  # H0 doubles until the dense array fits
+
+
+def test_sim_capped_search_is_exact_within_cap(sim, oracle_mod, small_pair):
+    """With a finite cap the query returns the exact NN when d2 <= cap and 'not found' otherwise."""
+    refc = small_pair["ref"][:, :3].copy()
+    q = small_pair["reading"][:, :3].copy()
+    ib, db = oracle_mod.nn_brute(q, refc)
+    for cap in (0.0004, 0.01, 0.25, 4.0):
+        for warm in (None, ib, np.zeros(len(q), np.int64)):
+            ig, dg = sim(q, refc, warm=warm, cap=cap)
+            inside = db <= np.float32(cap)
+            assert np.array_equal(ig[inside], ib[inside]) and np.array_equal(dg[inside], db[inside])
+            assert (ig[~inside] == -1).all() and np.isinf(dg[~inside]).all()
