@@ -261,6 +261,11 @@ int run_icp(ls_ctx* ctx, const ls_icp_params* prm, const float4* reading_dev, in
     CU(cudaMemsetAsync(ctx->phase_ns, 0, (size_t)prm->max_iterations * 6 * sizeof(unsigned long long), ctx->stream));
   }
   hp.phase_ns = want_phase ? ctx->phase_ns : nullptr;
+  static unsigned int* warp_cyc_dev = nullptr;
+  const bool want_warp = getenv("LS_WARP_PROFILE") != nullptr;
+  if (want_warp && !warp_cyc_dev) cudaMalloc((void**)&warp_cyc_dev, 8192 * sizeof(unsigned int));
+  if (want_warp) cudaMemsetAsync(warp_cyc_dev, 0, 8192 * sizeof(unsigned int), ctx->stream);
+  hp.warp_cyc = want_warp ? warp_cyc_dev : nullptr;
   std::memcpy(hp.T0, T0, sizeof(hp.T0));
   CU(cudaMemcpyAsync(ctx->prob, &hp, sizeof(hp), cudaMemcpyHostToDevice, ctx->stream));
   IcpParamsDev dp;
@@ -297,6 +302,12 @@ int run_icp(ls_ctx* ctx, const ls_icp_params* prm, const float4* reading_dev, in
       fprintf(stderr, "[ls] it %2d: %8.1f %8.1f %8.1f %8.1f %8.1f | %8.1f\n", it, (q[1] - q[0]) * 1e-3, (q[2] - q[1]) * 1e-3,
               (q[3] - q[2]) * 1e-3, (q[4] - q[3]) * 1e-3, (q[5] - q[4]) * 1e-3, (q[5] - q[0]) * 1e-3);
     }
+  }
+  if (want_warp) {
+    std::vector<unsigned int> wc(8192);
+    cudaMemcpy(wc.data(), warp_cyc_dev, wc.size() * sizeof(unsigned int), cudaMemcpyDeviceToHost);
+    FILE* f = fopen(getenv("LS_WARP_PROFILE"), "wb");
+    if (f) { fwrite(wc.data(), sizeof(unsigned int), wc.size(), f); fclose(f); }
   }
   std::memcpy(T_out, w.T_out, 16 * sizeof(float));
   if (stats) {

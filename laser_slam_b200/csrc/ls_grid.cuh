@@ -77,12 +77,14 @@ struct Best {
 
 // tests/sim instruments the query (candidates examined, table entries loaded) to tune H0/leaf_split
 #if defined(LS_SIM_COUNTERS) && !defined(__CUDA_ARCH__)
-extern thread_local long long ls_sim_cand, ls_sim_entries;
+extern thread_local long long ls_sim_cand, ls_sim_entries, ls_sim_steps;
 #define LS_CNT_CAND() (++ls_sim_cand)
 #define LS_CNT_ENTRY() (++ls_sim_entries)
+#define LS_CNT_STEP() (++ls_sim_steps)   /* one dependent round trip to memory */
 #else
 #define LS_CNT_CAND() ((void)0)
 #define LS_CNT_ENTRY() ((void)0)
+#define LS_CNT_STEP() ((void)0)
 #endif
 
 #if defined(__CUDA_ARCH__)
@@ -158,62 +160,65 @@ LS_HD void consider_pt(const float4 p, int pos, float qx, float qy, float qz, Be
 LS_HD void scan_range(const float4* pts, uint32_t a, uint32_t e, float qx, float qy, float qz, Best& b) {
   uint32_t pos = a;
   for (; pos + 4 <= e; pos += 4) {
+    LS_CNT_STEP();
     const float4 p0 = ld_pt(pts + pos), p1 = ld_pt(pts + pos + 1), p2 = ld_pt(pts + pos + 2), p3 = ld_pt(pts + pos + 3);
     consider_pt(p0, (int)pos, qx, qy, qz, b);
     consider_pt(p1, (int)pos + 1, qx, qy, qz, b);
     consider_pt(p2, (int)pos + 2, qx, qy, qz, b);
     consider_pt(p3, (int)pos + 3, qx, qy, qz, b);
   }
+  if (pos < e) LS_CNT_STEP();
   for (; pos < e; ++pos) consider(pts, (int)pos, qx, qy, qz, b);
 }
 
-// ---- ball query, level 2 table (all entries are leaves; x-runs are contiguous) -------------------
+// ---- ball query, level 2 table (all entries are leaves) ---------------------------------------------
+// Points are sorted x-fastest, then y, then z, so for one z-slab the sub-cells (y0..y1, x0..x1) lie inside
+// ONE contiguous run [start(z,y0,x0), end(z,y1,x1)).  The run also holds the few cells of the interior rows
+// whose x is outside [x0,x1]; scanning them costs a handful of extra distance evaluations but turns
+// "two dependent entry loads + a scan per row" into: all slab entries in flight at once, then <= 4 streams.
 LS_HD void visit_l2(const Grid& g, const Entry* tab, float lox, float loy, float loz, const float4* pts,
                     float qx, float qy, float qz, Best& b) {
   const float R = ball_radius(b.d2, g.margin);
   const int x0 = coord_sub(qx - R, lox, g.inv2), x1 = coord_sub(qx + R, lox, g.inv2);
   const int y0 = coord_sub(qy - R, loy, g.inv2), y1 = coord_sub(qy + R, loy, g.inv2);
   const int z0 = coord_sub(qz - R, loz, g.inv2), z1 = coord_sub(qz + R, loz, g.inv2);
-  // home row first: the nearest candidates shrink the ball before the other rows are tested
-  const int hy = coord_sub(qy, loy, g.inv2), hz = coord_sub(qz, loz, g.inv2);
-  {
-    const Entry e0 = ld_entry(tab + (hz * 4 + hy) * 4 + x0);
-    const Entry e1 = ld_entry(tab + (hz * 4 + hy) * 4 + x1);
-    scan_range(pts, e0.start, e1.start + (uint32_t)e1.meta, qx, qy, qz, b);
-  }
-  for (int z = z0; z <= z1; ++z) {
-    const float gz = gap(qz, cell_lo(loz, z, g.H2), cell_lo(loz, z + 1, g.H2), g.margin);
-    const float gz2 = gz * gz;
-    if (gz2 * LS_SHRINK > b.d2) continue;
-    for (int y = y0; y <= y1; ++y) {
-      if (y == hy && z == hz) continue;
-      const float gy = gap(qy, cell_lo(loy, y, g.H2), cell_lo(loy, y + 1, g.H2), g.margin);
-      const float lb = gy * gy + gz2;
-      if (lb * LS_SHRINK > b.d2) continue;
-      const Entry e0 = ld_entry(tab + (z * 4 + y) * 4 + x0);
-      const Entry e1 = ld_entry(tab + (z * 4 + y) * 4 + x1);
-      scan_range(pts, e0.start, e1.start + (uint32_t)e1.meta, qx, qy, qz, b);
+  uint32_t ra[4], re[4];
+  LS_CNT_STEP();
+#pragma unroll
+  for (int dz = 0; dz < 4; ++dz) {
+    const int z = z0 + dz;
+    ra[dz] = 0u;
+    re[dz] = 0u;
+    if (z <= z1) {
+      const float gz = gap(qz, cell_lo(loz, z, g.H2), cell_lo(loz, z + 1, g.H2), g.margin);
+      if (!((gz * gz) * LS_SHRINK > b.d2)) {
+        const Entry e0 = ld_entry(tab + (z * 4 + y0) * 4 + x0);
+        const Entry e1 = ld_entry(tab + (z * 4 + y1) * 4 + x1);
+        ra[dz] = e0.start;
+        re[dz] = e1.start + (uint32_t)e1.meta;
+      }
     }
   }
+#pragma unroll
+  for (int dz = 0; dz < 4; ++dz) scan_range(pts, ra[dz], re[dz], qx, qy, qz, b);
 }
 
 // ---- ball query, level 1 table -----------------------------------------------------------------
+LS_HD void visit_l1_cell(const Grid& g, const Entry e, const Entry* tab2, float cx, float cy, float cz,
+                         const float4* pts, float qx, float qy, float qz, Best& b) {
+  if (e.meta > 0) {
+    scan_range(pts, e.start, e.start + (uint32_t)e.meta, qx, qy, qz, b);
+  } else if (e.meta < 0) {
+    visit_l2(g, tab2 + (size_t)(~e.meta) * 64, cx, cy, cz, pts, qx, qy, qz, b);
+  }
+}
+
 LS_HD void visit_l1(const Grid& g, const Entry* tab, const Entry* tab2, float lox, float loy, float loz,
                     const float4* pts, float qx, float qy, float qz, Best& b) {
   const float R = ball_radius(b.d2, g.margin);
   const int x0 = coord_sub(qx - R, lox, g.inv1), x1 = coord_sub(qx + R, lox, g.inv1);
   const int y0 = coord_sub(qy - R, loy, g.inv1), y1 = coord_sub(qy + R, loy, g.inv1);
   const int z0 = coord_sub(qz - R, loz, g.inv1), z1 = coord_sub(qz + R, loz, g.inv1);
-  const int hx = coord_sub(qx, lox, g.inv1), hy = coord_sub(qy, loy, g.inv1), hz = coord_sub(qz, loz, g.inv1);
-  {
-    const Entry e = ld_entry(tab + (hz * 4 + hy) * 4 + hx);
-    if (e.meta > 0) {
-      scan_range(pts, e.start, e.start + (uint32_t)e.meta, qx, qy, qz, b);
-    } else if (e.meta < 0) {
-      visit_l2(g, tab2 + (size_t)(~e.meta) * 64, cell_lo(lox, hx, g.H1), cell_lo(loy, hy, g.H1), cell_lo(loz, hz, g.H1), pts,
-               qx, qy, qz, b);
-    }
-  }
   for (int z = z0; z <= z1; ++z) {
     const float cz = cell_lo(loz, z, g.H1);
     const float gz = gap(qz, cz, cell_lo(loz, z + 1, g.H1), g.margin);
@@ -225,31 +230,30 @@ LS_HD void visit_l1(const Grid& g, const Entry* tab, const Entry* tab2, float lo
       const float lbyz = gy * gy + gz2;
       if (lbyz * LS_SHRINK > b.d2) continue;
       for (int x = x0; x <= x1; ++x) {
-        if (x == hx && y == hy && z == hz) continue;
         const float cx = cell_lo(lox, x, g.H1);
         const float gx = gap(qx, cx, cell_lo(lox, x + 1, g.H1), g.margin);
         const float lb = gx * gx + lbyz;
         if (lb * LS_SHRINK > b.d2) continue;
-        const Entry e = ld_entry(tab + (z * 4 + y) * 4 + x);
-        if (e.meta > 0) {
-          scan_range(pts, e.start, e.start + (uint32_t)e.meta, qx, qy, qz, b);
-        } else if (e.meta < 0) {
-          visit_l2(g, tab2 + (size_t)(~e.meta) * 64, cx, cy, cz, pts, qx, qy, qz, b);
-        }
+        LS_CNT_STEP();
+        visit_l1_cell(g, ld_entry(tab + (z * 4 + y) * 4 + x), tab2, cx, cy, cz, pts, qx, qy, qz, b);
       }
     }
   }
 }
 
 // one level-0 cell (leaf scan or descent)
-LS_HD void visit_top_cell(const Grid& g, const GridView& v, int x, int y, int z, float cx, float cy, float cz, float qx,
-                          float qy, float qz, Best& b) {
-  const Entry e = ld_entry(v.top + ((size_t)z * g.dim[1] + y) * g.dim[0] + x);
+LS_HD void visit_top_entry(const Grid& g, const GridView& v, const Entry e, float cx, float cy, float cz, float qx,
+                           float qy, float qz, Best& b) {
   if (e.meta > 0) {
     scan_range(v.pts, e.start, e.start + (uint32_t)e.meta, qx, qy, qz, b);
   } else if (e.meta < 0) {
     visit_l1(g, v.tab1 + (size_t)(~e.meta) * 64, v.tab2, cx, cy, cz, v.pts, qx, qy, qz, b);
   }
+}
+LS_HD void visit_top_cell(const Grid& g, const GridView& v, int x, int y, int z, float cx, float cy, float cz, float qx,
+                          float qy, float qz, Best& b) {
+  LS_CNT_STEP();
+  visit_top_entry(g, v, ld_entry(v.top + ((size_t)z * g.dim[1] + y) * g.dim[0] + x), cx, cy, cz, qx, qy, qz, b);
 }
 
 // ---- large balls: depth-first walk of the occupancy pyramid (empty space costs one mask load per
@@ -265,6 +269,7 @@ LS_HDN void pyramid_query(const Grid& g, const GridView& v, float qx, float qy, 
     if (mk[sp] == 0ull) { --sp; continue; }
     const int bit = ctz64(mk[sp]);
     mk[sp] &= mk[sp] - 1ull;
+    LS_CNT_STEP();
     const int cl = lvl[sp] - 1;  // level of the child cell
     const int cx = bx[sp] + (bit & 3), cy = by[sp] + ((bit >> 2) & 3), cz = bz[sp] + (bit >> 4);
     const float Hc = g.H0 * (float)(1 << (2 * cl));
@@ -295,10 +300,6 @@ LS_HD void ball_query(const Grid& g, const GridView& v, float qx, float qy, floa
     pyramid_query(g, v, qx, qy, qz, b);
     return;
   }
-  const int hx = coord_top(qx, g.org[0], g.inv0, g.dim[0]), hy = coord_top(qy, g.org[1], g.inv0, g.dim[1]),
-            hz = coord_top(qz, g.org[2], g.inv0, g.dim[2]);
-  visit_top_cell(g, v, hx, hy, hz, cell_lo(g.org[0], hx, g.H0), cell_lo(g.org[1], hy, g.H0), cell_lo(g.org[2], hz, g.H0),
-                 qx, qy, qz, b);
   for (int z = z0; z <= z1; ++z) {
     const float cz = cell_lo(g.org[2], z, g.H0);
     const float gz = gap(qz, cz, cell_lo(g.org[2], z + 1, g.H0), g.margin);
@@ -310,7 +311,6 @@ LS_HD void ball_query(const Grid& g, const GridView& v, float qx, float qy, floa
       const float lbyz = gy * gy + gz2;
       if (lbyz * LS_SHRINK > b.d2) continue;
       for (int x = x0; x <= x1; ++x) {
-        if (x == hx && y == hy && z == hz) continue;
         const float cx = cell_lo(g.org[0], x, g.H0);
         const float gx = gap(qx, cx, cell_lo(g.org[0], x + 1, g.H0), g.margin);
         const float lb = gx * gx + lbyz;
@@ -380,7 +380,7 @@ LS_HD Best nn_search(const Grid& g, const GridView& v, float qx, float qy, float
   b.pos = -1;
   if (g.m <= 0) { b.idx = -1; b.d2 = INFINITY; return b; }
   if (warm_pos >= 0) consider(v.pts, warm_pos, qx, qy, qz, b);
-  else if (!(cap_d2 < INFINITY)) seed_query(g, v, qx, qy, qz, b);
+  else seed_query(g, v, qx, qy, qz, b);  // candidates beyond the cap are simply not accepted
   ball_query(g, v, qx, qy, qz, b);
   if (b.pos < 0) { b.idx = -1; b.d2 = INFINITY; }
   return b;

@@ -95,6 +95,7 @@ struct IcpProblem {
   float* T_hist;  // max_iterations*16 floats or null
   int want_matches;  // 1: finish with an uncapped NN pass so ids/d2 hold every point's true match
   unsigned long long* phase_ns;  // debug: max_iterations*6 globaltimer stamps (CTA 0) or null
+  unsigned int* warp_cyc;        // debug: per-warp clock cycles of phase A at iteration 10, or null
   float T0[16];
 };
 
@@ -529,22 +530,30 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     if (P.phase_ns && cta == 0 && tid == 0) P.phase_ns[iter * 6 + (slot)] = globaltimer_ns(); \
   } while (0)
 
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int* p) {
   unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+}
+__device__ __forceinline__ void red_release_inc(unsigned int* p) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
 }
 
 // All CTAs of one problem.  `epoch` is the number of arrivals expected so far (kept in a register).
+//
+// Deliberately NOT an acquire: an acquire at gpu scope makes ptxas emit CCTL.IVALL (invalidate the whole
+// L1) -- per poll, that let a waiting CTA keep flushing the L1 of the CTA still searching on the same SM.
+// Everything one CTA produces for another (histograms, accumulators, their clearing) is either an L2
+// atomic or read back with ld.global.cg, i.e. served by L2, the point of coherence; per-query state
+// (pos/d2/ids) is only ever touched by its owning thread.  So the arrive is a release (prior writes are
+// performed at L2 before the counter moves) and the wait is a relaxed poll: L1 keeps the read-only map.
 __device__ __forceinline__ void problem_barrier(unsigned int* ctr, unsigned int n_ctas, unsigned int& epoch) {
   __syncthreads();
   if (threadIdx.x == 0) {
     epoch += n_ctas;
-    __threadfence();
-    atomicAdd(ctr, 1u);
-    while (ld_acquire_u32(ctr) < epoch) {
+    red_release_inc(ctr);
+    while (ld_relaxed_u32(ctr) < epoch) {
     }
-    __threadfence();
   }
   __syncthreads();
 }
@@ -606,7 +615,7 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
   __shared__ Grid g;
   __shared__ float T_iter[16], T_last[16];
   __shared__ unsigned int hist_s[2048];
-  __shared__ unsigned long long acc_s[28];
+  __shared__ unsigned long long acc_w[kIcpThreads / 32][28];
   __shared__ SelectOut sel;
   __shared__ unsigned int ws[kIcpThreads / 32];
   __shared__ double qh[kMaxSmooth + 2][4];
@@ -648,6 +657,7 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
     // ---------------- phase A: K2 nearest neighbour + level-1 histogram ----------------
     for (int k = tid; k < 2048; k += kIcpThreads) hist_s[k] = 0u;
     __syncthreads();
+    const long long wc0 = clock64();
     for (int i = q_begin + tid; i < q_end; i += kIcpThreads) {
       const float4 r = __ldg(P.rd + i);
       float sx, sy, sz;
@@ -659,6 +669,10 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
       P.ids[i] = b.idx;
       const unsigned int key = __float_as_uint(b.d2);
       if (key <= 0x7f800000u) atomicAdd(&hist_s[key >> 21], 1u);  // non-negative; +inf (no match in cap) -> bin 1020
+    }
+    if (P.warp_cyc && iter == 10) {
+      __syncwarp();
+      if (lane == 0) P.warp_cyc[cta * (kIcpThreads / 32) + (tid >> 5)] = (unsigned int)(clock64() - wc0);
     }
     __syncthreads();
     for (int k = tid; k < 1024; k += kIcpThreads) {
@@ -731,58 +745,66 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
     block_select(W->hist[par][2], 1024, rem2, false, 0.f, &sel, ws);
     const float limit = __uint_as_float((prefix12 << 10) | sel.bin);
     cap = fmaxf(limit * 2.0f, 1e-12f);  // guess for the next iteration (verified there)
-    if (tid < 28) acc_s[tid] = 0ull;
+    // One query per thread per pass (a CTA normally holds <= one query per thread): every product is
+    // quantised to 2^-22 and reduced across the warp at once (REDUX), so no per-thread accumulator array
+    // has to live in registers.  Integer sums are exact, hence independent of any ordering.
+    if (tid < 28 * (kIcpThreads / 32)) acc_w[tid / 28][tid % 28] = 0ull;
     __syncthreads();
-    long long a[27];
+    for (int base = q_begin; base < q_end; base += kIcpThreads) {
+      const int i = base + tid;
+      bool keep = false;
+      float f[6], e = 0.f;
 #pragma unroll
-    for (int k = 0; k < 27; ++k) a[k] = 0;
-    int kept = 0;
-    for (int i = q_begin + tid; i < q_end; i += kIcpThreads) {
-      const float d = P.d2[i];
-      if (!(d <= limit)) continue;
-      const int pos = P.pos[i];
-      if (pos < 0) continue;
-      ++kept;
-      const float4 r = __ldg(P.rd + i);
-      float sx, sy, sz;
-      xform_point(T_iter, r.x, r.y, r.z, sx, sy, sz);
-      const float4 q = __ldg(P.view.pts + pos);
-      const float4 nn = __ldg(P.nrm + pos);
-      float f[6];
-      {
-        float u = sy * nn.z, v = sz * nn.y;
-        f[0] = u - v;
-        u = sz * nn.x; v = sx * nn.z;
-        f[1] = u - v;
-        u = sx * nn.y; v = sy * nn.x;
-        f[2] = u - v;
+      for (int k = 0; k < 6; ++k) f[k] = 0.f;
+      if (i < q_end) {
+        const float d = P.d2[i];
+        const int pos = P.pos[i];
+        if (d <= limit && pos >= 0) {
+          keep = true;
+          const float4 r = __ldg(P.rd + i);
+          float sx, sy, sz;
+          xform_point(T_iter, r.x, r.y, r.z, sx, sy, sz);
+          const float4 q = __ldg(P.view.pts + pos);
+          const float4 nn = __ldg(P.nrm + pos);
+          float u = sy * nn.z, v = sz * nn.y;
+          f[0] = u - v;
+          u = sz * nn.x; v = sx * nn.z;
+          f[1] = u - v;
+          u = sx * nn.y; v = sy * nn.x;
+          f[2] = u - v;
+          f[3] = nn.x; f[4] = nn.y; f[5] = nn.z;
+          const float dx = sx - q.x, dy = sy - q.y, dz = sz - q.z;
+          e = dx * nn.x;
+          float t = dy * nn.y;
+          e = e + t;
+          t = dz * nn.z;
+          e = e + t;
+        }
       }
-      f[3] = nn.x; f[4] = nn.y; f[5] = nn.z;
-      const float dx = sx - q.x, dy = sy - q.y, dz = sz - q.z;
-      float e = dx * nn.x;
-      float t = dy * nn.y;
-      e = e + t;
-      t = dz * nn.z;
-      e = e + t;
+      const unsigned int kmask = __ballot_sync(0xffffffffu, keep);
+      if (kmask == 0u) continue;  // warp-uniform
       int k = 0;
 #pragma unroll
       for (int rr = 0; rr < 6; ++rr)
 #pragma unroll
-        for (int cc = rr; cc < 6; ++cc, ++k) a[k] += __float2ll_rn((f[rr] * f[cc]) * 4194304.0f);
+        for (int cc = rr; cc < 6; ++cc, ++k) {
+          const long long s = warp_sum_ll(keep ? __float2ll_rn((f[rr] * f[cc]) * 4194304.0f) : 0ll);
+          if (lane == 0) acc_w[tid >> 5][k] += (unsigned long long)s;
+        }
 #pragma unroll
-      for (int rr = 0; rr < 6; ++rr) a[21 + rr] += __float2ll_rn((f[rr] * e) * 4194304.0f);
-    }
-#pragma unroll
-    for (int k = 0; k < 27; ++k) {
-      const long long s = warp_sum_ll(a[k]);
-      if (lane == 0 && s != 0) atomicAdd(&acc_s[k], (unsigned long long)s);
-    }
-    {
-      const int ks = __reduce_add_sync(0xffffffffu, kept);
-      if (lane == 0 && ks) atomicAdd(&acc_s[27], (unsigned long long)ks);
+      for (int rr = 0; rr < 6; ++rr) {
+        const long long s = warp_sum_ll(keep ? __float2ll_rn((f[rr] * e) * 4194304.0f) : 0ll);
+        if (lane == 0) acc_w[tid >> 5][21 + rr] += (unsigned long long)s;
+      }
+      if (lane == 0) acc_w[tid >> 5][27] += (unsigned long long)__popc(kmask);
     }
     __syncthreads();
-    if (tid < 28 && acc_s[tid] != 0ull) atomicAdd(&W->acc[par][tid], acc_s[tid]);
+    if (tid < 28) {
+      unsigned long long t = 0ull;
+#pragma unroll
+      for (int w = 0; w < kIcpThreads / 32; ++w) t += acc_w[w][tid];
+      if (t != 0ull) atomicAdd(&W->acc[par][tid], t);
+    }
     problem_barrier(&W->barrier, G, epoch);
     LS_STAMP(4);
 

@@ -12,7 +12,7 @@
 
 #include "../../laser_slam_b200/csrc/ls_grid.cuh"
 
-thread_local long long ls::ls_sim_cand = 0, ls::ls_sim_entries = 0;
+thread_local long long ls::ls_sim_cand = 0, ls::ls_sim_entries = 0, ls::ls_sim_steps = 0;
 
 namespace {
 struct SimGrid {
@@ -150,12 +150,13 @@ void sim_nn(const float* q3, int n, const float* refc3, int m, float cell, int m
   for (int i = 0; i < n; ++i) {
     ls::ls_sim_cand = 0;
     ls::ls_sim_entries = 0;
+    ls::ls_sim_steps = 0;
     const int warm = (warm_ids && warm_ids[i] >= 0) ? pos_of[warm_ids[i]] : -1;
     const ls::Best b = ls::nn_search(S.g, v, q3[3 * i], q3[3 * i + 1], q3[3 * i + 2], warm, cap_d2);
     ids[i] = b.idx;
     d2[i] = b.d2;
     if (per_query_cand) per_query_cand[i] = (int32_t)ls::ls_sim_cand;
-    if (per_query_entries) per_query_entries[i] = (int32_t)ls::ls_sim_entries;
+    if (per_query_entries) per_query_entries[i] = (int32_t)(ls::ls_sim_entries | (ls::ls_sim_steps << 16));
     cand += ls::ls_sim_cand;
     ent += ls::ls_sim_entries;
     cmax = std::max(cmax, ls::ls_sim_cand);

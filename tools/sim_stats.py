@@ -14,6 +14,9 @@ def sim_nn(q, refc, cell=1.0, max_cells=1 << 22, split=32, warm=None, cap=np.inf
     w = np.ascontiguousarray(warm, np.int32) if warm is not None else None
     L.sim_nn(q.ctypes.data, len(q), refc.ctypes.data, len(refc), cell, max_cells, split,
              w.ctypes.data if w is not None else None, ids.ctypes.data, d2.ctypes.data, st.ctypes.data, pc.ctypes.data, pe.ctypes.data, cap)
+    global LAST_STEPS
+    LAST_STEPS = pe >> 16
+    pe = pe & 0xffff
     return ids, d2, st, pc, pe
 
 if __name__ == "__main__":
@@ -40,5 +43,7 @@ if __name__ == "__main__":
             print(f"   CAP {mult}x limit ({lim*mult:.4f}): found {np.isfinite(d3).mean():.3f} kept-set eq {np.array_equal(i3[dk2<=lim], ik2[dk2<=lim])} cand mean {pc.mean():.1f} pct99/99.9/max {np.percentile(pc,[99,99.9,100])} entries mean {pe.mean():.1f} {np.percentile(pe,[99,99.9,100])}")
             cost = (pc + pe).reshape(-1, 32)
             print("      per-warp max mean", cost.max(1).mean(), "sum mean", cost.sum(1).mean(), "sum max", cost.sum(1).max(), "max max", cost.max())
+            st_ = LAST_STEPS.reshape(-1, 32)
+            print(f"      STEPS mean {LAST_STEPS.mean():.1f} pct50/99/max {np.percentile(LAST_STEPS,[50,99,100])} per-warp max: mean {st_.max(1).mean():.1f} max {st_.max()}")
             i4, d4, st4, pc, pe = sim_nn(q, refc, cell, split=split, warm=None, cap=float(lim * mult))
             print(f"      COLD capped: found {np.isfinite(d4).mean():.3f} cand mean {pc.mean():.1f} pct99/99.9/max {np.percentile(pc,[99,99.9,100])} entries mean {pe.mean():.1f} {np.percentile(pe,[99,99.9,100])}")
