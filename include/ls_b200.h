@@ -141,6 +141,58 @@ int ls_icp_register_submap(ls_ctx* ctx, const ls_icp_params* prm, const ls_map* 
 int ls_map_assemble(ls_ctx* ctx, const ls_map* map, int n_parts, const uint64_t* part_ids,
                     const float* T_parts, float* out4, float* out_normals3, int* m_out);
 
+/* ---- pose graph ------------------------------------------------------------------------------------
+ * Replaces gtsam::ISAM2 as IncrementalEstimator uses it (laser_slam/src/incremental_estimator.cpp:17-20,
+ * 151-163 estimate, 165-266 estimateAndRemove, 268-291 registerPrior).  Poses are 7 doubles
+ * {qw,qx,qy,qz,tx,ty,tz}; a factor is what LaserTrack::makeMeasurementFactor /
+ * makeRelativeMeasurementFactor build (laser_slam/src/laser_track.cpp:431-458):
+ *   LS_FACTOR_PRIOR    error = Local(meas, T(key_a))
+ *   LS_FACTOR_BETWEEN  error = Local(meas, T(key_a)^-1 * T(key_b)); fix_a != 0 freezes node a at fixed_a
+ * whitened by sigma[6] ([translation x3; rotation x3], gtsam::noiseModel::Diagonal::Sigmas); robust != 0
+ * wraps it in Robust(Cauchy(1)) (laser_track.cpp:37-64, incremental_estimator.cpp:29-48). */
+#define LS_FACTOR_PRIOR 0
+#define LS_FACTOR_BETWEEN 1
+
+typedef struct ls_pg ls_pg;
+
+typedef struct ls_factor {
+  int32_t type;
+  int32_t robust;
+  int32_t fix_a;
+  int32_t reserved;
+  uint64_t key_a, key_b; /* prior: key_a (key_b ignored) */
+  double meas[7];
+  double sigma[6];
+  double fixed_a[7];
+} ls_factor;
+
+typedef struct ls_pg_stats {
+  int iterations, n_poses, n_factors, n_border; /* n_border = factors outside the per-track chains */
+  double cost_first, cost_last;                 /* robust cost at the first / last linearisation point */
+  double last_step_max;                         /* max |component| of the last update */
+  float device_ms;
+} ls_pg_stats;
+
+int ls_pg_create(int device, ls_pg** out);
+void ls_pg_destroy(ls_pg* pg);
+const char* ls_pg_last_error(const ls_pg* pg);
+uint64_t ls_pg_launch_count(const ls_pg* pg);
+int ls_pg_num_poses(const ls_pg* pg);
+int ls_pg_num_factors(const ls_pg* pg);
+/* gtsam::Values::insert for new nodes; within one track_id the insertion order is the time order
+ * (curves::DiscreteSE3Curve::extend, laser_track.cpp:573-582).  track_ids may be NULL (all track 0). */
+int ls_pg_add_poses(ls_pg* pg, const uint64_t* keys, const uint32_t* track_ids, const double* poses7, int n);
+int ls_pg_set_poses(ls_pg* pg, const uint64_t* keys, const double* poses7, int n);
+/* isam2.update(newFactors, ...): out_indices (may be NULL) receives ISAM2Result::newFactorsIndices. */
+int ls_pg_add_factors(ls_pg* pg, const ls_factor* factors, int n, uint64_t* out_indices);
+/* isam2.update(..., removeFactorIndices) (incremental_estimator.cpp:258). */
+int ls_pg_remove_factors(ls_pg* pg, const uint64_t* indices, int n);
+/* gn_iters Gauss-Newton iterations over the whole graph on the device (3 = one estimate() call:
+ * update(new) + update() + update(), incremental_estimator.cpp:156-159). */
+int ls_pg_optimize(ls_pg* pg, int gn_iters, ls_pg_stats* stats);
+/* isam2.calculateEstimate(): all keys and poses (either pointer may be NULL); *n = number of poses. */
+int ls_pg_get_poses(const ls_pg* pg, uint64_t* out_keys, double* out_poses7, int* n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,6 +40,21 @@ class IcpStats(ctypes.Structure):
                 ("grid_tables", ctypes.c_int), ("grid_overflow", ctypes.c_int)]
 
 
+class Factor(ctypes.Structure):
+    _fields_ = [("type", ctypes.c_int32), ("robust", ctypes.c_int32), ("fix_a", ctypes.c_int32),
+                ("reserved", ctypes.c_int32), ("key_a", ctypes.c_uint64), ("key_b", ctypes.c_uint64),
+                ("meas", ctypes.c_double * 7), ("sigma", ctypes.c_double * 6), ("fixed_a", ctypes.c_double * 7)]
+
+
+class PgStats(ctypes.Structure):
+    _fields_ = [("iterations", ctypes.c_int), ("n_poses", ctypes.c_int), ("n_factors", ctypes.c_int),
+                ("n_border", ctypes.c_int), ("cost_first", ctypes.c_double), ("cost_last", ctypes.c_double),
+                ("last_step_max", ctypes.c_double), ("device_ms", ctypes.c_float)]
+
+
+FACTOR_PRIOR, FACTOR_BETWEEN = 0, 1
+
+
 def build(force=False):
     """Compile libls_b200.so in-tree (nvcc cross-compiles sm_100a without a GPU)."""
     src_dir = os.path.join(_HERE, "csrc")
@@ -82,6 +97,21 @@ def lib():
         L.ls_map_scan_size.argtypes = [vp, u64]
         L.ls_icp_register_submap.argtypes = [vp, PP, vp, u64, ci, vp, vp, vp, vp, PS, vp, vp, vp]
         L.ls_map_assemble.argtypes = [vp, vp, ci, vp, vp, vp, vp, ctypes.POINTER(ci)]
+        L.ls_pg_create.argtypes = [ci, ctypes.POINTER(vp)]
+        L.ls_pg_destroy.argtypes = [vp]
+        L.ls_pg_destroy.restype = None
+        L.ls_pg_last_error.argtypes = [vp]
+        L.ls_pg_last_error.restype = ctypes.c_char_p
+        L.ls_pg_launch_count.argtypes = [vp]
+        L.ls_pg_launch_count.restype = u64
+        L.ls_pg_num_poses.argtypes = [vp]
+        L.ls_pg_num_factors.argtypes = [vp]
+        L.ls_pg_add_poses.argtypes = [vp, vp, vp, vp, ci]
+        L.ls_pg_set_poses.argtypes = [vp, vp, vp, ci]
+        L.ls_pg_add_factors.argtypes = [vp, ctypes.POINTER(Factor), ci, vp]
+        L.ls_pg_remove_factors.argtypes = [vp, vp, ci]
+        L.ls_pg_optimize.argtypes = [vp, ci, ctypes.POINTER(PgStats)]
+        L.ls_pg_get_poses.argtypes = [vp, vp, vp, ctypes.POINTER(ci)]
         _lib = L
     return _lib
 
@@ -294,3 +324,75 @@ def correct_rigid(T):
     o = np.empty(16, np.float32)
     lib().ls_correct_rigid(t.ctypes.data, o.ctypes.data)
     return from_colmajor(o)
+
+
+class PoseGraph:
+    """Device pose graph (gtsam::ISAM2 as IncrementalEstimator uses it).  Poses: rows [qw,qx,qy,qz,tx,ty,tz]."""
+
+    def __init__(self, device=0):
+        self._h = ctypes.c_void_p()
+        rc = lib().ls_pg_create(device, ctypes.byref(self._h))
+        if rc != 0:
+            raise LsError(f"ls_pg_create(device={device}) failed with {rc}: no usable CUDA device (no CPU fallback)")
+
+    def close(self):
+        if self._h:
+            lib().ls_pg_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc == LS_ERR_CONVERGENCE:
+            raise ConvergenceError(lib().ls_pg_last_error(self._h).decode())
+        if rc != 0:
+            raise LsError(f"rc={rc}: {lib().ls_pg_last_error(self._h).decode()}")
+
+    @property
+    def launch_count(self):
+        return int(lib().ls_pg_launch_count(self._h))
+
+    def add_poses(self, keys, poses7, track_ids=None):
+        keys = np.ascontiguousarray(keys, np.uint64)
+        poses7 = np.ascontiguousarray(poses7, np.float64).reshape(-1, 7)
+        tr = np.ascontiguousarray(track_ids, np.uint32) if track_ids is not None else None
+        self._check(lib().ls_pg_add_poses(self._h, keys.ctypes.data, _ptr(tr), poses7.ctypes.data, len(keys)))
+
+    def set_poses(self, keys, poses7):
+        keys = np.ascontiguousarray(keys, np.uint64)
+        poses7 = np.ascontiguousarray(poses7, np.float64).reshape(-1, 7)
+        self._check(lib().ls_pg_set_poses(self._h, keys.ctypes.data, poses7.ctypes.data, len(keys)))
+
+    def add_factors(self, factors):
+        """factors: iterable of dicts (type, key_a, key_b, meas[7], sigma[6], robust, fix_a, fixed_a[7]).  Returns indices."""
+        arr = (Factor * len(factors))()
+        for i, f in enumerate(factors):
+            a = arr[i]
+            a.type, a.robust, a.fix_a = int(f["type"]), int(f.get("robust", 0)), int(f.get("fix_a", 0))
+            a.key_a, a.key_b = int(f["key_a"]), int(f.get("key_b", 0))
+            a.meas[:] = [float(x) for x in f["meas"]]
+            a.sigma[:] = [float(x) for x in f["sigma"]]
+            a.fixed_a[:] = [float(x) for x in f.get("fixed_a", [1, 0, 0, 0, 0, 0, 0])]
+        idx = np.zeros(max(len(factors), 1), np.uint64)
+        self._check(lib().ls_pg_add_factors(self._h, arr, len(factors), idx.ctypes.data))
+        return idx[:len(factors)]
+
+    def remove_factors(self, indices):
+        idx = np.ascontiguousarray(indices, np.uint64)
+        self._check(lib().ls_pg_remove_factors(self._h, idx.ctypes.data, len(idx)))
+
+    def optimize(self, gn_iters=3):
+        st = PgStats()
+        self._check(lib().ls_pg_optimize(self._h, gn_iters, ctypes.byref(st)))
+        return st
+
+    def poses(self):
+        n = ctypes.c_int(lib().ls_pg_num_poses(self._h))
+        keys = np.zeros(max(n.value, 1), np.uint64)
+        poses = np.zeros((max(n.value, 1), 7), np.float64)
+        self._check(lib().ls_pg_get_poses(self._h, keys.ctypes.data, poses.ctypes.data, ctypes.byref(n)))
+        return keys[:n.value], poses[:n.value]
