@@ -1,0 +1,58 @@
+// IncrementalEstimator -- public interface of reference laser_slam/include/laser_slam/incremental_estimator.hpp:17-81;
+// the iSAM2 object is replaced by a device pose graph (ls_pg_*).
+#ifndef LASER_SLAM_INCREMENTAL_ESTIMATOR_HPP_
+#define LASER_SLAM_INCREMENTAL_ESTIMATOR_HPP_
+
+#include <memory>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "laser_slam/common.hpp"
+#include "laser_slam/laser_track.hpp"
+#include "laser_slam/parameters.hpp"
+
+namespace laser_slam {
+
+class IncrementalEstimator {
+ public:
+  explicit IncrementalEstimator(const EstimatorParams& parameters, unsigned int n_laser_slam_workers = 1u);
+  ~IncrementalEstimator();
+  IncrementalEstimator(const IncrementalEstimator&) = delete;
+  IncrementalEstimator& operator=(const IncrementalEstimator&) = delete;
+
+  void processLoopClosure(const RelativePose& loop_closure);
+  Pose getCurrentPose(unsigned int laser_track_id = 0u) const;
+  std::shared_ptr<LaserTrack> getLaserTrack(unsigned int laser_track_id);
+  std::vector<std::shared_ptr<LaserTrack> > getAllLaserTracks();
+
+  gtsam::Values estimate(const gtsam::NonlinearFactorGraph& new_factors, const gtsam::Values& new_values,
+                         laser_slam::Time timestamp_ns = 0u);
+  gtsam::Values estimateAndRemove(const gtsam::NonlinearFactorGraph& new_factors,
+                                  const gtsam::NonlinearFactorGraph& new_associations_factors,
+                                  const gtsam::Values& new_values, const std::vector<unsigned int>& affected_worker_ids,
+                                  laser_slam::Time timestamp_ns = 0u);
+  gtsam::Values registerPrior(const gtsam::NonlinearFactorGraph& new_factors, const gtsam::Values& new_values,
+                              const unsigned int worker_id);
+
+  const ls_pg_stats& getLastSolveStats() const { return last_stats_; }
+
+ private:
+  gtsam::Values updateGraph(const gtsam::NonlinearFactorGraph& factors, const gtsam::Values& values,
+                            const std::vector<uint64_t>& remove, std::vector<uint64_t>* new_indices);
+  unsigned int n_laser_slam_workers_;
+  mutable std::recursive_mutex full_class_mutex_;
+  std::vector<std::shared_ptr<LaserTrack> > laser_tracks_;
+  ls_pg* graph_ = nullptr;
+  ls_ctx* icp_ctx_ = nullptr;  // loop-closure ICP (sub-map <-> sub-map)
+  ls_icp_params icp_params_;
+  gtsam::NoiseModel loop_closure_noise_model_, first_association_noise_model_;
+  std::unordered_map<unsigned int, size_t> factor_indices_to_remove_;
+  std::vector<std::vector<unsigned int> > linked_workers_;
+  EstimatorParams params_;
+  ls_pg_stats last_stats_;
+};
+
+}  // namespace laser_slam
+
+#endif  // LASER_SLAM_INCREMENTAL_ESTIMATOR_HPP_

@@ -1,0 +1,104 @@
+// LaserTrack -- public interface of reference laser_slam/include/laser_slam/laser_track.hpp:17-236, implemented
+// over the B200 C ABI (include/ls_b200.h): scans live in a device ring (ls_map_*), the scan-to-sub-map ICP is
+// ls_icp_register_submap, factors are ls_factor records.
+#ifndef LASER_SLAM_LASER_TRACK_HPP_
+#define LASER_SLAM_LASER_TRACK_HPP_
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "laser_slam/common.hpp"
+#include "laser_slam/parameters.hpp"
+
+namespace laser_slam {
+
+class LaserTrack {
+ public:
+  explicit LaserTrack(const LaserTrackParams& parameters, unsigned int laser_track_id = 0u);
+  ~LaserTrack();
+  LaserTrack(const LaserTrack&) = delete;
+  LaserTrack& operator=(const LaserTrack&) = delete;
+
+  void processPose(const Pose& pose);
+  void processLaserScan(const LaserScan& scan);
+  void processPoseAndLaserScan(const Pose& pose, const LaserScan& in_scan,
+                               gtsam::NonlinearFactorGraph* newFactors = NULL, gtsam::Values* newValues = NULL,
+                               bool* is_prior = NULL);
+
+  void getLastPointCloud(DataPoints* out_point_cloud) const;
+  void getPointCloudOfTimeInterval(const std::pair<Time, Time>& times_ns, DataPoints* out_point_cloud) const;
+  void getLocalCloudInWorldFrame(const Time& timestamp, DataPoints* out_point_cloud) const;
+  const std::vector<LaserScan>& getLaserScans() const;
+  void getTrajectory(Trajectory* trajectory) const;
+  void getOdometryTrajectory(Trajectory* out_trajectory) const;
+  void getCovariances(std::vector<Covariance>* out_covariances) const;
+  Pose getCurrentPose() const;
+  Pose getPreviousPose() const;
+  Time getMinTime() const;
+  Time getMaxTime() const;
+  void getLaserScansTimes(std::vector<Time>* out_times_ns) const;
+
+  void appendPriorFactors(const curves::Time& prior_time_ns, gtsam::NonlinearFactorGraph* graph) const;
+  void appendOdometryFactors(const curves::Time& optimization_min_time_ns, const curves::Time& optimization_max_time_ns,
+                             const gtsam::NoiseModel& noise_model, gtsam::NonlinearFactorGraph* graph) const;
+  void appendICPFactors(const curves::Time& optimization_min_time_ns, const curves::Time& optimization_max_time_ns,
+                        const gtsam::NoiseModel& noise_model, gtsam::NonlinearFactorGraph* graph) const;
+  void appendLoopClosureFactors(const curves::Time& optimization_min_time_ns, const curves::Time& optimization_max_time_ns,
+                                const gtsam::NoiseModel& noise_model, gtsam::NonlinearFactorGraph* graph) const;
+
+  void initializeGTSAMValues(const std::vector<Key>& keys, gtsam::Values* values) const;
+  void updateFromGTSAMValues(const gtsam::Values& values);
+
+  size_t getNumScans() const;
+  Pose findNearestPose(const Time& timestamp_ns) const;
+  void buildSubMapAroundTime(const curves::Time& time_ns, const unsigned int sub_maps_radius, DataPoints* submap_out) const;
+  Key getValueKey(const curves::Time& time_ns) const;  // the leaf of trajectory_.getValueExpression(time)
+  SE3 evaluate(const curves::Time& time_ns) const;
+  void getScanMatchingTimes(std::map<Time, double>* scan_matching_times) const;
+  void saveTrajectory(const std::string& filename) const;
+
+  // (new) ICP results and run statistics, for tests and the bench
+  const RelativePoseVector& getIcpTransformations() const { return icp_transformations_; }
+  const ls_icp_stats& getLastIcpStats() const { return last_icp_stats_; }
+  ls_ctx* context() const { return ctx_; }
+  unsigned int id() const { return laser_track_id_; }
+
+ private:
+  struct Node { SE3 value; Key key; };
+  ls_factor makeRelativeMeasurementFactor(const RelativePose& m, const gtsam::NoiseModel& noise, bool fix_first_node = false) const;
+  ls_factor makeMeasurementFactor(const Pose& pose_measurement, const gtsam::NoiseModel& noise) const;
+  void computeICPTransformations();
+  void localScanToSubMap();
+  const Pose& findPose(const Time& timestamp_ns) const;
+  Pose& findPose(const Time& timestamp_ns);
+  Key extendTrajectory(const Time& timestamp_ns, const SE3& value);
+  size_t scanIndexAtTime(const curves::Time& time_ns) const;
+  uint64_t residentScan(size_t index) const;  // device id of laser_scans_[index], uploading it if it was evicted
+  void assembleSubMap(const std::vector<size_t>& scan_indices, const std::vector<PointMatcher::TransformationParameters>& Ts,
+                      DataPoints* out) const;
+
+  unsigned int laser_track_id_;
+  PoseVector pose_measurements_;
+  RelativePoseVector odometry_measurements_, icp_transformations_, loop_closures_;
+  std::vector<LaserScan> laser_scans_;
+  std::map<Time, Node> trajectory_;  // curves::DiscreteSE3Curve: time -> (value, key)
+  mutable std::recursive_mutex full_laser_track_mutex_;
+  std::vector<Covariance> covariances_;
+  gtsam::NoiseModel prior_noise_model_, odometry_noise_model_, icp_noise_model_;
+  std::map<Time, double> scan_matching_times_;
+  LaserTrackParams params_;
+  ls_icp_params icp_params_;
+  ls_icp_stats last_icp_stats_;
+  // device side
+  ls_ctx* ctx_ = nullptr;
+  ls_map* map_ = nullptr;
+  int map_capacity_ = 0, map_max_pts_ = 0;
+  mutable std::map<size_t, uint64_t> resident_;  // scan index -> device scan id
+  static constexpr double kDistanceBetweenPriorPoses_m = 100.0;
+};
+
+}  // namespace laser_slam
+
+#endif  // LASER_SLAM_LASER_TRACK_HPP_

@@ -157,8 +157,9 @@ __global__ void pg_linearize_kernel(int F, const FactorDev* __restrict__ fac, co
 // thread per pose; incident factors through a CSR list (fixed order => deterministic sums)
 __global__ void pg_assemble_kernel(int P, const int* __restrict__ inc_ptr, const int* __restrict__ inc_fac,
                                    const FactorDev* __restrict__ fac, const double* __restrict__ Ja,
-                                   const double* __restrict__ Jb, const double* __restrict__ r, double* __restrict__ D,
-                                   double* __restrict__ Bsub, double* __restrict__ g) {
+                                   const double* __restrict__ Jb, const double* __restrict__ r,
+                                   const int* __restrict__ damp, double* __restrict__ D, double* __restrict__ Bsub,
+                                   double* __restrict__ g) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= P) return;
   double d[36], b[36], gg[6];
@@ -191,6 +192,12 @@ __global__ void pg_assemble_kernel(int P, const int* __restrict__ inc_ptr, const
           b[6 * i + j] += s;
         }
     }
+  }
+  if (damp[k]) {
+    // Gauge damping on the first pose of a track that has no prior / fixed-node factor of its own (its prior
+    // was removed when the track got linked, incremental_estimator.cpp:212-237): added to H only, never to g,
+    // so the Gauss-Newton fixed point is unchanged while the chain block becomes positive definite.
+    for (int i = 0; i < 3; ++i) { d[7 * i] += 1.0; d[7 * (3 + i)] += 4.0; }  // sigma 1 m / 0.5 rad: << any real factor
   }
   for (int i = 0; i < 36; ++i) { D[36 * (size_t)k + i] = d[i]; Bsub[36 * (size_t)k + i] = b[i]; }
   for (int i = 0; i < 6; ++i) g[6 * (size_t)k + i] = gg[i];
@@ -449,7 +456,8 @@ struct ls_pg {
   FactorDev* d_fac = nullptr;
   double *d_poses = nullptr, *d_Ja = nullptr, *d_Jb = nullptr, *d_r = nullptr, *d_D = nullptr, *d_B = nullptr,
          *d_g = nullptr, *d_Ld = nullptr, *d_Ls = nullptr, *d_Z = nullptr, *d_S = nullptr, *d_rhs = nullptr, *d_cost = nullptr;
-  int *d_inc_ptr = nullptr, *d_inc_fac = nullptr, *d_extra = nullptr, *d_track_begin = nullptr, *d_fail = nullptr;
+  int *d_inc_ptr = nullptr, *d_inc_fac = nullptr, *d_extra = nullptr, *d_track_begin = nullptr, *d_fail = nullptr,
+      *d_damp = nullptr;
   unsigned long long* d_dmax = nullptr;
 };
 
@@ -501,7 +509,7 @@ void ls_pg_destroy(ls_pg* pg) {
   if (pg->stream) cudaStreamSynchronize(pg->stream);
   void* bufs[] = {pg->d_fac, pg->d_poses, pg->d_Ja, pg->d_Jb, pg->d_r, pg->d_D, pg->d_B, pg->d_g, pg->d_Ld, pg->d_Ls, pg->d_Z,
                   pg->d_S, pg->d_rhs, pg->d_cost, pg->d_inc_ptr, pg->d_inc_fac, pg->d_extra, pg->d_track_begin, pg->d_fail,
-                  pg->d_dmax};
+                  pg->d_dmax, pg->d_damp};
   for (void* b : bufs)
     if (b) cudaFree(b);
   if (pg->stream) cudaStreamDestroy(pg->stream);
@@ -630,11 +638,22 @@ int ls_pg_optimize(ls_pg* pg, int gn_iters, ls_pg_stats* stats) {
   }
   const int F = (int)fd.size();
   if (F == 0) return LS_OK;
-  for (int t = 0; t < n_tracks; ++t)
-    if (!anchored[t])
-      return pg_fail(pg, LS_ERR_STATE,
-                     "a track has neither a prior nor a fixed-node factor: its chain block is singular "
-                     "(prior removal after linking tracks is not supported by the bordered solver yet)");
+  // a track without prior / fixed-node factor must at least be tied to the rest by a border factor
+  std::vector<int> damp(P, 0);
+  {
+    std::vector<char> linked(n_tracks, 0);
+    for (int fi : extra_fac) {
+      if (fd[fi].ia >= 0) linked[track_of_pos[fd[fi].ia]] = 1;
+      linked[track_of_pos[fd[fi].ib]] = 1;
+    }
+    for (int t = 0; t < n_tracks; ++t)
+      if (!anchored[t]) {
+        if (!linked[t])
+          return pg_fail(pg, LS_ERR_STATE, "a track has no prior, no fixed-node factor and no link to another track: "
+                                           "the graph has a free gauge");
+        damp[track_begin[t]] = 1;
+      }
+  }
   const int E = (int)extra_fac.size();
   const int n = 6 * E, n16 = ((n + NB - 1) / NB) * NB, ncol = n + 1;
   // incidence lists
@@ -664,7 +683,8 @@ int ls_pg_optimize(ls_pg* pg, int gn_iters, ls_pg_stats* stats) {
     const size_t cap = (size_t)P + P / 4 + 64;
     if ((rc = grow(pg, &pg->d_poses, cap * 7)) || (rc = grow(pg, &pg->d_D, cap * 36)) || (rc = grow(pg, &pg->d_B, cap * 36)) ||
         (rc = grow(pg, &pg->d_g, cap * 6)) || (rc = grow(pg, &pg->d_Ld, cap * 36)) || (rc = grow(pg, &pg->d_Ls, cap * 36)) ||
-        (rc = grow(pg, &pg->d_inc_ptr, cap + 1)) || (rc = grow(pg, &pg->d_track_begin, cap + 1)))
+        (rc = grow(pg, &pg->d_inc_ptr, cap + 1)) || (rc = grow(pg, &pg->d_track_begin, cap + 1)) ||
+        (rc = grow(pg, &pg->d_damp, cap + 1)))
       return rc;
     pg->capP = cap;
   }
@@ -693,6 +713,7 @@ int ls_pg_optimize(ls_pg* pg, int gn_iters, ls_pg_stats* stats) {
   PGCU(cudaMemcpyAsync(pg->d_inc_fac, inc_fac.data(), inc_fac.size() * sizeof(int), cudaMemcpyHostToDevice, st));
   if (E) PGCU(cudaMemcpyAsync(pg->d_extra, extra_fac.data(), (size_t)E * sizeof(int), cudaMemcpyHostToDevice, st));
   PGCU(cudaMemcpyAsync(pg->d_track_begin, track_begin.data(), track_begin.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  PGCU(cudaMemcpyAsync(pg->d_damp, damp.data(), (size_t)P * sizeof(int), cudaMemcpyHostToDevice, st));
   PGCU(cudaMemsetAsync(pg->d_fail, 0, sizeof(int), st));
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
@@ -704,7 +725,7 @@ int ls_pg_optimize(ls_pg* pg, int gn_iters, ls_pg_stats* stats) {
     PGCU(cudaMemsetAsync(pg->d_dmax, 0, sizeof(unsigned long long), st));
     pg_linearize_kernel<<<(F + 127) / 128, 128, 0, st>>>(F, pg->d_fac, pg->d_poses, pg->d_Ja, pg->d_Jb, pg->d_r, pg->d_cost);
     pg_assemble_kernel<<<(P + 127) / 128, 128, 0, st>>>(P, pg->d_inc_ptr, pg->d_inc_fac, pg->d_fac, pg->d_Ja, pg->d_Jb, pg->d_r,
-                                                        pg->d_D, pg->d_B, pg->d_g);
+                                                        pg->d_damp, pg->d_D, pg->d_B, pg->d_g);
     pg_chain_factor_kernel<<<(n_tracks + 31) / 32, 32, 0, st>>>(n_tracks, pg->d_track_begin, pg->d_D, pg->d_B, pg->d_Ld, pg->d_Ls,
                                                                 pg->d_fail);
     pg_chain_solve_kernel<<<(ncol + 63) / 64, 64, 0, st>>>(P, ncol, pg->d_fac, pg->d_extra, pg->d_Ja, pg->d_Jb, pg->d_g, pg->d_Ld,

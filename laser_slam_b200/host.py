@@ -1,0 +1,97 @@
+"""ctypes access to the C test hooks of the C++ host layer (laser_slam_b200/host/host_capi.cpp): drives
+laser_slam::IncrementalEstimator / LaserTrack the way the ROS worker's scanCallback does
+(reference laser_slam_ros/src/laser_slam_worker.cpp:124-173)."""
+import ctypes
+import os
+
+import numpy as np
+
+from . import IcpStats, LsError, ConvergenceError, LS_ERR_CONVERGENCE, build as _build_all
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_build", "libls_host.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            _build_all()
+        L = ctypes.CDLL(LIB_PATH)
+        vp, ci, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+        L.lsh_create.restype = vp
+        L.lsh_create.argtypes = [ci, ci, ci, ci, ci, ci, ci, ci, ctypes.c_char_p, ctypes.c_char_p, ci]
+        L.lsh_destroy.argtypes = [vp]
+        L.lsh_destroy.restype = None
+        L.lsh_last_error.argtypes = [vp]
+        L.lsh_last_error.restype = ctypes.c_char_p
+        L.lsh_step.argtypes = [vp, ci, i64, vp, vp, vp, ci, vp, ctypes.POINTER(IcpStats)]
+        L.lsh_loop_closure.argtypes = [vp, ci, i64, ci, i64, vp]
+        L.lsh_trajectory.argtypes = [vp, ci, vp, vp, ci]
+        L.lsh_num_scans.argtypes = [vp, ci]
+        L.lsh_build_submap.argtypes = [vp, ci, i64, ci, vp, vp, ci]
+        _lib = L
+    return _lib
+
+
+class Estimator:
+    """laser_slam::IncrementalEstimator with n_workers LaserTracks."""
+
+    def __init__(self, n_workers=1, nscan_in_sub_map=4, use_icp_factors=True, use_odom_factors=True, robust_icp=True,
+                 device=0, do_icp_step_on_loop_closures=False, loop_closures_sub_maps_radius=2, icp_yaml_path=None):
+        err = ctypes.create_string_buffer(512)
+        self._h = lib().lsh_create(n_workers, nscan_in_sub_map, int(use_icp_factors), int(use_odom_factors), int(robust_icp),
+                                   device, int(do_icp_step_on_loop_closures), loop_closures_sub_maps_radius,
+                                   icp_yaml_path.encode() if icp_yaml_path else None, err, 512)
+        if not self._h:
+            raise LsError(err.value.decode() or "lsh_create failed")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().lsh_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc == LS_ERR_CONVERGENCE:
+            raise ConvergenceError(lib().lsh_last_error(self._h).decode())
+        if rc < 0:
+            raise LsError(lib().lsh_last_error(self._h).decode())
+        return rc
+
+    def step(self, worker, time_ns, pose7, features4, normals3):
+        """One scan callback; returns (icp T_a_b as 7 doubles, IcpStats)."""
+        f = np.ascontiguousarray(features4, np.float32)
+        nr = np.ascontiguousarray(normals3, np.float32)
+        p = np.ascontiguousarray(pose7, np.float64)
+        out = np.zeros(7, np.float64)
+        st = IcpStats()
+        self._check(lib().lsh_step(self._h, worker, int(time_ns), p.ctypes.data, f.ctypes.data, nr.ctypes.data, f.shape[0],
+                                   out.ctypes.data, ctypes.byref(st)))
+        return out, st
+
+    def loop_closure(self, track_a, time_a, track_b, time_b, w_T_a_b7):
+        p = np.ascontiguousarray(w_T_a_b7, np.float64)
+        self._check(lib().lsh_loop_closure(self._h, track_a, int(time_a), track_b, int(time_b), p.ctypes.data))
+
+    def trajectory(self, worker=0):
+        n = self._check(lib().lsh_trajectory(self._h, worker, None, None, 0))
+        times = np.zeros(max(n, 1), np.int64)
+        poses = np.zeros((max(n, 1), 7), np.float64)
+        self._check(lib().lsh_trajectory(self._h, worker, times.ctypes.data, poses.ctypes.data, n))
+        return times[:n], poses[:n]
+
+    def num_scans(self, worker=0):
+        return self._check(lib().lsh_num_scans(self._h, worker))
+
+    def build_submap(self, worker, time_ns, radius, cap_points):
+        f = np.zeros((cap_points, 4), np.float32)
+        nr = np.zeros((cap_points, 3), np.float32)
+        m = self._check(lib().lsh_build_submap(self._h, worker, int(time_ns), radius, f.ctypes.data, nr.ctypes.data, cap_points))
+        return f[:m], nr[:m]

@@ -1,0 +1,216 @@
+// IncrementalEstimator over the B200 C ABI.  Control flow follows reference
+// laser_slam/src/incremental_estimator.cpp (cited per function); gtsam::ISAM2 is replaced by the device pose
+// graph (ls_pg_*): every update runs three Gauss-Newton iterations over the whole graph, mirroring
+// isam2_.update(new) + update() + update() (reference :156-159, :258-262, :272-289).
+#include "laser_slam/incremental_estimator.hpp"
+
+#include <algorithm>
+#include <fstream>
+#include <sstream>
+#include <stdexcept>
+
+namespace laser_slam {
+
+namespace {
+#define LS_CHECK(cond, msg)                                             \
+  do {                                                                  \
+    if (!(cond)) throw std::logic_error(std::string("CHECK failed: ") + (msg)); \
+  } while (0)
+}  // namespace
+
+// reference :12-61
+IncrementalEstimator::IncrementalEstimator(const EstimatorParams& parameters, unsigned int n_laser_slam_workers)
+    : n_laser_slam_workers_(n_laser_slam_workers), params_(parameters) {
+  std::memset(&last_stats_, 0, sizeof(last_stats_));
+  if (ls_pg_create(params_.laser_track_params.cuda_device, &graph_) != LS_OK)
+    throw std::runtime_error("ls_pg_create failed: no usable CUDA device (no CPU fallback)");
+  for (unsigned int i = 0u; i < n_laser_slam_workers_; ++i)
+    laser_tracks_.push_back(std::make_shared<LaserTrack>(params_.laser_track_params, i));
+  loop_closure_noise_model_ = gtsam::NoiseModel{params_.loop_closure_noise_model, params_.add_m_estimator_on_loop_closures};
+  first_association_noise_model_ = gtsam::NoiseModel{{{0.05, 0.05, 0.05, 0.015, 0.015, 0.015}}, false};  // reference :40-48
+  // same chain as the lidar odometry (reference :50-60)
+  ls_icp_default_params(&icp_params_);
+  std::ifstream ifs(params_.laser_track_params.icp_configuration_file.c_str());
+  if (ifs.good()) {
+    std::stringstream ss;
+    ss << ifs.rdbuf();
+    if (ls_icp_params_from_yaml(ss.str().c_str(), &icp_params_) != LS_OK) throw std::runtime_error("unsupported ICP chain");
+  } else {
+    icp_params_.trim_ratio = 0.85f;
+    icp_params_.min_diff_trans = 0.001f;
+    icp_params_.smooth_length = 3;
+  }
+}
+
+IncrementalEstimator::~IncrementalEstimator() {
+  laser_tracks_.clear();
+  if (icp_ctx_) ls_b200_destroy(icp_ctx_);
+  if (graph_) ls_pg_destroy(graph_);
+}
+
+// reference :63-149
+void IncrementalEstimator::processLoopClosure(const RelativePose& loop_closure) {
+  std::lock_guard<std::recursive_mutex> lock(full_class_mutex_);
+  LS_CHECK(loop_closure.track_id_a < laser_tracks_.size() && loop_closure.track_id_b < laser_tracks_.size(), "bad track id");
+  LaserTrack& track_a = *laser_tracks_[loop_closure.track_id_a];
+  LaserTrack& track_b = *laser_tracks_[loop_closure.track_id_b];
+  if (loop_closure.track_id_a == loop_closure.track_id_b)
+    LS_CHECK(loop_closure.time_a_ns < loop_closure.time_b_ns, "Loop closure has invalid time.");
+  LS_CHECK(loop_closure.time_a_ns >= track_a.getMinTime() && loop_closure.time_a_ns <= track_a.getMaxTime(), "Loop closure has invalid time.");
+  LS_CHECK(loop_closure.time_b_ns >= track_b.getMinTime() && loop_closure.time_b_ns <= track_b.getMaxTime(), "Loop closure has invalid time.");
+
+  RelativePose updated = loop_closure;
+  // world-frame correction -> relative pose of the two nodes (reference :78-87)
+  const SE3 T_w_a = track_a.evaluate(loop_closure.time_a_ns);
+  const SE3 T_w_b = track_b.evaluate(loop_closure.time_b_ns);
+  updated.T_a_b = T_w_a.inverse() * loop_closure.T_a_b * T_w_b;
+
+  if (params_.do_icp_step_on_loop_closures) {  // reference :89-115; a ConvergenceError propagates here
+    const PointMatcher::TransformationParameters initial_guess =
+        PointMatcher::TransformationParameters::cast(updated.T_a_b.getTransformationMatrix());
+    DataPoints sub_map_a, sub_map_b;
+    track_a.buildSubMapAroundTime(loop_closure.time_a_ns, params_.loop_closures_sub_maps_radius, &sub_map_a);
+    track_b.buildSubMapAroundTime(loop_closure.time_b_ns, params_.loop_closures_sub_maps_radius, &sub_map_b);
+    if (!icp_ctx_ && ls_b200_init(params_.laser_track_params.cuda_device, &icp_ctx_) != LS_OK)
+      throw std::runtime_error("ls_b200_init failed");
+    PointMatcher::TransformationParameters icp_solution;
+    const int off = sub_map_a.descriptorOffset("normals");
+    LS_CHECK(off >= 0, "sub-map without normals");
+    const int rc = ls_icp_register(icp_ctx_, &icp_params_, sub_map_b.features.data(), (int)sub_map_b.getNbPoints(),
+                                   sub_map_a.features.data(), sub_map_a.descriptors.data() + off, (int)sub_map_a.descriptorDim,
+                                   (int)sub_map_a.getNbPoints(), initial_guess.data(), icp_solution.data(), NULL, NULL, NULL, NULL);
+    if (rc == LS_ERR_CONVERGENCE) throw PointMatcher::ConvergenceError(ls_b200_last_error(icp_ctx_));
+    if (rc != LS_OK) throw std::runtime_error(std::string("ls_icp_register: ") + ls_b200_last_error(icp_ctx_));
+    updated.T_a_b = convertTransformationMatrixToSE3(icp_solution);
+  }
+
+  // loop-closure factor, once with the loop-closure noise and once with the looser "first association" noise
+  // (reference :117-133)
+  auto make = [&](const gtsam::NoiseModel& noise) {
+    ls_factor f;
+    std::memset(&f, 0, sizeof(f));
+    f.type = LS_FACTOR_BETWEEN;
+    f.robust = noise.cauchy ? 1 : 0;
+    f.key_a = track_a.getValueKey(updated.time_a_ns);
+    f.key_b = track_b.getValueKey(updated.time_b_ns);
+    updated.T_a_b.toArray7(f.meas);
+    for (int i = 0; i < 6; ++i) f.sigma[i] = noise.sigmas[i];
+    SE3().toArray7(f.fixed_a);
+    return f;
+  };
+  gtsam::NonlinearFactorGraph new_factors, new_associations_factors;
+  new_factors.push_back(make(loop_closure_noise_model_));
+  new_associations_factors.push_back(make(first_association_noise_model_));
+
+  std::vector<unsigned int> affected_worker_ids{loop_closure.track_id_a, loop_closure.track_id_b};
+  gtsam::Values new_values;
+  const gtsam::Values result = estimateAndRemove(new_factors, new_associations_factors, new_values, affected_worker_ids,
+                                                 updated.time_b_ns);
+  for (auto& track : laser_tracks_) track->updateFromGTSAMValues(result);  // reference :145-147
+}
+
+Pose IncrementalEstimator::getCurrentPose(unsigned int laser_track_id) const {
+  std::lock_guard<std::recursive_mutex> lock(full_class_mutex_);
+  return laser_tracks_.at(laser_track_id)->getCurrentPose();
+}
+
+gtsam::Values IncrementalEstimator::updateGraph(const gtsam::NonlinearFactorGraph& factors, const gtsam::Values& values,
+                                                const std::vector<uint64_t>& remove, std::vector<uint64_t>* new_indices) {
+  auto fail = [&](const char* what) { throw std::runtime_error(std::string(what) + ": " + ls_pg_last_error(graph_)); };
+  if (!values.empty()) {
+    std::vector<uint64_t> keys;
+    std::vector<uint32_t> tracks;
+    std::vector<double> poses;
+    for (const auto& kv : values) {
+      keys.push_back(kv.first);
+      tracks.push_back((uint32_t)(kv.first >> 48));  // keys carry the track id (LaserTrack::extendTrajectory)
+      double a[7];
+      kv.second.toArray7(a);
+      poses.insert(poses.end(), a, a + 7);
+    }
+    if (ls_pg_add_poses(graph_, keys.data(), tracks.data(), poses.data(), (int)keys.size()) != LS_OK) fail("ls_pg_add_poses");
+  }
+  if (!remove.empty() && ls_pg_remove_factors(graph_, remove.data(), (int)remove.size()) != LS_OK) fail("ls_pg_remove_factors");
+  std::vector<uint64_t> idx(factors.size());
+  if (!factors.empty() && ls_pg_add_factors(graph_, factors.factors().data(), (int)factors.size(), idx.data()) != LS_OK)
+    fail("ls_pg_add_factors");
+  if (new_indices) *new_indices = idx;
+  const int rc = ls_pg_optimize(graph_, 3, &last_stats_);
+  if (rc != LS_OK) fail("ls_pg_optimize");
+  int n = 0;
+  ls_pg_get_poses(graph_, NULL, NULL, &n);
+  std::vector<uint64_t> keys(n);
+  std::vector<double> poses(7 * (size_t)n);
+  ls_pg_get_poses(graph_, keys.data(), poses.data(), &n);
+  gtsam::Values result;  // isam2_.calculateEstimate(): every value
+  for (int i = 0; i < n; ++i) result.insert(keys[i], SE3::fromArray7(&poses[7 * (size_t)i]));
+  return result;
+}
+
+// reference :151-163
+gtsam::Values IncrementalEstimator::estimate(const gtsam::NonlinearFactorGraph& new_factors, const gtsam::Values& new_values,
+                                             laser_slam::Time) {
+  std::lock_guard<std::recursive_mutex> lock(full_class_mutex_);
+  return updateGraph(new_factors, new_values, {}, nullptr);
+}
+
+// reference :165-266
+gtsam::Values IncrementalEstimator::estimateAndRemove(const gtsam::NonlinearFactorGraph& new_factors,
+                                                      const gtsam::NonlinearFactorGraph& new_associations_factors,
+                                                      const gtsam::Values& new_values,
+                                                      const std::vector<unsigned int>& affected_worker_ids, laser_slam::Time) {
+  std::lock_guard<std::recursive_mutex> lock(full_class_mutex_);
+  LS_CHECK(affected_worker_ids.size() == 2u, "exactly two affected workers");
+  std::vector<uint64_t> factor_indices_to_remove;
+  const unsigned int first = affected_worker_ids[0], second = affected_worker_ids[1];
+  if (first != second) {
+    int g_first = -1, g_second = -1;
+    for (size_t g = 0; g < linked_workers_.size(); ++g) {
+      if (std::find(linked_workers_[g].begin(), linked_workers_[g].end(), first) != linked_workers_[g].end()) g_first = (int)g;
+      if (std::find(linked_workers_[g].begin(), linked_workers_[g].end(), second) != linked_workers_[g].end()) g_second = (int)g;
+    }
+    LS_CHECK(g_first >= 0 && g_second >= 0, "both workers must have registered a prior before they are linked");
+    if (g_first != g_second) {
+      // keep the group holding worker 0, dissolve the other one and drop its prior (reference :208-237)
+      const bool first_has_zero = std::find(linked_workers_[g_first].begin(), linked_workers_[g_first].end(), 0u) != linked_workers_[g_first].end();
+      const int keep = first_has_zero ? g_first : g_second, drop = first_has_zero ? g_second : g_first;
+      for (unsigned int worker_id : linked_workers_[drop]) {
+        auto it = factor_indices_to_remove_.find(worker_id);
+        if (it != factor_indices_to_remove_.end()) {
+          factor_indices_to_remove.push_back(it->second);
+          factor_indices_to_remove_.erase(it);
+        }
+        linked_workers_[keep].push_back(worker_id);
+      }
+      LS_CHECK(factor_indices_to_remove.size() == 1u, "exactly one prior to remove");
+      linked_workers_.erase(linked_workers_.begin() + drop);
+    }
+  }
+  // a removed prior means this is the first association of two groups: use the looser factor (reference :251-256)
+  const gtsam::NonlinearFactorGraph& to_add = factor_indices_to_remove.empty() ? new_factors : new_associations_factors;
+  return updateGraph(to_add, new_values, factor_indices_to_remove, nullptr);
+}
+
+// reference :268-291
+gtsam::Values IncrementalEstimator::registerPrior(const gtsam::NonlinearFactorGraph& new_factors, const gtsam::Values& new_values,
+                                                  const unsigned int worker_id) {
+  std::lock_guard<std::recursive_mutex> lock(full_class_mutex_);
+  std::vector<uint64_t> idx;
+  const gtsam::Values result = updateGraph(new_factors, new_values, {}, &idx);
+  LS_CHECK(idx.size() == 1u, "registerPrior expects exactly one new factor");
+  if (worker_id > 0u) factor_indices_to_remove_.insert(std::make_pair(worker_id, (size_t)idx[0]));
+  linked_workers_.push_back(std::vector<unsigned int>{worker_id});
+  return result;
+}
+
+std::shared_ptr<LaserTrack> IncrementalEstimator::getLaserTrack(unsigned int laser_track_id) {
+  std::lock_guard<std::recursive_mutex> lock(full_class_mutex_);
+  LS_CHECK(laser_track_id < laser_tracks_.size(), "bad laser track id");
+  return laser_tracks_[laser_track_id];
+}
+std::vector<std::shared_ptr<LaserTrack> > IncrementalEstimator::getAllLaserTracks() {
+  std::lock_guard<std::recursive_mutex> lock(full_class_mutex_);
+  return laser_tracks_;
+}
+
+}  // namespace laser_slam

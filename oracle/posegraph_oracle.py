@@ -204,10 +204,17 @@ def retract(poses, delta):
     return out
 
 
-def gauss_newton_step(factors, keys, poses):
+def gauss_newton_step(factors, keys, poses, damp_keys=()):
+    """One Gauss-Newton step.  damp_keys: poses that get the gauge damping diag(1 x3, 4 x3) added to H only
+    ([DEFINED]: first pose of a track whose prior was removed after linking, incremental_estimator.cpp:212-237;
+    the fixed point is unchanged because the gradient is untouched)."""
     r, Ja, Jb, ia, ib, cost = linearize(factors, keys, poses)
     P = len(keys)
     rows, cols, vals = [], [], []
+    index = {int(k): i for i, k in enumerate(keys)}
+    for dk in damp_keys:
+        i = index[int(dk)]
+        rows.append(6 * i + np.arange(6)); cols.append(6 * i + np.arange(6)); vals.append(np.array([1.0] * 3 + [4.0] * 3))
     g = np.zeros(6 * P)
     blk = np.arange(6)
     for f in range(len(factors)):
@@ -222,12 +229,12 @@ def gauss_newton_step(factors, keys, poses):
     return retract(poses, delta), float(np.abs(delta).max()), cost
 
 
-def optimize(factors, keys, poses, iters=3, tol=0.0):
+def optimize(factors, keys, poses, iters=3, tol=0.0, damp_keys=()):
     """`iters` Gauss-Newton iterations (3 = one IncrementalEstimator::estimate call).  Returns poses, history."""
     poses = np.asarray(poses, np.float64).copy()
     hist = []
     for _ in range(iters):
-        poses, dmax, cost = gauss_newton_step(factors, keys, poses)
+        poses, dmax, cost = gauss_newton_step(factors, keys, poses, damp_keys)
         hist.append((dmax, cost))
         if dmax < tol:
             break

@@ -170,6 +170,49 @@ def lib_num_factors(g):
 
 
 @pytest.mark.gpu
+def test_gpu_prior_removed_after_linking_tracks():
+    """estimateAndRemove: the second track loses its prior once a loop closure links it to track 0
+    (reference incremental_estimator.cpp:212-237); the solver damps its gauge instead of refusing."""
+    import laser_slam_b200 as ls
+    rng = np.random.default_rng(11)
+    sig = [0.005] * 3 + [0.0015] * 3
+    loose = [0.05] * 3 + [0.015] * 3
+    keys, init, tracks, factors, truth = [], [], [], [], []
+    for t in range(2):
+        pose = rand_pose(rng, 5.0, 0.2)
+        for k in range(40):
+            key = 1000 * (t + 1) + k
+            keys.append(key); tracks.append(t)
+            if k == 0:
+                factors.append(pg.make_factor(pg.PRIOR, key, 0, pose, [1e-7] * 6))
+            else:
+                rel = rand_pose(rng, 0.5, 0.04)
+                factors.append(pg.make_factor(pg.BETWEEN, key - 1, key, pg.se3_compose(rel, rand_pose(rng, 0.004, 0.001)), sig, robust=1))
+                pose = pg.se3_compose(pose, rel)
+            truth.append(pose)
+            init.append(pg.se3_compose(pose, rand_pose(rng, 0.02, 0.004)))
+    keys = np.array(keys, np.uint64); init = np.stack(init); truth = np.stack(truth)
+    g = ls.PoseGraph(0)
+    g.add_poses(keys, init, np.array(tracks))
+    idx = g.add_factors(factors)
+    g.optimize(3)
+    o, _ = pg.optimize(factors, keys, init, iters=3)
+    # link: first-association factor (loose noise) replaces the prior of track 1
+    lc = pg.make_factor(pg.BETWEEN, 1010, 2020, pg.se3_compose(pg.se3_inverse(truth[10]), truth[40 + 20]), loose)
+    prior1 = [i for i, f in enumerate(factors) if f["type"] == pg.PRIOR and f["key_a"] == 2000][0]
+    g.remove_factors([idx[prior1]])
+    g.add_factors([lc])
+    st = g.optimize(3)
+    f2 = [f for i, f in enumerate(factors) if i != prior1] + [lc]
+    o2, _ = pg.optimize(f2, keys, o, iters=3, damp_keys=[2000])
+    est = g.poses()[1]
+    assert st.n_border == 1
+    assert np.abs(est[:, 4:] - o2[:, 4:]).max() < 1e-7
+    assert np.abs(est[:, 4:] - truth[:, 4:]).max() < 0.1
+    g.close()
+
+
+@pytest.mark.gpu
 def test_gpu_errors():
     import laser_slam_b200 as ls
     g = ls.PoseGraph(0)
