@@ -224,14 +224,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    gather_buf = torch.zeros(world * 8, dtype=torch.float32, device="cuda") if world > 1 else None
+    from laser_slam_b200 import dist as lsd
+    exchange = lsd.Exchange(rank, world, device=local)   # ls_comm_* (one ncclAllGather of 32 B/rank) when world > 1
 
     def share_pose_delta(T):
-        """One 32-byte {delta[6], status, key} record per rank per step; NCCL all-gather."""
-        if world == 1:
-            return
-        rec = torch.tensor([T[0, 3], T[1, 3], T[2, 3], T[2, 1], T[0, 2], T[1, 0], 0.0, float(rank)], dtype=torch.float32).cuda()
-        dist.all_gather_into_tensor(gather_buf, rec)
+        """One 32-byte {delta[6], status, key} record per rank per step."""
+        if world > 1:
+            exchange.allgather(lsd.pose_record(T, status=0, key=rank))
 
     # ------------------------------------------------------------------ resident arm (value)
     mp = ctx.create_map(POOL + 2, N_SCAN)
@@ -295,10 +294,8 @@ def main():
     clocks = sampler.summary()
 
     # ------------------------------------------------------------------ reduce over ranks (max time)
-    times = torch.tensor([t_res, t_e2e], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    t_res, t_e2e = float(times[0]), float(times[1])
+    t_res, t_e2e = lsd.max_over_ranks([t_res, t_e2e], device=local)
+    exchange.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -193,6 +193,26 @@ int ls_pg_optimize(ls_pg* pg, int gn_iters, ls_pg_stats* stats);
 /* isam2.calculateEstimate(): all keys and poses (either pointer may be NULL); *n = number of poses. */
 int ls_pg_get_poses(const ls_pg* pg, uint64_t* out_keys, double* out_poses7, int* n);
 
+/* ---- multi-GPU -----------------------------------------------------------------------------------------
+ * The path shards by independent tracks, one per GPU (the reference's n_laser_slam_workers LaserTracks,
+ * laser_slam/src/incremental_estimator.cpp:22-26); the only exchange is one 32-byte record per rank per step
+ * so that every rank can feed the shared estimator: a single ncclAllGather over NVLink.  NCCL is resolved at
+ * run time (dlopen), so single-GPU users need no NCCL at all. */
+typedef struct ls_comm ls_comm;
+
+typedef struct ls_pose_record {
+  float delta[6];  /* translation x3, rotation vector x3 of the step's T_a_b */
+  int32_t status;  /* return code of the registration that produced it */
+  int32_t key;     /* caller-defined (e.g. scan counter) */
+} ls_pose_record;  /* 32 bytes */
+
+int ls_comm_unique_id(void* id128);                       /* rank 0: ncclGetUniqueId -> 128 bytes to broadcast */
+int ls_comm_init(int device, int rank, int nranks, const void* id128, ls_comm** out);
+void ls_comm_destroy(ls_comm* comm);
+const char* ls_comm_last_error(const ls_comm* comm);
+/* all[nranks] <- every rank's record (rank order). */
+int ls_comm_allgather_pose_records(ls_comm* comm, const ls_pose_record* mine, ls_pose_record* all);
+
 #ifdef __cplusplus
 }
 #endif
