@@ -121,15 +121,15 @@ int ensure_capacity(ls_ctx* ctx, int n, int m, int max_cells, int max_iter) {
     if ((rc = dev_alloc(ctx, &ctx->A.pkey, (size_t)cap))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->ref_stage, (size_t)cap))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->ref_nrm_stage, (size_t)cap))) return rc;
-    const int tcap = cap / 16 + 1024;  // a table exists only for a cell with > leaf_split (>= 16) points
-    if ((rc = dev_alloc(ctx, &ctx->A.tab1, (size_t)tcap * 64))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->A.tab2, (size_t)tcap * 64))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->A.cnt1, (size_t)tcap * 64))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->A.cnt2, (size_t)tcap * 64))) return rc;
+    // a fine table exists only for a level-0 cell with > leaf_split (>= 16) points; the pool is also capped at
+    // ~1.5 GB (cells beyond the pool stay leaves: slower, still exact, flagged in stats.grid_overflow)
+    int tcap = cap / 17 + 1024;
+    const int tmax = (int)((size_t)1536 * 1024 * 1024 / ((size_t)LS_FB3 * 12));
+    if (tcap > tmax) tcap = tmax;
+    if ((rc = dev_alloc(ctx, &ctx->A.tab1, (size_t)tcap * LS_FB3))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->A.cnt1, (size_t)tcap * LS_FB3))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->A.tab1_cell, (size_t)tcap))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->A.tab2_key1, (size_t)tcap))) return rc;
-    CU(cudaMemsetAsync(ctx->A.cnt1, 0, (size_t)tcap * 64 * sizeof(uint32_t), ctx->stream));
-    CU(cudaMemsetAsync(ctx->A.cnt2, 0, (size_t)tcap * 64 * sizeof(uint32_t), ctx->stream));
+    CU(cudaMemsetAsync(ctx->A.cnt1, 0, (size_t)tcap * LS_FB3 * sizeof(uint32_t), ctx->stream));
     ctx->A.tab_cap = tcap;
     ctx->tab_cap = tcap;
     ctx->m_cap = cap;
@@ -199,12 +199,7 @@ int enqueue_build(ls_ctx* ctx, const Parts& parts, const Resolved& r, const floa
   LAUNCH_CHECK();
   count1_kernel<<<pb, 256, 0, ctx->stream>>>(ctx->bs, ctx->A, m);
   LAUNCH_CHECK();
-  const int tb = ctx->sm_count * 4;
-  tables_kernel<1><<<tb, 256, 0, ctx->stream>>>(ctx->bs, ctx->A);
-  LAUNCH_CHECK();
-  count2_kernel<<<pb, 256, 0, ctx->stream>>>(ctx->bs, ctx->A, m);
-  LAUNCH_CHECK();
-  tables_kernel<2><<<tb, 256, 0, ctx->stream>>>(ctx->bs, ctx->A);
+  tables_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->bs, ctx->A);
   LAUNCH_CHECK();
   scatter_kernel<<<pb, 256, 0, ctx->stream>>>(ctx->A, m);
   LAUNCH_CHECK();
@@ -242,7 +237,6 @@ int run_icp(ls_ctx* ctx, const ls_icp_params* prm, const float4* reading_dev, in
   hp.bs = ctx->bs;
   hp.view.top = ctx->A.top;
   hp.view.tab1 = ctx->A.tab1;
-  hp.view.tab2 = ctx->A.tab2;
   hp.view.pts = ctx->A.srt_pts;
   hp.view.pyr = ctx->A.pyr;
   hp.nrm = ctx->A.srt_nrm;
@@ -324,7 +318,7 @@ int run_icp(ls_ctx* ctx, const ls_icp_params* prm, const float4* reading_dev, in
     stats->device_ms = ms;
     stats->build_ms = bms;
     stats->grid_cells = ctx->h_grid->n_cells0;
-    stats->grid_tables = ctx->h_grid->n_tab1 + ctx->h_grid->n_tab2;
+    stats->grid_tables = ctx->h_grid->n_tab1;
     stats->grid_overflow = ctx->h_grid->overflow;
   }
   if (getenv("LS_DEBUG")) {
@@ -422,7 +416,7 @@ void ls_b200_destroy(ls_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   void* bufs[] = {ctx->A.sub_pts, ctx->A.sub_nrm, ctx->A.srt_pts, ctx->A.srt_nrm, ctx->A.pkey, ctx->A.top, ctx->A.cnt0,
-                  ctx->A.tab1, ctx->A.cnt1, ctx->A.tab1_cell, ctx->A.tab2, ctx->A.cnt2, ctx->A.tab2_key1, ctx->A.pyr, ctx->bs,
+                  ctx->A.tab1, ctx->A.cnt1, ctx->A.tab1_cell, ctx->A.pyr, ctx->bs,
                   ctx->reading, ctx->rd, ctx->ref_stage, ctx->ref_nrm_stage, ctx->nrm_raw, ctx->pos, ctx->d2, ctx->ids,
                   ctx->work, ctx->prob, ctx->T_hist, ctx->T0_dev};
   for (void* b : bufs)
@@ -512,7 +506,7 @@ int ls_nn_query(ls_ctx* ctx, const ls_icp_params* prm, const float* reading4, in
   if ((rc = enqueue_build(ctx, parts, r, T0))) return rc;
   reading_kernel<<<blocks_for(n, 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(ctx->bs, ctx->reading, n, ctx->rd);
   LAUNCH_CHECK();
-  GridView v{ctx->A.top, ctx->A.tab1, ctx->A.tab2, ctx->A.srt_pts, ctx->A.pyr};
+  GridView v{ctx->A.top, ctx->A.tab1, ctx->A.srt_pts, ctx->A.pyr};
   nn_query_kernel<<<blocks_for(n, 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(ctx->bs, v, ctx->rd, n, ctx->ids, ctx->d2);
   LAUNCH_CHECK();
   CU(cudaMemcpyAsync(ids, ctx->ids, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

@@ -6,25 +6,27 @@
 //   id  = argmin_j (d2(q, p_j), j) lexicographic  -> lowest reference index wins exact ties
 //   d2  = fl(fl(fl(dx*dx) + fl(dy*dy)) + fl(dz*dz)), float32, no FMA
 //
-// Structure: a three-level sparse voxel grid.  The hash of a point is its lattice cell -- a perfect
-// hash over the map's bounding box, so a lookup is one indexed load, never a probe sequence:
-//   level 0  dense array of cells of edge H0 over the bounding box        (Entry top[nx*ny*nz])
-//   level 1  cells holding more than `leaf_split` points get a 4x4x4 table of H0/4 sub-cells
-//   level 2  level-1 cells holding more than `leaf_split` points get a 4x4x4 table of H0/16 cells
-// Points are stored sorted by (level-0 cell, level-1 sub-cell, level-2 sub-cell), x fastest, as
-// float4 {x, y, z, original index bits}, so every cell at every level is one contiguous range and
-// a row of x-adjacent level-2 cells is one contiguous candidate run.  Lidar density varies by
-// ~1000x between the near ground rings and the far field; three levels keep a leaf at tens of
-// points in both regimes.
+// Structure: a two-level sparse voxel grid under an occupancy pyramid.  The hash of a point is its lattice
+// cell -- a perfect hash over the map's bounding box, so a lookup is one indexed load, never a probe sequence:
+//   level 0  dense array of cells of edge H0 over the bounding box                (Entry top[nx*ny*nz])
+//   level 1  a cell holding more than `leaf_split` points owns ONE direct table of LS_FB^3 fine cells of
+//            edge H0/LS_FB (LS_FB = 8: 12.5 cm at H0 = 1 m)
+//   above    occupancy pyramid: 64-bit child masks at edges H0*4^l up to a single root (empty-space skipping
+//            for wide balls, greedy seed for cold queries)
+// Points are stored sorted by (level-0 cell, fine cell), x fastest, as float4 {x, y, z, original index bits}:
+// every cell is one contiguous range and a row of x-adjacent fine cells is one contiguous candidate run.
+// Why two levels with a wide table (round 1 went through a three-level 4x4x4 design first): the query is
+// latency bound on DEPENDENT loads; top entry -> row entries (all independent) -> candidates is three round
+// trips, where the 4-ary hierarchy needed one more per sub-cell of every level (profiles/r1_history.md).
 //
-// Exactness: the query is a ball query around a real candidate (the previous iteration's match, or
-// a seed found by descending the grid), with radius sqrt(best).  Loop bounds come from the same
-// monotone float cell-coordinate function that binned the points, so they are a superset of the
-// cells a closer point could be in; per-cell pruning uses a geometric lower bound widened by
-// `margin` and is only taken when strictly greater than the current best, so ties are never pruned.
+// Exactness: the query is a ball query around a real candidate (the previous iteration's match, or a seed found
+// by descending the grid), radius sqrt(best).  Loop bounds come from the same monotone float cell-coordinate
+// function that binned the points, so they are a superset of the cells a closer point could be in; per-cell
+// pruning uses a geometric lower bound widened by `margin` and is only taken when strictly greater than the
+// current best, so ties are never pruned.
 //
-// This header is also compiled for the host by tests/sim (CPU simulation of the query against
-// brute force).  The product never runs it on the CPU.
+// This header is also compiled for the host by tests/sim (CPU simulation of the query against brute force).
+// The product never runs it on the CPU.
 #pragma once
 #include <cfloat>
 #include <climits>
@@ -33,6 +35,12 @@
 #include <vector_types.h>
 
 #include "ls_math.cuh"
+
+#ifndef LS_FB
+#define LS_FB 8  // fine cells per level-0 cell edge (8: 12.5 cm at H0 = 1 m; 16 was measured too: faster warm
+                 // iterations, slower build and cold iteration, 8x the table memory)
+#endif
+#define LS_FB3 (LS_FB * LS_FB * LS_FB)
 
 namespace ls {
 
@@ -43,15 +51,15 @@ struct Entry {
 
 struct Grid {
   float org[3];  // lower corner of the level-0 lattice, centred coordinates
-  float H0, H1, H2;
-  float inv0, inv1, inv2;
+  float H0, H1;      // H1 = H0 / LS_FB
+  float inv0, inv1;
   int dim[3];
   int n_cells0;
   float margin;     // absolute slack (metres) covering float rounding of cell boundaries
   float mu[3];      // reference mean (float32) subtracted from the map
   int m;            // number of map points
   int leaf_split;   // a cell with more points than this is subdivided
-  int n_tab1, n_tab2;
+  int n_tab1;
   int overflow;     // set if a table pool was exhausted (cells then stay leaves: slower, still exact)
   // occupancy pyramid above level 0: level l (1..n_pyr) has cells of edge H0*4^l, each a 64-bit mask
   // of its non-empty 4x4x4 children; the top level is a single cell.
@@ -63,8 +71,7 @@ struct Grid {
 
 struct GridView {
   const Entry* top;
-  const Entry* tab1;
-  const Entry* tab2;
+  const Entry* tab1;  // fine tables, LS_FB3 entries each (all leaves)
   const float4* pts;  // sorted {x,y,z,idx}
   const unsigned long long* pyr;  // occupancy masks, levels 1..n_pyr
 };
@@ -118,7 +125,7 @@ LS_HD int coord_top(float v, float o, float inv, int n) {
 }
 LS_HD int coord_sub(float v, float lo, float inv) {
   float t = floorf((v - lo) * inv);
-  t = fminf(fmaxf(t, 0.0f), 3.0f);
+  t = fminf(fmaxf(t, 0.0f), (float)(LS_FB - 1));
   return (int)t;
 }
 LS_HD float cell_lo(float o, int c, float H) { return o + (float)c * H; }
@@ -171,83 +178,39 @@ LS_HD void scan_range(const float4* pts, uint32_t a, uint32_t e, float qx, float
   for (; pos < e; ++pos) consider(pts, (int)pos, qx, qy, qz, b);
 }
 
-// ---- ball query, level 2 table (all entries are leaves) ---------------------------------------------
-// Points are sorted x-fastest, then y, then z, so for one z-slab the sub-cells (y0..y1, x0..x1) lie inside
-// ONE contiguous run [start(z,y0,x0), end(z,y1,x1)).  The run also holds the few cells of the interior rows
-// whose x is outside [x0,x1]; scanning them costs a handful of extra distance evaluations but turns
-// "two dependent entry loads + a scan per row" into: all slab entries in flight at once, then <= 4 streams.
-LS_HD void visit_l2(const Grid& g, const Entry* tab, float lox, float loy, float loz, const float4* pts,
-                    float qx, float qy, float qz, Best& b) {
-  const float R = ball_radius(b.d2, g.margin);
-  const int x0 = coord_sub(qx - R, lox, g.inv2), x1 = coord_sub(qx + R, lox, g.inv2);
-  const int y0 = coord_sub(qy - R, loy, g.inv2), y1 = coord_sub(qy + R, loy, g.inv2);
-  const int z0 = coord_sub(qz - R, loz, g.inv2), z1 = coord_sub(qz + R, loz, g.inv2);
-  uint32_t ra[4], re[4];
-  LS_CNT_STEP();
-#pragma unroll
-  for (int dz = 0; dz < 4; ++dz) {
-    const int z = z0 + dz;
-    ra[dz] = 0u;
-    re[dz] = 0u;
-    if (z <= z1) {
-      const float gz = gap(qz, cell_lo(loz, z, g.H2), cell_lo(loz, z + 1, g.H2), g.margin);
-      if (!((gz * gz) * LS_SHRINK > b.d2)) {
-        const Entry e0 = ld_entry(tab + (z * 4 + y0) * 4 + x0);
-        const Entry e1 = ld_entry(tab + (z * 4 + y1) * 4 + x1);
-        ra[dz] = e0.start;
-        re[dz] = e1.start + (uint32_t)e1.meta;
-      }
-    }
-  }
-#pragma unroll
-  for (int dz = 0; dz < 4; ++dz) scan_range(pts, ra[dz], re[dz], qx, qy, qz, b);
-}
-
-// ---- ball query, level 1 table -----------------------------------------------------------------
-LS_HD void visit_l1_cell(const Grid& g, const Entry e, const Entry* tab2, float cx, float cy, float cz,
-                         const float4* pts, float qx, float qy, float qz, Best& b) {
-  if (e.meta > 0) {
-    scan_range(pts, e.start, e.start + (uint32_t)e.meta, qx, qy, qz, b);
-  } else if (e.meta < 0) {
-    visit_l2(g, tab2 + (size_t)(~e.meta) * 64, cx, cy, cz, pts, qx, qy, qz, b);
-  }
-}
-
-LS_HD void visit_l1(const Grid& g, const Entry* tab, const Entry* tab2, float lox, float loy, float loz,
-                    const float4* pts, float qx, float qy, float qz, Best& b) {
+// ---- ball query inside one fine table (all entries are leaves) ---------------------------------------
+// Points are sorted x-fastest, so for a row (z, y) the fine cells x0..x1 are ONE contiguous run
+// [start(z,y,x0), end(z,y,x1)): two entry loads, then a stream of candidates.
+LS_HD void visit_fine(const Grid& g, const Entry* tab, float lox, float loy, float loz, const float4* pts,
+                      float qx, float qy, float qz, Best& b) {
   const float R = ball_radius(b.d2, g.margin);
   const int x0 = coord_sub(qx - R, lox, g.inv1), x1 = coord_sub(qx + R, lox, g.inv1);
   const int y0 = coord_sub(qy - R, loy, g.inv1), y1 = coord_sub(qy + R, loy, g.inv1);
   const int z0 = coord_sub(qz - R, loz, g.inv1), z1 = coord_sub(qz + R, loz, g.inv1);
   for (int z = z0; z <= z1; ++z) {
-    const float cz = cell_lo(loz, z, g.H1);
-    const float gz = gap(qz, cz, cell_lo(loz, z + 1, g.H1), g.margin);
+    const float gz = gap(qz, cell_lo(loz, z, g.H1), cell_lo(loz, z + 1, g.H1), g.margin);
     const float gz2 = gz * gz;
     if (gz2 * LS_SHRINK > b.d2) continue;
-    for (int y = y0; y <= y1; ++y) {
-      const float cy = cell_lo(loy, y, g.H1);
-      const float gy = gap(qy, cy, cell_lo(loy, y + 1, g.H1), g.margin);
-      const float lbyz = gy * gy + gz2;
-      if (lbyz * LS_SHRINK > b.d2) continue;
-      for (int x = x0; x <= x1; ++x) {
-        const float cx = cell_lo(lox, x, g.H1);
-        const float gx = gap(qx, cx, cell_lo(lox, x + 1, g.H1), g.margin);
-        const float lb = gx * gx + lbyz;
-        if (lb * LS_SHRINK > b.d2) continue;
-        LS_CNT_STEP();
-        visit_l1_cell(g, ld_entry(tab + (z * 4 + y) * 4 + x), tab2, cx, cy, cz, pts, qx, qy, qz, b);
-      }
+    const Entry* row = tab + (z * LS_FB + y0) * LS_FB;
+    for (int y = y0; y <= y1; ++y, row += LS_FB) {
+      const float gy = gap(qy, cell_lo(loy, y, g.H1), cell_lo(loy, y + 1, g.H1), g.margin);
+      const float lb = gy * gy + gz2;
+      if (lb * LS_SHRINK > b.d2) continue;
+      LS_CNT_STEP();
+      const Entry e0 = ld_entry(row + x0);
+      const Entry e1 = ld_entry(row + x1);
+      scan_range(pts, e0.start, e1.start + (uint32_t)e1.meta, qx, qy, qz, b);
     }
   }
 }
 
-// one level-0 cell (leaf scan or descent)
+// one level-0 cell (leaf scan or fine table)
 LS_HD void visit_top_entry(const Grid& g, const GridView& v, const Entry e, float cx, float cy, float cz, float qx,
                            float qy, float qz, Best& b) {
   if (e.meta > 0) {
     scan_range(v.pts, e.start, e.start + (uint32_t)e.meta, qx, qy, qz, b);
   } else if (e.meta < 0) {
-    visit_l1(g, v.tab1 + (size_t)(~e.meta) * 64, v.tab2, cx, cy, cz, v.pts, qx, qy, qz, b);
+    visit_fine(g, v.tab1 + (size_t)(~e.meta) * LS_FB3, cx, cy, cz, v.pts, qx, qy, qz, b);
   }
 }
 LS_HD void visit_top_cell(const Grid& g, const GridView& v, int x, int y, int z, float cx, float cy, float cz, float qx,
@@ -358,14 +321,18 @@ LS_HDN void seed_query(const Grid& g, const GridView& v, float qx, float qy, flo
   if (e.meta > 0) { scan_range(v.pts, e.start, e.start + (uint32_t)e.meta, qx, qy, qz, b); return; }
   const float lox = cell_lo(g.org[0], cx, g.H0), loy = cell_lo(g.org[1], cy, g.H0), loz = cell_lo(g.org[2], cz, g.H0);
   const int fx = coord_sub(qx, lox, g.inv1), fy = coord_sub(qy, loy, g.inv1), fz = coord_sub(qz, loz, g.inv1);
-  const Entry e1 = ld_entry(v.tab1 + (size_t)(~e.meta) * 64 + (fz * 4 + fy) * 4 + fx);
-  if (e1.meta == 0) { consider(v.pts, (int)e.start, qx, qy, qz, b); return; }
-  if (e1.meta > 0) { scan_range(v.pts, e1.start, e1.start + (uint32_t)e1.meta, qx, qy, qz, b); return; }
-  const float l1x = cell_lo(lox, fx, g.H1), l1y = cell_lo(loy, fy, g.H1), l1z = cell_lo(loz, fz, g.H1);
-  const int hx = coord_sub(qx, l1x, g.inv2), hy = coord_sub(qy, l1y, g.inv2), hz = coord_sub(qz, l1z, g.inv2);
-  const Entry e2 = ld_entry(v.tab2 + (size_t)(~e1.meta) * 64 + (hz * 4 + hy) * 4 + hx);
-  if (e2.meta == 0) { consider(v.pts, (int)e1.start, qx, qy, qz, b); return; }
-  scan_range(v.pts, e2.start, e2.start + (uint32_t)e2.meta, qx, qy, qz, b);
+  const Entry* tab = v.tab1 + (size_t)(~e.meta) * LS_FB3;
+  const Entry e1 = ld_entry(tab + (fz * LS_FB + fy) * LS_FB + fx);
+  if (e1.meta != 0) { scan_range(v.pts, e1.start, e1.start + (uint32_t)e1.meta, qx, qy, qz, b); return; }
+  // empty home cell: the 3x3 rows around it (x-run of three cells each) almost always hold a close point
+  const int xa = fx > 0 ? fx - 1 : 0, xb = fx < LS_FB - 1 ? fx + 1 : LS_FB - 1;
+  for (int z = (fz > 0 ? fz - 1 : 0); z <= (fz < LS_FB - 1 ? fz + 1 : LS_FB - 1); ++z)
+    for (int y = (fy > 0 ? fy - 1 : 0); y <= (fy < LS_FB - 1 ? fy + 1 : LS_FB - 1); ++y) {
+      const Entry r0 = ld_entry(tab + (z * LS_FB + y) * LS_FB + xa);
+      const Entry r1 = ld_entry(tab + (z * LS_FB + y) * LS_FB + xb);
+      scan_range(v.pts, r0.start, r1.start + (uint32_t)r1.meta, qx, qy, qz, b);
+    }
+  if (b.pos < 0) consider(v.pts, (int)e.start, qx, qy, qz, b);  // still nothing: any point of the level-0 cell
 }
 
 // Exact 1-NN within a squared-distance cap.  warm_pos: sorted position of the previous iteration's
@@ -402,12 +369,7 @@ LS_HD void top_origin(const Grid& g, int c0, float& lox, float& loy, float& loz)
   loz = cell_lo(g.org[2], cz, g.H0);
 }
 LS_HD int sub_index(float x, float y, float z, float lox, float loy, float loz, float inv) {
-  return (coord_sub(z, loz, inv) * 4 + coord_sub(y, loy, inv)) * 4 + coord_sub(x, lox, inv);
-}
-LS_HD void sub_origin(int f, float lox, float loy, float loz, float H, float& ox, float& oy, float& oz) {
-  ox = cell_lo(lox, f & 3, H);
-  oy = cell_lo(loy, (f >> 2) & 3, H);
-  oz = cell_lo(loz, f >> 4, H);
+  return (coord_sub(z, loz, inv) * LS_FB + coord_sub(y, loy, inv)) * LS_FB + coord_sub(x, lox, inv);
 }
 
 // Grid geometry from the centred bounding box (single thread on the device; host in tests/sim).
@@ -429,11 +391,9 @@ LS_HDN void grid_setup(Grid& g, const float* lo, const float* hi, float cell_siz
     H = H * 2.0f;
   }
   g.H0 = H;
-  g.H1 = H * 0.25f;
-  g.H2 = H * 0.0625f;
+  g.H1 = H / (float)LS_FB;  // LS_FB is a power of two: exact
   g.inv0 = 1.0f / g.H0;
   g.inv1 = 1.0f / g.H1;
-  g.inv2 = 1.0f / g.H2;
   int n = 1;
   for (int a = 0; a < 3; ++a) {
     g.org[a] = lo[a];
@@ -447,7 +407,6 @@ LS_HDN void grid_setup(Grid& g, const float* lo, const float* hi, float cell_siz
   g.m = m;
   g.leaf_split = leaf_split > 0 ? leaf_split : 32;
   g.n_tab1 = 0;
-  g.n_tab2 = 0;
   g.overflow = 0;
   for (int a = 0; a < 3; ++a) g.pdim[0][a] = g.dim[a];
   g.poff[0] = 0;

@@ -24,7 +24,7 @@ constexpr int kScanTile = 4096;       // level-0 cells per scan block
 constexpr int kScanThreads = 512;
 constexpr int kIcpThreads = 512;
 constexpr int kMaxSmooth = 15;
-constexpr uint32_t kTag1 = 1u << 30, kTag2 = 2u << 30, kKeyMask = (1u << 30) - 1u;
+constexpr uint32_t kTag1 = 1u << 31, kKeyMask = (1u << 31) - 1u;  // pkey: tag | key (fine keys < 2^31)
 
 struct Parts {
   int n_parts;
@@ -51,12 +51,9 @@ struct BuildArrays {
   uint32_t* pkey;    // per point: tag | deepest cell key found so far
   Entry* top;
   uint32_t* cnt0;
-  Entry* tab1;
+  Entry* tab1;           // fine tables, LS_FB3 entries each
   uint32_t* cnt1;
-  uint32_t* tab1_cell;   // level-0 cell of each level-1 table
-  Entry* tab2;
-  uint32_t* cnt2;
-  uint32_t* tab2_key1;   // level-1 key (table*64+sub) of each level-2 table
+  uint32_t* tab1_cell;   // level-0 cell of each fine table
   int tab_cap;
   unsigned long long* pyr;  // occupancy pyramid masks
 };
@@ -365,74 +362,47 @@ __global__ void __launch_bounds__(256) count1_kernel(const BuildState* __restric
     const float4 p = A.sub_pts[i];
     float lx, ly, lz;
     top_origin(g, (int)c0, lx, ly, lz);
-    const uint32_t key = (uint32_t)(~e.meta) * 64u + (uint32_t)sub_index(p.x, p.y, p.z, lx, ly, lz, g.inv1);
+    const uint32_t key = (uint32_t)(~e.meta) * (uint32_t)LS_FB3 + (uint32_t)sub_index(p.x, p.y, p.z, lx, ly, lz, g.inv1);
     atomicAdd(&A.cnt1[key], 1u);
     A.pkey[i] = kTag1 | key;
   }
 }
 
-// one warp per table: exclusive scan of 64 counts, allocate child tables for heavy sub-cells
-template <int LEVEL>
+// one CTA per fine table: exclusive scan of its LS_FB3 counts -> Entry{start, count}
 __global__ void __launch_bounds__(256) tables_kernel(BuildState* bs, BuildArrays A) {
-  const int n_tab = LEVEL == 1 ? min(bs->grid.n_tab1, A.tab_cap) : min(bs->grid.n_tab2, A.tab_cap);
-  const int split = bs->grid.leaf_split;
-  const int lane = threadIdx.x & 31;
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_tab; t += warps) {
-    uint32_t* cnt = (LEVEL == 1 ? A.cnt1 : A.cnt2) + (size_t)t * 64;
-    Entry* tab = (LEVEL == 1 ? A.tab1 : A.tab2) + (size_t)t * 64;
-    uint32_t base;
-    if (LEVEL == 1) {
-      base = A.top[A.tab1_cell[t]].start;
-    } else {
-      base = A.tab1[A.tab2_key1[t]].start;
+  const int n_tab = min(bs->grid.n_tab1, A.tab_cap);
+  constexpr int per = LS_FB3 / 256;  // 2 (LS_FB 8) or 16 (LS_FB 16) consecutive cells per thread
+  __shared__ unsigned int ws[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int t = blockIdx.x; t < n_tab; t += gridDim.x) {
+    const uint32_t* cnt = A.cnt1 + (size_t)t * LS_FB3;
+    Entry* tab = A.tab1 + (size_t)t * LS_FB3;
+    const uint32_t base = A.top[A.tab1_cell[t]].start;
+    unsigned int c[per], loc = 0;
+#pragma unroll
+    for (int k = 0; k < per; ++k) {
+      c[k] = cnt[threadIdx.x * per + k];
+      loc += c[k];
     }
-    const unsigned int c0 = cnt[2 * lane], c1 = cnt[2 * lane + 1];
-    const unsigned int loc = c0 + c1;
     unsigned int incl = loc;
     for (int o = 1; o < 32; o <<= 1) {
       const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += v;
     }
-    const unsigned int ex = base + incl - loc;
-    Entry e0, e1;
-    e0.start = ex; e0.meta = (int)c0;
-    e1.start = ex + c0; e1.meta = (int)c1;
-    if (LEVEL == 1) {
-      if ((int)c0 > split) {
-        const int t2 = atomicAdd(&bs->grid.n_tab2, 1);
-        if (t2 < A.tab_cap) { e0.meta = ~t2; A.tab2_key1[t2] = (uint32_t)t * 64u + 2u * lane; cnt[2 * lane] = 0u; }
-        else bs->grid.overflow = 1;
-      }
-      if ((int)c1 > split) {
-        const int t2 = atomicAdd(&bs->grid.n_tab2, 1);
-        if (t2 < A.tab_cap) { e1.meta = ~t2; A.tab2_key1[t2] = (uint32_t)t * 64u + 2u * lane + 1u; cnt[2 * lane + 1] = 0u; }
-        else bs->grid.overflow = 1;
-      }
+    __syncthreads();
+    if (lane == 31) ws[warp] = incl;
+    __syncthreads();
+    unsigned int woff = 0;
+    for (int w = 0; w < warp; ++w) woff += ws[w];
+    unsigned int run = base + woff + incl - loc;
+#pragma unroll
+    for (int k = 0; k < per; ++k) {
+      Entry e;
+      e.start = run;
+      e.meta = (int)c[k];
+      tab[threadIdx.x * per + k] = e;
+      run += c[k];
     }
-    tab[2 * lane] = e0;
-    tab[2 * lane + 1] = e1;
-  }
-}
-
-// ---- K1e: level-2 histogram -------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) count2_kernel(const BuildState* __restrict__ bs, BuildArrays A, int m) {
-  __shared__ Grid g;
-  if (threadIdx.x == 0) g = bs->grid;
-  __syncthreads();
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
-    const uint32_t k = A.pkey[i];
-    if ((k & ~kKeyMask) != kTag1) continue;
-    const uint32_t key1 = k & kKeyMask;
-    const Entry e1 = A.tab1[key1];
-    if (e1.meta >= 0) continue;
-    const float4 p = A.sub_pts[i];
-    float lx, ly, lz, mx, my, mz;
-    top_origin(g, (int)A.tab1_cell[key1 >> 6], lx, ly, lz);
-    sub_origin((int)(key1 & 63u), lx, ly, lz, g.H1, mx, my, mz);
-    const uint32_t key2 = (uint32_t)(~e1.meta) * 64u + (uint32_t)sub_index(p.x, p.y, p.z, mx, my, mz, g.inv2);
-    atomicAdd(&A.cnt2[key2], 1u);
-    A.pkey[i] = kTag2 | key2;
   }
 }
 
@@ -442,8 +412,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(BuildArrays A, int m) {
     const uint32_t k = A.pkey[i];
     const uint32_t tag = k & ~kKeyMask, key = k & kKeyMask;
     uint32_t pos;
-    if (tag == kTag2) pos = A.tab2[key].start + atomicSub(&A.cnt2[key], 1u) - 1u;
-    else if (tag == kTag1) pos = A.tab1[key].start + atomicSub(&A.cnt1[key], 1u) - 1u;
+    if (tag == kTag1) pos = A.tab1[key].start + atomicSub(&A.cnt1[key], 1u) - 1u;
     else pos = A.top[key].start + atomicSub(&A.cnt0[key], 1u) - 1u;
     float4 p = A.sub_pts[i];
     p.w = __int_as_float(i);
@@ -642,10 +611,10 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
 
   // Trim-aware search cap (squared metres).  TrimmedDistOutlierFilter keeps matches with d2 <= limit,
   // so a match only has to be exact if d2 <= limit; searching inside a ball of radius sqrt(cap) with
-  // cap >= limit finds exactly those.  cap is a GUESS (first iteration: 1 m^2, then 2x the previous
+  // cap >= limit finds exactly those.  cap is a GUESS (first iteration: 0.25 m^2, then 2x the previous
   // limit) that is VERIFIED every iteration: points without a match inside the cap are counted in the
   // +inf histogram bin, and if the quantile lands in that bin the search is redone with a larger cap.
-  float cap = 1.0f;
+  float cap = 0.25f;
   unsigned int epoch = 0;
   int hist_count = 1;  // entries in qh/th
   int iter = 0, converged = 0, max_reached = 0, last_kept = 0;

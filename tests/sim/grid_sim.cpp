@@ -17,7 +17,7 @@ thread_local long long ls::ls_sim_cand = 0, ls::ls_sim_entries = 0, ls::ls_sim_s
 namespace {
 struct SimGrid {
   ls::Grid g;
-  std::vector<ls::Entry> top, tab1, tab2;
+  std::vector<ls::Entry> top, tab1;
   std::vector<float4> pts;
   std::vector<unsigned long long> pyr;
 };
@@ -32,47 +32,29 @@ void build(SimGrid& S, const float* refc3, int m, float cell, int max_cells, int
   if (m == 0) { lo[0] = lo[1] = lo[2] = 0; hi[0] = hi[1] = hi[2] = 0; }
   ls::grid_setup(S.g, lo, hi, cell, max_cells, split, m);
   const ls::Grid& g = S.g;
-  struct Key { int c0, f1, f2, idx; };
+  struct Key { int c0, f1, idx; };
   std::vector<Key> keys(m);
   std::vector<int> cnt0(g.n_cells0, 0);
   for (int i = 0; i < m; ++i) {
-    keys[i] = {ls::top_index(g, refc3[3 * i], refc3[3 * i + 1], refc3[3 * i + 2]), -1, -1, i};
+    keys[i] = {ls::top_index(g, refc3[3 * i], refc3[3 * i + 1], refc3[3 * i + 2]), -1, i};
     cnt0[keys[i].c0]++;
   }
-  // level 1
   std::vector<int> tabidx0(g.n_cells0, -1);
   int n1 = 0;
   for (int c = 0; c < g.n_cells0; ++c)
     if (cnt0[c] > g.leaf_split) tabidx0[c] = n1++;
-  std::vector<int> cnt1((size_t)n1 * 64, 0);
+  std::vector<int> cnt1((size_t)n1 * LS_FB3, 0);
   for (int i = 0; i < m; ++i) {
     const int t = tabidx0[keys[i].c0];
     if (t < 0) continue;
     float lx, ly, lz;
     ls::top_origin(g, keys[i].c0, lx, ly, lz);
     keys[i].f1 = ls::sub_index(refc3[3 * i], refc3[3 * i + 1], refc3[3 * i + 2], lx, ly, lz, g.inv1);
-    cnt1[(size_t)t * 64 + keys[i].f1]++;
-  }
-  std::vector<int> tabidx1((size_t)n1 * 64, -1);
-  int n2 = 0;
-  for (size_t k = 0; k < cnt1.size(); ++k)
-    if (cnt1[k] > g.leaf_split) tabidx1[k] = n2++;
-  std::vector<int> cnt2((size_t)n2 * 64, 0);
-  for (int i = 0; i < m; ++i) {
-    const int t = tabidx0[keys[i].c0];
-    if (t < 0) continue;
-    const int t2 = tabidx1[(size_t)t * 64 + keys[i].f1];
-    if (t2 < 0) continue;
-    float lx, ly, lz, mx, my, mz;
-    ls::top_origin(g, keys[i].c0, lx, ly, lz);
-    ls::sub_origin(keys[i].f1, lx, ly, lz, g.H1, mx, my, mz);
-    keys[i].f2 = ls::sub_index(refc3[3 * i], refc3[3 * i + 1], refc3[3 * i + 2], mx, my, mz, g.inv2);
-    cnt2[(size_t)t2 * 64 + keys[i].f2]++;
+    cnt1[(size_t)t * LS_FB3 + keys[i].f1]++;
   }
   std::sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) {
     if (a.c0 != b.c0) return a.c0 < b.c0;
     if (a.f1 != b.f1) return a.f1 < b.f1;
-    if (a.f2 != b.f2) return a.f2 < b.f2;
     return a.idx > b.idx;  // deliberately NOT index order: the GPU scatter order is arbitrary
   });
   S.pts.resize(m);
@@ -82,8 +64,7 @@ void build(SimGrid& S, const float* refc3, int m, float cell, int max_cells, int
     S.pts[i] = p;
   }
   S.top.assign(g.n_cells0, ls::Entry{0, 0});
-  S.tab1.assign((size_t)n1 * 64, ls::Entry{0, 0});
-  S.tab2.assign((size_t)n2 * 64, ls::Entry{0, 0});
+  S.tab1.assign((size_t)n1 * LS_FB3, ls::Entry{0, 0});
   uint32_t run = 0;
   for (int c = 0; c < g.n_cells0; ++c) {
     S.top[c].start = run;
@@ -93,25 +74,14 @@ void build(SimGrid& S, const float* refc3, int m, float cell, int max_cells, int
       continue;
     }
     S.top[c].meta = ~tabidx0[c];
-    for (int f = 0; f < 64; ++f) {
-      const size_t k = (size_t)tabidx0[c] * 64 + f;
+    for (int f = 0; f < LS_FB3; ++f) {
+      const size_t k = (size_t)tabidx0[c] * LS_FB3 + f;
       S.tab1[k].start = run;
-      if (tabidx1[k] < 0) {
-        S.tab1[k].meta = cnt1[k];
-        run += cnt1[k];
-        continue;
-      }
-      S.tab1[k].meta = ~tabidx1[k];
-      for (int h = 0; h < 64; ++h) {
-        const size_t k2 = (size_t)tabidx1[k] * 64 + h;
-        S.tab2[k2].start = run;
-        S.tab2[k2].meta = cnt2[k2];
-        run += cnt2[k2];
-      }
+      S.tab1[k].meta = cnt1[k];
+      run += cnt1[k];
     }
   }
   S.g.n_tab1 = n1;
-  S.g.n_tab2 = n2;
   // occupancy pyramid
   S.pyr.assign(g.n_pyr_cells, 0ull);
   for (int l = 1; l <= g.n_pyr; ++l) {
@@ -145,7 +115,7 @@ void sim_nn(const float* q3, int n, const float* refc3, int m, float cell, int m
   build(S, refc3, m, cell, max_cells, split);
   std::vector<int> pos_of(m);
   for (int i = 0; i < m; ++i) pos_of[ls::f2i(S.pts[i].w)] = i;
-  ls::GridView v{S.top.data(), S.tab1.data(), S.tab2.data(), S.pts.data(), S.pyr.data()};
+  ls::GridView v{S.top.data(), S.tab1.data(), S.pts.data(), S.pyr.data()};
   long long cand = 0, ent = 0, cmax = 0;
   for (int i = 0; i < n; ++i) {
     ls::ls_sim_cand = 0;
@@ -165,7 +135,7 @@ void sim_nn(const float* q3, int n, const float* refc3, int m, float cell, int m
     stats[0] = n ? (double)cand / n : 0;
     stats[1] = n ? (double)ent / n : 0;
     stats[2] = (double)cmax;
-    stats[3] = S.g.n_tab1 + 1e-6 * S.g.n_tab2;
+    stats[3] = S.g.n_tab1;
     stats[4] = S.g.H0;
     stats[5] = S.g.n_cells0;
   }
