@@ -135,6 +135,16 @@ int ls_icp_register_submap(ls_ctx* ctx, const ls_icp_params* prm, const ls_map* 
                            float T_out[16], ls_icp_stats* stats, int32_t* opt_ids, float* opt_d2,
                            float* opt_T_iter_hist);
 
+/* `batch` independent scan -> sub-map registrations in ONE cooperative launch (several LaserTracks hosted on one
+ * GPU: the reference's n_laser_slam_workers tracks, laser_slam/src/incremental_estimator.cpp:22-26).  Problem b
+ * uses reading_ids[b], its n_parts[b] parts follow each other in part_ids / T_parts (16 floats per part),
+ * T0s / T_outs hold 16 floats per problem, statuses[b] is LS_OK or LS_ERR_CONVERGENCE (then T_out == T0).
+ * Results are bit-identical to separate ls_icp_register_submap calls.  1 <= batch <= 16. */
+int ls_icp_register_submap_batch(ls_ctx* ctx, const ls_icp_params* prm, const ls_map* map, int batch,
+                                 const uint64_t* reading_ids, const int* n_parts, const uint64_t* part_ids,
+                                 const float* T_parts, const float* T0s, float* T_outs, ls_icp_stats* stats,
+                                 int* statuses);
+
 /* Assemble a sub-map and download it (LaserTrack::buildSubMapAroundTime,
  * LaserTrack::getLocalCloudInWorldFrame laser_track.cpp:247-266).  out4: 4*M floats,
  * out_normals3: 3*M floats (may be NULL); returns M through *m_out. */

@@ -97,6 +97,7 @@ def lib():
         L.ls_map_scan_size.argtypes = [vp, u64]
         L.ls_icp_register_submap.argtypes = [vp, PP, vp, u64, ci, vp, vp, vp, vp, PS, vp, vp, vp]
         L.ls_map_assemble.argtypes = [vp, vp, ci, vp, vp, vp, vp, ctypes.POINTER(ci)]
+        L.ls_icp_register_submap_batch.argtypes = [vp, PP, vp, ci, vp, vp, vp, vp, vp, vp, vp, vp]
         L.ls_pg_create.argtypes = [ci, ctypes.POINTER(vp)]
         L.ls_pg_destroy.argtypes = [vp]
         L.ls_pg_destroy.restype = None
@@ -301,6 +302,51 @@ class Map:
         if want_hist:
             out["T_iter_hist"] = hist[:st.iterations].reshape(-1, 4, 4).transpose(0, 2, 1).copy()
         return out
+
+    def prepare(self, reading_id, part_ids, T_parts, T0, params=None):
+        """Marshal one registration's arguments once; returns a zero-argument callable that performs the C call
+        (ls_icp_register_submap) and returns (rc, T_out 4x4, stats).  For callers that pre-stage their inputs."""
+        p = params or default_params()
+        ids_arr = np.ascontiguousarray(part_ids, np.uint64)
+        tp = np.ascontiguousarray(np.stack([colmajor(T) for T in T_parts]), np.float32)
+        t0 = colmajor(T0)
+        tout = np.empty(16, np.float32)
+        st = IcpStats()
+        fn = lib().ls_icp_register_submap
+        args = (self.ctx._h, ctypes.byref(p), self._h, ctypes.c_uint64(reading_id), len(ids_arr), ids_arr.ctypes.data,
+                tp.ctypes.data, t0.ctypes.data, tout.ctypes.data, ctypes.byref(st), None, None, None)
+        keep = (p, ids_arr, tp, t0)
+
+        def call(_fn=fn, _args=args, _tout=tout, _st=st, _keep=keep):
+            return _fn(*_args), _tout, _st
+        return call
+
+    def prepare_batch(self, problems, params=None):
+        """problems: list of (reading_id, part_ids, T_parts, T0).  Marshals once; returns a callable performing
+        ls_icp_register_submap_batch and returning (rc, statuses, T_outs (B,4,4 col-major flat 16), stats array)."""
+        p = params or default_params()
+        B = len(problems)
+        rids = np.ascontiguousarray([pr[0] for pr in problems], np.uint64)
+        nparts = np.ascontiguousarray([len(pr[1]) for pr in problems], np.int32)
+        pids = np.ascontiguousarray(np.concatenate([np.asarray(pr[1], np.uint64) for pr in problems]), np.uint64)
+        tparts = np.ascontiguousarray(np.concatenate([np.stack([colmajor(T) for T in pr[2]]) for pr in problems]), np.float32)
+        t0s = np.ascontiguousarray(np.stack([colmajor(pr[3]) for pr in problems]), np.float32)
+        touts = np.empty((B, 16), np.float32)
+        stats = (IcpStats * B)()
+        statuses = np.zeros(B, np.int32)
+        fn = lib().ls_icp_register_submap_batch
+        args = (self.ctx._h, ctypes.byref(p), self._h, B, rids.ctypes.data, nparts.ctypes.data, pids.ctypes.data,
+                tparts.ctypes.data, t0s.ctypes.data, touts.ctypes.data, ctypes.cast(stats, ctypes.c_void_p), statuses.ctypes.data)
+        keep = (p, rids, nparts, pids, tparts, t0s)
+
+        def call(_fn=fn, _args=args, _keep=keep):
+            return _fn(*_args), statuses, touts, stats
+        return call
+
+    def register_batch(self, problems, params=None):
+        rc, statuses, touts, stats = self.prepare_batch(problems, params)()
+        self.ctx._check(rc if rc < 0 else 0)
+        return [dict(T=from_colmajor(touts[b]), rc=int(statuses[b]), stats=stats[b]) for b in range(len(problems))]
 
     def assemble(self, part_ids, T_parts, want_normals=True):
         ids_arr = np.ascontiguousarray(part_ids, np.uint64)

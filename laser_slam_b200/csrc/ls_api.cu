@@ -14,35 +14,42 @@ using namespace ls;
 
 #define LS_VERSION 100
 
-struct ls_ctx {
-  int device = 0;
-  int sm_count = 0;
-  int icp_ctas = 0;  // co-resident CTAs for the cooperative ICP kernel
+// Everything one registration needs on the device.  A context owns one workspace per concurrently
+// running problem (ls_icp_register_submap_batch); single-problem entry points use workspace 0.
+struct Workspace {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
-  std::string err;
-  uint64_t launches = 0;
-  // capacities
   int n_cap = 0, m_cap = 0, cells_cap = 0, tab_cap = 0, hist_cap = 0;
-  // device buffers
   BuildArrays A{};
   BuildState* bs = nullptr;
-  float4 *reading = nullptr, *rd = nullptr;  // raw reading (one-shot path), pre-transformed reading
-  float4 *ref_stage = nullptr, *ref_nrm_stage = nullptr;  // one-shot reference staging (scan-frame)
-  float* nrm_raw = nullptr;                  // raw normals staging
+  float4 *reading = nullptr, *rd = nullptr;               // raw reading (one-shot path), pre-transformed reading
+  float4 *ref_stage = nullptr, *ref_nrm_stage = nullptr;  // one-shot reference staging (scan frame)
+  float* nrm_raw = nullptr;                               // raw normals staging
   size_t nrm_raw_cap = 0;
   int* pos = nullptr;
   float* d2 = nullptr;
   int* ids = nullptr;
+  float4* miss = nullptr;
   IcpWork* work = nullptr;
-  IcpProblem* prob = nullptr;
   float* T_hist = nullptr;
   unsigned long long* phase_ns = nullptr;  // debug (LS_PHASE_TIMING=1)
   float* T0_dev = nullptr;
-  // pinned host mirror for small results
-  IcpWork* h_work = nullptr;  // only the tail (results) is read
+  IcpWork* h_work = nullptr;  // pinned host mirrors of the small results
   Grid* h_grid = nullptr;
+  IcpProblem hp;              // host copy of this problem's descriptor
 };
+
+struct ls_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int icp_ctas = 0;  // co-resident CTAs for the cooperative ICP kernel
+  std::string err;
+  uint64_t launches = 0;
+  std::vector<Workspace*> ws;
+  IcpProblem* probs_dev = nullptr;   // [kMaxBatch]
+  IcpProblem* probs_host = nullptr;  // pinned
+};
+constexpr int kMaxBatch = 16;
 
 struct ls_scan_slot {
   float4* pts = nullptr;
@@ -100,52 +107,53 @@ inline int blocks_for(int n, int threads, int cap) {
   return b > cap ? cap : b;
 }
 
-int ensure_capacity(ls_ctx* ctx, int n, int m, int max_cells, int max_iter) {
-  if (n > ctx->n_cap) {
+int ensure_capacity(ls_ctx* ctx, Workspace* w, int n, int m, int max_cells, int max_iter) {
+  if (n > w->n_cap) {
     const int cap = n + n / 8 + 1024;
     int rc;
-    if ((rc = dev_alloc(ctx, &ctx->reading, (size_t)cap))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->rd, (size_t)cap))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->pos, (size_t)cap))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->d2, (size_t)cap))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->ids, (size_t)cap))) return rc;
-    ctx->n_cap = cap;
+    if ((rc = dev_alloc(ctx, &w->reading, (size_t)cap))) return rc;
+    if ((rc = dev_alloc(ctx, &w->rd, (size_t)cap))) return rc;
+    if ((rc = dev_alloc(ctx, &w->pos, (size_t)cap))) return rc;
+    if ((rc = dev_alloc(ctx, &w->d2, (size_t)cap))) return rc;
+    if ((rc = dev_alloc(ctx, &w->ids, (size_t)cap))) return rc;
+    if ((rc = dev_alloc(ctx, &w->miss, (size_t)cap))) return rc;
+    w->n_cap = cap;
   }
-  if (m > ctx->m_cap) {
+  if (m > w->m_cap) {
     const int cap = m + m / 8 + 1024;
     int rc;
-    if ((rc = dev_alloc(ctx, &ctx->A.sub_pts, (size_t)cap))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->A.sub_nrm, (size_t)cap))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->A.srt_pts, (size_t)cap))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->A.srt_nrm, (size_t)cap))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->A.pkey, (size_t)cap))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->ref_stage, (size_t)cap))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->ref_nrm_stage, (size_t)cap))) return rc;
+    if ((rc = dev_alloc(ctx, &w->A.sub_pts, (size_t)cap))) return rc;
+    if ((rc = dev_alloc(ctx, &w->A.sub_nrm, (size_t)cap))) return rc;
+    if ((rc = dev_alloc(ctx, &w->A.srt_pts, (size_t)cap))) return rc;
+    if ((rc = dev_alloc(ctx, &w->A.srt_nrm, (size_t)cap))) return rc;
+    if ((rc = dev_alloc(ctx, &w->A.pkey, (size_t)cap))) return rc;
+    if ((rc = dev_alloc(ctx, &w->ref_stage, (size_t)cap))) return rc;
+    if ((rc = dev_alloc(ctx, &w->ref_nrm_stage, (size_t)cap))) return rc;
     // a fine table exists only for a level-0 cell with > leaf_split (>= 16) points; the pool is also capped at
     // ~1.5 GB (cells beyond the pool stay leaves: slower, still exact, flagged in stats.grid_overflow)
     int tcap = cap / 17 + 1024;
     const int tmax = (int)((size_t)1536 * 1024 * 1024 / ((size_t)LS_FB3 * 12));
     if (tcap > tmax) tcap = tmax;
-    if ((rc = dev_alloc(ctx, &ctx->A.tab1, (size_t)tcap * LS_FB3))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->A.cnt1, (size_t)tcap * LS_FB3))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->A.tab1_cell, (size_t)tcap))) return rc;
-    CU(cudaMemsetAsync(ctx->A.cnt1, 0, (size_t)tcap * LS_FB3 * sizeof(uint32_t), ctx->stream));
-    ctx->A.tab_cap = tcap;
-    ctx->tab_cap = tcap;
-    ctx->m_cap = cap;
+    if ((rc = dev_alloc(ctx, &w->A.tab1, (size_t)tcap * LS_FB3))) return rc;
+    if ((rc = dev_alloc(ctx, &w->A.cnt1, (size_t)tcap * LS_FB3))) return rc;
+    if ((rc = dev_alloc(ctx, &w->A.tab1_cell, (size_t)tcap))) return rc;
+    CU(cudaMemsetAsync(w->A.cnt1, 0, (size_t)tcap * LS_FB3 * sizeof(uint32_t), w->stream));
+    w->A.tab_cap = tcap;
+    w->tab_cap = tcap;
+    w->m_cap = cap;
   }
-  if (max_cells > ctx->cells_cap) {
+  if (max_cells > w->cells_cap) {
     int rc;
-    if ((rc = dev_alloc(ctx, &ctx->A.top, (size_t)max_cells + 1))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->A.cnt0, (size_t)max_cells + 1))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->A.pyr, (size_t)max_cells / 2 + 4096))) return rc;
-    CU(cudaMemsetAsync(ctx->A.cnt0, 0, ((size_t)max_cells + 1) * sizeof(uint32_t), ctx->stream));
-    ctx->cells_cap = max_cells;
+    if ((rc = dev_alloc(ctx, &w->A.top, (size_t)max_cells + 1))) return rc;
+    if ((rc = dev_alloc(ctx, &w->A.cnt0, (size_t)max_cells + 1))) return rc;
+    if ((rc = dev_alloc(ctx, &w->A.pyr, (size_t)max_cells / 2 + 4096))) return rc;
+    CU(cudaMemsetAsync(w->A.cnt0, 0, ((size_t)max_cells + 1) * sizeof(uint32_t), w->stream));
+    w->cells_cap = max_cells;
   }
-  if (max_iter > ctx->hist_cap) {
+  if (max_iter > w->hist_cap) {
     int rc;
-    if ((rc = dev_alloc(ctx, &ctx->T_hist, (size_t)max_iter * 16))) return rc;
-    ctx->hist_cap = max_iter;
+    if ((rc = dev_alloc(ctx, &w->T_hist, (size_t)max_iter * 16))) return rc;
+    w->hist_cap = max_iter;
   }
   return LS_OK;
 }
@@ -175,93 +183,104 @@ int check_params(ls_ctx* ctx, const ls_icp_params* p) {
 }
 
 // Build the spatial hash over the sub-map described by `parts` (device pointers), then pre-transform
-// the reading.  Everything is enqueued on ctx->stream; nothing synchronises.
-int enqueue_build(ls_ctx* ctx, const Parts& parts, const Resolved& r, const float* T0_host) {
+// the reading.  Everything is enqueued on w->stream; nothing synchronises.
+int enqueue_build(ls_ctx* ctx, Workspace* w, const Parts& parts, const Resolved& r, const float* T0_host) {
   const int m = parts.offset[parts.n_parts];
-  reset_build_kernel<<<1, 32, 0, ctx->stream>>>(ctx->bs);
+  reset_build_kernel<<<1, 32, 0, w->stream>>>(w->bs);
   LAUNCH_CHECK();
-  CU(cudaMemcpyAsync(ctx->T0_dev, T0_host, 16 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(w->T0_dev, T0_host, 16 * sizeof(float), cudaMemcpyHostToDevice, w->stream));
   const int pb = blocks_for(m, 256, ctx->sm_count * 8);
-  assemble_kernel<<<pb, 256, 0, ctx->stream>>>(parts, ctx->A.sub_pts, ctx->A.sub_nrm, ctx->bs);
+  assemble_kernel<<<pb, 256, 0, w->stream>>>(parts, w->A.sub_pts, w->A.sub_nrm, w->bs);
   LAUNCH_CHECK();
-  setup_kernel<<<1, 32, 0, ctx->stream>>>(ctx->bs, m, r.cell, r.max_cells, r.split, ctx->T0_dev);
+  setup_kernel<<<1, 32, 0, w->stream>>>(w->bs, m, r.cell, r.max_cells, r.split, w->T0_dev);
   LAUNCH_CHECK();
-  count0_kernel<<<pb, 256, 0, ctx->stream>>>(ctx->bs, ctx->A, m);
+  count0_kernel<<<pb, 256, 0, w->stream>>>(w->bs, w->A, m);
   LAUNCH_CHECK();
   const int tiles = (r.max_cells + kScanTile - 1) / kScanTile;
-  scan_reduce_kernel<<<tiles, kScanThreads, 0, ctx->stream>>>(ctx->bs, ctx->A.cnt0);
+  scan_reduce_kernel<<<tiles, kScanThreads, 0, w->stream>>>(w->bs, w->A.cnt0);
   LAUNCH_CHECK();
-  scan_apply_kernel<<<tiles, kScanThreads, 0, ctx->stream>>>(ctx->bs, ctx->A);
+  scan_apply_kernel<<<tiles, kScanThreads, 0, w->stream>>>(w->bs, w->A);
   LAUNCH_CHECK();
-  pyramid1_kernel<<<blocks_for(r.max_cells / 16 + 1, 256, ctx->sm_count * 4), 256, 0, ctx->stream>>>(ctx->bs, ctx->A);
+  pyramid1_kernel<<<blocks_for(r.max_cells / 16 + 1, 256, ctx->sm_count * 4), 256, 0, w->stream>>>(w->bs, w->A);
   LAUNCH_CHECK();
-  pyramid_up_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->bs, ctx->A);
+  pyramid_up_kernel<<<1, 1024, 0, w->stream>>>(w->bs, w->A);
   LAUNCH_CHECK();
-  count1_kernel<<<pb, 256, 0, ctx->stream>>>(ctx->bs, ctx->A, m);
+  count1_kernel<<<pb, 256, 0, w->stream>>>(w->bs, w->A, m);
   LAUNCH_CHECK();
-  tables_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->bs, ctx->A);
+  tables_kernel<<<ctx->sm_count * 8, 256, 0, w->stream>>>(w->bs, w->A);
   LAUNCH_CHECK();
-  scatter_kernel<<<pb, 256, 0, ctx->stream>>>(ctx->A, m);
+  scatter_kernel<<<pb, 256, 0, w->stream>>>(w->A, m);
   LAUNCH_CHECK();
   return LS_OK;
 }
 
-int upload_normals(ls_ctx* ctx, const float* normals, int stride, int n, float4* dst) {
+int upload_normals(ls_ctx* ctx, Workspace* w, const float* normals, int stride, int n, float4* dst) {
   const size_t need = (size_t)n * (size_t)(stride <= 8 ? stride : 3);
-  if (need > ctx->nrm_raw_cap) {
+  if (need > w->nrm_raw_cap) {
     int rc;
-    if ((rc = dev_alloc(ctx, &ctx->nrm_raw, need + 4096))) return rc;
-    ctx->nrm_raw_cap = need + 4096;
+    if ((rc = dev_alloc(ctx, &w->nrm_raw, need + 4096))) return rc;
+    w->nrm_raw_cap = need + 4096;
   }
   int dstride = stride;
   if (stride <= 8) {
-    CU(cudaMemcpyAsync(ctx->nrm_raw, normals, need * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(w->nrm_raw, normals, need * sizeof(float), cudaMemcpyHostToDevice, w->stream));
   } else {
-    CU(cudaMemcpy2DAsync(ctx->nrm_raw, 3 * sizeof(float), normals, (size_t)stride * sizeof(float), 3 * sizeof(float),
-                         (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpy2DAsync(w->nrm_raw, 3 * sizeof(float), normals, (size_t)stride * sizeof(float), 3 * sizeof(float),
+                         (size_t)n, cudaMemcpyHostToDevice, w->stream));
     dstride = 3;
   }
-  expand_normals_kernel<<<blocks_for(n, 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(ctx->nrm_raw, dstride, n, dst);
+  expand_normals_kernel<<<blocks_for(n, 256, ctx->sm_count * 8), 256, 0, w->stream>>>(w->nrm_raw, dstride, n, dst);
   LAUNCH_CHECK();
   return LS_OK;
 }
 
-// Run the persistent ICP kernel on the already-built map + resident reading; fetch results.
-int run_icp(ls_ctx* ctx, const ls_icp_params* prm, const float4* reading_dev, int n, const float T0[16],
-            float T_out[16], ls_icp_stats* stats, int32_t* opt_ids, float* opt_d2, float* opt_T_hist, int m) {
-  reading_kernel<<<blocks_for(n, 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(ctx->bs, reading_dev, n, ctx->rd);
+// Stage one problem for the persistent ICP kernel: pre-transform the reading, clear the scratch, fill the
+// problem descriptor.  Enqueued on the workspace's stream; nothing synchronises.
+int prep_icp(ls_ctx* ctx, Workspace* w, const ls_icp_params* prm, const float4* reading_dev, int n, const float T0[16],
+             bool want_matches, bool want_hist) {
+  reading_kernel<<<blocks_for(n, 256, ctx->sm_count * 8), 256, 0, w->stream>>>(w->bs, reading_dev, n, w->rd);
   LAUNCH_CHECK();
-  CU(cudaEventRecord(ctx->ev1, ctx->stream));
-  CU(cudaMemsetAsync(ctx->work, 0, sizeof(IcpWork), ctx->stream));
-  IcpProblem hp;
-  hp.bs = ctx->bs;
-  hp.view.top = ctx->A.top;
-  hp.view.tab1 = ctx->A.tab1;
-  hp.view.pts = ctx->A.srt_pts;
-  hp.view.pyr = ctx->A.pyr;
-  hp.nrm = ctx->A.srt_nrm;
-  hp.rd = ctx->rd;
+  CU(cudaEventRecord(w->ev1, w->stream));
+  CU(cudaMemsetAsync(w->work, 0, sizeof(IcpWork), w->stream));
+  IcpProblem& hp = w->hp;
+  hp.bs = w->bs;
+  hp.view.top = w->A.top;
+  hp.view.tab1 = w->A.tab1;
+  hp.view.pts = w->A.srt_pts;
+  hp.view.pyr = w->A.pyr;
+  hp.nrm = w->A.srt_nrm;
+  hp.rd = w->rd;
   hp.n = n;
-  hp.pos = ctx->pos;
-  hp.d2 = ctx->d2;
-  hp.ids = ctx->ids;
-  hp.work = ctx->work;
-  hp.T_hist = opt_T_hist ? ctx->T_hist : nullptr;
-  hp.want_matches = (opt_ids || opt_d2) ? 1 : 0;
+  hp.pos = w->pos;
+  hp.d2 = w->d2;
+  hp.ids = w->ids;
+  hp.miss = w->miss;
+  hp.work = w->work;
+  hp.T_hist = want_hist ? w->T_hist : nullptr;
+  hp.want_matches = want_matches ? 1 : 0;
   const bool want_phase = getenv("LS_PHASE_TIMING") != nullptr;
   if (want_phase) {
-    if (ctx->phase_ns) cudaFree(ctx->phase_ns);
-    CU(cudaMalloc((void**)&ctx->phase_ns, (size_t)prm->max_iterations * 6 * sizeof(unsigned long long)));
-    CU(cudaMemsetAsync(ctx->phase_ns, 0, (size_t)prm->max_iterations * 6 * sizeof(unsigned long long), ctx->stream));
+    if (w->phase_ns) cudaFree(w->phase_ns);
+    CU(cudaMalloc((void**)&w->phase_ns, (size_t)prm->max_iterations * 6 * sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(w->phase_ns, 0, (size_t)prm->max_iterations * 6 * sizeof(unsigned long long), w->stream));
   }
-  hp.phase_ns = want_phase ? ctx->phase_ns : nullptr;
-  static unsigned int* warp_cyc_dev = nullptr;
-  const bool want_warp = getenv("LS_WARP_PROFILE") != nullptr;
-  if (want_warp && !warp_cyc_dev) cudaMalloc((void**)&warp_cyc_dev, 8192 * sizeof(unsigned int));
-  if (want_warp) cudaMemsetAsync(warp_cyc_dev, 0, 8192 * sizeof(unsigned int), ctx->stream);
-  hp.warp_cyc = want_warp ? warp_cyc_dev : nullptr;
+  hp.phase_ns = want_phase ? w->phase_ns : nullptr;
+  hp.warp_cyc = nullptr;
   std::memcpy(hp.T0, T0, sizeof(hp.T0));
-  CU(cudaMemcpyAsync(ctx->prob, &hp, sizeof(hp), cudaMemcpyHostToDevice, ctx->stream));
+  return LS_OK;
+}
+
+// One cooperative launch over `batch` staged problems (workspaces 0..batch-1): the grid is partitioned into
+// `batch` groups of CTAs, each with its own barrier.  Runs on workspace 0's stream after every workspace's
+// staging has finished; on return the results are on the host (pinned mirrors).
+int launch_icp(ls_ctx* ctx, const ls_icp_params* prm, int batch, int n_max) {
+  Workspace* w0 = ctx->ws[0];
+  for (int b = 1; b < batch; ++b) {
+    CU(cudaEventRecord(ctx->ws[b]->ev2, ctx->ws[b]->stream));
+    CU(cudaStreamWaitEvent(w0->stream, ctx->ws[b]->ev2, 0));
+  }
+  for (int b = 0; b < batch; ++b) ctx->probs_host[b] = ctx->ws[b]->hp;
+  CU(cudaMemcpyAsync(ctx->probs_dev, ctx->probs_host, sizeof(IcpProblem) * (size_t)batch, cudaMemcpyHostToDevice, w0->stream));
   IcpParamsDev dp;
   dp.max_iterations = prm->max_iterations;
   dp.trim_ratio = prm->trim_ratio;
@@ -269,71 +288,80 @@ int run_icp(ls_ctx* ctx, const ls_icp_params* prm, const float4* reading_dev, in
   dp.min_diff_rot = prm->min_diff_rot;
   dp.min_diff_trans = prm->min_diff_trans;
   dp.smooth_length = prm->smooth_length;
-  int ctas = (n + 31) / 32;
-  if (ctas > ctx->icp_ctas) ctas = ctx->icp_ctas;
+  int ctas = ctx->icp_ctas / batch;   // CTAs per problem; every CTA of the grid must be co-resident
+  const int need = (n_max + 31) / 32;
+  if (ctas > need) ctas = need;
   if (ctas < 1) ctas = 1;
-  const IcpProblem* probs = ctx->prob;
+  const IcpProblem* probs = ctx->probs_dev;
   void* args[] = {(void*)&probs, (void*)&ctas, (void*)&dp};
-  CU(cudaLaunchCooperativeKernel((void*)icp_kernel, dim3(ctas), dim3(kIcpThreads), args, 0, ctx->stream));
+  CU(cudaLaunchCooperativeKernel((void*)icp_kernel, dim3(ctas * batch), dim3(kIcpThreads), args, 0, w0->stream));
   ++ctx->launches;
-  CU(cudaEventRecord(ctx->ev2, ctx->stream));
-  // results: small struct + optional arrays
-  CU(cudaMemcpyAsync(ctx->h_work, ctx->work, sizeof(IcpWork), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->h_grid, &ctx->bs->grid, sizeof(Grid), cudaMemcpyDeviceToHost, ctx->stream));
-  if (opt_ids) CU(cudaMemcpyAsync(opt_ids, ctx->ids, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  if (opt_d2) CU(cudaMemcpyAsync(opt_d2, ctx->d2, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-  if (opt_T_hist)
-    CU(cudaMemcpyAsync(opt_T_hist, ctx->T_hist, (size_t)prm->max_iterations * 16 * sizeof(float), cudaMemcpyDeviceToHost,
-                       ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
-  const IcpWork& w = *ctx->h_work;
-  if (want_phase) {
+  CU(cudaEventRecord(w0->ev2, w0->stream));
+  for (int b = 0; b < batch; ++b) {
+    Workspace* w = ctx->ws[b];
+    CU(cudaMemcpyAsync(w->h_work, w->work, sizeof(IcpWork), cudaMemcpyDeviceToHost, w0->stream));
+    CU(cudaMemcpyAsync(w->h_grid, &w->bs->grid, sizeof(Grid), cudaMemcpyDeviceToHost, w0->stream));
+  }
+  return LS_OK;
+}
+
+// After launch_icp + a synchronise of workspace 0's stream: unpack one problem's results.
+int fetch_icp(ls_ctx* ctx, Workspace* w, const ls_icp_params* prm, int n, const float T0[16], float T_out[16],
+              ls_icp_stats* stats) {
+  const IcpWork& wk = *w->h_work;
+  if (getenv("LS_PHASE_TIMING") && w->phase_ns) {
     std::vector<unsigned long long> ph((size_t)prm->max_iterations * 6);
-    cudaMemcpy(ph.data(), ctx->phase_ns, ph.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaMemcpy(ph.data(), w->phase_ns, ph.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     fprintf(stderr, "[ls] phase us per iteration: A(nn) B(sel1) C(sel2) D(sel3+acc) E(solve) | total\n");
-    for (int it = 0; it < w.iterations && it < prm->max_iterations; ++it) {
+    for (int it = 0; it < wk.iterations && it < prm->max_iterations; ++it) {
       const unsigned long long* q = &ph[(size_t)it * 6];
       fprintf(stderr, "[ls] it %2d: %8.1f %8.1f %8.1f %8.1f %8.1f | %8.1f\n", it, (q[1] - q[0]) * 1e-3, (q[2] - q[1]) * 1e-3,
               (q[3] - q[2]) * 1e-3, (q[4] - q[3]) * 1e-3, (q[5] - q[4]) * 1e-3, (q[5] - q[0]) * 1e-3);
     }
   }
-  if (want_warp) {
-    std::vector<unsigned int> wc(8192);
-    cudaMemcpy(wc.data(), warp_cyc_dev, wc.size() * sizeof(unsigned int), cudaMemcpyDeviceToHost);
-    FILE* f = fopen(getenv("LS_WARP_PROFILE"), "wb");
-    if (f) { fwrite(wc.data(), sizeof(unsigned int), wc.size(), f); fclose(f); }
-  }
-  std::memcpy(T_out, w.T_out, 16 * sizeof(float));
+  if (getenv("LS_DEBUG"))
+    fprintf(stderr, "[ls] status %d fail_code %d iters %d kept %d limit %g\n", wk.status, wk.fail_code, wk.iterations, wk.last_kept,
+            wk.last_limit);
+  std::memcpy(T_out, wk.T_out, 16 * sizeof(float));
   if (stats) {
     std::memset(stats, 0, sizeof(*stats));
-    stats->iterations = w.iterations;
-    stats->converged = w.converged;
-    stats->max_iter_reached = w.max_iter_reached;
-    stats->last_kept = w.last_kept;
-    stats->last_limit = w.last_limit;
-    stats->used_ratio = n > 0 ? (float)w.last_kept / (float)n : 0.f;
+    stats->iterations = wk.iterations;
+    stats->converged = wk.converged;
+    stats->max_iter_reached = wk.max_iter_reached;
+    stats->last_kept = wk.last_kept;
+    stats->last_limit = wk.last_limit;
+    stats->used_ratio = n > 0 ? (float)wk.last_kept / (float)n : 0.f;
     float ms = 0.f, bms = 0.f;
-    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev2);
-    cudaEventElapsedTime(&bms, ctx->ev0, ctx->ev1);
+    cudaEventElapsedTime(&ms, w->ev0, ctx->ws[0]->ev2);  // staging of this problem .. end of the (shared) ICP launch
+    cudaEventElapsedTime(&bms, w->ev0, w->ev1);
     stats->device_ms = ms;
     stats->build_ms = bms;
-    stats->grid_cells = ctx->h_grid->n_cells0;
-    stats->grid_tables = ctx->h_grid->n_tab1;
-    stats->grid_overflow = ctx->h_grid->overflow;
+    stats->grid_cells = w->h_grid->n_cells0;
+    stats->grid_tables = w->h_grid->n_tab1;
+    stats->grid_overflow = w->h_grid->overflow;
   }
-  if (getenv("LS_DEBUG")) {
-    fprintf(stderr, "[ls] status %d fail_code %d iters %d kept %d limit %g total %u bins %u %u %u rem %u %u %u\n", w.status,
-            w.fail_code, w.iterations, w.last_kept, w.last_limit, w.dbg_total, w.dbg_bin[0], w.dbg_bin[1], w.dbg_bin[2],
-            w.dbg_rem[0], w.dbg_rem[1], w.dbg_rem[2]);
-    fprintf(stderr, "[ls] A diag %g %g %g %g %g %g  x %g %g %g %g %g %g\n", w.dbg_A[0], w.dbg_A[1], w.dbg_A[2], w.dbg_A[3],
-            w.dbg_A[4], w.dbg_A[5], w.dbg_x[0], w.dbg_x[1], w.dbg_x[2], w.dbg_x[3], w.dbg_x[4], w.dbg_x[5]);
-  }
-  if (w.status != 0) {
+  if (wk.status != 0) {
     std::memcpy(T_out, T0, 16 * sizeof(float));
     return fail(ctx, LS_ERR_CONVERGENCE, "ICP: no point to minimise / non-finite transformation");
   }
-  (void)m;
   return LS_OK;
+}
+
+// single problem: stage on workspace 0, launch, optional arrays, fetch
+int run_icp(ls_ctx* ctx, const ls_icp_params* prm, const float4* reading_dev, int n, const float T0[16],
+            float T_out[16], ls_icp_stats* stats, int32_t* opt_ids, float* opt_d2, float* opt_T_hist, int m) {
+  Workspace* w = ctx->ws[0];
+  int rc;
+  if ((rc = prep_icp(ctx, w, prm, reading_dev, n, T0, opt_ids || opt_d2, opt_T_hist != nullptr))) return rc;
+  if ((rc = launch_icp(ctx, prm, 1, n))) return rc;
+  if (opt_ids) CU(cudaMemcpyAsync(opt_ids, w->ids, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, w->stream));
+  if (opt_d2) CU(cudaMemcpyAsync(opt_d2, w->d2, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, w->stream));
+  if (opt_T_hist)
+    CU(cudaMemcpyAsync(opt_T_hist, w->T_hist, (size_t)prm->max_iterations * 16 * sizeof(float), cudaMemcpyDeviceToHost,
+                       w->stream));
+  CU(cudaStreamSynchronize(w->stream));
+  (void)m;
+  return fetch_icp(ctx, w, prm, n, T0, T_out, stats);
 }
 
 bool is_identity16(const float* T) {
@@ -376,6 +404,45 @@ extern "C" {
 
 int ls_b200_version(void) { return LS_VERSION; }
 
+namespace {
+Workspace* new_workspace() {
+  Workspace* w = new Workspace();
+  bool ok = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreate(&w->ev0) == cudaSuccess && cudaEventCreate(&w->ev1) == cudaSuccess &&
+            cudaEventCreate(&w->ev2) == cudaSuccess && cudaMalloc((void**)&w->bs, sizeof(BuildState)) == cudaSuccess &&
+            cudaMalloc((void**)&w->work, sizeof(IcpWork)) == cudaSuccess &&
+            cudaMalloc((void**)&w->T0_dev, 64 * sizeof(float)) == cudaSuccess &&
+            cudaMallocHost((void**)&w->h_work, sizeof(IcpWork)) == cudaSuccess &&
+            cudaMallocHost((void**)&w->h_grid, sizeof(Grid)) == cudaSuccess;
+  if (!ok) return nullptr;  // partially built workspace is leaked only on an out-of-memory init failure
+  return w;
+}
+void free_workspace(Workspace* w) {
+  if (!w) return;
+  if (w->stream) cudaStreamSynchronize(w->stream);
+  void* bufs[] = {w->A.sub_pts, w->A.sub_nrm, w->A.srt_pts, w->A.srt_nrm, w->A.pkey, w->A.top, w->A.cnt0, w->A.tab1, w->A.cnt1,
+                  w->A.tab1_cell, w->A.pyr, w->bs, w->reading, w->rd, w->ref_stage, w->ref_nrm_stage, w->nrm_raw, w->pos, w->d2,
+                  w->ids, w->miss, w->work, w->T_hist, w->T0_dev, w->phase_ns};
+  for (void* b : bufs)
+    if (b) cudaFree(b);
+  if (w->h_work) cudaFreeHost(w->h_work);
+  if (w->h_grid) cudaFreeHost(w->h_grid);
+  if (w->ev0) cudaEventDestroy(w->ev0);
+  if (w->ev1) cudaEventDestroy(w->ev1);
+  if (w->ev2) cudaEventDestroy(w->ev2);
+  if (w->stream) cudaStreamDestroy(w->stream);
+  delete w;
+}
+int ensure_workspaces(ls_ctx* ctx, int count) {
+  while ((int)ctx->ws.size() < count) {
+    Workspace* w = new_workspace();
+    if (!w) return fail(ctx, LS_ERR_NOMEM, "workspace allocation failed");
+    ctx->ws.push_back(w);
+  }
+  return LS_OK;
+}
+}  // namespace
+
 int ls_b200_init(int device, ls_ctx** out) {
   if (!out) return LS_ERR_ARG;
   *out = nullptr;
@@ -393,20 +460,13 @@ int ls_b200_init(int device, ls_ctx** out) {
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(LS_ERR_CUDA);
   if (!prop.cooperativeLaunch) return bail(LS_ERR_CUDA);
   ctx->sm_count = prop.multiProcessorCount;
-  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(LS_ERR_CUDA);
-  if (cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
-      cudaEventCreate(&ctx->ev2) != cudaSuccess)
-    return bail(LS_ERR_CUDA);
   int occ = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, icp_kernel, kIcpThreads, 0) != cudaSuccess || occ < 1)
     return bail(LS_ERR_CUDA);
   ctx->icp_ctas = occ * ctx->sm_count;
-  if (cudaMalloc((void**)&ctx->bs, sizeof(BuildState)) != cudaSuccess) return bail(LS_ERR_NOMEM);
-  if (cudaMalloc((void**)&ctx->work, sizeof(IcpWork)) != cudaSuccess) return bail(LS_ERR_NOMEM);
-  if (cudaMalloc((void**)&ctx->prob, sizeof(IcpProblem)) != cudaSuccess) return bail(LS_ERR_NOMEM);
-  if (cudaMalloc((void**)&ctx->T0_dev, 64 * sizeof(float)) != cudaSuccess) return bail(LS_ERR_NOMEM);
-  if (cudaMallocHost((void**)&ctx->h_work, sizeof(IcpWork)) != cudaSuccess) return bail(LS_ERR_NOMEM);
-  if (cudaMallocHost((void**)&ctx->h_grid, sizeof(Grid)) != cudaSuccess) return bail(LS_ERR_NOMEM);
+  if (ensure_workspaces(ctx, 1) != LS_OK) return bail(LS_ERR_NOMEM);
+  if (cudaMalloc((void**)&ctx->probs_dev, sizeof(IcpProblem) * kMaxBatch) != cudaSuccess) return bail(LS_ERR_NOMEM);
+  if (cudaMallocHost((void**)&ctx->probs_host, sizeof(IcpProblem) * kMaxBatch) != cudaSuccess) return bail(LS_ERR_NOMEM);
   *out = ctx;
   return LS_OK;
 }
@@ -414,19 +474,9 @@ int ls_b200_init(int device, ls_ctx** out) {
 void ls_b200_destroy(ls_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  void* bufs[] = {ctx->A.sub_pts, ctx->A.sub_nrm, ctx->A.srt_pts, ctx->A.srt_nrm, ctx->A.pkey, ctx->A.top, ctx->A.cnt0,
-                  ctx->A.tab1, ctx->A.cnt1, ctx->A.tab1_cell, ctx->A.pyr, ctx->bs,
-                  ctx->reading, ctx->rd, ctx->ref_stage, ctx->ref_nrm_stage, ctx->nrm_raw, ctx->pos, ctx->d2, ctx->ids,
-                  ctx->work, ctx->prob, ctx->T_hist, ctx->T0_dev};
-  for (void* b : bufs)
-    if (b) cudaFree(b);
-  if (ctx->h_work) cudaFreeHost(ctx->h_work);
-  if (ctx->h_grid) cudaFreeHost(ctx->h_grid);
-  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
-  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-  if (ctx->ev2) cudaEventDestroy(ctx->ev2);
-  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  for (Workspace* w : ctx->ws) free_workspace(w);
+  if (ctx->probs_dev) cudaFree(ctx->probs_dev);
+  if (ctx->probs_host) cudaFreeHost(ctx->probs_host);
   delete ctx;
 }
 
@@ -461,22 +511,23 @@ int ls_icp_register(ls_ctx* ctx, const ls_icp_params* prm, const float* reading4
   if (stats) std::memset(stats, 0, sizeof(*stats));
   if (n == 0 || m == 0) return fail(ctx, LS_ERR_CONVERGENCE, "empty reading or reference");
   CU(cudaSetDevice(ctx->device));
+  Workspace* w = ctx->ws[0];
   const Resolved r = resolve(prm);
-  if ((rc = ensure_capacity(ctx, n, m, r.max_cells, prm->max_iterations))) return rc;
-  CU(cudaEventRecord(ctx->ev0, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->reading, reading4, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->ref_stage, ref4, (size_t)m * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-  if ((rc = upload_normals(ctx, ref_normals, normals_stride, m, ctx->ref_nrm_stage))) return rc;
+  if ((rc = ensure_capacity(ctx, w, n, m, r.max_cells, prm->max_iterations))) return rc;
+  CU(cudaEventRecord(w->ev0, w->stream));
+  CU(cudaMemcpyAsync(w->reading, reading4, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, w->stream));
+  CU(cudaMemcpyAsync(w->ref_stage, ref4, (size_t)m * sizeof(float4), cudaMemcpyHostToDevice, w->stream));
+  if ((rc = upload_normals(ctx, w, ref_normals, normals_stride, m, w->ref_nrm_stage))) return rc;
   Parts parts;
   std::memset(&parts, 0, sizeof(parts));
   parts.n_parts = 1;
   parts.offset[0] = 0;
   parts.offset[1] = m;
-  parts.pts[0] = ctx->ref_stage;
-  parts.nrm[0] = ctx->ref_nrm_stage;
+  parts.pts[0] = w->ref_stage;
+  parts.nrm[0] = w->ref_nrm_stage;
   parts.identity[0] = 1;
-  if ((rc = enqueue_build(ctx, parts, r, T0))) return rc;
-  return run_icp(ctx, prm, ctx->reading, n, T0, T_out, stats, opt_ids, opt_d2, opt_T_iter_hist, m);
+  if ((rc = enqueue_build(ctx, w, parts, r, T0))) return rc;
+  return run_icp(ctx, prm, w->reading, n, T0, T_out, stats, opt_ids, opt_d2, opt_T_iter_hist, m);
 }
 
 int ls_nn_query(ls_ctx* ctx, const ls_icp_params* prm, const float* reading4, int n, const float* ref4, int m,
@@ -491,27 +542,28 @@ int ls_nn_query(ls_ctx* ctx, const ls_icp_params* prm, const float* reading4, in
     return LS_OK;
   }
   CU(cudaSetDevice(ctx->device));
+  Workspace* w = ctx->ws[0];
   const Resolved r = resolve(prm);
-  if ((rc = ensure_capacity(ctx, n, m, r.max_cells, 1))) return rc;
-  CU(cudaMemcpyAsync(ctx->reading, reading4, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->ref_stage, ref4, (size_t)m * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemsetAsync(ctx->ref_nrm_stage, 0, (size_t)m * sizeof(float4), ctx->stream));
+  if ((rc = ensure_capacity(ctx, w, n, m, r.max_cells, 1))) return rc;
+  CU(cudaMemcpyAsync(w->reading, reading4, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, w->stream));
+  CU(cudaMemcpyAsync(w->ref_stage, ref4, (size_t)m * sizeof(float4), cudaMemcpyHostToDevice, w->stream));
+  CU(cudaMemsetAsync(w->ref_nrm_stage, 0, (size_t)m * sizeof(float4), w->stream));
   Parts parts;
   std::memset(&parts, 0, sizeof(parts));
   parts.n_parts = 1;
   parts.offset[1] = m;
-  parts.pts[0] = ctx->ref_stage;
-  parts.nrm[0] = ctx->ref_nrm_stage;
+  parts.pts[0] = w->ref_stage;
+  parts.nrm[0] = w->ref_nrm_stage;
   parts.identity[0] = 1;
-  if ((rc = enqueue_build(ctx, parts, r, T0))) return rc;
-  reading_kernel<<<blocks_for(n, 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(ctx->bs, ctx->reading, n, ctx->rd);
+  if ((rc = enqueue_build(ctx, w, parts, r, T0))) return rc;
+  reading_kernel<<<blocks_for(n, 256, ctx->sm_count * 8), 256, 0, w->stream>>>(w->bs, w->reading, n, w->rd);
   LAUNCH_CHECK();
-  GridView v{ctx->A.top, ctx->A.tab1, ctx->A.srt_pts, ctx->A.pyr};
-  nn_query_kernel<<<blocks_for(n, 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(ctx->bs, v, ctx->rd, n, ctx->ids, ctx->d2);
+  GridView v{w->A.top, w->A.tab1, w->A.srt_pts, w->A.pyr};
+  nn_query_kernel<<<blocks_for(n, 256, ctx->sm_count * 8), 256, 0, w->stream>>>(w->bs, v, w->rd, n, w->ids, w->d2);
   LAUNCH_CHECK();
-  CU(cudaMemcpyAsync(ids, ctx->ids, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaMemcpyAsync(d2, ctx->d2, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaMemcpyAsync(ids, w->ids, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, w->stream));
+  CU(cudaMemcpyAsync(d2, w->d2, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, w->stream));
+  CU(cudaStreamSynchronize(w->stream));
   return LS_OK;
 }
 
@@ -522,22 +574,23 @@ int ls_transform_cloud(ls_ctx* ctx, const float T[16], const float* in4, const f
     return fail(ctx, LS_ERR_ARG, "bad argument");
   if (n == 0) return LS_OK;
   CU(cudaSetDevice(ctx->device));
+  Workspace* w = ctx->ws[0];
   int rc;
-  if ((rc = ensure_capacity(ctx, n, n, 64, 1))) return rc;
-  CU(cudaMemcpyAsync(ctx->T0_dev + 16, T, 16 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->reading, in4, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-  if (normals && (rc = upload_normals(ctx, normals, normals_stride, n, ctx->ref_nrm_stage))) return rc;
-  transform_kernel<<<blocks_for(n, 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(
-      ctx->T0_dev + 16, ctx->reading, normals ? ctx->ref_nrm_stage : nullptr, n, ctx->rd, ctx->A.sub_nrm);
+  if ((rc = ensure_capacity(ctx, w, n, n, 64, 1))) return rc;
+  CU(cudaMemcpyAsync(w->T0_dev + 16, T, 16 * sizeof(float), cudaMemcpyHostToDevice, w->stream));
+  CU(cudaMemcpyAsync(w->reading, in4, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, w->stream));
+  if (normals && (rc = upload_normals(ctx, w, normals, normals_stride, n, w->ref_nrm_stage))) return rc;
+  transform_kernel<<<blocks_for(n, 256, ctx->sm_count * 8), 256, 0, w->stream>>>(
+      w->T0_dev + 16, w->reading, normals ? w->ref_nrm_stage : nullptr, n, w->rd, w->A.sub_nrm);
   LAUNCH_CHECK();
-  CU(cudaMemcpyAsync(out4, ctx->rd, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(out4, w->rd, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, w->stream));
   if (normals) {
-    pack_normals_kernel<<<blocks_for(n, 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(ctx->A.sub_nrm, n,
-                                                                                         (float*)ctx->A.srt_nrm);
+    pack_normals_kernel<<<blocks_for(n, 256, ctx->sm_count * 8), 256, 0, w->stream>>>(w->A.sub_nrm, n,
+                                                                                         (float*)w->A.srt_nrm);
     LAUNCH_CHECK();
-    CU(cudaMemcpyAsync(out_normals3, ctx->A.srt_nrm, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(out_normals3, w->A.srt_nrm, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, w->stream));
   }
-  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaStreamSynchronize(w->stream));
   return LS_OK;
 }
 
@@ -568,7 +621,7 @@ void ls_map_destroy(ls_map* map) {
   if (!map) return;
   if (map->ctx) {
     cudaSetDevice(map->ctx->device);
-    cudaStreamSynchronize(map->ctx->stream);
+    for (Workspace* w : map->ctx->ws) cudaStreamSynchronize(w->stream);
   }
   for (auto& s : map->slots) {
     if (s.pts) cudaFree(s.pts);
@@ -584,15 +637,16 @@ int ls_map_push_scan(ls_map* map, const float* features4, const float* normals, 
   if (!features4 || !normals || normals_stride < 3 || n < 0 || n > map->max_pts || !scan_id)
     return fail(ctx, LS_ERR_ARG, "bad argument (n=%d, max=%d)", n, map->max_pts);
   CU(cudaSetDevice(ctx->device));
+  Workspace* w = ctx->ws[0];
   const uint64_t id = map->next_id++;
   ls_scan_slot& s = map->slots[id % (uint64_t)map->capacity];
   s.used = false;
   if (n > 0) {
-    CU(cudaMemcpyAsync(s.pts, features4, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-    int rc = upload_normals(ctx, normals, normals_stride, n, s.nrm);
+    CU(cudaMemcpyAsync(s.pts, features4, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, w->stream));
+    int rc = upload_normals(ctx, w, normals, normals_stride, n, s.nrm);
     if (rc) return rc;
     // the staging buffer for normals is reused by the next upload: wait for the expand kernel
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(w->stream));
   }
   s.n = n;
   s.id = id;
@@ -623,11 +677,59 @@ int ls_icp_register_submap(ls_ctx* ctx, const ls_icp_params* prm, const ls_map* 
   const int n = rs->n, m = parts.offset[n_parts];
   if (n == 0 || m == 0) return fail(ctx, LS_ERR_CONVERGENCE, "empty reading or reference");
   CU(cudaSetDevice(ctx->device));
+  Workspace* w = ctx->ws[0];
   const Resolved r = resolve(prm);
-  if ((rc = ensure_capacity(ctx, n, m, r.max_cells, prm->max_iterations))) return rc;
-  CU(cudaEventRecord(ctx->ev0, ctx->stream));
-  if ((rc = enqueue_build(ctx, parts, r, T0))) return rc;
+  if ((rc = ensure_capacity(ctx, w, n, m, r.max_cells, prm->max_iterations))) return rc;
+  CU(cudaEventRecord(w->ev0, w->stream));
+  if ((rc = enqueue_build(ctx, w, parts, r, T0))) return rc;
   return run_icp(ctx, prm, rs->pts, n, T0, T_out, stats, opt_ids, opt_d2, opt_T_iter_hist, m);
+}
+
+// Several independent scan -> sub-map registrations in ONE cooperative launch (the multi-robot case: the
+// reference's n_laser_slam_workers tracks, reference incremental_estimator.cpp:22-26, hosted on one GPU).
+// Problem b stages on its own stream (assembly + hash build overlap across problems); the persistent kernel's
+// grid is split into `batch` CTA groups, each with its own barrier, so one problem's barrier / solve latency is
+// filled by the others' search.  Results are bit-identical to `batch` separate ls_icp_register_submap calls.
+int ls_icp_register_submap_batch(ls_ctx* ctx, const ls_icp_params* prm, const ls_map* map, int batch,
+                                 const uint64_t* reading_ids, const int* n_parts, const uint64_t* part_ids,
+                                 const float* T_parts, const float* T0s, float* T_outs, ls_icp_stats* stats, int* statuses) {
+  if (!ctx) return LS_ERR_ARG;
+  if (!map || map->ctx != ctx || batch < 1 || batch > kMaxBatch || !reading_ids || !n_parts || !part_ids || !T_parts || !T0s ||
+      !T_outs || !statuses)
+    return fail(ctx, LS_ERR_ARG, "bad argument (1 <= batch <= %d)", kMaxBatch);
+  int rc = check_params(ctx, prm);
+  if (rc) return rc;
+  CU(cudaSetDevice(ctx->device));
+  if ((rc = ensure_workspaces(ctx, batch))) return rc;
+  const Resolved r = resolve(prm);
+  std::vector<int> ns(batch);
+  int n_max = 0, part_off = 0;
+  for (int b = 0; b < batch; ++b) {
+    Workspace* w = ctx->ws[b];
+    const float* T0 = T0s + 16 * b;
+    std::memcpy(T_outs + 16 * b, T0, 16 * sizeof(float));
+    const ls_scan_slot* rs = find_slot(map, reading_ids[b]);
+    if (!rs) return fail(ctx, LS_ERR_STATE, "reading scan %llu is not resident", (unsigned long long)reading_ids[b]);
+    Parts parts;
+    if ((rc = make_parts(ctx, map, n_parts[b], part_ids + part_off, T_parts + 16 * (size_t)part_off, &parts))) return rc;
+    part_off += n_parts[b];
+    const int n = rs->n, m = parts.offset[n_parts[b]];
+    if (n == 0 || m == 0) return fail(ctx, LS_ERR_ARG, "empty reading or reference in a batch (use the single call)");
+    ns[b] = n;
+    n_max = n > n_max ? n : n_max;
+    if ((rc = ensure_capacity(ctx, w, n, m, r.max_cells, prm->max_iterations))) return rc;
+    CU(cudaEventRecord(w->ev0, w->stream));
+    if ((rc = enqueue_build(ctx, w, parts, r, T0))) return rc;
+    if ((rc = prep_icp(ctx, w, prm, rs->pts, n, T0, false, false))) return rc;
+  }
+  if ((rc = launch_icp(ctx, prm, batch, n_max))) return rc;
+  CU(cudaStreamSynchronize(ctx->ws[0]->stream));
+  for (int b = 0; b < batch; ++b) {
+    const int st = fetch_icp(ctx, ctx->ws[b], prm, ns[b], T0s + 16 * b, T_outs + 16 * b, stats ? stats + b : nullptr);
+    if (st < 0) return st;
+    statuses[b] = st;
+  }
+  return LS_OK;
 }
 
 int ls_map_assemble(ls_ctx* ctx, const ls_map* map, int n_parts, const uint64_t* part_ids, const float* T_parts,
@@ -641,20 +743,21 @@ int ls_map_assemble(ls_ctx* ctx, const ls_map* map, int n_parts, const uint64_t*
   *m_out = m;
   if (m == 0) return LS_OK;
   CU(cudaSetDevice(ctx->device));
-  if ((rc = ensure_capacity(ctx, 1, m, 64, 1))) return rc;
-  reset_build_kernel<<<1, 32, 0, ctx->stream>>>(ctx->bs);
+  Workspace* w = ctx->ws[0];
+  if ((rc = ensure_capacity(ctx, w, 1, m, 64, 1))) return rc;
+  reset_build_kernel<<<1, 32, 0, w->stream>>>(w->bs);
   LAUNCH_CHECK();
-  assemble_kernel<<<blocks_for(m, 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(parts, ctx->A.sub_pts, ctx->A.sub_nrm,
-                                                                                   ctx->bs);
+  assemble_kernel<<<blocks_for(m, 256, ctx->sm_count * 8), 256, 0, w->stream>>>(parts, w->A.sub_pts, w->A.sub_nrm,
+                                                                                   w->bs);
   LAUNCH_CHECK();
-  CU(cudaMemcpyAsync(out4, ctx->A.sub_pts, (size_t)m * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(out4, w->A.sub_pts, (size_t)m * sizeof(float4), cudaMemcpyDeviceToHost, w->stream));
   if (out_normals3) {
-    pack_normals_kernel<<<blocks_for(m, 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(ctx->A.sub_nrm, m,
-                                                                                         (float*)ctx->A.srt_nrm);
+    pack_normals_kernel<<<blocks_for(m, 256, ctx->sm_count * 8), 256, 0, w->stream>>>(w->A.sub_nrm, m,
+                                                                                         (float*)w->A.srt_nrm);
     LAUNCH_CHECK();
-    CU(cudaMemcpyAsync(out_normals3, ctx->A.srt_nrm, (size_t)m * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(out_normals3, w->A.srt_nrm, (size_t)m * 3 * sizeof(float), cudaMemcpyDeviceToHost, w->stream));
   }
-  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaStreamSynchronize(w->stream));
   return LS_OK;
 }
 

@@ -88,6 +88,7 @@ struct IcpProblem {
   int* pos;
   float* d2;
   int* ids;
+  float4* miss;  // per query: {position of the last search that found nothing, radius proven empty} (w == 0: none)
   IcpWork* work;
   float* T_hist;  // max_iterations*16 floats or null
   int want_matches;  // 1: finish with an uncapped NN pass so ids/d2 hold every point's true match
@@ -522,6 +523,7 @@ __device__ __forceinline__ void problem_barrier(unsigned int* ctr, unsigned int 
     epoch += n_ctas;
     red_release_inc(ctr);
     while (ld_relaxed_u32(ctr) < epoch) {
+      __nanosleep(64);  // the polling thread shares its SM's issue slots with a CTA that is still working
     }
   }
   __syncthreads();
@@ -607,7 +609,10 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
   chunk = (chunk + 31) & ~31;
   const int q_begin = min(n, cta * chunk), q_end = min(n, q_begin + chunk);
 
-  for (int i = q_begin + tid; i < q_end; i += kIcpThreads) P.pos[i] = -1;
+  for (int i = q_begin + tid; i < q_end; i += kIcpThreads) {
+    P.pos[i] = -1;
+    P.miss[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
 
   // Trim-aware search cap (squared metres).  TrimmedDistOutlierFilter keeps matches with d2 <= limit,
   // so a match only has to be exact if d2 <= limit; searching inside a ball of radius sqrt(cap) with
@@ -631,9 +636,28 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
       const float4 r = __ldg(P.rd + i);
       float sx, sy, sz;
       xform_point(T_iter, r.x, r.y, r.z, sx, sy, sz);
+      // Triangle inequality: a search at s_old proved that no map point lies within r_old of it; after the
+      // query moved by delta no point can lie within r_old - delta of the new position.  If that still exceeds
+      // the current cap the outcome ("no match inside the cap") is already known and the search is skipped.
+      const float4 ms = P.miss[i];
+      if (ms.w > 0.f) {
+        const float delta = sqrtf(dist2(sx, sy, sz, ms.x, ms.y, ms.z));
+        const float rem = ms.w * 0.99999f - delta * 1.00001f - g.margin;
+        if (rem > 0.f && (rem * rem) * 0.99999f > cap) {
+          P.d2[i] = INFINITY;
+          P.ids[i] = -1;
+          atomicAdd(&hist_s[1020], 1u);
+          continue;
+        }
+      }
       const int warm = P.pos[i];
       const Best b = nn_search(g, P.view, sx, sy, sz, warm, cap);
-      if (b.pos >= 0) P.pos[i] = b.pos;  // keep the last real match as the next warm start
+      if (b.pos >= 0) {
+        P.pos[i] = b.pos;  // keep the last real match as the next warm start
+        if (ms.w > 0.f) P.miss[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else if (cap < INFINITY) {
+        P.miss[i] = make_float4(sx, sy, sz, sqrtf(cap));
+      }
       P.d2[i] = b.d2;
       P.ids[i] = b.idx;
       const unsigned int key = __float_as_uint(b.d2);

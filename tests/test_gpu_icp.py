@@ -252,3 +252,26 @@ def test_full_size_properties(gpu_ctx, config2):
     assert np.abs(d["T"][:3, 3] - a["T"][:3, 3]).max() < 1e-3
     assert a["stats"].last_kept == int(np.float32(len(config2["reading"])) * np.float32(0.75)) + 1 or a["stats"].last_kept >= 98304
     assert (a["ids"] >= 0).all() and (a["ids"] < len(config2["ref"])).all()
+
+
+def test_batched_registrations_equal_separate_calls(gpu_ctx, scans, traj):
+    """ls_icp_register_submap_batch: several tracks in one cooperative launch, bit-identical to separate calls."""
+    import laser_slam_b200 as ls
+    truth, odom = traj
+    mp = gpu_ctx.create_map(8, 131072)
+    sid = [mp.push_scan(*scans[k]) for k in range(6)]
+    p = ls.default_params(max_iterations=12, use_differential=0)
+    problems = []
+    for ref, rd, ks in [(3, 4, [3, 2, 1, 0]), (4, 5, [4, 3, 2]), (2, 3, [2, 1]), (1, 2, [1, 0])]:
+        Ts = [np.eye(4, dtype=np.float32) if k == ref else (np.linalg.inv(truth[ref]) @ truth[k]).astype(np.float32) for k in ks]
+        T0 = (np.linalg.inv(truth[ref]) @ odom[rd]).astype(np.float32)
+        problems.append((sid[rd], [sid[k] for k in ks], Ts, T0))
+    single = [mp.register(*pr, p) for pr in problems]
+    for B in (1, 2, 4):
+        batch = mp.register_batch(problems[:B], p)
+        for b in range(B):
+            assert batch[b]["rc"] == 0 and np.array_equal(batch[b]["T"], single[b]["T"]), (B, b)
+            assert batch[b]["stats"].iterations == 12 and batch[b]["stats"].last_kept == single[b]["stats"].last_kept
+    again = mp.register(*problems[0], p)           # workspace 0 is still consistent after a batch
+    assert np.array_equal(again["T"], single[0]["T"])
+    mp.close()

@@ -21,3 +21,12 @@ for k in ("cell_size", "leaf_split"):
 for rep in range(reps):
     g = mp.register(sid[4], [sid[3], sid[2], sid[1], sid[0]], Tparts, T0, p)
     print(f"rep {rep}: device {g['stats'].device_ms:.3f} ms build {g['stats'].build_ms:.3f} ms iters {g['stats'].iterations}")
+
+B = int(os.environ.get("LS_BATCH", "0"))
+if B:
+    import time
+    probs = [(sid[4], [sid[3], sid[2], sid[1], sid[0]], Tparts, T0)] * B
+    call = mp.prepare_batch(probs, p)
+    for rep in range(reps + 1):
+        t0 = time.perf_counter(); rc, statuses, touts, stats = call(); dt = time.perf_counter() - t0
+        print(f"batch {B} rep {rep}: wall {dt*1e3:.3f} ms -> {dt*1e3/B:.3f} ms/registration, device {stats[0].device_ms:.3f} ms, rc {rc} {list(statuses)}")
