@@ -193,9 +193,10 @@ def cpu_baseline_sample():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours")
+    ap.add_argument("--tracks", type=int, default=8, help="independent sequences (tracks) hosted per GPU, batched per launch")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -212,12 +213,12 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = ls.Context(local)
-    truth, odom, scans = make_pool(rank)   # one independent sequence (track) per GPU
+    B = args.tracks
+    # B independent sequences (tracks) per GPU -- the reference's n_laser_slam_workers LaserTracks hosted on one device
+    tracks = [make_pool(rank * B + t) for t in range(B)]
     prm = ls.default_params(max_iterations=ITERS, use_differential=0)
-
-    # pinned host staging of the pool (what a caller's DataPoints buffers would be)
-    feats = [torch.from_numpy(s[0]).pin_memory() for s in scans]
-    nrms = [torch.from_numpy(s[1]).pin_memory() for s in scans]
+    feats = [[torch.from_numpy(s[0]).pin_memory() for s in tr[2]] for tr in tracks]   # pinned host staging
+    nrms = [[torch.from_numpy(s[1]).pin_memory() for s in tr[2]] for tr in tracks]
 
     def barrier():
         if world > 1:
@@ -232,42 +233,43 @@ def main():
         if world > 1:
             exchange.allgather(lsd.pose_record(T, status=0, key=rank))
 
-    # ------------------------------------------------------------------ resident arm (value)
-    mp = ctx.create_map(POOL + 2, N_SCAN)
-    sid = [mp.push_scan_raw(feats[k].data_ptr(), nrms[k].data_ptr(), 3, N_SCAN) for k in range(POOL)]
-    hist = [walk(s) for s in range(K_MAP + 1)]
-    dev_ms, icp_ms = [], []
-
-    # Per-step arguments (which scans form the sub-map, their float32 transforms, the initial guess) are what
-    # LaserTrack::localScanToSubMap hands to the ICP; they are staged before the clock starts so the timed region
-    # is the C-ABI call itself, not Python matrix algebra.
     n_total = args.warmup + args.steps
 
-    def stage(hist_list, sid_of, mp_obj, n_steps):
-        calls, infos = [], []
-        h = list(hist_list)
+    def stage_track(t, n_steps):
+        """Per-step arguments of track t (sub-map scans, their float32 transforms, initial guess): what
+        LaserTrack::localScanToSubMap hands to the ICP.  Staged before the clock starts."""
+        truth, odom, _ = tracks[t]
+        h = [walk(s) for s in range(K_MAP + 1)]
+        out = []
         for s in range(n_steps):
             idx = walk(s + K_MAP + 1)
             h.append(idx)
             ref, ks, Ts = submap_parts(truth, h)
             T0 = (np.linalg.inv(truth[ref]) @ odom[idx]).astype(np.float32) if abs(idx - ref) == 1 else np.eye(4, dtype=np.float32)
-            calls.append((idx, ks, Ts, T0))
-            infos.append((ref, idx))
-        return calls, infos, h
+            out.append((idx, ref, ks, Ts, T0))
+        return out
 
-    staged, infos, hist = stage(hist, sid, mp, n_total)
-    prepared = [mp.prepare(sid[idx], [sid[k] for k in ks], Ts, T0, prm) for (idx, ks, Ts, T0) in staged]
+    staged = [stage_track(t, n_total) for t in range(B)]
+
+    # ------------------------------------------------------------------ resident arm (value)
+    mp = ctx.create_map(B * POOL + 2, N_SCAN)
+    sid = [[mp.push_scan_raw(feats[t][k].data_ptr(), nrms[t][k].data_ptr(), 3, N_SCAN) for k in range(POOL)] for t in range(B)]
+    prepared = []
+    for s in range(n_total):
+        probs = [(sid[t][staged[t][s][0]], [sid[t][k] for k in staged[t][s][2]], staged[t][s][3], staged[t][s][4]) for t in range(B)]
+        prepared.append(mp.prepare_batch(probs, prm))
+    dev_ms, icp_ms = [], []
 
     def step_resident(s, record):
-        rc, tout, st = prepared[s]()
-        if rc != 0:
-            raise RuntimeError(f"registration failed rc={rc}")
+        rc, statuses, touts, stats = prepared[s]()
+        if rc != 0 or statuses.any():
+            raise RuntimeError(f"registration failed rc={rc} {list(statuses)}")
         if world > 1:
-            share_pose_delta(ls.from_colmajor(tout))
+            share_pose_delta(ls.from_colmajor(touts[0]))
         if record:
-            dev_ms.append(st.device_ms)
-            icp_ms.append(st.device_ms - st.build_ms)
-        return tout
+            dev_ms.append(max(st.device_ms for st in stats))
+            icp_ms.append(stats[0].icp_ms)
+        return touts
 
     for s in range(args.warmup):
         step_resident(s, False)
@@ -281,26 +283,36 @@ def main():
     barrier()
     t_res = time.perf_counter() - t0
     launches = ctx.launch_count - launches0
-    truth_rel = np.linalg.inv(truth[infos[-1][0]]) @ truth[infos[-1][1]]
-    pose_err = float(np.abs(ls.from_colmajor(last)[:3, 3] - truth_rel[:3, 3]).max())
+    idx, ref = staged[0][n_total - 1][0], staged[0][n_total - 1][1]
+    truth_rel = np.linalg.inv(tracks[0][0][ref]) @ tracks[0][0][idx]
+    pose_err = float(np.abs(ls.from_colmajor(last[0])[:3, 3] - truth_rel[:3, 3]).max())
+
+    # single-stream latency (one track, one registration per launch), a few steps
+    lat = []
+    for s in range(min(20, n_total)):
+        g = mp.register(sid[0][staged[0][s][0]], [sid[0][k] for k in staged[0][s][2]], staged[0][s][3], staged[0][s][4], prm)
+        lat.append(g["stats"].device_ms)
+    single_ms = float(np.median(lat))
 
     # ------------------------------------------------------------------ end-to-end arm (host buffers)
-    mp2 = ctx.create_map(K_MAP + 3, N_SCAN)
-    hist2, sid2 = [], {}
-    for s in range(K_MAP + 1):
-        idx = walk(s)
-        hist2.append(idx)
-        sid2[idx] = mp2.push_scan_raw(feats[idx].data_ptr(), nrms[idx].data_ptr(), 3, N_SCAN)
-
-    staged2, _, _ = stage(hist2, None, mp2, n_total)
+    # every step uploads the new scan of every track from pinned host memory, then registers the batch
+    mp2 = ctx.create_map(B * 16, N_SCAN)   # ring: every track keeps its last K_MAP+1 scans resident with slack
+    sid2 = [dict() for _ in range(B)]
+    for t in range(B):
+        for s in range(K_MAP + 1):
+            k = walk(s)
+            sid2[t][k] = mp2.push_scan_raw(feats[t][k].data_ptr(), nrms[t][k].data_ptr(), 3, N_SCAN)
 
     def step_e2e(s):
-        idx, ks, Ts, T0 = staged2[s]
-        sid2[idx] = mp2.push_scan_raw(feats[idx].data_ptr(), nrms[idx].data_ptr(), 3, N_SCAN)   # H2D from pinned memory
-        g = mp2.register(sid2[idx], [sid2[k] for k in ks], Ts, T0, prm)                          # D2H of T + stats inside
+        probs = []
+        for t in range(B):
+            idx, ref, ks, Ts, T0 = staged[t][s]
+            sid2[t][idx] = mp2.push_scan_raw(feats[t][idx].data_ptr(), nrms[t][idx].data_ptr(), 3, N_SCAN)   # H2D, pinned
+            probs.append((sid2[t][idx], [sid2[t][k] for k in ks], Ts, T0))
+        out = mp2.register_batch(probs, prm)                                                                   # D2H of T + stats inside
         if world > 1:
-            share_pose_delta(g["T"])
-        return g
+            share_pose_delta(out[0]["T"])
+        return out
 
     for s in range(args.warmup):
         step_e2e(s)
@@ -330,26 +342,32 @@ def main():
             traffic = json.load(open(prof)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roof = {"bound": "hbm", "kernel": "ls::icp_kernel (persistent: NN query + trimmed select + normal equations, 30 iterations)",
-            "achieved": ALG_BYTES_ICP / t_icp / 1e9, "peak": peak, "unit": "GB/s", "frac": ALG_BYTES_ICP / t_icp / 1e9 / peak,
-            "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": ALG_BYTES_ICP,
-            "kernel_ms": t_icp * 1e3,
-            "registration": {"algorithmic_bytes": ALG_BYTES_REG, "device_ms": t_dev * 1e3,
-                             "achieved": ALG_BYTES_REG / t_dev / 1e9, "frac": ALG_BYTES_REG / t_dev / 1e9 / peak}}
+    roof = {"bound": "hbm", "kernel": f"ls::icp_kernel (persistent: NN query + trimmed select + normal equations, 30 iterations, "
+                                      f"{B} registrations per launch)",
+            "achieved": B * ALG_BYTES_ICP / t_icp / 1e9, "peak": peak, "unit": "GB/s",
+            "frac": B * ALG_BYTES_ICP / t_icp / 1e9 / peak,
+            "traffic": traffic, "traffic_note": "ncu dram bytes of a ONE-registration launch (profiles/r1_icp_kernel_summary.json)",
+            "peak_source": peak_src, "algorithmic_bytes_per_launch": B * ALG_BYTES_ICP, "kernel_ms": t_icp * 1e3,
+            "registration": {"algorithmic_bytes": ALG_BYTES_REG, "device_ms_per_batch": t_dev * 1e3,
+                             "achieved": B * ALG_BYTES_REG / t_dev / 1e9, "frac": B * ALG_BYTES_REG / t_dev / 1e9 / peak}}
     cpu = cpu_baseline_sample() if args.gpus == 1 else None
     out = {
         "metric": "ICP registrations/s (131072-pt scan vs 524288-pt map, 30 iterations)",
-        "value": world * args.steps / t_res, "unit": "registrations/s", "n_gpus": args.gpus, "steps": args.steps,
+        "value": world * B * args.steps / t_res, "unit": "registrations/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: scan-to-local-map ICP, 131072-pt scan vs 524288-pt rolling map (4 scans), 30 iterations, "
-                               "one independent sequence per GPU",
-                   "l2": f"inputs larger than L2: {POOL} resident scans/rank cycled ({POOL * N_SCAN * 32 / 1e6:.0f} MB) + ~70 MB workspace",
-                   "collective": "none on the data path; one 32 B/rank NCCL all-gather of pose deltas per step when n_gpus > 1",
+        "config": {"workload": "configs[1]: scan-to-local-map ICP, 131072-pt scan vs 524288-pt rolling map (4 scans), 30 iterations",
+                   "tracks_per_gpu": B, "registrations_per_step": world * B,
+                   "concurrency": f"{B} independent sequences (tracks) per GPU; one step registers the next scan of every track in "
+                                  f"one cooperative launch (ls_icp_register_submap_batch)",
+                   "single_stream_ms_per_registration": single_ms,
+                   "l2": f"inputs larger than L2: {B * POOL} resident scans/rank cycled ({B * POOL * N_SCAN * 32 / 1e6:.0f} MB) "
+                         f"+ {B} x ~170 MB workspaces",
+                   "collective": "none on the data path; one 32 B/rank NCCL all-gather of pose records per step when n_gpus > 1",
                    "final_pose_err_vs_truth_m": pose_err},
-        "e2e": {"value": world * args.steps / t_e2e, "unit": "registrations/s",
-                "h2d_bytes_per_step": N_SCAN * 16 + N_SCAN * 12 + 16 * 4 * (K_MAP + 1) + 8 * (K_MAP + 1),
-                "d2h_bytes_per_step": 64 + 44 + 2 * 16896},
+        "e2e": {"value": world * B * args.steps / t_e2e, "unit": "registrations/s",
+                "h2d_bytes_per_step": B * (N_SCAN * 16 + N_SCAN * 12 + 16 * 4 * (K_MAP + 1) + 8 * (K_MAP + 1)),
+                "d2h_bytes_per_step": B * (64 + 48 + 2 * 16896)},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
     }
     if cpu:

@@ -66,6 +66,7 @@ typedef struct ls_icp_stats {
   int grid_cells;       /* level-0 cells */
   int grid_tables;      /* level-1 + level-2 tables */
   int grid_overflow;    /* 1 if a table pool overflowed (slower, still exact) */
+  float icp_ms;         /* CUDA-event duration of the persistent ICP kernel launch (shared by a batch) */
 } ls_icp_stats;
 
 /* ---- context ------------------------------------------------------------------------------- */

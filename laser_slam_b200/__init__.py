@@ -37,7 +37,7 @@ class IcpStats(ctypes.Structure):
     _fields_ = [("iterations", ctypes.c_int), ("converged", ctypes.c_int), ("max_iter_reached", ctypes.c_int),
                 ("last_kept", ctypes.c_int), ("last_limit", ctypes.c_float), ("used_ratio", ctypes.c_float),
                 ("device_ms", ctypes.c_float), ("build_ms", ctypes.c_float), ("grid_cells", ctypes.c_int),
-                ("grid_tables", ctypes.c_int), ("grid_overflow", ctypes.c_int)]
+                ("grid_tables", ctypes.c_int), ("grid_overflow", ctypes.c_int), ("icp_ms", ctypes.c_float)]
 
 
 class Factor(ctypes.Structure):

@@ -18,7 +18,7 @@ using namespace ls;
 // running problem (ls_icp_register_submap_batch); single-problem entry points use workspace 0.
 struct Workspace {
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev_launch = nullptr;
   int n_cap = 0, m_cap = 0, cells_cap = 0, tab_cap = 0, hist_cap = 0;
   BuildArrays A{};
   BuildState* bs = nullptr;
@@ -294,6 +294,7 @@ int launch_icp(ls_ctx* ctx, const ls_icp_params* prm, int batch, int n_max) {
   if (ctas < 1) ctas = 1;
   const IcpProblem* probs = ctx->probs_dev;
   void* args[] = {(void*)&probs, (void*)&ctas, (void*)&dp};
+  CU(cudaEventRecord(w0->ev_launch, w0->stream));
   CU(cudaLaunchCooperativeKernel((void*)icp_kernel, dim3(ctas * batch), dim3(kIcpThreads), args, 0, w0->stream));
   ++ctx->launches;
   CU(cudaEventRecord(w0->ev2, w0->stream));
@@ -331,11 +332,13 @@ int fetch_icp(ls_ctx* ctx, Workspace* w, const ls_icp_params* prm, int n, const 
     stats->last_kept = wk.last_kept;
     stats->last_limit = wk.last_limit;
     stats->used_ratio = n > 0 ? (float)wk.last_kept / (float)n : 0.f;
-    float ms = 0.f, bms = 0.f;
+    float ms = 0.f, bms = 0.f, kms = 0.f;
     cudaEventElapsedTime(&ms, w->ev0, ctx->ws[0]->ev2);  // staging of this problem .. end of the (shared) ICP launch
     cudaEventElapsedTime(&bms, w->ev0, w->ev1);
+    cudaEventElapsedTime(&kms, ctx->ws[0]->ev_launch, ctx->ws[0]->ev2);
     stats->device_ms = ms;
     stats->build_ms = bms;
+    stats->icp_ms = kms;
     stats->grid_cells = w->h_grid->n_cells0;
     stats->grid_tables = w->h_grid->n_tab1;
     stats->grid_overflow = w->h_grid->overflow;
@@ -409,7 +412,8 @@ Workspace* new_workspace() {
   Workspace* w = new Workspace();
   bool ok = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreate(&w->ev0) == cudaSuccess && cudaEventCreate(&w->ev1) == cudaSuccess &&
-            cudaEventCreate(&w->ev2) == cudaSuccess && cudaMalloc((void**)&w->bs, sizeof(BuildState)) == cudaSuccess &&
+            cudaEventCreate(&w->ev2) == cudaSuccess && cudaEventCreate(&w->ev_launch) == cudaSuccess &&
+            cudaMalloc((void**)&w->bs, sizeof(BuildState)) == cudaSuccess &&
             cudaMalloc((void**)&w->work, sizeof(IcpWork)) == cudaSuccess &&
             cudaMalloc((void**)&w->T0_dev, 64 * sizeof(float)) == cudaSuccess &&
             cudaMallocHost((void**)&w->h_work, sizeof(IcpWork)) == cudaSuccess &&
@@ -430,6 +434,7 @@ void free_workspace(Workspace* w) {
   if (w->ev0) cudaEventDestroy(w->ev0);
   if (w->ev1) cudaEventDestroy(w->ev1);
   if (w->ev2) cudaEventDestroy(w->ev2);
+  if (w->ev_launch) cudaEventDestroy(w->ev_launch);
   if (w->stream) cudaStreamDestroy(w->stream);
   delete w;
 }
