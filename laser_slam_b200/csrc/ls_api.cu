@@ -29,6 +29,7 @@ struct Workspace {
   int* pos = nullptr;
   float* d2 = nullptr;
   int* ids = nullptr;
+  float* d2_out = nullptr;
   float4* miss = nullptr;
   IcpWork* work = nullptr;
   float* T_hist = nullptr;
@@ -117,6 +118,10 @@ int ensure_capacity(ls_ctx* ctx, Workspace* w, int n, int m, int max_cells, int 
     if ((rc = dev_alloc(ctx, &w->d2, (size_t)cap))) return rc;
     if ((rc = dev_alloc(ctx, &w->ids, (size_t)cap))) return rc;
     if ((rc = dev_alloc(ctx, &w->miss, (size_t)cap))) return rc;
+    if ((rc = dev_alloc(ctx, &w->d2_out, (size_t)cap))) return rc;
+    if ((rc = dev_alloc(ctx, &w->A.qkey, (size_t)cap))) return rc;
+    if ((rc = dev_alloc(ctx, &w->A.qperm, (size_t)cap))) return rc;
+    if ((rc = dev_alloc(ctx, &w->A.rd_s, (size_t)cap))) return rc;
     w->n_cap = cap;
   }
   if (m > w->m_cap) {
@@ -137,6 +142,8 @@ int ensure_capacity(ls_ctx* ctx, Workspace* w, int n, int m, int max_cells, int 
     if ((rc = dev_alloc(ctx, &w->A.tab1, (size_t)tcap * LS_FB3))) return rc;
     if ((rc = dev_alloc(ctx, &w->A.cnt1, (size_t)tcap * LS_FB3))) return rc;
     if ((rc = dev_alloc(ctx, &w->A.tab1_cell, (size_t)tcap))) return rc;
+    if ((rc = dev_alloc(ctx, &w->A.qtab_local, (size_t)tcap * LS_FB3))) return rc;
+    if ((rc = dev_alloc(ctx, &w->A.qtab_total, (size_t)tcap))) return rc;
     CU(cudaMemsetAsync(w->A.cnt1, 0, (size_t)tcap * LS_FB3 * sizeof(uint32_t), w->stream));
     w->A.tab_cap = tcap;
     w->tab_cap = tcap;
@@ -147,6 +154,7 @@ int ensure_capacity(ls_ctx* ctx, Workspace* w, int n, int m, int max_cells, int 
     if ((rc = dev_alloc(ctx, &w->A.top, (size_t)max_cells + 1))) return rc;
     if ((rc = dev_alloc(ctx, &w->A.cnt0, (size_t)max_cells + 1))) return rc;
     if ((rc = dev_alloc(ctx, &w->A.pyr, (size_t)max_cells / 2 + 4096))) return rc;
+    if ((rc = dev_alloc(ctx, &w->A.qtop_start, (size_t)max_cells + 1))) return rc;
     CU(cudaMemsetAsync(w->A.cnt0, 0, ((size_t)max_cells + 1) * sizeof(uint32_t), w->stream));
     w->cells_cap = max_cells;
   }
@@ -238,7 +246,20 @@ int upload_normals(ls_ctx* ctx, Workspace* w, const float* normals, int stride, 
 // problem descriptor.  Enqueued on the workspace's stream; nothing synchronises.
 int prep_icp(ls_ctx* ctx, Workspace* w, const ls_icp_params* prm, const float4* reading_dev, int n, const float T0[16],
              bool want_matches, bool want_hist) {
-  reading_kernel<<<blocks_for(n, 256, ctx->sm_count * 8), 256, 0, w->stream>>>(w->bs, reading_dev, n, w->rd);
+  const int scan_tiles = (resolve(prm).max_cells + kScanTile - 1) / kScanTile;
+  const int qb = blocks_for(n, 256, ctx->sm_count * 8);
+  reading_kernel<<<qb, 256, 0, w->stream>>>(w->bs, reading_dev, n, w->rd);
+  LAUNCH_CHECK();
+  // order the queries by the map's cell keys (see q_count_kernel)
+  q_count_kernel<<<qb, 256, 0, w->stream>>>(w->bs, w->A, w->rd, n);
+  LAUNCH_CHECK();
+  q_tables_kernel<<<ctx->sm_count * 8, 256, 0, w->stream>>>(w->bs, w->A);
+  LAUNCH_CHECK();
+  q_scan_reduce_kernel<<<scan_tiles, kScanThreads, 0, w->stream>>>(w->bs, w->A);
+  LAUNCH_CHECK();
+  q_scan_apply_kernel<<<scan_tiles, kScanThreads, 0, w->stream>>>(w->bs, w->A);
+  LAUNCH_CHECK();
+  q_scatter_kernel<<<qb, 256, 0, w->stream>>>(w->A, w->rd, n);
   LAUNCH_CHECK();
   CU(cudaEventRecord(w->ev1, w->stream));
   CU(cudaMemsetAsync(w->work, 0, sizeof(IcpWork), w->stream));
@@ -249,11 +270,13 @@ int prep_icp(ls_ctx* ctx, Workspace* w, const ls_icp_params* prm, const float4* 
   hp.view.pts = w->A.srt_pts;
   hp.view.pyr = w->A.pyr;
   hp.nrm = w->A.srt_nrm;
-  hp.rd = w->rd;
+  hp.rd = w->A.rd_s;
   hp.n = n;
   hp.pos = w->pos;
   hp.d2 = w->d2;
   hp.ids = w->ids;
+  hp.d2_out = w->d2_out;
+  hp.qperm = w->A.qperm;
   hp.miss = w->miss;
   hp.work = w->work;
   hp.T_hist = want_hist ? w->T_hist : nullptr;
@@ -358,7 +381,7 @@ int run_icp(ls_ctx* ctx, const ls_icp_params* prm, const float4* reading_dev, in
   if ((rc = prep_icp(ctx, w, prm, reading_dev, n, T0, opt_ids || opt_d2, opt_T_hist != nullptr))) return rc;
   if ((rc = launch_icp(ctx, prm, 1, n))) return rc;
   if (opt_ids) CU(cudaMemcpyAsync(opt_ids, w->ids, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, w->stream));
-  if (opt_d2) CU(cudaMemcpyAsync(opt_d2, w->d2, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, w->stream));
+  if (opt_d2) CU(cudaMemcpyAsync(opt_d2, w->d2_out, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, w->stream));
   if (opt_T_hist)
     CU(cudaMemcpyAsync(opt_T_hist, w->T_hist, (size_t)prm->max_iterations * 16 * sizeof(float), cudaMemcpyDeviceToHost,
                        w->stream));
@@ -426,7 +449,8 @@ void free_workspace(Workspace* w) {
   if (w->stream) cudaStreamSynchronize(w->stream);
   void* bufs[] = {w->A.sub_pts, w->A.sub_nrm, w->A.srt_pts, w->A.srt_nrm, w->A.pkey, w->A.top, w->A.cnt0, w->A.tab1, w->A.cnt1,
                   w->A.tab1_cell, w->A.pyr, w->bs, w->reading, w->rd, w->ref_stage, w->ref_nrm_stage, w->nrm_raw, w->pos, w->d2,
-                  w->ids, w->miss, w->work, w->T_hist, w->T0_dev, w->phase_ns};
+                  w->ids, w->miss, w->work, w->T_hist, w->T0_dev, w->phase_ns, w->d2_out, w->A.qkey, w->A.qperm, w->A.rd_s,
+                  w->A.qtab_local, w->A.qtab_total, w->A.qtop_start};
   for (void* b : bufs)
     if (b) cudaFree(b);
   if (w->h_work) cudaFreeHost(w->h_work);

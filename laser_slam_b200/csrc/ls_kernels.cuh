@@ -56,6 +56,13 @@ struct BuildArrays {
   uint32_t* tab1_cell;   // level-0 cell of each fine table
   int tab_cap;
   unsigned long long* pyr;  // occupancy pyramid masks
+  // query ordering (same keys as the map): rank -> query
+  uint32_t* qkey;        // per query: tag | cell key
+  uint32_t* qtop_start;  // per level-0 cell: first rank
+  uint32_t* qtab_local;  // per fine cell: rank offset inside its table
+  uint32_t* qtab_total;  // per table: number of queries
+  uint32_t* qperm;       // rank -> original query index
+  float4* rd_s;          // pre-transformed reading in rank order
 };
 
 struct IcpParamsDev {
@@ -86,8 +93,10 @@ struct IcpProblem {
   const float4* rd;   // pre-transformed reading
   int n;
   int* pos;
-  float* d2;
-  int* ids;
+  float* d2;            // per rank (internal)
+  int* ids;             // original order, written by the final pass only
+  float* d2_out;        // original order, written by the final pass only
+  const uint32_t* qperm;  // rank -> original query index
   float4* miss;  // per query: {position of the last search that found nothing, radius proven empty} (w == 0: none)
   IcpWork* work;
   float* T_hist;  // max_iterations*16 floats or null
@@ -422,6 +431,156 @@ __global__ void __launch_bounds__(256) scatter_kernel(BuildArrays A, int m) {
   }
 }
 
+// ---- query ordering ----------------------------------------------------------------------------------------
+// The reading is processed in the order of the map's own cell keys (level-0 cell, fine cell): threads of a warp
+// then walk the same rows and candidates (L1 reuse, convergent loops) instead of 32 different places along a
+// lidar ring.  It is a counting sort that borrows the map's histogram arrays -- they are all zero again once the
+// map's scatter has run, and the cursors below return them to zero.  Results do not depend on the order: every
+// reduction of the ICP kernel is an exact integer sum.
+__global__ void __launch_bounds__(256) q_count_kernel(const BuildState* __restrict__ bs, BuildArrays A,
+                                                      const float4* __restrict__ rd, int n) {
+  __shared__ Grid g;
+  if (threadIdx.x == 0) g = bs->grid;
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = __ldg(rd + i);
+    const int c0 = top_index(g, p.x, p.y, p.z);
+    const Entry e = A.top[c0];
+    uint32_t key;
+    if (e.meta < 0) {
+      float lx, ly, lz;
+      top_origin(g, c0, lx, ly, lz);
+      key = (uint32_t)(~e.meta) * (uint32_t)LS_FB3 + (uint32_t)sub_index(p.x, p.y, p.z, lx, ly, lz, g.inv1);
+      atomicAdd(&A.cnt1[key], 1u);
+      key |= kTag1;
+    } else {
+      key = (uint32_t)c0;
+      atomicAdd(&A.cnt0[c0], 1u);
+    }
+    A.qkey[i] = key;
+  }
+}
+
+__global__ void __launch_bounds__(256) q_tables_kernel(BuildState* bs, BuildArrays A) {
+  const int n_tab = min(bs->grid.n_tab1, A.tab_cap);
+  constexpr int per = LS_FB3 / 256;
+  __shared__ unsigned int ws[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int t = blockIdx.x; t < n_tab; t += gridDim.x) {
+    const uint32_t* cnt = A.cnt1 + (size_t)t * LS_FB3;
+    unsigned int c[per], loc = 0;
+#pragma unroll
+    for (int k = 0; k < per; ++k) {
+      c[k] = cnt[threadIdx.x * per + k];
+      loc += c[k];
+    }
+    unsigned int incl = loc;
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    __syncthreads();
+    if (lane == 31) ws[warp] = incl;
+    __syncthreads();
+    unsigned int woff = 0, total = 0;
+    for (int w = 0; w < 8; ++w) {
+      if (w < warp) woff += ws[w];
+      total += ws[w];
+    }
+    unsigned int run = woff + incl - loc;
+#pragma unroll
+    for (int k = 0; k < per; ++k) {
+      A.qtab_local[(size_t)t * LS_FB3 + threadIdx.x * per + k] = run;
+      run += c[k];
+    }
+    if (threadIdx.x == 0) A.qtab_total[t] = total;
+  }
+}
+
+__device__ __forceinline__ unsigned int q_cell_count(const BuildArrays& A, int c) {
+  const Entry e = A.top[c];
+  return e.meta < 0 ? A.qtab_total[~e.meta] : A.cnt0[c];
+}
+
+__global__ void __launch_bounds__(kScanThreads) q_scan_reduce_kernel(BuildState* bs, BuildArrays A) {
+  const int n = bs->grid.n_cells0;
+  const int base = blockIdx.x * kScanTile;
+  if (base >= n) return;
+  unsigned int s = 0;
+  for (int k = threadIdx.x; k < kScanTile; k += kScanThreads) {
+    const int c = base + k;
+    if (c < n) s += q_cell_count(A, c);
+  }
+  s = __reduce_add_sync(0xffffffffu, s);
+  __shared__ unsigned int ws[kScanThreads / 32];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = 0;
+    for (int w = 0; w < kScanThreads / 32; ++w) t += ws[w];
+    bs->tile_sums[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(kScanThreads) q_scan_apply_kernel(BuildState* bs, BuildArrays A) {
+  const int n = bs->grid.n_cells0;
+  const int base = blockIdx.x * kScanTile;
+  if (base >= n) return;
+  __shared__ unsigned int ws[kScanThreads / 32];
+  __shared__ unsigned int tile_off;
+  unsigned int s = 0;
+  for (int u = threadIdx.x; u < (int)blockIdx.x; u += kScanThreads) s += bs->tile_sums[u];
+  s = __reduce_add_sync(0xffffffffu, s);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = 0;
+    for (int w = 0; w < kScanThreads / 32; ++w) t += ws[w];
+    tile_off = t;
+  }
+  __syncthreads();
+  constexpr int per = kScanTile / kScanThreads;
+  unsigned int c[per], loc = 0;
+  const int first = base + threadIdx.x * per;
+#pragma unroll
+  for (int k = 0; k < per; ++k) {
+    c[k] = (first + k < n) ? q_cell_count(A, first + k) : 0u;
+    loc += c[k];
+  }
+  unsigned int incl = loc;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  __syncthreads();
+  if (lane == 31) ws[warp] = incl;
+  __syncthreads();
+  unsigned int woff = 0;
+  for (int w = 0; w < warp; ++w) woff += ws[w];
+  unsigned int run = tile_off + woff + incl - loc;
+#pragma unroll
+  for (int k = 0; k < per; ++k) {
+    if (first + k < n) A.qtop_start[first + k] = run;
+    run += c[k];
+  }
+}
+
+__global__ void __launch_bounds__(256) q_scatter_kernel(BuildArrays A, const float4* __restrict__ rd, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t k = A.qkey[i];
+    uint32_t rank;
+    if (k & kTag1) {
+      const uint32_t key = k & kKeyMask;
+      rank = A.qtop_start[A.tab1_cell[key / (uint32_t)LS_FB3]] + A.qtab_local[key] + atomicSub(&A.cnt1[key], 1u) - 1u;
+    } else {
+      rank = A.qtop_start[k] + atomicSub(&A.cnt0[k], 1u) - 1u;
+    }
+    A.rd_s[rank] = __ldg(rd + i);
+    A.qperm[rank] = (uint32_t)i;
+  }
+}
+
 // ---- reading pre-transform: R' = T_refMean_dataIn * R ----------------------------------------------
 __global__ void __launch_bounds__(256) reading_kernel(const BuildState* __restrict__ bs, const float4* __restrict__ in,
                                                       int n, float4* __restrict__ out) {
@@ -645,7 +804,6 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
         const float rem = ms.w * 0.99999f - delta * 1.00001f - g.margin;
         if (rem > 0.f && (rem * rem) * 0.99999f > cap) {
           P.d2[i] = INFINITY;
-          P.ids[i] = -1;
           atomicAdd(&hist_s[1020], 1u);
           continue;
         }
@@ -659,7 +817,6 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
         P.miss[i] = make_float4(sx, sy, sz, sqrtf(cap));
       }
       P.d2[i] = b.d2;
-      P.ids[i] = b.idx;
       const unsigned int key = __float_as_uint(b.d2);
       if (key <= 0x7f800000u) atomicAdd(&hist_s[key >> 21], 1u);  // non-negative; +inf (no match in cap) -> bin 1020
     }
@@ -883,8 +1040,9 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
       float sx, sy, sz;
       xform_point(T_last, r.x, r.y, r.z, sx, sy, sz);
       const Best b = nn_search(g, P.view, sx, sy, sz, P.pos[i], INFINITY);
-      P.d2[i] = b.d2;
-      P.ids[i] = b.idx;
+      const uint32_t orig = __ldg(P.qperm + i);
+      P.d2_out[orig] = b.d2;
+      P.ids[orig] = b.idx;
     }
   }
 
