@@ -316,7 +316,8 @@ int launch_icp(ls_ctx* ctx, const ls_icp_params* prm, int batch, int n_max) {
   if (ctas > need) ctas = need;
   if (ctas < 1) ctas = 1;
   const IcpProblem* probs = ctx->probs_dev;
-  void* args[] = {(void*)&probs, (void*)&ctas, (void*)&dp};
+  int dynamic = batch > 1 ? 1 : 0;  // several problems: warps pull work from per-problem counters
+  void* args[] = {(void*)&probs, (void*)&ctas, (void*)&dp, (void*)&dynamic};
   CU(cudaEventRecord(w0->ev_launch, w0->stream));
   CU(cudaLaunchCooperativeKernel((void*)icp_kernel, dim3(ctas * batch), dim3(kIcpThreads), args, 0, w0->stream));
   ++ctx->launches;

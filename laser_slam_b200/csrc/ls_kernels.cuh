@@ -78,6 +78,7 @@ struct IcpWork {
   unsigned int pad0[31];
   unsigned int hist[2][3][2048];
   unsigned long long acc[2][32];
+  unsigned int qctr[2];  // phase-A work counters (next unclaimed query), one per iteration parity
   float T_out[16];
   int status, iterations, converged, max_iter_reached, last_kept;
   float last_limit;
@@ -733,8 +734,53 @@ __device__ __forceinline__ void block_select(const unsigned int* ghist, int nbin
   __syncthreads();
 }
 
+// Per-query state accessors.  With dynamic scheduling the state crosses CTAs (written by whichever warp claimed
+// the query, read by the static owner in phases B-D): then it goes through L2 (.cg), never through L1.
+template <bool CG, typename T>
+__device__ __forceinline__ T ld_state(const T* p) {
+  return CG ? __ldcg(p) : *p;
+}
+template <bool CG, typename T>
+__device__ __forceinline__ void st_state(T* p, T v) {
+  if (CG) __stcg(p, v);
+  else *p = v;
+}
+
+// Phase A for one query: transform, (maybe) skip, search inside the cap, record the outcome.
+template <bool CG>
+__device__ __forceinline__ void phase_a_query(const Grid& g, const IcpProblem& P, const float* T_iter, int i, float cap,
+                                              unsigned int* hist_s) {
+  const float4 r = __ldg(P.rd + i);
+  float sx, sy, sz;
+  xform_point(T_iter, r.x, r.y, r.z, sx, sy, sz);
+  // Triangle inequality: a search at s_old proved that no map point lies within r_old of it; after the query
+  // moved by delta no point can lie within r_old - delta of the new position.  If that still exceeds the current
+  // cap the outcome ("no match inside the cap") is already known and the search is skipped.
+  const float4 ms = ld_state<CG>(P.miss + i);
+  if (ms.w > 0.f) {
+    const float delta = sqrtf(dist2(sx, sy, sz, ms.x, ms.y, ms.z));
+    const float rem = ms.w * 0.99999f - delta * 1.00001f - g.margin;
+    if (rem > 0.f && (rem * rem) * 0.99999f > cap) {
+      st_state<CG>(P.d2 + i, INFINITY);
+      atomicAdd(&hist_s[1020], 1u);
+      return;
+    }
+  }
+  const int warm = ld_state<CG>(P.pos + i);
+  const Best b = nn_search(g, P.view, sx, sy, sz, warm, cap);
+  if (b.pos >= 0) {
+    st_state<CG>(P.pos + i, b.pos);  // keep the last real match as the next warm start
+    if (ms.w > 0.f) st_state<CG>(P.miss + i, make_float4(0.f, 0.f, 0.f, 0.f));
+  } else if (cap < INFINITY) {
+    st_state<CG>(P.miss + i, make_float4(sx, sy, sz, sqrtf(cap)));
+  }
+  st_state<CG>(P.d2 + i, b.d2);
+  const unsigned int key = __float_as_uint(b.d2);
+  if (key <= 0x7f800000u) atomicAdd(&hist_s[key >> 21], 1u);  // non-negative; +inf (no match in cap) -> bin 1020
+}
+
 __global__ void __launch_bounds__(kIcpThreads, 2)
-icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParamsDev prm) {
+icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParamsDev prm, int dynamic) {
   const int pi = blockIdx.x / ctas_per_problem;
   const int cta = blockIdx.x - pi * ctas_per_problem;
   const IcpProblem& P = probs[pi];
@@ -768,10 +814,13 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
   chunk = (chunk + 31) & ~31;
   const int q_begin = min(n, cta * chunk), q_end = min(n, q_begin + chunk);
 
+  // Per-query state (pos, d2, miss) is written by whichever warp claimed the query in phase A and read by the
+  // static owner in phases B-D, i.e. it crosses CTAs: always accessed with .cg (L2) loads/stores, never through L1.
   for (int i = q_begin + tid; i < q_end; i += kIcpThreads) {
-    P.pos[i] = -1;
-    P.miss[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __stcg(P.pos + i, -1);
+    __stcg(P.miss + i, make_float4(0.f, 0.f, 0.f, 0.f));
   }
+  (void)lane;
 
   // Trim-aware search cap (squared metres).  TrimmedDistOutlierFilter keeps matches with d2 <= limit,
   // so a match only has to be exact if d2 <= limit; searching inside a ball of radius sqrt(cap) with
@@ -780,6 +829,7 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
   // +inf histogram bin, and if the quantile lands in that bin the search is redone with a larger cap.
   float cap = 0.25f;
   unsigned int epoch = 0;
+  problem_barrier(&W->barrier, G, epoch);  // the state initialised above is read by other CTAs
   int hist_count = 1;  // entries in qh/th
   int iter = 0, converged = 0, max_reached = 0, last_kept = 0;
   float last_limit = 0.f;
@@ -790,39 +840,22 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
     // ---------------- phase A: K2 nearest neighbour + level-1 histogram ----------------
     for (int k = tid; k < 2048; k += kIcpThreads) hist_s[k] = 0u;
     __syncthreads();
-    const long long wc0 = clock64();
-    for (int i = q_begin + tid; i < q_end; i += kIcpThreads) {
-      const float4 r = __ldg(P.rd + i);
-      float sx, sy, sz;
-      xform_point(T_iter, r.x, r.y, r.z, sx, sy, sz);
-      // Triangle inequality: a search at s_old proved that no map point lies within r_old of it; after the
-      // query moved by delta no point can lie within r_old - delta of the new position.  If that still exceeds
-      // the current cap the outcome ("no match inside the cap") is already known and the search is skipped.
-      const float4 ms = P.miss[i];
-      if (ms.w > 0.f) {
-        const float delta = sqrtf(dist2(sx, sy, sz, ms.x, ms.y, ms.z));
-        const float rem = ms.w * 0.99999f - delta * 1.00001f - g.margin;
-        if (rem > 0.f && (rem * rem) * 0.99999f > cap) {
-          P.d2[i] = INFINITY;
-          atomicAdd(&hist_s[1020], 1u);
-          continue;
-        }
+    if (dynamic) {
+      // Dynamic scheduling (several problems per launch): warps claim 32 consecutive queries at a time from the
+      // problem's counter, so every warp of the problem runs out of work at (almost) the same moment instead of
+      // parking at the barrier -- and starving the co-resident CTA of another problem -- while the slowest
+      // static chunk finishes.
+      for (;;) {
+        unsigned int base = 0;
+        if (lane == 0) base = atomicAdd(&W->qctr[par], 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= (unsigned int)n) break;
+        const int i = (int)base + lane;
+        if (i < n) phase_a_query<true>(g, P, T_iter, i, cap, hist_s);
       }
-      const int warm = P.pos[i];
-      const Best b = nn_search(g, P.view, sx, sy, sz, warm, cap);
-      if (b.pos >= 0) {
-        P.pos[i] = b.pos;  // keep the last real match as the next warm start
-        if (ms.w > 0.f) P.miss[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      } else if (cap < INFINITY) {
-        P.miss[i] = make_float4(sx, sy, sz, sqrtf(cap));
-      }
-      P.d2[i] = b.d2;
-      const unsigned int key = __float_as_uint(b.d2);
-      if (key <= 0x7f800000u) atomicAdd(&hist_s[key >> 21], 1u);  // non-negative; +inf (no match in cap) -> bin 1020
-    }
-    if (P.warp_cyc && iter == 10) {
-      __syncwarp();
-      if (lane == 0) P.warp_cyc[cta * (kIcpThreads / 32) + (tid >> 5)] = (unsigned int)(clock64() - wc0);
+    } else {
+      // One problem owns the whole grid: one query per thread, state stays in the owning SM's L1.
+      for (int i = q_begin + tid; i < q_end; i += kIcpThreads) phase_a_query<false>(g, P, T_iter, i, cap, hist_s);
     }
     __syncthreads();
     for (int k = tid; k < 1024; k += kIcpThreads) {
@@ -848,8 +881,10 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
       }
       cap = cap < 64.0f ? cap * 16.0f : INFINITY;
       problem_barrier(&W->barrier, G, epoch);  // everyone has read the histogram
-      if (cta == 0)
+      if (cta == 0) {
         for (int k = tid; k < 2048; k += kIcpThreads) W->hist[par][0][k] = 0u;
+        if (tid == 0) W->qctr[par] = 0u;
+      }
       problem_barrier(&W->barrier, G, epoch);
       continue;  // redo phase A of this iteration with the larger cap
     }
@@ -858,11 +893,12 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
       unsigned int* h = &W->hist[par ^ 1][0][0];
       for (int k = tid; k < 3 * 2048; k += kIcpThreads) h[k] = 0u;
       if (tid < 32) W->acc[par ^ 1][tid] = 0ull;
+      if (tid == 0) W->qctr[par ^ 1] = 0u;
     }
     for (int k = tid; k < 2048; k += kIcpThreads) hist_s[k] = 0u;
     __syncthreads();
     for (int i = q_begin + tid; i < q_end; i += kIcpThreads) {
-      const unsigned int key = __float_as_uint(P.d2[i]);
+      const unsigned int key = __float_as_uint(dynamic ? __ldcg(P.d2 + i) : P.d2[i]);
       if (key < 0x7f800000u && (key >> 21) == bin1) atomicAdd(&hist_s[(key >> 10) & 2047u], 1u);
     }
     __syncthreads();
@@ -880,7 +916,7 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
     __syncthreads();
     const unsigned int prefix12 = (bin1 << 11) | bin2;
     for (int i = q_begin + tid; i < q_end; i += kIcpThreads) {
-      const unsigned int key = __float_as_uint(P.d2[i]);
+      const unsigned int key = __float_as_uint(dynamic ? __ldcg(P.d2 + i) : P.d2[i]);
       if (key < 0x7f800000u && (key >> 10) == prefix12) atomicAdd(&hist_s[key & 1023u], 1u);
     }
     __syncthreads();
@@ -907,8 +943,8 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
 #pragma unroll
       for (int k = 0; k < 6; ++k) f[k] = 0.f;
       if (i < q_end) {
-        const float d = P.d2[i];
-        const int pos = P.pos[i];
+        const float d = dynamic ? __ldcg(P.d2 + i) : P.d2[i];
+        const int pos = dynamic ? __ldcg(P.pos + i) : P.pos[i];
         if (d <= limit && pos >= 0) {
           keep = true;
           const float4 r = __ldg(P.rd + i);
@@ -1039,7 +1075,7 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
       const float4 r = __ldg(P.rd + i);
       float sx, sy, sz;
       xform_point(T_last, r.x, r.y, r.z, sx, sy, sz);
-      const Best b = nn_search(g, P.view, sx, sy, sz, P.pos[i], INFINITY);
+      const Best b = nn_search(g, P.view, sx, sy, sz, __ldcg(P.pos + i), INFINITY);
       const uint32_t orig = __ldg(P.qperm + i);
       P.d2_out[orig] = b.d2;
       P.ids[orig] = b.idx;
