@@ -30,7 +30,6 @@ struct Workspace {
   float* d2 = nullptr;
   int* ids = nullptr;
   float* d2_out = nullptr;
-  float4* miss = nullptr;
   IcpWork* work = nullptr;
   float* T_hist = nullptr;
   unsigned long long* phase_ns = nullptr;  // debug (LS_PHASE_TIMING=1)
@@ -117,7 +116,6 @@ int ensure_capacity(ls_ctx* ctx, Workspace* w, int n, int m, int max_cells, int 
     if ((rc = dev_alloc(ctx, &w->pos, (size_t)cap))) return rc;
     if ((rc = dev_alloc(ctx, &w->d2, (size_t)cap))) return rc;
     if ((rc = dev_alloc(ctx, &w->ids, (size_t)cap))) return rc;
-    if ((rc = dev_alloc(ctx, &w->miss, (size_t)cap))) return rc;
     if ((rc = dev_alloc(ctx, &w->d2_out, (size_t)cap))) return rc;
     if ((rc = dev_alloc(ctx, &w->A.qkey, (size_t)cap))) return rc;
     if ((rc = dev_alloc(ctx, &w->A.qperm, (size_t)cap))) return rc;
@@ -277,7 +275,6 @@ int prep_icp(ls_ctx* ctx, Workspace* w, const ls_icp_params* prm, const float4* 
   hp.ids = w->ids;
   hp.d2_out = w->d2_out;
   hp.qperm = w->A.qperm;
-  hp.miss = w->miss;
   hp.work = w->work;
   hp.T_hist = want_hist ? w->T_hist : nullptr;
   hp.want_matches = want_matches ? 1 : 0;
@@ -450,7 +447,7 @@ void free_workspace(Workspace* w) {
   if (w->stream) cudaStreamSynchronize(w->stream);
   void* bufs[] = {w->A.sub_pts, w->A.sub_nrm, w->A.srt_pts, w->A.srt_nrm, w->A.pkey, w->A.top, w->A.cnt0, w->A.tab1, w->A.cnt1,
                   w->A.tab1_cell, w->A.pyr, w->bs, w->reading, w->rd, w->ref_stage, w->ref_nrm_stage, w->nrm_raw, w->pos, w->d2,
-                  w->ids, w->miss, w->work, w->T_hist, w->T0_dev, w->phase_ns, w->d2_out, w->A.qkey, w->A.qperm, w->A.rd_s,
+                  w->ids, w->work, w->T_hist, w->T0_dev, w->phase_ns, w->d2_out, w->A.qkey, w->A.qperm, w->A.rd_s,
                   w->A.qtab_local, w->A.qtab_total, w->A.qtop_start};
   for (void* b : bufs)
     if (b) cudaFree(b);

@@ -98,7 +98,6 @@ struct IcpProblem {
   int* ids;             // original order, written by the final pass only
   float* d2_out;        // original order, written by the final pass only
   const uint32_t* qperm;  // rank -> original query index
-  float4* miss;  // per query: {position of the last search that found nothing, radius proven empty} (w == 0: none)
   IcpWork* work;
   float* T_hist;  // max_iterations*16 floats or null
   int want_matches;  // 1: finish with an uncapped NN pass so ids/d2 hold every point's true match
@@ -753,27 +752,9 @@ __device__ __forceinline__ void phase_a_query(const Grid& g, const IcpProblem& P
   const float4 r = __ldg(P.rd + i);
   float sx, sy, sz;
   xform_point(T_iter, r.x, r.y, r.z, sx, sy, sz);
-  // Triangle inequality: a search at s_old proved that no map point lies within r_old of it; after the query
-  // moved by delta no point can lie within r_old - delta of the new position.  If that still exceeds the current
-  // cap the outcome ("no match inside the cap") is already known and the search is skipped.
-  const float4 ms = ld_state<CG>(P.miss + i);
-  if (ms.w > 0.f) {
-    const float delta = sqrtf(dist2(sx, sy, sz, ms.x, ms.y, ms.z));
-    const float rem = ms.w * 0.99999f - delta * 1.00001f - g.margin;
-    if (rem > 0.f && (rem * rem) * 0.99999f > cap) {
-      st_state<CG>(P.d2 + i, INFINITY);
-      atomicAdd(&hist_s[1020], 1u);
-      return;
-    }
-  }
   const int warm = ld_state<CG>(P.pos + i);
   const Best b = nn_search(g, P.view, sx, sy, sz, warm, cap);
-  if (b.pos >= 0) {
-    st_state<CG>(P.pos + i, b.pos);  // keep the last real match as the next warm start
-    if (ms.w > 0.f) st_state<CG>(P.miss + i, make_float4(0.f, 0.f, 0.f, 0.f));
-  } else if (cap < INFINITY) {
-    st_state<CG>(P.miss + i, make_float4(sx, sy, sz, sqrtf(cap)));
-  }
+  if (b.pos >= 0) st_state<CG>(P.pos + i, b.pos);  // keep the last real match as the next warm start
   st_state<CG>(P.d2 + i, b.d2);
   const unsigned int key = __float_as_uint(b.d2);
   if (key <= 0x7f800000u) atomicAdd(&hist_s[key >> 21], 1u);  // non-negative; +inf (no match in cap) -> bin 1020
@@ -818,7 +799,6 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
   // static owner in phases B-D, i.e. it crosses CTAs: always accessed with .cg (L2) loads/stores, never through L1.
   for (int i = q_begin + tid; i < q_end; i += kIcpThreads) {
     __stcg(P.pos + i, -1);
-    __stcg(P.miss + i, make_float4(0.f, 0.f, 0.f, 0.f));
   }
   (void)lane;
 
