@@ -126,6 +126,16 @@ int ls_map_push_scan(ls_map* map, const float* features4, const float* normals, 
                      uint64_t* scan_id);
 int ls_map_scan_size(const ls_map* map, uint64_t scan_id); /* points, or <0 if evicted/unknown */
 
+/* Surface normals on the device: replaces the SurfaceNormal / SamplingSurfaceNormal
+ * DataPointsFilters the reference applies to every input scan and to the sub-map
+ * (laser_slam/configurations/icp_default.yaml:5-7, laser_slam/src/laser_track.cpp:27,146).  For every point: exact
+ * `knn` nearest neighbours (self included), covariance, eigenvector of the smallest eigenvalue, flipped towards the
+ * sensor (origin of the scan frame).  Points with fewer than 3 neighbours get a zero normal.  3 <= knn <= 16.
+ * Unlike the reference's filter this one is deterministic (no rand()-based sub-sampling). */
+int ls_estimate_normals(ls_ctx* ctx, const float* features4, int n, int knn, float* out_normals3);
+/* ls_map_push_scan for clouds that arrive without normals: they are estimated on the device into the slot. */
+int ls_map_push_scan_estimate_normals(ls_map* map, const float* features4, int n, int knn, uint64_t* scan_id);
+
 /* Scan -> sub-map registration on resident data.  The reference is the concatenation, in order,
  * of scans part_ids[0..n_parts) each transformed by T_parts[16*p..] (float32, already passed
  * through correctTransformationMatrix by the caller; an exact identity matrix copies the scan

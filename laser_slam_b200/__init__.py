@@ -97,6 +97,8 @@ def lib():
         L.ls_map_scan_size.argtypes = [vp, u64]
         L.ls_icp_register_submap.argtypes = [vp, PP, vp, u64, ci, vp, vp, vp, vp, PS, vp, vp, vp]
         L.ls_map_assemble.argtypes = [vp, vp, ci, vp, vp, vp, vp, ctypes.POINTER(ci)]
+        L.ls_estimate_normals.argtypes = [vp, vp, ci, ci, vp]
+        L.ls_map_push_scan_estimate_normals.argtypes = [vp, vp, ci, ci, ctypes.POINTER(u64)]
         L.ls_icp_register_submap_batch.argtypes = [vp, PP, vp, ci, vp, vp, vp, vp, vp, vp, vp, vp]
         L.ls_pg_create.argtypes = [ci, ctypes.POINTER(vp)]
         L.ls_pg_destroy.argtypes = [vp]
@@ -236,6 +238,13 @@ class Context:
                                              _ptr(nout)))
         return (out, nout) if normals3 is not None else out
 
+    def estimate_normals(self, pts4, knn=10):
+        """Surface normals of a cloud (scan frame) on the device: exact kNN -> covariance -> smallest eigenvector."""
+        pts4 = _f32c(pts4, 4)
+        out = np.empty((max(pts4.shape[0], 1), 3), np.float32)
+        self._check(lib().ls_estimate_normals(self._h, pts4.ctypes.data, pts4.shape[0], knn, out.ctypes.data))
+        return out[:pts4.shape[0]]
+
     def create_map(self, capacity_scans, max_pts_per_scan):
         return Map(self, capacity_scans, max_pts_per_scan)
 
@@ -267,6 +276,12 @@ class Map:
         sid = ctypes.c_uint64(0)
         self.ctx._check(lib().ls_map_push_scan(self._h, f.ctypes.data, nrm.ctypes.data, nrm.shape[1], f.shape[0],
                                                ctypes.byref(sid)))
+        return sid.value
+
+    def push_scan_estimate_normals(self, features4, knn=10):
+        f = _f32c(features4, 4)
+        sid = ctypes.c_uint64(0)
+        self.ctx._check(lib().ls_map_push_scan_estimate_normals(self._h, f.ctypes.data, f.shape[0], knn, ctypes.byref(sid)))
         return sid.value
 
     def push_scan_raw(self, feat_ptr, nrm_ptr, nrm_stride, n):

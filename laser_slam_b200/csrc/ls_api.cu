@@ -682,6 +682,71 @@ int ls_map_push_scan(ls_map* map, const float* features4, const float* normals, 
   return LS_OK;
 }
 
+namespace {
+// Normals of a device-resident cloud (float4, scan frame) into nrm_out (float4, same order): build the cloud's own
+// spatial hash on workspace 0, then exact kNN + covariance + smallest eigenvector per point.
+int enqueue_normals(ls_ctx* ctx, Workspace* w, const float4* pts_dev, int n, int knn, float4* nrm_out) {
+  ls_icp_params dflt;
+  ls_icp_default_params(&dflt);
+  const Resolved r = resolve(&dflt);
+  int rc;
+  if ((rc = ensure_capacity(ctx, w, n, n, r.max_cells, 1))) return rc;
+  Parts parts;
+  std::memset(&parts, 0, sizeof(parts));
+  parts.n_parts = 1;
+  parts.offset[1] = n;
+  parts.pts[0] = pts_dev;
+  parts.nrm[0] = pts_dev;  // normals are an output here; the assembly pass just needs a readable array
+  parts.identity[0] = 1;
+  const float I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  if ((rc = enqueue_build(ctx, w, parts, r, I))) return rc;
+  GridView v{w->A.top, w->A.tab1, w->A.srt_pts, w->A.pyr};
+  knn_normals_kernel<<<blocks_for(n, 128, ctx->sm_count * 16), 128, 0, w->stream>>>(w->bs, v, w->A.sub_pts, n, knn, nrm_out);
+  LAUNCH_CHECK();
+  return LS_OK;
+}
+}  // namespace
+
+int ls_estimate_normals(ls_ctx* ctx, const float* features4, int n, int knn, float* out_normals3) {
+  if (!ctx) return LS_ERR_ARG;
+  if (!features4 || !out_normals3 || n < 0 || knn < 3 || knn > LS_KNN_MAX) return fail(ctx, LS_ERR_ARG, "bad argument (3 <= knn <= %d)", LS_KNN_MAX);
+  if (n == 0) return LS_OK;
+  CU(cudaSetDevice(ctx->device));
+  Workspace* w = ctx->ws[0];
+  int rc;
+  if ((rc = ensure_capacity(ctx, w, n, n, 64, 1))) return rc;
+  CU(cudaMemcpyAsync(w->reading, features4, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, w->stream));
+  if ((rc = enqueue_normals(ctx, w, w->reading, n, knn, w->ref_nrm_stage))) return rc;
+  pack_normals_kernel<<<blocks_for(n, 256, ctx->sm_count * 8), 256, 0, w->stream>>>(w->ref_nrm_stage, n, (float*)w->A.srt_nrm);
+  LAUNCH_CHECK();
+  CU(cudaMemcpyAsync(out_normals3, w->A.srt_nrm, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, w->stream));
+  CU(cudaStreamSynchronize(w->stream));
+  return LS_OK;
+}
+
+int ls_map_push_scan_estimate_normals(ls_map* map, const float* features4, int n, int knn, uint64_t* scan_id) {
+  if (!map) return LS_ERR_ARG;
+  ls_ctx* ctx = map->ctx;
+  if (!features4 || n < 0 || n > map->max_pts || !scan_id || knn < 3 || knn > LS_KNN_MAX)
+    return fail(ctx, LS_ERR_ARG, "bad argument (n=%d, max=%d, 3 <= knn <= %d)", n, map->max_pts, LS_KNN_MAX);
+  CU(cudaSetDevice(ctx->device));
+  Workspace* w = ctx->ws[0];
+  const uint64_t id = map->next_id++;
+  ls_scan_slot& s = map->slots[id % (uint64_t)map->capacity];
+  s.used = false;
+  if (n > 0) {
+    CU(cudaMemcpyAsync(s.pts, features4, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, w->stream));
+    int rc = enqueue_normals(ctx, w, s.pts, n, knn, s.nrm);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(w->stream));
+  }
+  s.n = n;
+  s.id = id;
+  s.used = true;
+  *scan_id = id;
+  return LS_OK;
+}
+
 int ls_map_scan_size(const ls_map* map, uint64_t scan_id) {
   if (!map) return LS_ERR_ARG;
   const ls_scan_slot* s = find_slot(map, scan_id);

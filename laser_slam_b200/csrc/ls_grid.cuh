@@ -76,10 +76,48 @@ struct GridView {
   const unsigned long long* pyr;  // occupancy masks, levels 1..n_pyr
 };
 
+// Accumulator of the traversal.  `bound()` is the squared distance beyond which a candidate cannot matter
+// (cells are pruned against it), `offer()` takes one candidate.  Best = 1-NN with the lowest-index tie-break.
 struct Best {
   float d2;
   int idx;  // original reference index
   int pos;  // sorted position
+  LS_HD float bound() const { return d2; }
+  LS_HD void offer(float d, int i, int p) {
+    if (d < d2 || (d == d2 && i < idx)) {
+      d2 = d;
+      idx = i;
+      pos = p;
+    }
+  }
+};
+
+// K nearest (K <= LS_KNN_MAX at run time), ascending by (d2, index); a candidate offered twice is kept once.
+#define LS_KNN_MAX 16
+struct TopK {
+  float d[LS_KNN_MAX];
+  int id[LS_KNN_MAX];
+  int k;
+  float cap;  // only candidates with d2 <= cap are of interest in this round
+  LS_HD void reset(int kk) {
+    k = kk;
+    cap = INFINITY;
+    for (int j = 0; j < LS_KNN_MAX; ++j) { d[j] = INFINITY; id[j] = INT_MAX; }
+  }
+  LS_HD float bound() const { return fminf(d[k - 1], cap); }
+  LS_HD void offer(float dist, int i, int) {
+    if (dist > cap || !(dist < d[k - 1] || (dist == d[k - 1] && i < id[k - 1]))) return;
+    for (int j = 0; j < k; ++j)
+      if (id[j] == i) return;  // already listed (the balls of successive rounds overlap)
+    int j = k - 1;
+    while (j > 0 && (dist < d[j - 1] || (dist == d[j - 1] && i < id[j - 1]))) {
+      d[j] = d[j - 1];
+      id[j] = id[j - 1];
+      --j;
+    }
+    d[j] = dist;
+    id[j] = i;
+  }
 };
 
 // tests/sim instruments the query (candidates examined, table entries loaded) to tune H0/leaf_split
@@ -142,23 +180,21 @@ LS_HD float gap(float q, float lo, float hi, float m) {
 
 LS_HD float ball_radius(float best_d2, float margin) { return sqrtf(best_d2) * 1.000001f + margin; }
 
-// The candidate test (branch-free selects: a data-dependent branch per candidate was measured ~1.6x slower).
-LS_HD void consider_pt(const float4 p, int pos, float qx, float qy, float qz, Best& b) {
-  const float d = dist2(qx, qy, qz, p.x, p.y, p.z);
-  const int idx = f2i(p.w);
-  if (d < b.d2 || (d == b.d2 && idx < b.idx)) {
-    b.d2 = d;
-    b.idx = idx;
-    b.pos = pos;
-  }
+// The candidate test (for Best: branch-free selects; a data-dependent branch per candidate was measured ~1.6x
+// slower).
+template <class Acc>
+LS_HD void consider_pt(const float4 p, int pos, float qx, float qy, float qz, Acc& b) {
+  b.offer(dist2(qx, qy, qz, p.x, p.y, p.z), f2i(p.w), pos);
 }
-LS_HD void consider(const float4* pts, int pos, float qx, float qy, float qz, Best& b) {
+template <class Acc>
+LS_HD void consider(const float4* pts, int pos, float qx, float qy, float qz, Acc& b) {
   consider_pt(ld_pt(pts + pos), pos, qx, qy, qz, b);
 }
 
 // candidates are independent loads: issue four before touching any (memory-level parallelism).
 // (A single loop with a predicated tail was measured 1.6x slower than this main loop + scalar tail.)
-LS_HD void scan_range(const float4* pts, uint32_t a, uint32_t e, float qx, float qy, float qz, Best& b) {
+template <class Acc>
+LS_HD void scan_range(const float4* pts, uint32_t a, uint32_t e, float qx, float qy, float qz, Acc& b) {
   uint32_t pos = a;
   for (; pos + 4 <= e; pos += 4) {
     LS_CNT_STEP();
@@ -175,21 +211,22 @@ LS_HD void scan_range(const float4* pts, uint32_t a, uint32_t e, float qx, float
 // ---- ball query inside one fine table (all entries are leaves) ---------------------------------------
 // Points are sorted x-fastest, so for a row (z, y) the fine cells x0..x1 are ONE contiguous run
 // [start(z,y,x0), end(z,y,x1)): two entry loads, then a stream of candidates.
+template <class Acc>
 LS_HD void visit_fine(const Grid& g, const Entry* tab, float lox, float loy, float loz, const float4* pts,
-                      float qx, float qy, float qz, Best& b) {
-  const float R = ball_radius(b.d2, g.margin);
+                      float qx, float qy, float qz, Acc& b) {
+  const float R = ball_radius(b.bound(), g.margin);
   const int x0 = coord_sub(qx - R, lox, g.inv1), x1 = coord_sub(qx + R, lox, g.inv1);
   const int y0 = coord_sub(qy - R, loy, g.inv1), y1 = coord_sub(qy + R, loy, g.inv1);
   const int z0 = coord_sub(qz - R, loz, g.inv1), z1 = coord_sub(qz + R, loz, g.inv1);
   for (int z = z0; z <= z1; ++z) {
     const float gz = gap(qz, cell_lo(loz, z, g.H1), cell_lo(loz, z + 1, g.H1), g.margin);
     const float gz2 = gz * gz;
-    if (gz2 * LS_SHRINK > b.d2) continue;
+    if (gz2 * LS_SHRINK > b.bound()) continue;
     const Entry* row = tab + (z * LS_FB + y0) * LS_FB;
     for (int y = y0; y <= y1; ++y, row += LS_FB) {
       const float gy = gap(qy, cell_lo(loy, y, g.H1), cell_lo(loy, y + 1, g.H1), g.margin);
       const float lb = gy * gy + gz2;
-      if (lb * LS_SHRINK > b.d2) continue;
+      if (lb * LS_SHRINK > b.bound()) continue;
       LS_CNT_STEP();
       const Entry e0 = ld_entry(row + x0);
       const Entry e1 = ld_entry(row + x1);
@@ -199,23 +236,26 @@ LS_HD void visit_fine(const Grid& g, const Entry* tab, float lox, float loy, flo
 }
 
 // one level-0 cell (leaf scan or fine table)
+template <class Acc>
 LS_HD void visit_top_entry(const Grid& g, const GridView& v, const Entry e, float cx, float cy, float cz, float qx,
-                           float qy, float qz, Best& b) {
+                           float qy, float qz, Acc& b) {
   if (e.meta > 0) {
     scan_range(v.pts, e.start, e.start + (uint32_t)e.meta, qx, qy, qz, b);
   } else if (e.meta < 0) {
     visit_fine(g, v.tab1 + (size_t)(~e.meta) * LS_FB3, cx, cy, cz, v.pts, qx, qy, qz, b);
   }
 }
+template <class Acc>
 LS_HD void visit_top_cell(const Grid& g, const GridView& v, int x, int y, int z, float cx, float cy, float cz, float qx,
-                          float qy, float qz, Best& b) {
+                          float qy, float qz, Acc& b) {
   LS_CNT_STEP();
   visit_top_entry(g, v, ld_entry(v.top + ((size_t)z * g.dim[1] + y) * g.dim[0] + x), cx, cy, cz, qx, qy, qz, b);
 }
 
 // ---- large balls: depth-first walk of the occupancy pyramid (empty space costs one mask load per
 // 64 cells instead of one entry load per cell) -------------------------------------------------------
-LS_HDN void pyramid_query(const Grid& g, const GridView& v, float qx, float qy, float qz, Best& b) {
+template <class Acc>
+LS_HDN void pyramid_query(const Grid& g, const GridView& v, float qx, float qy, float qz, Acc& b) {
   int lvl[8], bx[8], by[8], bz[8];
   unsigned long long mk[8];
   int sp = 0;
@@ -235,7 +275,7 @@ LS_HDN void pyramid_query(const Grid& g, const GridView& v, float qx, float qy, 
     const float gy = gap(qy, ly, cell_lo(g.org[1], cy + 1, Hc), g.margin);
     const float gz = gap(qz, lz, cell_lo(g.org[2], cz + 1, Hc), g.margin);
     const float lb = gx * gx + (gy * gy + gz * gz);
-    if (lb * LS_SHRINK > b.d2) continue;
+    if (lb * LS_SHRINK > b.bound()) continue;
     if (cl == 0) {
       visit_top_cell(g, v, cx, cy, cz, lx, ly, lz, qx, qy, qz, b);
     } else {
@@ -248,8 +288,9 @@ LS_HDN void pyramid_query(const Grid& g, const GridView& v, float qx, float qy, 
 }
 
 // ---- ball query, level 0 -----------------------------------------------------------------------
-LS_HD void ball_query(const Grid& g, const GridView& v, float qx, float qy, float qz, Best& b) {
-  const float R = ball_radius(b.d2, g.margin);
+template <class Acc>
+LS_HD void ball_query(const Grid& g, const GridView& v, float qx, float qy, float qz, Acc& b) {
+  const float R = ball_radius(b.bound(), g.margin);
   const int x0 = coord_top(qx - R, g.org[0], g.inv0, g.dim[0]), x1 = coord_top(qx + R, g.org[0], g.inv0, g.dim[0]);
   const int y0 = coord_top(qy - R, g.org[1], g.inv0, g.dim[1]), y1 = coord_top(qy + R, g.org[1], g.inv0, g.dim[1]);
   const int z0 = coord_top(qz - R, g.org[2], g.inv0, g.dim[2]), z1 = coord_top(qz + R, g.org[2], g.inv0, g.dim[2]);
@@ -261,17 +302,17 @@ LS_HD void ball_query(const Grid& g, const GridView& v, float qx, float qy, floa
     const float cz = cell_lo(g.org[2], z, g.H0);
     const float gz = gap(qz, cz, cell_lo(g.org[2], z + 1, g.H0), g.margin);
     const float gz2 = gz * gz;
-    if (gz2 * LS_SHRINK > b.d2) continue;
+    if (gz2 * LS_SHRINK > b.bound()) continue;
     for (int y = y0; y <= y1; ++y) {
       const float cy = cell_lo(g.org[1], y, g.H0);
       const float gy = gap(qy, cy, cell_lo(g.org[1], y + 1, g.H0), g.margin);
       const float lbyz = gy * gy + gz2;
-      if (lbyz * LS_SHRINK > b.d2) continue;
+      if (lbyz * LS_SHRINK > b.bound()) continue;
       for (int x = x0; x <= x1; ++x) {
         const float cx = cell_lo(g.org[0], x, g.H0);
         const float gx = gap(qx, cx, cell_lo(g.org[0], x + 1, g.H0), g.margin);
         const float lb = gx * gx + lbyz;
-        if (lb * LS_SHRINK > b.d2) continue;
+        if (lb * LS_SHRINK > b.bound()) continue;
         visit_top_cell(g, v, x, y, z, cx, cy, cz, qx, qy, qz, b);
       }
     }
@@ -345,6 +386,24 @@ LS_HD Best nn_search(const Grid& g, const GridView& v, float qx, float qy, float
   ball_query(g, v, qx, qy, qz, b);
   if (b.pos < 0) { b.idx = -1; b.d2 = INFINITY; }
   return b;
+}
+
+// Exact K nearest neighbours (ties: lower index first) by verified expanding balls: a round searches the ball of
+// radius R exactly (pruned by the running K-th distance); if K points lie inside it they are the K nearest,
+// otherwise R doubles.  Fewer than K points in the whole map leaves the tail of the list at +inf / INT_MAX.
+LS_HDN void knn_search(const Grid& g, const GridView& v, float qx, float qy, float qz, int k, TopK& t) {
+  t.reset(k);
+  if (g.m <= 0) return;
+  const float extent = g.H0 * (float)(g.dim[0] + g.dim[1] + g.dim[2]) + 1.0f;
+  float R = g.H1;
+  for (int round = 0; round < 64; ++round) {
+    t.cap = R * R;
+    ball_query(g, v, qx, qy, qz, t);
+    if (t.d[k - 1] <= t.cap) break;  // K points inside the ball: exact
+    // the ball already covered every cell (query assumed within ~extent of the map): nothing more to find
+    if (R > extent + fabsf(qx - g.org[0]) + fabsf(qy - g.org[1]) + fabsf(qz - g.org[2])) break;
+    R = R * 2.0f;
+  }
 }
 
 // Cell keys used by the build (same functions => same membership as the query assumes).

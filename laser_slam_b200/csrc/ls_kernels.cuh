@@ -646,6 +646,56 @@ __global__ void __launch_bounds__(256) nn_query_kernel(const BuildState* __restr
   }
 }
 
+// ---- surface normals ---------------------------------------------------------------------
+// Replaces the SurfaceNormal / SamplingSurfaceNormal DataPointsFilters the reference runs on every scan and on the
+// whole sub-map (reference laser_slam/configurations/icp_default.yaml:5-7, laser_slam/src/laser_track.cpp:27,146):
+// exact K nearest neighbours (self included) over the cloud's own spatial hash, covariance of the neighbourhood
+// accumulated in double in (d2, index) order, eigenvector of the smallest eigenvalue, flipped towards the sensor
+// (the origin of the scan frame).  Deterministic; bit-comparable with oracle lso_knn_normals.
+__global__ void __launch_bounds__(128) knn_normals_kernel(const BuildState* __restrict__ bs, GridView view,
+                                                           const float4* __restrict__ pts_c /* centred, original order */,
+                                                           int n, int k, float4* __restrict__ out) {
+  __shared__ Grid g;
+  if (threadIdx.x == 0) g = bs->grid;
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 q = __ldg(pts_c + i);
+    TopK t;
+    knn_search(g, view, q.x, q.y, q.z, k, t);
+    int cnt = 0;
+    double mx = 0.0, my = 0.0, mz = 0.0;
+    for (int j = 0; j < k; ++j) {
+      if (t.id[j] == INT_MAX) break;
+      const float4 p = __ldg(pts_c + t.id[j]);
+      mx = mx + (double)p.x;
+      my = my + (double)p.y;
+      mz = mz + (double)p.z;
+      ++cnt;
+    }
+    float4 nn = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cnt >= 3) {
+      const double inv = 1.0 / (double)cnt;
+      mx = mx * inv; my = my * inv; mz = mz * inv;
+      double C[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      for (int j = 0; j < cnt; ++j) {
+        const float4 p = __ldg(pts_c + t.id[j]);
+        const double dx = (double)p.x - mx, dy = (double)p.y - my, dz = (double)p.z - mz;
+        C[0] = C[0] + dx * dx; C[1] = C[1] + dx * dy; C[2] = C[2] + dx * dz;
+        C[4] = C[4] + dy * dy; C[5] = C[5] + dy * dz; C[8] = C[8] + dz * dz;
+      }
+      C[3] = C[1]; C[6] = C[2]; C[7] = C[5];
+      double nv[3];
+      smallest_eigvec3(C, nv);
+      // towards the sensor: the vector from the point to the scan-frame origin is -(p_centred + mu)
+      const double ox = (double)q.x + (double)g.mu[0], oy = (double)q.y + (double)g.mu[1], oz = (double)q.z + (double)g.mu[2];
+      const double dot = nv[0] * ox + (nv[1] * oy + nv[2] * oz);
+      const double sgn = dot > 0.0 ? -1.0 : 1.0;
+      nn = make_float4((float)(sgn * nv[0]), (float)(sgn * nv[1]), (float)(sgn * nv[2]), 0.f);
+    }
+    out[i] = nn;
+  }
+}
+
 // ================================================================================================
 // Persistent ICP kernel
 // ================================================================================================

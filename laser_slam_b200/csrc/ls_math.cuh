@@ -272,6 +272,49 @@ LS_HDN double quat_angular_distance(const double* a, const double* b) {
   return 2.0 * atan2(sqrt(x * x + y * y + z * z), fabs(w));
 }
 
+// Unit eigenvector of the smallest eigenvalue of a symmetric 3x3 (row-major) by cyclic Jacobi in double,
+// fixed sweep order; ties between eigenvalues -> lowest index.  Surface normal of a neighbourhood covariance.
+LS_HDN void smallest_eigvec3(const double* C, double* n) {
+  double a[9], v[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  for (int i = 0; i < 9; ++i) a[i] = C[i];
+  for (int sweep = 0; sweep < 40; ++sweep) {
+    const double off = a[1] * a[1] + a[2] * a[2] + a[5] * a[5];
+    const double dg = a[0] * a[0] + a[4] * a[4] + a[8] * a[8];
+    if (!(off > 1e-40 * dg)) break;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        const double apq = a[p * 3 + q];
+        if (apq == 0.0) continue;
+        const double theta = (a[q * 3 + q] - a[p * 3 + p]) / (2.0 * apq);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < 3; ++k) {
+          const double akp = a[k * 3 + p], akq = a[k * 3 + q];
+          a[k * 3 + p] = c * akp - s * akq;
+          a[k * 3 + q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < 3; ++k) {
+          const double apk = a[p * 3 + k], aqk = a[q * 3 + k];
+          a[p * 3 + k] = c * apk - s * aqk;
+          a[q * 3 + k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < 3; ++k) {
+          const double vkp = v[k * 3 + p], vkq = v[k * 3 + q];
+          v[k * 3 + p] = c * vkp - s * vkq;
+          v[k * 3 + q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  int m = 0;
+  if (a[4] < a[m * 4]) m = 1;
+  if (a[8] < a[m * 4]) m = 2;
+  const double x = v[m], y = v[3 + m], z = v[6 + m];
+  const double inv = 1.0 / sqrt(x * x + y * y + z * z);
+  n[0] = x * inv;
+  n[1] = y * inv;
+  n[2] = z * inv;
+}
+
 // RigidTransformation::checkParameters / correctParameters (reference common.hpp:136-149 path)
 LS_HDN int check_rigid(const float* T) {
   const float a = T[0], b = T[4], c = T[8], d = T[1], e = T[5], f = T[9], g = T[2], h = T[6], i = T[10];

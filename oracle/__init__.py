@@ -55,6 +55,8 @@ def lib():
         L.lso_solve_step.restype = ci
         L.lso_mat4_mul.argtypes = [vp, vp, vp]
         L.lso_sincos.argtypes = [ctypes.c_double, vp, vp]
+        L.lso_knn_self.argtypes = [vp, ci, ci, vp, vp, ci]
+        L.lso_knn_normals.argtypes = [vp, ci, ci, vp, ci]
         L.lso_icp.argtypes = [vp, ci, vp, vp, ci, ci, vp, ctypes.POINTER(IcpParams), vp,
                               ctypes.POINTER(IcpStats), vp, vp, vp]
         L.lso_icp.restype = ci
@@ -172,6 +174,22 @@ def mat4_mul(A, B):
     c = np.empty(16, np.float32)
     lib().lso_mat4_mul(a.ctypes.data, b.ctypes.data, c.ctypes.data)
     return from_colmajor(c)
+
+
+def knn_self(pts4, k, num_threads=1):
+    pts4 = _f32(pts4)
+    n = pts4.shape[0]
+    ids = np.empty((n, k), np.int32)
+    d2 = np.empty((n, k), np.float32)
+    lib().lso_knn_self(pts4.ctypes.data, n, k, ids.ctypes.data, d2.ctypes.data, num_threads)
+    return ids, d2
+
+
+def knn_normals(pts4, k=10, num_threads=1):
+    pts4 = _f32(pts4)
+    out = np.empty((pts4.shape[0], 3), np.float32)
+    lib().lso_knn_normals(pts4.ctypes.data, pts4.shape[0], k, out.ctypes.data, num_threads)
+    return out
 
 
 def sincos(x):

@@ -153,6 +153,38 @@ struct KdTree {
     if (pd <= best) search(far, q, best, best_id);
   }
 
+  // K nearest, ascending by (d2, index) -- the lexicographic order that makes ties reproducible
+  void knn_rec(int node, const float* q, int k, float* bd, int* bi) const {
+    const KdNode& nd = nodes[node];
+    if (nd.dim < 0) {
+      for (int i = nd.left; i < nd.right; ++i) {
+        const int id = perm[i];
+        const float d = dist2(q, pts + 3 * id);
+        if (d < bd[k - 1] || (d == bd[k - 1] && id < bi[k - 1])) {
+          int j = k - 1;
+          while (j > 0 && (d < bd[j - 1] || (d == bd[j - 1] && id < bi[j - 1]))) {
+            bd[j] = bd[j - 1];
+            bi[j] = bi[j - 1];
+            --j;
+          }
+          bd[j] = d;
+          bi[j] = id;
+        }
+      }
+      return;
+    }
+    const float diff = q[nd.dim] - nd.cut;
+    const int near = diff < 0.f ? nd.left : nd.right;
+    const int far = diff < 0.f ? nd.right : nd.left;
+    knn_rec(near, q, k, bd, bi);
+    const float pd = diff * diff;
+    if (pd <= bd[k - 1]) knn_rec(far, q, k, bd, bi);
+  }
+  void knn(const float* q, int k, float* bd, int* bi) const {
+    for (int j = 0; j < k; ++j) { bd[j] = INFINITY; bi[j] = std::numeric_limits<int>::max(); }
+    if (!nodes.empty()) knn_rec(0, q, k, bd, bi);
+  }
+
   void nn(const float* q, int* id, float* d2) const {
     float best = INFINITY;
     int bid = -1;  // libnabo: unfound = -1 / +inf
@@ -576,6 +608,111 @@ int lso_solve_step(const double A[36], const double b[6], float T_step[16], doub
 }
 
 void lso_mat4_mul(const float* A, const float* B, float* C) { mat4_mul(A, B, C); }
+
+// [DEFINED] eigenvector of the smallest eigenvalue of a symmetric 3x3 (row-major): cyclic Jacobi in double with
+// a fixed sweep order; equal eigenvalues -> lowest index.
+static void smallest_eigvec3(const double C[9], double n[3]) {
+  double a[9], v[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  for (int i = 0; i < 9; ++i) a[i] = C[i];
+  for (int sweep = 0; sweep < 40; ++sweep) {
+    const double off = a[1] * a[1] + a[2] * a[2] + a[5] * a[5];
+    const double dg = a[0] * a[0] + a[4] * a[4] + a[8] * a[8];
+    if (!(off > 1e-40 * dg)) break;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        const double apq = a[p * 3 + q];
+        if (apq == 0.0) continue;
+        const double theta = (a[q * 3 + q] - a[p * 3 + p]) / (2.0 * apq);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < 3; ++k) {
+          const double akp = a[k * 3 + p], akq = a[k * 3 + q];
+          a[k * 3 + p] = c * akp - s * akq;
+          a[k * 3 + q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < 3; ++k) {
+          const double apk = a[p * 3 + k], aqk = a[q * 3 + k];
+          a[p * 3 + k] = c * apk - s * aqk;
+          a[q * 3 + k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < 3; ++k) {
+          const double vkp = v[k * 3 + p], vkq = v[k * 3 + q];
+          v[k * 3 + p] = c * vkp - s * vkq;
+          v[k * 3 + q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  int m = 0;
+  if (a[4] < a[m * 4]) m = 1;
+  if (a[8] < a[m * 4]) m = 2;
+  const double x = v[m], y = v[3 + m], z = v[6 + m];
+  const double inv = 1.0 / std::sqrt(x * x + y * y + z * z);
+  n[0] = x * inv; n[1] = y * inv; n[2] = z * inv;
+}
+
+// Exact k nearest neighbours (self included, ties by index) of every point of a cloud within the cloud itself,
+// on the coordinates centred like ICP::compute centres a reference.  ids: n*k, d2: n*k (ascending).
+void lso_knn_self(const float* feat4, int n, int k, int32_t* ids, float* d2, int num_threads) {
+  float mu[3];
+  lso_mean(feat4, n, mu);
+  std::vector<float> c(3 * (size_t)n);
+  for (int i = 0; i < n; ++i)
+    for (int a = 0; a < 3; ++a) c[3 * (size_t)i + a] = feat4[4 * (size_t)i + a] - mu[a];
+  KdTree tree;
+  tree.init(c.data(), n);
+#pragma omp parallel for schedule(static) num_threads(num_threads > 0 ? num_threads : 1)
+  for (int i = 0; i < n; ++i) tree.knn(&c[3 * (size_t)i], k, d2 + (size_t)i * k, ids + (size_t)i * k);
+}
+
+// Surface normals (upstream: SurfaceNormalDataPointsFilter + orientation towards the sensor,
+// icp_default.yaml:5-7).  [DEFINED]: neighbourhood = exact k-NN (self included) on the centred float32 cloud;
+// mean and covariance accumulated in double in (d2, index) order; eigenvector of the smallest eigenvalue (Jacobi);
+// flipped so that it points towards the scan-frame origin; fewer than 3 neighbours -> zero normal.
+void lso_knn_normals(const float* feat4, int n, int k, float* out3, int num_threads) {
+  float mu[3];
+  lso_mean(feat4, n, mu);
+  std::vector<float> c(3 * (size_t)n);
+  for (int i = 0; i < n; ++i)
+    for (int a = 0; a < 3; ++a) c[3 * (size_t)i + a] = feat4[4 * (size_t)i + a] - mu[a];
+  KdTree tree;
+  tree.init(c.data(), n);
+#pragma omp parallel for schedule(static) num_threads(num_threads > 0 ? num_threads : 1)
+  for (int i = 0; i < n; ++i) {
+    float bd[64];
+    int bi[64];
+    tree.knn(&c[3 * (size_t)i], k, bd, bi);
+    int cnt = 0;
+    double mx = 0.0, my = 0.0, mz = 0.0;
+    for (int j = 0; j < k; ++j) {
+      if (bi[j] == std::numeric_limits<int>::max()) break;
+      mx = mx + (double)c[3 * (size_t)bi[j]];
+      my = my + (double)c[3 * (size_t)bi[j] + 1];
+      mz = mz + (double)c[3 * (size_t)bi[j] + 2];
+      ++cnt;
+    }
+    float nn[3] = {0.f, 0.f, 0.f};
+    if (cnt >= 3) {
+      const double inv = 1.0 / (double)cnt;
+      mx = mx * inv; my = my * inv; mz = mz * inv;
+      double C[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      for (int j = 0; j < cnt; ++j) {
+        const double dx = (double)c[3 * (size_t)bi[j]] - mx, dy = (double)c[3 * (size_t)bi[j] + 1] - my,
+                     dz = (double)c[3 * (size_t)bi[j] + 2] - mz;
+        C[0] = C[0] + dx * dx; C[1] = C[1] + dx * dy; C[2] = C[2] + dx * dz;
+        C[4] = C[4] + dy * dy; C[5] = C[5] + dy * dz; C[8] = C[8] + dz * dz;
+      }
+      C[3] = C[1]; C[6] = C[2]; C[7] = C[5];
+      double nv[3];
+      smallest_eigvec3(C, nv);
+      const double ox = (double)c[3 * (size_t)i] + (double)mu[0], oy = (double)c[3 * (size_t)i + 1] + (double)mu[1],
+                   oz = (double)c[3 * (size_t)i + 2] + (double)mu[2];
+      const double dot = nv[0] * ox + (nv[1] * oy + nv[2] * oz);
+      const double sgn = dot > 0.0 ? -1.0 : 1.0;
+      nn[0] = (float)(sgn * nv[0]); nn[1] = (float)(sgn * nv[1]); nn[2] = (float)(sgn * nv[2]);
+    }
+    out3[3 * (size_t)i] = nn[0]; out3[3 * (size_t)i + 1] = nn[1]; out3[3 * (size_t)i + 2] = nn[2];
+  }
+}
 void lso_sincos(double x, double* s, double* c) { det_sincos(x, s, c); }
 
 // PointMatcher::ICP::compute with identity reading/reference filters

@@ -42,6 +42,8 @@ void lso_normal_equations(const float* step4, int n, const float* ref_c3, const 
 int lso_solve_step(const double A[36], const double b[6], float T_step[16], double x_out[6]);
 void lso_mat4_mul(const float* A, const float* B, float* C);
 void lso_sincos(double x, double* s, double* c);
+void lso_knn_self(const float* feat4, int n, int k, int32_t* ids, float* d2, int num_threads);
+void lso_knn_normals(const float* feat4, int n, int k, float* out3, int num_threads);
 int lso_icp(const float* reading4, int n, const float* ref4, const float* ref_normals, int nstride, int m,
             const float T0[16], const lso_icp_params* prm, float T_out[16], lso_icp_stats* stats,
             int32_t* ids_hist, float* d2_last, float* T_iter_hist);
