@@ -651,7 +651,7 @@ __global__ void __launch_bounds__(256) nn_query_kernel(const BuildState* __restr
 // whole sub-map (reference laser_slam/configurations/icp_default.yaml:5-7, laser_slam/src/laser_track.cpp:27,146):
 // exact K nearest neighbours (self included) over the cloud's own spatial hash, covariance of the neighbourhood
 // accumulated in double in (d2, index) order, eigenvector of the smallest eigenvalue, flipped towards the sensor
-// (the origin of the scan frame).  Deterministic; bit-comparable with oracle lso_knn_normals.
+// (the origin of the scan frame).  Deterministic; bit-comparable with the CPU restatement in oracle/.
 __global__ void __launch_bounds__(128) knn_normals_kernel(const BuildState* __restrict__ bs, GridView view,
                                                            const float4* __restrict__ pts_c /* centred, original order */,
                                                            int n, int k, float4* __restrict__ out) {
