@@ -22,7 +22,11 @@ namespace ls {
 constexpr int kMaxParts = 16;
 constexpr int kScanTile = 4096;       // level-0 cells per scan block
 constexpr int kScanThreads = 512;
-constexpr int kIcpThreads = 512;
+#ifndef LS_ICP_THREADS
+#define LS_ICP_THREADS 512
+#endif
+constexpr int kIcpThreads = LS_ICP_THREADS;
+constexpr int kIcpCtasPerSm = 1024 / kIcpThreads;
 constexpr int kMaxSmooth = 15;
 constexpr uint32_t kTag1 = 1u << 31, kKeyMask = (1u << 31) - 1u;  // pkey: tag | key (fine keys < 2^31)
 
@@ -746,8 +750,8 @@ struct SelectOut {
 // If `first` the rank is derived from the total: k = (unsigned)((float)total * ratio), clamped.
 __device__ __forceinline__ void block_select(const unsigned int* ghist, int nbins, unsigned int k, bool first,
                                              float ratio, SelectOut* out, unsigned int* ws) {
-  const int per = nbins / kIcpThreads;  // 2 or 4
-  unsigned int c[4], loc = 0;
+  const int per = nbins / kIcpThreads;
+  unsigned int c[2048 / kIcpThreads], loc = 0;
   for (int j = 0; j < per; ++j) {
     c[j] = __ldcg(ghist + threadIdx.x * per + j);
     loc += c[j];
@@ -810,7 +814,7 @@ __device__ __forceinline__ void phase_a_query(const Grid& g, const IcpProblem& P
   if (key <= 0x7f800000u) atomicAdd(&hist_s[key >> 21], 1u);  // non-negative; +inf (no match in cap) -> bin 1020
 }
 
-__global__ void __launch_bounds__(kIcpThreads, 2)
+__global__ void __launch_bounds__(kIcpThreads, kIcpCtasPerSm)
 icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParamsDev prm, int dynamic) {
   const int pi = blockIdx.x / ctas_per_problem;
   const int cta = blockIdx.x - pi * ctas_per_problem;
