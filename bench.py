@@ -38,34 +38,57 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons sampled DURING the timed region.  NVML in-process (the library nvidia-smi itself
+    reads; no process is spawned next to the measurement); `nvidia-smi --query-gpu` only if NVML cannot be loaded."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    BAD = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, gpu):
         super().__init__(daemon=True)
-        self.gpu, self.samples, self.stop_flag = gpu, [], False
+        self.gpu, self.samples, self.stop_flag, self.source = gpu, [], False, "nvml"
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            phys = gpu
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                tok = vis.split(",")[gpu].strip()
+                phys = int(tok) if tok.isdigit() else None
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys) if phys is not None else pynvml.nvmlDeviceGetHandleByUUID(tok)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h, self.source = None, "nvidia-smi"
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                if self.h is not None:
+                    sm = float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                    try:
+                        mask = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                    except Exception:
+                        mask = int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                    self.samples.append((sm, self.max_sm, [n for n, bit in self.BAD if mask & bit]))
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    f = [x.strip() for x in out.split(",")]
+                    if len(f) >= 8:
+                        self.samples.append((float(f[1]), float(f[2]),
+                                             [n for (n, _), v in zip(self.BAD, f[4:8]) if v.lower().startswith("active")]))
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05 if self.h is not None else 0.25)
 
     def summary(self):
         self.stop_flag = True
-        sm = [float(s[1]) for s in self.samples if len(s) > 2 and s[1].replace(".", "").isdigit()]
-        mx = [float(s[2]) for s in self.samples if len(s) > 2 and s[2].replace(".", "").isdigit()]
-        reasons = set()
-        for s in self.samples:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+        sm = [s[0] for s in self.samples]
+        mx = [s[1] for s in self.samples]
+        reasons = sorted({r for s in self.samples for r in s[2]})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.samples)}
+                "reasons": reasons, "samples": len(self.samples), "source": self.source}
 
 
 def make_pool(seq):
@@ -215,7 +238,10 @@ def main():
     ctx = ls.Context(local)
     B = args.tracks
     # B independent sequences (tracks) per GPU -- the reference's n_laser_slam_workers LaserTracks hosted on one device
-    tracks = [make_pool(rank * B + t) for t in range(B)]
+    seq_base = int(os.environ.get('LS_BENCH_SEQ_BASE', '0'))   # diagnostic: run another rank's tracks on this one
+    # every rank drives the SAME B synthetic sequences: per-GPU work is then identical by construction (the cost of a
+    # registration varies by +-25 % with where along the street the vehicle is), which is what weak scaling assumes
+    tracks = [make_pool(seq_base + t) for t in range(B)]
     prm = ls.default_params(max_iterations=ITERS, use_differential=0)
     feats = [[torch.from_numpy(s[0]).pin_memory() for s in tr[2]] for tr in tracks]   # pinned host staging
     nrms = [[torch.from_numpy(s[1]).pin_memory() for s in tr[2]] for tr in tracks]
@@ -226,12 +252,20 @@ def main():
         torch.cuda.synchronize()
 
     from laser_slam_b200 import dist as lsd
-    exchange = lsd.Exchange(rank, world, device=local)   # ls_comm_* (one ncclAllGather of 32 B/rank) when world > 1
+    exchange = lsd.Exchange(rank, world, device=None if os.environ.get('LS_BENCH_NO_COMM') else local)   # ls_comm_* (one ncclAllGather of 32 B/rank) when world > 1
+
+    xmode = os.environ.get("LS_BENCH_EXCHANGE", "split")   # split | blocking | none (diagnostic)
 
     def share_pose_delta(T):
-        """One 32-byte {delta[6], status, key} record per rank per step."""
-        if world > 1:
-            exchange.allgather(lsd.pose_record(T, status=0, key=rank))
+        """One 32-byte {delta[6], status, key} record per rank per step.  Split-phase: the records
+        of step s are collected when step s+1 posts its own (the estimator consumes factors asynchronously)."""
+        if world > 1 and xmode != "none":
+            rec = lsd.pose_record(T, status=0, key=rank)
+            if xmode == "blocking":
+                exchange.allgather(rec)
+            else:
+                exchange.collect()
+                exchange.post(rec)
 
     n_total = args.warmup + args.steps
 
@@ -269,6 +303,10 @@ def main():
         if record:
             dev_ms.append(max(st.device_ms for st in stats))
             icp_ms.append(stats[0].icp_ms)
+            if os.environ.get("LS_BENCH_TRACE"):
+                print(f"[trace] step {s}: icp {stats[0].icp_ms:.2f} ms; per track last_limit " +
+                      " ".join(f"{st.last_limit:.4f}" for st in stats) + " kept " + " ".join(str(st.last_kept) for st in stats),
+                      file=sys.stderr, flush=True)
         return touts
 
     for s in range(args.warmup):
@@ -280,6 +318,7 @@ def main():
     t0 = time.perf_counter()
     for s in range(args.steps):
         last = step_resident(args.warmup + s, True)
+    exchange.collect()   # the last step's records, inside the timed region
     barrier()
     t_res = time.perf_counter() - t0
     launches = ctx.launch_count - launches0
@@ -320,6 +359,7 @@ def main():
     t0 = time.perf_counter()
     for s in range(args.steps):
         step_e2e(args.warmup + s)
+    exchange.collect()
     barrier()
     t_e2e = time.perf_counter() - t0
     clocks = sampler.summary()
@@ -362,8 +402,9 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "configs[1]: scan-to-local-map ICP, 131072-pt scan vs 524288-pt rolling map (4 scans), 30 iterations",
                    "tracks_per_gpu": B, "registrations_per_step": world * B,
-                   "concurrency": f"{B} independent sequences (tracks) per GPU; one step registers the next scan of every track in "
-                                  f"one cooperative launch (ls_icp_register_submap_batch)",
+                   "concurrency": f"{B} independent sequences (tracks) per GPU (the same {B} synthetic sequences on every rank, so "
+                                  f"per-GPU work is identical); one step registers the next scan of every track in one "
+                                  f"cooperative launch (ls_icp_register_submap_batch)",
                    "single_stream_ms_per_registration": single_ms,
                    "l2": f"inputs larger than L2: {B * POOL} resident scans/rank cycled ({B * POOL * N_SCAN * 32 / 1e6:.0f} MB) "
                          f"+ {B} x ~170 MB workspaces",

@@ -233,6 +233,13 @@ void ls_comm_destroy(ls_comm* comm);
 const char* ls_comm_last_error(const ls_comm* comm);
 /* all[nranks] <- every rank's record (rank order). */
 int ls_comm_allgather_pose_records(ls_comm* comm, const ls_pose_record* mine, ls_pose_record* all);
+/* The same in two halves: begin() only enqueues (copy in, ncclAllGather, copy out) on the communicator's stream
+ * and returns; end() waits for it.  A track posts its step's record and collects it before posting the next one,
+ * so the slowest rank of a step no longer stalls the others on the host (the estimator consumes the factors
+ * asynchronously anyway, reference incremental_estimator.cpp:151-163).  One exchange in flight at a time
+ * (LS_ERR_STATE otherwise). */
+int ls_comm_allgather_pose_records_begin(ls_comm* comm, const ls_pose_record* mine);
+int ls_comm_allgather_pose_records_end(ls_comm* comm, ls_pose_record* all);
 
 #ifdef __cplusplus
 }

@@ -65,6 +65,7 @@ struct ls_comm {
   ls_pose_record* d_send = nullptr;
   ls_pose_record* d_recv = nullptr;
   ls_pose_record* h_pinned = nullptr;  // [1 + nranks]
+  bool pending = false;                // a begin() without its end()
   std::string err;
 };
 
@@ -122,8 +123,9 @@ void ls_comm_destroy(ls_comm* c) {
 
 const char* ls_comm_last_error(const ls_comm* c) { return c ? c->err.c_str() : "null communicator"; }
 
-int ls_comm_allgather_pose_records(ls_comm* c, const ls_pose_record* mine, ls_pose_record* all) {
-  if (!c || !mine || !all) return LS_ERR_ARG;
+int ls_comm_allgather_pose_records_begin(ls_comm* c, const ls_pose_record* mine) {
+  if (!c || !mine) return LS_ERR_ARG;
+  if (c->pending) return LS_ERR_STATE;
   if (cudaSetDevice(c->device) != cudaSuccess) return LS_ERR_CUDA;
   c->h_pinned[0] = *mine;
   if (cudaMemcpyAsync(c->d_send, &c->h_pinned[0], sizeof(ls_pose_record), cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
@@ -134,11 +136,25 @@ int ls_comm_allgather_pose_records(ls_comm* c, const ls_pose_record* mine, ls_po
     return LS_ERR_NCCL;
   }
   if (cudaMemcpyAsync(&c->h_pinned[1], c->d_recv, sizeof(ls_pose_record) * (size_t)c->nranks, cudaMemcpyDeviceToHost, c->stream) !=
-          cudaSuccess ||
-      cudaStreamSynchronize(c->stream) != cudaSuccess)
+      cudaSuccess)
     return LS_ERR_CUDA;
+  c->pending = true;
+  return LS_OK;
+}
+
+int ls_comm_allgather_pose_records_end(ls_comm* c, ls_pose_record* all) {
+  if (!c || !all) return LS_ERR_ARG;
+  if (!c->pending) return LS_ERR_STATE;
+  if (cudaSetDevice(c->device) != cudaSuccess) return LS_ERR_CUDA;
+  c->pending = false;
+  if (cudaStreamSynchronize(c->stream) != cudaSuccess) return LS_ERR_CUDA;
   std::memcpy(all, &c->h_pinned[1], sizeof(ls_pose_record) * (size_t)c->nranks);
   return LS_OK;
+}
+
+int ls_comm_allgather_pose_records(ls_comm* c, const ls_pose_record* mine, ls_pose_record* all) {
+  const int rc = ls_comm_allgather_pose_records_begin(c, mine);
+  return rc != LS_OK ? rc : ls_comm_allgather_pose_records_end(c, all);
 }
 
 }  // extern "C"

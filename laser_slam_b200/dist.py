@@ -49,6 +49,8 @@ class Exchange:
             L.ls_comm_destroy.argtypes = [ctypes.c_void_p]
             L.ls_comm_destroy.restype = None
             L.ls_comm_allgather_pose_records.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+            L.ls_comm_allgather_pose_records_begin.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+            L.ls_comm_allgather_pose_records_end.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
             uid = np.zeros(128, np.uint8)
             if rank == 0 and L.ls_comm_unique_id(uid.ctypes.data) != 0:
                 raise RuntimeError("ls_comm_unique_id failed (NCCL not loadable)")
@@ -80,7 +82,35 @@ class Exchange:
         dist.all_gather(bufs, t)
         return np.concatenate([b.numpy() for b in bufs]).view(RECORD_DTYPE)
 
+    def post(self, rec):
+        """Split-phase all-gather: enqueue this rank's record and return; `collect()` returns the gathered records.
+        At most one exchange in flight.  Falls back to the blocking path off NCCL (gloo tests, world 1)."""
+        if self._comm is None:
+            self._posted = self.allgather(rec)
+            return
+        mine = np.array(rec, RECORD_DTYPE).reshape(1)
+        self._mine = mine  # keep alive until the call returns (copied to pinned memory inside)
+        rc = self._L.ls_comm_allgather_pose_records_begin(self._comm, mine.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f"ls_comm_allgather_pose_records_begin failed with {rc}")
+        self._posted = True
+
+    def collect(self):
+        """Records of the exchange posted last, or None if nothing is in flight."""
+        p = getattr(self, "_posted", None)
+        if p is None:
+            return None
+        self._posted = None
+        if p is True:
+            out = np.zeros(self.world, RECORD_DTYPE)
+            rc = self._L.ls_comm_allgather_pose_records_end(self._comm, out.ctypes.data)
+            if rc != 0:
+                raise RuntimeError(f"ls_comm_allgather_pose_records_end failed with {rc}")
+            return out
+        return p
+
     def close(self):
+        self.collect()
         if self._comm is not None:
             self._L.ls_comm_destroy(self._comm)
             self._comm = None
