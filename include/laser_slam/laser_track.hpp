@@ -54,6 +54,10 @@ class LaserTrack {
   size_t getNumScans() const;
   Pose findNearestPose(const Time& timestamp_ns) const;
   void buildSubMapAroundTime(const curves::Time& time_ns, const unsigned int sub_maps_radius, DataPoints* submap_out) const;
+  // The same sub-map left on the device: its scans are pushed into a new ring of `ctx` (caller destroys it with
+  // ls_map_destroy) and described by (ids, 16 floats per part), ready for ls_icp_register_submaps.
+  void stageSubMapAroundTime(const curves::Time& time_ns, const unsigned int sub_maps_radius, ls_ctx* ctx, ls_map** ring_out,
+                             std::vector<uint64_t>* ids_out, std::vector<float>* T_parts_out) const;
   Key getValueKey(const curves::Time& time_ns) const;  // the leaf of trajectory_.getValueExpression(time)
   SE3 evaluate(const curves::Time& time_ns) const;
   void getScanMatchingTimes(std::map<Time, double>* scan_matching_times) const;
@@ -76,6 +80,8 @@ class LaserTrack {
   Key extendTrajectory(const Time& timestamp_ns, const SE3& value);
   size_t scanIndexAtTime(const curves::Time& time_ns) const;
   uint64_t residentScan(size_t index) const;  // device id of laser_scans_[index], uploading it if it was evicted
+  void describeSubMapAroundTime(const curves::Time& time_ns, const unsigned int sub_maps_radius, std::vector<size_t>* scan_indices,
+                                std::vector<PointMatcher::TransformationParameters>* Ts) const;
   void assembleSubMap(const std::vector<size_t>& scan_indices, const std::vector<PointMatcher::TransformationParameters>& Ts,
                       DataPoints* out) const;
 

@@ -156,6 +156,17 @@ int ls_icp_register_submap_batch(ls_ctx* ctx, const ls_icp_params* prm, const ls
                                  const float* T_parts, const float* T0s, float* T_outs, ls_icp_stats* stats,
                                  int* statuses);
 
+/* Sub-map <-> sub-map registration on resident data: the loop-closure ICP of
+ * IncrementalEstimator::processLoopClosure (laser_slam/src/incremental_estimator.cpp:90-115) without the two
+ * buildSubMapAroundTime clouds (laser_slam/src/laser_track.cpp:602-651) visiting the host.  Reference = parts of
+ * ref_map (normals included), reading = parts of reading_map, each part transformed by its T (an exact identity
+ * copies the scan verbatim); the two maps may be the same object.  T_out maps reading coordinates into reference
+ * coordinates.  Bit-identical to ls_map_assemble of both sides followed by ls_icp_register. */
+int ls_icp_register_submaps(ls_ctx* ctx, const ls_icp_params* prm, const ls_map* ref_map, int n_ref_parts,
+                            const uint64_t* ref_part_ids, const float* T_ref_parts, const ls_map* reading_map,
+                            int n_reading_parts, const uint64_t* reading_part_ids, const float* T_reading_parts,
+                            const float T0[16], float T_out[16], ls_icp_stats* stats);
+
 /* Assemble a sub-map and download it (LaserTrack::buildSubMapAroundTime,
  * LaserTrack::getLocalCloudInWorldFrame laser_track.cpp:247-266).  out4: 4*M floats,
  * out_normals3: 3*M floats (may be NULL); returns M through *m_out. */

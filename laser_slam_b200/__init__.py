@@ -97,6 +97,7 @@ def lib():
         L.ls_map_scan_size.argtypes = [vp, u64]
         L.ls_icp_register_submap.argtypes = [vp, PP, vp, u64, ci, vp, vp, vp, vp, PS, vp, vp, vp]
         L.ls_map_assemble.argtypes = [vp, vp, ci, vp, vp, vp, vp, ctypes.POINTER(ci)]
+        L.ls_icp_register_submaps.argtypes = [vp, PP, vp, ci, vp, vp, vp, ci, vp, vp, vp, vp, PS]
         L.ls_estimate_normals.argtypes = [vp, vp, ci, ci, vp]
         L.ls_map_push_scan_estimate_normals.argtypes = [vp, vp, ci, ci, ctypes.POINTER(u64)]
         L.ls_icp_register_submap_batch.argtypes = [vp, PP, vp, ci, vp, vp, vp, vp, vp, vp, vp, vp]
@@ -362,6 +363,26 @@ class Map:
         rc, statuses, touts, stats = self.prepare_batch(problems, params)()
         self.ctx._check(rc if rc < 0 else 0)
         return [dict(T=from_colmajor(touts[b]), rc=int(statuses[b]), stats=stats[b]) for b in range(len(problems))]
+
+    def register_submaps(self, ref_ids, T_refs, reading_map, reading_ids, T_readings, T0, params=None,
+                         raise_on_convergence=True):
+        """Sub-map <-> sub-map ICP with both clouds assembled on the device (the loop-closure ICP of
+        IncrementalEstimator::processLoopClosure, reference incremental_estimator.cpp:90-115).  `self` holds the
+        reference parts, `reading_map` the reading parts (may be the same map)."""
+        p = params or default_params()
+        ra = np.ascontiguousarray(ref_ids, np.uint64)
+        rt = np.ascontiguousarray(np.stack([colmajor(T) for T in T_refs]), np.float32)
+        da = np.ascontiguousarray(reading_ids, np.uint64)
+        dt = np.ascontiguousarray(np.stack([colmajor(T) for T in T_readings]), np.float32)
+        t0 = colmajor(T0)
+        tout = np.empty(16, np.float32)
+        st = IcpStats()
+        rc = lib().ls_icp_register_submaps(self.ctx._h, ctypes.byref(p), self._h, len(ra), ra.ctypes.data, rt.ctypes.data,
+                                           reading_map._h, len(da), da.ctypes.data, dt.ctypes.data, t0.ctypes.data,
+                                           tout.ctypes.data, ctypes.byref(st))
+        if rc != LS_ERR_CONVERGENCE or raise_on_convergence:
+            self.ctx._check(rc)
+        return dict(T=from_colmajor(tout), stats=st, rc=rc)
 
     def assemble(self, part_ids, T_parts, want_normals=True):
         ids_arr = np.ascontiguousarray(part_ids, np.uint64)

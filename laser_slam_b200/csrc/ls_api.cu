@@ -777,6 +777,38 @@ int ls_icp_register_submap(ls_ctx* ctx, const ls_icp_params* prm, const ls_map* 
   return run_icp(ctx, prm, rs->pts, n, T0, T_out, stats, opt_ids, opt_d2, opt_T_iter_hist, m);
 }
 
+// Sub-map <-> sub-map registration with both clouds assembled on the device (the loop-closure ICP of
+// IncrementalEstimator::processLoopClosure, reference incremental_estimator.cpp:90-115, whose two
+// buildSubMapAroundTime clouds never have to visit the host).  Bit-identical to ls_map_assemble of both sides
+// followed by ls_icp_register.
+int ls_icp_register_submaps(ls_ctx* ctx, const ls_icp_params* prm, const ls_map* ref_map, int n_ref_parts,
+                            const uint64_t* ref_part_ids, const float* T_ref_parts, const ls_map* reading_map,
+                            int n_reading_parts, const uint64_t* reading_part_ids, const float* T_reading_parts,
+                            const float T0[16], float T_out[16], ls_icp_stats* stats) {
+  if (!ctx) return LS_ERR_ARG;
+  if (!ref_map || ref_map->ctx != ctx || !reading_map || reading_map->ctx != ctx || !ref_part_ids || !T_ref_parts ||
+      !reading_part_ids || !T_reading_parts || !T0 || !T_out)
+    return fail(ctx, LS_ERR_ARG, "bad argument");
+  int rc = check_params(ctx, prm);
+  if (rc) return rc;
+  std::memcpy(T_out, T0, 16 * sizeof(float));
+  if (stats) std::memset(stats, 0, sizeof(*stats));
+  Parts ref, rd;
+  if ((rc = make_parts(ctx, ref_map, n_ref_parts, ref_part_ids, T_ref_parts, &ref))) return rc;
+  if ((rc = make_parts(ctx, reading_map, n_reading_parts, reading_part_ids, T_reading_parts, &rd))) return rc;
+  const int n = rd.offset[n_reading_parts], m = ref.offset[n_ref_parts];
+  if (n == 0 || m == 0) return fail(ctx, LS_ERR_CONVERGENCE, "empty reading or reference");
+  CU(cudaSetDevice(ctx->device));
+  Workspace* w = ctx->ws[0];
+  const Resolved r = resolve(prm);
+  if ((rc = ensure_capacity(ctx, w, n, m, r.max_cells, prm->max_iterations))) return rc;
+  CU(cudaEventRecord(w->ev0, w->stream));
+  assemble_points_kernel<<<blocks_for(n, 256, ctx->sm_count * 8), 256, 0, w->stream>>>(rd, w->reading);
+  LAUNCH_CHECK();
+  if ((rc = enqueue_build(ctx, w, ref, r, T0))) return rc;
+  return run_icp(ctx, prm, w->reading, n, T0, T_out, stats, nullptr, nullptr, nullptr, m);
+}
+
 // Several independent scan -> sub-map registrations in ONE cooperative launch (the multi-robot case: the
 // reference's n_laser_slam_workers tracks, reference incremental_estimator.cpp:22-26, hosted on one GPU).
 // Problem b stages on its own stream (assembly + hash build overlap across problems); the persistent kernel's

@@ -175,6 +175,22 @@ __global__ void __launch_bounds__(256) assemble_kernel(const __grid_constant__ P
   }
 }
 
+// points only (the reading side of a sub-map <-> sub-map registration): same arithmetic as assemble_kernel
+__global__ void __launch_bounds__(256) assemble_points_kernel(const __grid_constant__ Parts parts, float4* __restrict__ out) {
+  const int total = parts.offset[parts.n_parts];
+  int p = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    while (i >= parts.offset[p + 1]) ++p;
+    float4 a = __ldg(parts.pts[p] + (i - parts.offset[p]));
+    if (!parts.identity[p]) {
+      float x, y, z;
+      xform_point(parts.T[p], a.x, a.y, a.z, x, y, z);
+      a.x = x; a.y = y; a.z = z;
+    }
+    out[i] = a;
+  }
+}
+
 // normals descriptor (stride floats per point) -> float4
 __global__ void expand_normals_kernel(const float* __restrict__ raw, int stride, int n, float4* __restrict__ out) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {

@@ -68,19 +68,29 @@ void IncrementalEstimator::processLoopClosure(const RelativePose& loop_closure) 
   if (params_.do_icp_step_on_loop_closures) {  // reference :89-115; a ConvergenceError propagates here
     const PointMatcher::TransformationParameters initial_guess =
         PointMatcher::TransformationParameters::cast(updated.T_a_b.getTransformationMatrix());
-    DataPoints sub_map_a, sub_map_b;
-    track_a.buildSubMapAroundTime(loop_closure.time_a_ns, params_.loop_closures_sub_maps_radius, &sub_map_a);
-    track_b.buildSubMapAroundTime(loop_closure.time_b_ns, params_.loop_closures_sub_maps_radius, &sub_map_b);
     if (!icp_ctx_ && ls_b200_init(params_.laser_track_params.cuda_device, &icp_ctx_) != LS_OK)
       throw std::runtime_error("ls_b200_init failed");
+    // both sub-maps are assembled on the device (ls_icp_register_submaps): the scans go up once, nothing comes back
+    // but the 4x4
+    ls_map *ring_a = nullptr, *ring_b = nullptr;
+    std::vector<uint64_t> ids_a, ids_b;
+    std::vector<float> T_a, T_b;
     PointMatcher::TransformationParameters icp_solution;
-    const int off = sub_map_a.descriptorOffset("normals");
-    LS_CHECK(off >= 0, "sub-map without normals");
-    const int rc = ls_icp_register(icp_ctx_, &icp_params_, sub_map_b.features.data(), (int)sub_map_b.getNbPoints(),
-                                   sub_map_a.features.data(), sub_map_a.descriptors.data() + off, (int)sub_map_a.descriptorDim,
-                                   (int)sub_map_a.getNbPoints(), initial_guess.data(), icp_solution.data(), NULL, NULL, NULL, NULL);
+    int rc = LS_OK;
+    try {
+      track_a.stageSubMapAroundTime(loop_closure.time_a_ns, params_.loop_closures_sub_maps_radius, icp_ctx_, &ring_a, &ids_a, &T_a);
+      track_b.stageSubMapAroundTime(loop_closure.time_b_ns, params_.loop_closures_sub_maps_radius, icp_ctx_, &ring_b, &ids_b, &T_b);
+      rc = ls_icp_register_submaps(icp_ctx_, &icp_params_, ring_a, (int)ids_a.size(), ids_a.data(), T_a.data(), ring_b,
+                                   (int)ids_b.size(), ids_b.data(), T_b.data(), initial_guess.data(), icp_solution.data(), NULL);
+    } catch (...) {
+      if (ring_a) ls_map_destroy(ring_a);
+      if (ring_b) ls_map_destroy(ring_b);
+      throw;
+    }
+    ls_map_destroy(ring_a);
+    ls_map_destroy(ring_b);
     if (rc == LS_ERR_CONVERGENCE) throw PointMatcher::ConvergenceError(ls_b200_last_error(icp_ctx_));
-    if (rc != LS_OK) throw std::runtime_error(std::string("ls_icp_register: ") + ls_b200_last_error(icp_ctx_));
+    if (rc != LS_OK) throw std::runtime_error(std::string("ls_icp_register_submaps: ") + ls_b200_last_error(icp_ctx_));
     updated.T_a_b = convertTransformationMatrixToSE3(icp_solution);
   }
 

@@ -485,23 +485,63 @@ void LaserTrack::assembleSubMap(const std::vector<size_t>& scan_indices,
   ls_map_destroy(tmp);
 }
 
-// reference :602-651
-void LaserTrack::buildSubMapAroundTime(const curves::Time& time_ns, const unsigned int sub_maps_radius, DataPoints* submap_out) const {
-  std::lock_guard<std::recursive_mutex> lock(full_laser_track_mutex_);
-  LS_CHECK(submap_out != NULL, "null output");
+// reference :602-651: the centre scan verbatim, then up to `radius` scans before it (decreasing time stamps) and after
+// it (increasing), each re-expressed in the centre scan's frame
+void LaserTrack::describeSubMapAroundTime(const curves::Time& time_ns, const unsigned int sub_maps_radius,
+                                          std::vector<size_t>* scan_indices,
+                                          std::vector<PointMatcher::TransformationParameters>* Ts) const {
   const SE3 T_w_a = evaluate(time_ns);
   const size_t centre = scanIndexAtTime(time_ns);
-  std::vector<size_t> idx{centre};
-  std::vector<PointMatcher::TransformationParameters> Ts(1);
+  scan_indices->assign(1, centre);
+  Ts->assign(1, PointMatcher::TransformationParameters());
   auto add = [&](size_t i) {
     PointMatcher::TransformationParameters T = toFloatMatrix(T_w_a.inverse() * evaluate(laser_scans_[i].time_ns));
     correctTransformationMatrix(&T);
-    idx.push_back(i);
-    Ts.push_back(T);
+    scan_indices->push_back(i);
+    Ts->push_back(T);
   };
-  for (unsigned int i = 1; i <= sub_maps_radius && centre >= i; ++i) add(centre - i);                     // decreasing time stamps
-  for (unsigned int i = 1; i <= sub_maps_radius && centre + i < laser_scans_.size(); ++i) add(centre + i);  // increasing
+  for (unsigned int i = 1; i <= sub_maps_radius && centre >= i; ++i) add(centre - i);
+  for (unsigned int i = 1; i <= sub_maps_radius && centre + i < laser_scans_.size(); ++i) add(centre + i);
+}
+
+void LaserTrack::buildSubMapAroundTime(const curves::Time& time_ns, const unsigned int sub_maps_radius, DataPoints* submap_out) const {
+  std::lock_guard<std::recursive_mutex> lock(full_laser_track_mutex_);
+  LS_CHECK(submap_out != NULL, "null output");
+  std::vector<size_t> idx;
+  std::vector<PointMatcher::TransformationParameters> Ts;
+  describeSubMapAroundTime(time_ns, sub_maps_radius, &idx, &Ts);
   assembleSubMap(idx, Ts, submap_out);
+}
+
+void LaserTrack::stageSubMapAroundTime(const curves::Time& time_ns, const unsigned int sub_maps_radius, ls_ctx* ctx,
+                                       ls_map** ring_out, std::vector<uint64_t>* ids_out, std::vector<float>* T_parts_out) const {
+  std::lock_guard<std::recursive_mutex> lock(full_laser_track_mutex_);
+  LS_CHECK(ctx != NULL && ring_out != NULL && ids_out != NULL && T_parts_out != NULL, "null argument");
+  std::vector<size_t> idx;
+  std::vector<PointMatcher::TransformationParameters> Ts;
+  describeSubMapAroundTime(time_ns, sub_maps_radius, &idx, &Ts);
+  size_t max_pts = 1;
+  for (size_t i : idx) max_pts = std::max(max_pts, laser_scans_[i].scan.getNbPoints());
+  ls_map* ring = nullptr;
+  throwOnError(ctx, ls_map_create(ctx, (int)std::max<size_t>(2, idx.size()), (int)max_pts, &ring), "ls_map_create");
+  ids_out->clear();
+  T_parts_out->clear();
+  try {
+    for (size_t k = 0; k < idx.size(); ++k) {
+      const DataPoints& c = laser_scans_[idx[k]].scan;
+      const int off = c.descriptorOffset("normals");
+      LS_CHECK(off >= 0, "scan without normals");
+      uint64_t id = 0;
+      throwOnError(ctx, ls_map_push_scan(ring, c.features.data(), c.descriptors.data() + off, (int)c.descriptorDim,
+                                         (int)c.getNbPoints(), &id), "ls_map_push_scan");
+      ids_out->push_back(id);
+      T_parts_out->insert(T_parts_out->end(), Ts[k].data(), Ts[k].data() + 16);
+    }
+  } catch (...) {
+    ls_map_destroy(ring);
+    throw;
+  }
+  *ring_out = ring;
 }
 
 }  // namespace laser_slam

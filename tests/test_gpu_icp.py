@@ -275,3 +275,30 @@ def test_batched_registrations_equal_separate_calls(gpu_ctx, scans, traj):
     again = mp.register(*problems[0], p)           # workspace 0 is still consistent after a batch
     assert np.array_equal(again["T"], single[0]["T"])
     mp.close()
+
+
+def test_submap_to_submap_on_device_equals_assembled_register(gpu_ctx, scans, traj):
+    """ls_icp_register_submaps (loop-closure ICP, both clouds assembled on the device) is bit-identical
+    to ls_map_assemble of both sides followed by ls_icp_register; the two sides may live in different rings."""
+    import laser_slam_b200 as ls
+    truth, odom = traj
+    ring_a = gpu_ctx.create_map(4, 131072)
+    ring_b = gpu_ctx.create_map(4, 131072)
+    sa = [ring_a.push_scan(*scans[k]) for k in (1, 0, 2)]       # centre scan 1, then 0 and 2 in its frame
+    sb = [ring_b.push_scan(*scans[k]) for k in (4, 3)]          # centre scan 4, then 3
+    Ta = [np.eye(4, dtype=np.float32)] + [(np.linalg.inv(truth[1]) @ truth[k]).astype(np.float32) for k in (0, 2)]
+    Tb = [np.eye(4, dtype=np.float32), (np.linalg.inv(truth[4]) @ truth[3]).astype(np.float32)]
+    T0 = (np.linalg.inv(truth[1]) @ odom[4]).astype(np.float32)
+    p = ls.default_params(max_iterations=10, use_differential=0)
+    dev = ring_a.register_submaps(sa, Ta, ring_b, sb, Tb, T0, p)
+    ref, ref_n = ring_a.assemble(sa, Ta)
+    rd, _ = ring_b.assemble(sb, Tb)
+    host = gpu_ctx.icp_register(rd, ref, ref_n, T0, p)
+    assert dev["rc"] == 0 and np.array_equal(dev["T"], host["T"])
+    assert dev["stats"].iterations == host["stats"].iterations == 10 and dev["stats"].last_kept == host["stats"].last_kept
+    truth_rel = np.linalg.inv(truth[1]) @ truth[4]
+    assert np.abs(dev["T"][:3, 3] - truth_rel[:3, 3]).max() < 0.05
+    same = ring_a.register_submaps(sa[:2], Ta[:2], ring_a, sa[2:], Ta[2:], np.eye(4, dtype=np.float32), p)   # one ring, both sides
+    assert same["rc"] == 0 and np.abs(same["T"] - np.eye(4)).max() < 0.05
+    ring_a.close()
+    ring_b.close()
