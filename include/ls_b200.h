@@ -64,7 +64,7 @@ typedef struct ls_icp_stats {
   float device_ms;      /* CUDA-event time of the device work of this call */
   float build_ms;       /* of which: sub-map assembly + spatial-hash build */
   int grid_cells;       /* level-0 cells */
-  int grid_tables;      /* level-1 + level-2 tables */
+  int grid_tables;      /* fine (8x8x8) tables allocated */
   int grid_overflow;    /* 1 if a table pool overflowed (slower, still exact) */
   float icp_ms;         /* CUDA-event duration of the persistent ICP kernel launch (shared by a batch) */
 } ls_icp_stats;

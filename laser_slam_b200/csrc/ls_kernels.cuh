@@ -3,7 +3,7 @@
 //
 //   K0  assemble_kernel      sub-map = concat_p( T_p * scan_p ), exact mean sums, bounding box
 //                            (LaserTrack::localScanToSubMap, reference laser_slam/src/laser_track.cpp:476-486)
-//   K1  setup/count/scan/table/scatter kernels: three-level spatial hash build (counting sort)
+//   K1  setup/count/scan/table/scatter kernels: two-level spatial hash + occupancy pyramid build (counting sort)
 //                            (matcher->init(reference) inside ICP::compute, laser_track.cpp:496)
 //   K2..K4 icp_kernel        ONE persistent cooperative kernel for the whole ICP loop: per iteration
 //                            NN query (K2) -> exact trimmed-quantile radix select (K3) -> point-to-plane

@@ -1,7 +1,7 @@
 // CPU simulation of the CUDA grid build + exact NN query (test tool; not a product path).
 //
 // Compiles laser_slam_b200/csrc/ls_grid.cuh for the host (-ffp-contract=off) and builds the same
-// three-level structure the build kernels produce, so the query logic (loop bounds, pruning margins,
+// two-level structure (+ occupancy pyramid) the build kernels produce, so the query logic (loop bounds, pruning margins,
 // tie-break, seeding) can be checked against brute force here, where there is no GPU.  The CUDA
 // kernels are still checked on the GPU by tests/test_gpu_*.py; this only shortens the debug loop.
 #define LS_SIM_COUNTERS 1
@@ -107,7 +107,7 @@ void build(SimGrid& S, const float* refc3, int m, float cell, int max_cells, int
 extern "C" {
 // Exact NN of n queries (stride 3) over the centred reference (stride 3).  warm: optional previous
 // match ORIGINAL indices (-1 = cold).  stats (optional, 4 doubles): mean candidates, mean entry
-// loads, max candidates, #level-1 tables + 1e-6 * #level-2 tables.
+// loads, max candidates, number of fine tables, H0, number of level-0 cells.
 void sim_nn(const float* q3, int n, const float* refc3, int m, float cell, int max_cells, int split,
             const int32_t* warm_ids, int32_t* ids, float* d2, double* stats, int32_t* per_query_cand,
             int32_t* per_query_entries, float cap_d2) {

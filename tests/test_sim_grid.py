@@ -86,7 +86,7 @@ def test_sim_edge_cases(sim, oracle_mod):
     _check(sim, oracle_mod, far, cloud)                                 # queries far outside the bounding box
     ids, d2 = sim(q, np.zeros((0, 3), np.float32))                      # empty map: libnabo's "unfound"
     assert (ids == -1).all() and np.isinf(d2).all()
-    dense = (rng.normal(scale=0.01, size=(20000, 3))).astype(np.float32)  # everything in one level-2 cell
+    dense = (rng.normal(scale=0.01, size=(20000, 3))).astype(np.float32)  # everything in one fine cell
     _check(sim, oracle_mod, rng.normal(scale=0.02, size=(300, 3)).astype(np.float32), dense)
 
 
