@@ -124,6 +124,14 @@ void ls_map_destroy(ls_map* map);
  * addressable until `capacity_scans` newer scans have been pushed). */
 int ls_map_push_scan(ls_map* map, const float* features4, const float* normals, int normals_stride, int n,
                      uint64_t* scan_id);
+/* The same, enqueued on the map's own upload stream; returns at once.  The host buffers must stay valid (pinned
+ * memory, or the copies are synchronous after all) until ls_map_sync() or until a registration that uses the scan
+ * has returned.  Registrations wait for exactly the uploads they depend on, so the next scan can go up while the
+ * current one is being registered (the reference copies every scan twice on the host before its ICP starts,
+ * laser_track.cpp:143,197).  3 <= normals_stride <= 8. */
+int ls_map_push_scan_async(ls_map* map, const float* features4, const float* normals, int normals_stride, int n,
+                           uint64_t* scan_id);
+int ls_map_sync(ls_map* map); /* wait for every asynchronous upload of this map */
 int ls_map_scan_size(const ls_map* map, uint64_t scan_id); /* points, or <0 if evicted/unknown */
 
 /* Surface normals on the device: replaces the SurfaceNormal / SamplingSurfaceNormal

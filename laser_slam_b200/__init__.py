@@ -94,6 +94,8 @@ def lib():
         L.ls_map_destroy.argtypes = [vp]
         L.ls_map_destroy.restype = None
         L.ls_map_push_scan.argtypes = [vp, vp, vp, ci, ci, ctypes.POINTER(u64)]
+        L.ls_map_push_scan_async.argtypes = [vp, vp, vp, ci, ci, ctypes.POINTER(u64)]
+        L.ls_map_sync.argtypes = [vp]
         L.ls_map_scan_size.argtypes = [vp, u64]
         L.ls_icp_register_submap.argtypes = [vp, PP, vp, u64, ci, vp, vp, vp, vp, PS, vp, vp, vp]
         L.ls_map_assemble.argtypes = [vp, vp, ci, vp, vp, vp, vp, ctypes.POINTER(ci)]
@@ -290,6 +292,16 @@ class Map:
         sid = ctypes.c_uint64(0)
         self.ctx._check(lib().ls_map_push_scan(self._h, feat_ptr, nrm_ptr, nrm_stride, n, ctypes.byref(sid)))
         return sid.value
+
+    def push_scan_raw_async(self, feat_ptr, nrm_ptr, nrm_stride, n):
+        """ls_map_push_scan_async: enqueue the upload and return; the buffers (pinned) must stay valid until `sync()`
+        or until a registration that uses the scan has returned."""
+        sid = ctypes.c_uint64(0)
+        self.ctx._check(lib().ls_map_push_scan_async(self._h, feat_ptr, nrm_ptr, nrm_stride, n, ctypes.byref(sid)))
+        return sid.value
+
+    def sync(self):
+        self.ctx._check(lib().ls_map_sync(self._h))
 
     def scan_size(self, scan_id):
         return int(lib().ls_map_scan_size(self._h, scan_id))

@@ -57,13 +57,22 @@ struct ls_scan_slot {
   int n = 0;
   uint64_t id = 0;
   bool used = false;
+  cudaEvent_t ready = nullptr;  // recorded after an asynchronous upload; consumers wait on it
+  bool async = false;           // `ready` is meaningful
 };
 
+constexpr int kStageRing = 16;  // normals staging buffers of the asynchronous upload path
 struct ls_map {
   ls_ctx* ctx = nullptr;
   int capacity = 0, max_pts = 0;
   uint64_t next_id = 1;
   std::vector<ls_scan_slot> slots;
+  // asynchronous uploads (ls_map_push_scan_async): own stream, a small ring of raw-normals staging buffers
+  cudaStream_t up_stream = nullptr;
+  float* stage[kStageRing] = {};
+  size_t stage_cap[kStageRing] = {};
+  cudaEvent_t stage_free[kStageRing] = {};
+  uint64_t n_async = 0;
 };
 
 namespace {
@@ -400,7 +409,14 @@ const ls_scan_slot* find_slot(const ls_map* map, uint64_t id) {
   return nullptr;
 }
 
-int make_parts(ls_ctx* ctx, const ls_map* map, int n_parts, const uint64_t* part_ids, const float* T_parts, Parts* out) {
+// consumers of a slot filled by ls_map_push_scan_async order themselves behind its upload
+int wait_slot(const ls_scan_slot* s, cudaStream_t consumer) {
+  if (s->async && consumer && cudaStreamWaitEvent(consumer, s->ready, 0) != cudaSuccess) return LS_ERR_CUDA;
+  return LS_OK;
+}
+
+int make_parts(ls_ctx* ctx, const ls_map* map, int n_parts, const uint64_t* part_ids, const float* T_parts, Parts* out,
+               cudaStream_t consumer) {
   if (n_parts < 1 || n_parts > kMaxParts) return fail(ctx, LS_ERR_ARG, "n_parts must be in [1,%d]", kMaxParts);
   Parts& parts = *out;
   std::memset(&parts, 0, sizeof(parts));
@@ -410,6 +426,7 @@ int make_parts(ls_ctx* ctx, const ls_map* map, int n_parts, const uint64_t* part
     const ls_scan_slot* s = find_slot(map, part_ids[p]);
     if (!s) return fail(ctx, LS_ERR_STATE, "scan %llu is not resident (evicted or never pushed)",
                         (unsigned long long)part_ids[p]);
+    if (wait_slot(s, consumer) != LS_OK) return fail(ctx, LS_ERR_CUDA, "cudaStreamWaitEvent failed");
     parts.offset[p] = (int)off;
     parts.pts[p] = s->pts;
     parts.nrm[p] = s->nrm;
@@ -633,9 +650,14 @@ int ls_map_create(ls_ctx* ctx, int capacity_scans, int max_pts_per_scan, ls_map*
   map->capacity = capacity_scans;
   map->max_pts = max_pts_per_scan;
   map->slots.resize(capacity_scans);
+  if (cudaStreamCreateWithFlags(&map->up_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    ls_map_destroy(map);
+    return fail(ctx, LS_ERR_CUDA, "stream creation failed");
+  }
   for (auto& s : map->slots) {
     if (cudaMalloc((void**)&s.pts, (size_t)max_pts_per_scan * sizeof(float4)) != cudaSuccess ||
-        cudaMalloc((void**)&s.nrm, (size_t)max_pts_per_scan * sizeof(float4)) != cudaSuccess) {
+        cudaMalloc((void**)&s.nrm, (size_t)max_pts_per_scan * sizeof(float4)) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming) != cudaSuccess) {
       ls_map_destroy(map);
       return fail(ctx, LS_ERR_NOMEM, "map allocation failed");
     }
@@ -650,10 +672,17 @@ void ls_map_destroy(ls_map* map) {
     cudaSetDevice(map->ctx->device);
     for (Workspace* w : map->ctx->ws) cudaStreamSynchronize(w->stream);
   }
+  if (map->up_stream) cudaStreamSynchronize(map->up_stream);
   for (auto& s : map->slots) {
     if (s.pts) cudaFree(s.pts);
     if (s.nrm) cudaFree(s.nrm);
+    if (s.ready) cudaEventDestroy(s.ready);
   }
+  for (int k = 0; k < kStageRing; ++k) {
+    if (map->stage[k]) cudaFree(map->stage[k]);
+    if (map->stage_free[k]) cudaEventDestroy(map->stage_free[k]);
+  }
+  if (map->up_stream) cudaStreamDestroy(map->up_stream);
   delete map;
 }
 
@@ -668,6 +697,10 @@ int ls_map_push_scan(ls_map* map, const float* features4, const float* normals, 
   const uint64_t id = map->next_id++;
   ls_scan_slot& s = map->slots[id % (uint64_t)map->capacity];
   s.used = false;
+  if (s.async) {  // an earlier asynchronous upload into this slot must not land after this one
+    CU(cudaEventSynchronize(s.ready));
+    s.async = false;
+  }
   if (n > 0) {
     CU(cudaMemcpyAsync(s.pts, features4, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, w->stream));
     int rc = upload_normals(ctx, w, normals, normals_stride, n, s.nrm);
@@ -679,6 +712,58 @@ int ls_map_push_scan(ls_map* map, const float* features4, const float* normals, 
   s.id = id;
   s.used = true;
   *scan_id = id;
+  return LS_OK;
+}
+
+// Asynchronous variant: everything is enqueued on the map's own upload stream and the call returns; the host buffers
+// must stay valid (and should be pinned, or the copies degrade to synchronous ones) until ls_map_sync or until a
+// registration that uses the scan has returned.  Consumers order themselves behind the upload with the slot's event,
+// so scan s+1 can go up while scan s is being registered.
+int ls_map_push_scan_async(ls_map* map, const float* features4, const float* normals, int normals_stride, int n,
+                           uint64_t* scan_id) {
+  if (!map) return LS_ERR_ARG;
+  ls_ctx* ctx = map->ctx;
+  if (!features4 || !normals || normals_stride < 3 || normals_stride > 8 || n < 0 || n > map->max_pts || !scan_id)
+    return fail(ctx, LS_ERR_ARG, "bad argument (n=%d, max=%d, 3 <= normals_stride <= 8)", n, map->max_pts);
+  CU(cudaSetDevice(ctx->device));
+  const uint64_t id = map->next_id++;
+  ls_scan_slot& s = map->slots[id % (uint64_t)map->capacity];
+  s.used = false;
+  // a registration that still reads the evicted scan was synchronous, so it has returned; uploads into the same slot
+  // are ordered by the stream
+  if (n > 0) {
+    const int k = (int)(map->n_async++ % kStageRing);
+    const size_t need = (size_t)n * (size_t)normals_stride;
+    if (!map->stage_free[k]) CU(cudaEventCreateWithFlags(&map->stage_free[k], cudaEventDisableTiming));
+    else CU(cudaEventSynchronize(map->stage_free[k]));  // the upload that used this staging buffer 16 pushes ago
+    if (need > map->stage_cap[k]) {
+      if (map->stage[k]) CU(cudaFree(map->stage[k]));
+      map->stage[k] = nullptr;
+      map->stage_cap[k] = 0;
+      if (cudaMalloc((void**)&map->stage[k], (need + 1024) * sizeof(float)) != cudaSuccess)
+        return fail(ctx, LS_ERR_NOMEM, "staging allocation failed");
+      map->stage_cap[k] = need + 1024;
+    }
+    CU(cudaMemcpyAsync(s.pts, features4, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, map->up_stream));
+    CU(cudaMemcpyAsync(map->stage[k], normals, need * sizeof(float), cudaMemcpyHostToDevice, map->up_stream));
+    expand_normals_kernel<<<blocks_for(n, 256, ctx->sm_count * 8), 256, 0, map->up_stream>>>(map->stage[k], normals_stride, n, s.nrm);
+    LAUNCH_CHECK();
+    CU(cudaEventRecord(map->stage_free[k], map->up_stream));
+  }
+  CU(cudaEventRecord(s.ready, map->up_stream));
+  s.async = true;
+  s.n = n;
+  s.id = id;
+  s.used = true;
+  *scan_id = id;
+  return LS_OK;
+}
+
+int ls_map_sync(ls_map* map) {
+  if (!map) return LS_ERR_ARG;
+  ls_ctx* ctx = map->ctx;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(map->up_stream));
   return LS_OK;
 }
 
@@ -734,6 +819,10 @@ int ls_map_push_scan_estimate_normals(ls_map* map, const float* features4, int n
   const uint64_t id = map->next_id++;
   ls_scan_slot& s = map->slots[id % (uint64_t)map->capacity];
   s.used = false;
+  if (s.async) {
+    CU(cudaEventSynchronize(s.ready));
+    s.async = false;
+  }
   if (n > 0) {
     CU(cudaMemcpyAsync(s.pts, features4, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, w->stream));
     int rc = enqueue_normals(ctx, w, s.pts, n, knn, s.nrm);
@@ -765,11 +854,12 @@ int ls_icp_register_submap(ls_ctx* ctx, const ls_icp_params* prm, const ls_map* 
   const ls_scan_slot* rs = find_slot(map, reading_id);
   if (!rs) return fail(ctx, LS_ERR_STATE, "reading scan %llu is not resident", (unsigned long long)reading_id);
   Parts parts;
-  if ((rc = make_parts(ctx, map, n_parts, part_ids, T_parts, &parts))) return rc;
-  const int n = rs->n, m = parts.offset[n_parts];
-  if (n == 0 || m == 0) return fail(ctx, LS_ERR_CONVERGENCE, "empty reading or reference");
   CU(cudaSetDevice(ctx->device));
   Workspace* w = ctx->ws[0];
+  if ((rc = make_parts(ctx, map, n_parts, part_ids, T_parts, &parts, w->stream))) return rc;
+  if (wait_slot(rs, w->stream) != LS_OK) return fail(ctx, LS_ERR_CUDA, "cudaStreamWaitEvent failed");
+  const int n = rs->n, m = parts.offset[n_parts];
+  if (n == 0 || m == 0) return fail(ctx, LS_ERR_CONVERGENCE, "empty reading or reference");
   const Resolved r = resolve(prm);
   if ((rc = ensure_capacity(ctx, w, n, m, r.max_cells, prm->max_iterations))) return rc;
   CU(cudaEventRecord(w->ev0, w->stream));
@@ -794,12 +884,12 @@ int ls_icp_register_submaps(ls_ctx* ctx, const ls_icp_params* prm, const ls_map*
   std::memcpy(T_out, T0, 16 * sizeof(float));
   if (stats) std::memset(stats, 0, sizeof(*stats));
   Parts ref, rd;
-  if ((rc = make_parts(ctx, ref_map, n_ref_parts, ref_part_ids, T_ref_parts, &ref))) return rc;
-  if ((rc = make_parts(ctx, reading_map, n_reading_parts, reading_part_ids, T_reading_parts, &rd))) return rc;
-  const int n = rd.offset[n_reading_parts], m = ref.offset[n_ref_parts];
-  if (n == 0 || m == 0) return fail(ctx, LS_ERR_CONVERGENCE, "empty reading or reference");
   CU(cudaSetDevice(ctx->device));
   Workspace* w = ctx->ws[0];
+  if ((rc = make_parts(ctx, ref_map, n_ref_parts, ref_part_ids, T_ref_parts, &ref, w->stream))) return rc;
+  if ((rc = make_parts(ctx, reading_map, n_reading_parts, reading_part_ids, T_reading_parts, &rd, w->stream))) return rc;
+  const int n = rd.offset[n_reading_parts], m = ref.offset[n_ref_parts];
+  if (n == 0 || m == 0) return fail(ctx, LS_ERR_CONVERGENCE, "empty reading or reference");
   const Resolved r = resolve(prm);
   if ((rc = ensure_capacity(ctx, w, n, m, r.max_cells, prm->max_iterations))) return rc;
   CU(cudaEventRecord(w->ev0, w->stream));
@@ -835,7 +925,9 @@ int ls_icp_register_submap_batch(ls_ctx* ctx, const ls_icp_params* prm, const ls
     const ls_scan_slot* rs = find_slot(map, reading_ids[b]);
     if (!rs) return fail(ctx, LS_ERR_STATE, "reading scan %llu is not resident", (unsigned long long)reading_ids[b]);
     Parts parts;
-    if ((rc = make_parts(ctx, map, n_parts[b], part_ids + part_off, T_parts + 16 * (size_t)part_off, &parts))) return rc;
+    if ((rc = make_parts(ctx, map, n_parts[b], part_ids + part_off, T_parts + 16 * (size_t)part_off, &parts, w->stream)))
+      return rc;
+    if (wait_slot(rs, w->stream) != LS_OK) return fail(ctx, LS_ERR_CUDA, "cudaStreamWaitEvent failed");
     part_off += n_parts[b];
     const int n = rs->n, m = parts.offset[n_parts[b]];
     if (n == 0 || m == 0) return fail(ctx, LS_ERR_ARG, "empty reading or reference in a batch (use the single call)");
@@ -862,12 +954,12 @@ int ls_map_assemble(ls_ctx* ctx, const ls_map* map, int n_parts, const uint64_t*
   if (!map || map->ctx != ctx || !part_ids || !T_parts || !out4 || !m_out) return fail(ctx, LS_ERR_ARG, "bad argument");
   Parts parts;
   int rc;
-  if ((rc = make_parts(ctx, map, n_parts, part_ids, T_parts, &parts))) return rc;
+  CU(cudaSetDevice(ctx->device));
+  Workspace* w = ctx->ws[0];
+  if ((rc = make_parts(ctx, map, n_parts, part_ids, T_parts, &parts, w->stream))) return rc;
   const int m = parts.offset[n_parts];
   *m_out = m;
   if (m == 0) return LS_OK;
-  CU(cudaSetDevice(ctx->device));
-  Workspace* w = ctx->ws[0];
   if ((rc = ensure_capacity(ctx, w, 1, m, 64, 1))) return rc;
   reset_build_kernel<<<1, 32, 0, w->stream>>>(w->bs);
   LAUNCH_CHECK();

@@ -302,3 +302,29 @@ def test_submap_to_submap_on_device_equals_assembled_register(gpu_ctx, scans, tr
     assert same["rc"] == 0 and np.abs(same["T"] - np.eye(4)).max() < 0.05
     ring_a.close()
     ring_b.close()
+
+
+def test_async_scan_upload_is_ordered_before_its_consumers(gpu_ctx, scans, traj):
+    """ls_map_push_scan_async: a registration issued right after the asynchronous uploads waits for exactly the scans it
+    uses and returns the same bits as with synchronous uploads."""
+    import torch
+    import laser_slam_b200 as ls
+    truth, odom = traj
+    p = ls.default_params(max_iterations=8, use_differential=0)
+    Ts = [np.eye(4, dtype=np.float32)] + [(np.linalg.inv(truth[3]) @ truth[k]).astype(np.float32) for k in (2, 1)]
+    T0 = (np.linalg.inv(truth[3]) @ odom[4]).astype(np.float32)
+    ring = gpu_ctx.create_map(6, 131072)
+    sync_ids = [ring.push_scan(*scans[k]) for k in (3, 2, 1, 4)]
+    want = ring.register(sync_ids[3], sync_ids[:3], Ts, T0, p)
+    ring.close()
+    ring = gpu_ctx.create_map(6, 131072)
+    pinned = [(torch.from_numpy(scans[k][0]).pin_memory(), torch.from_numpy(scans[k][1]).pin_memory()) for k in (3, 2, 1, 4, 5, 0)]
+    ids = [ring.push_scan_raw_async(f.data_ptr(), n.data_ptr(), 3, f.shape[0]) for f, n in pinned[:4]]
+    later = [ring.push_scan_raw_async(f.data_ptr(), n.data_ptr(), 3, f.shape[0]) for f, n in pinned[4:]]  # still in flight
+    got = ring.register(ids[3], ids[:3], Ts, T0, p)
+    assert got["rc"] == 0 and np.array_equal(got["T"], want["T"]) and got["stats"].last_kept == want["stats"].last_kept
+    ring.sync()
+    assert ring.scan_size(later[0]) == 131072
+    again = ring.register(ids[3], ids[:3], Ts, T0, p)
+    assert np.array_equal(again["T"], want["T"])
+    ring.close()
