@@ -421,7 +421,7 @@ def main():
                    "final_pose_err_vs_truth_m": pose_err},
         "e2e": {"value": world * B * args.steps / t_e2e, "unit": "registrations/s",
                 "h2d_bytes_per_step": B * (N_SCAN * 16 + N_SCAN * 12 + 16 * 4 * (K_MAP + 1) + 8 * (K_MAP + 1)),
-                "d2h_bytes_per_step": B * (64 + 48 + 2 * 16896),
+                "d2h_bytes_per_step": B * (216 + 212),   # per registration: result block of the ICP scratch + grid header
                 "pipeline": "the scans of step s+1 are uploaded (ls_map_push_scan_async, own stream) while step s is "
                             "registered; every timed step issues one full set of uploads and reads its results back"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,

@@ -1,6 +1,7 @@
 // C-ABI implementation (include/ls_b200.h): context, device memory, kernel launches.
 // There is no CPU fallback anywhere in this file: every entry point needs a live CUDA device.
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -294,7 +295,6 @@ int prep_icp(ls_ctx* ctx, Workspace* w, const ls_icp_params* prm, const float4* 
     CU(cudaMemsetAsync(w->phase_ns, 0, (size_t)prm->max_iterations * 6 * sizeof(unsigned long long), w->stream));
   }
   hp.phase_ns = want_phase ? w->phase_ns : nullptr;
-  hp.warp_cyc = nullptr;
   std::memcpy(hp.T0, T0, sizeof(hp.T0));
   return LS_OK;
 }
@@ -330,7 +330,10 @@ int launch_icp(ls_ctx* ctx, const ls_icp_params* prm, int batch, int n_max) {
   CU(cudaEventRecord(w0->ev2, w0->stream));
   for (int b = 0; b < batch; ++b) {
     Workspace* w = ctx->ws[b];
-    CU(cudaMemcpyAsync(w->h_work, w->work, sizeof(IcpWork), cudaMemcpyDeviceToHost, w0->stream));
+    // only the results at the tail of the scratch come back (not the 48 KB of histograms in front of them)
+    constexpr size_t off = offsetof(IcpWork, T_out);
+    CU(cudaMemcpyAsync(reinterpret_cast<char*>(w->h_work) + off, reinterpret_cast<const char*>(w->work) + off,
+                       sizeof(IcpWork) - off, cudaMemcpyDeviceToHost, w0->stream));
     CU(cudaMemcpyAsync(w->h_grid, &w->bs->grid, sizeof(Grid), cudaMemcpyDeviceToHost, w0->stream));
   }
   return LS_OK;

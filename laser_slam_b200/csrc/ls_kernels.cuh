@@ -106,7 +106,6 @@ struct IcpProblem {
   float* T_hist;  // max_iterations*16 floats or null
   int want_matches;  // 1: finish with an uncapped NN pass so ids/d2 hold every point's true match
   unsigned long long* phase_ns;  // debug: max_iterations*6 globaltimer stamps (CTA 0) or null
-  unsigned int* warp_cyc;        // debug: per-warp clock cycles of phase A at iteration 10, or null
   float T0[16];
 };
 
