@@ -22,7 +22,7 @@ def build(force=False):
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
         os.makedirs(os.path.dirname(_LIB_PATH), exist_ok=True)
         cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-        subprocess.check_call([cxx, "-O2", "-fPIC", "-shared", "-std=c++17", "-o", _LIB_PATH, src])
+        subprocess.check_call([cxx, "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-o", _LIB_PATH, src])
     return _LIB_PATH
 
 
