@@ -1,4 +1,11 @@
-"""Config-2 registration on resident scans, a few repetitions (profiling / phase-timing driver)."""
+"""Config-2 registration on resident scans, a few repetitions (profiling / phase-timing driver).
+
+    python tools/prof_one.py [reps] [iterations]
+    LS_BATCH=8            also time an 8-problem cooperative launch
+    LS_PROF_Y=-6 LS_PROF_SCAN=14   where along the synthetic street (bench.py's pool starts at y = -20 m and its scans
+                          14-23 pass the dense facades that make its slowest steps; the default here is the sparser
+                          start of sequence 0)
+"""
 import sys, os, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -8,8 +15,14 @@ from laser_slam_b200 import synth
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 ctx = ls.Context(0)
-truth, odom = synth.trajectory(0, 8)
-scans = [synth.scan(truth[k], 0, k) for k in range(5)]
+k0 = int(os.environ.get("LS_PROF_SCAN", "0"))
+if "LS_PROF_Y" in os.environ or k0:
+    truth, odom = synth.trajectory(0, k0 + 8, y_start=float(os.environ.get("LS_PROF_Y", "-20")))
+    truth, odom = truth[k0:], odom[k0:]
+    scans = [synth.scan(truth[k], 0, k0 + k) for k in range(5)]
+else:
+    truth, odom = synth.trajectory(0, 8)
+    scans = [synth.scan(truth[k], 0, k) for k in range(5)]
 mp = ctx.create_map(8, 131072)
 sid = [mp.push_scan(*scans[k]) for k in range(5)]
 Tparts = [np.eye(4, dtype=np.float32) if k == 3 else (np.linalg.inv(truth[3]) @ truth[k]).astype(np.float32) for k in [3, 2, 1, 0]]
