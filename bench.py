@@ -355,8 +355,9 @@ def main():
         for t in range(B):
             idx, ref, ks, Ts, T0 = staged[t][s]
             probs.append((sid2[t][idx], [sid2[t][k] for k in ks], Ts, T0))
+        end = mp2.begin_batch(probs, prm)   # stage + launch step s, returns at once
         upload(s + 1)   # new ids in ring slots last used 16 pushes per track ago: nothing step s reads is overwritten
-        out = mp2.register_batch(probs, prm)                                                                   # D2H of T + stats inside
+        out = end()                                                                                            # wait; D2H of T + stats
         if world > 1:
             share_pose_delta(out[0]["T"])
         return out

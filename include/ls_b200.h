@@ -163,6 +163,13 @@ int ls_icp_register_submap_batch(ls_ctx* ctx, const ls_icp_params* prm, const ls
                                  const uint64_t* reading_ids, const int* n_parts, const uint64_t* part_ids,
                                  const float* T_parts, const float* T0s, float* T_outs, ls_icp_stats* stats,
                                  int* statuses);
+/* The same in two halves.  begin() stages every problem and launches; end() waits and fetches the results (same
+ * T_outs / stats / statuses as above).  In between the host is free -- typically to post the next scans with
+ * ls_map_push_scan_async -- but every other call that needs the context's workspaces returns LS_ERR_STATE. */
+int ls_icp_register_submap_batch_begin(ls_ctx* ctx, const ls_icp_params* prm, const ls_map* map, int batch,
+                                       const uint64_t* reading_ids, const int* n_parts, const uint64_t* part_ids,
+                                       const float* T_parts, const float* T0s);
+int ls_icp_register_submap_batch_end(ls_ctx* ctx, float* T_outs, ls_icp_stats* stats, int* statuses);
 
 /* Sub-map <-> sub-map registration on resident data: the loop-closure ICP of
  * IncrementalEstimator::processLoopClosure (laser_slam/src/incremental_estimator.cpp:90-115) without the two

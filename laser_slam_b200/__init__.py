@@ -103,6 +103,8 @@ def lib():
         L.ls_estimate_normals.argtypes = [vp, vp, ci, ci, vp]
         L.ls_map_push_scan_estimate_normals.argtypes = [vp, vp, ci, ci, ctypes.POINTER(u64)]
         L.ls_icp_register_submap_batch.argtypes = [vp, PP, vp, ci, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.ls_icp_register_submap_batch_begin.argtypes = [vp, PP, vp, ci, vp, vp, vp, vp, vp]
+        L.ls_icp_register_submap_batch_end.argtypes = [vp, vp, vp, vp]
         L.ls_pg_create.argtypes = [ci, ctypes.POINTER(vp)]
         L.ls_pg_destroy.argtypes = [vp]
         L.ls_pg_destroy.restype = None
@@ -370,6 +372,30 @@ class Map:
         def call(_fn=fn, _args=args, _keep=keep):
             return _fn(*_args), statuses, touts, stats
         return call
+
+    def begin_batch(self, problems, params=None):
+        """ls_icp_register_submap_batch_begin: stage and launch, return at once.  The returned callable is
+        ls_icp_register_submap_batch_end: it waits and returns the same list of dicts as `register_batch`."""
+        p = params or default_params()
+        B = len(problems)
+        rids = np.ascontiguousarray([pr[0] for pr in problems], np.uint64)
+        nparts = np.ascontiguousarray([len(pr[1]) for pr in problems], np.int32)
+        pids = np.ascontiguousarray(np.concatenate([np.asarray(pr[1], np.uint64) for pr in problems]), np.uint64)
+        tparts = np.ascontiguousarray(np.concatenate([np.stack([colmajor(T) for T in pr[2]]) for pr in problems]), np.float32)
+        t0s = np.ascontiguousarray(np.stack([colmajor(pr[3]) for pr in problems]), np.float32)
+        self.ctx._check(lib().ls_icp_register_submap_batch_begin(self.ctx._h, ctypes.byref(p), self._h, B, rids.ctypes.data,
+                                                                 nparts.ctypes.data, pids.ctypes.data, tparts.ctypes.data,
+                                                                 t0s.ctypes.data))
+
+        def end(_keep=(p, rids, nparts, pids, tparts, t0s)):
+            touts = np.empty((B, 16), np.float32)
+            stats = (IcpStats * B)()
+            statuses = np.zeros(B, np.int32)
+            rc = lib().ls_icp_register_submap_batch_end(self.ctx._h, touts.ctypes.data, ctypes.cast(stats, ctypes.c_void_p),
+                                                        statuses.ctypes.data)
+            self.ctx._check(rc if rc < 0 else 0)
+            return [dict(T=from_colmajor(touts[b]), rc=int(statuses[b]), stats=stats[b]) for b in range(B)]
+        return end
 
     def register_batch(self, problems, params=None):
         rc, statuses, touts, stats = self.prepare_batch(problems, params)()

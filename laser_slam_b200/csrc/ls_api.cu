@@ -49,6 +49,12 @@ struct ls_ctx {
   std::vector<Workspace*> ws;
   IcpProblem* probs_dev = nullptr;   // [kMaxBatch]
   IcpProblem* probs_host = nullptr;  // pinned
+  // a batch between ls_icp_register_submap_batch_begin and _end: the workspaces are busy
+  bool pending = false;
+  int pending_batch = 0;
+  std::vector<int> pending_n;
+  std::vector<float> pending_T0;
+  ls_icp_params pending_prm;
 };
 constexpr int kMaxBatch = 16;
 
@@ -87,6 +93,12 @@ int fail(ls_ctx* ctx, int code, const char* fmt, ...) {
   if (ctx) ctx->err = buf;
   return code;
 }
+
+// the workspaces are single-tenant: nothing that uses them may run between a batch's begin and end
+#define BUSY_CHECK(ctx)                                                                                       \
+  do {                                                                                                        \
+    if ((ctx)->pending) return fail((ctx), LS_ERR_STATE, "a batch is in flight (ls_icp_register_submap_batch_end first)"); \
+  } while (0)
 
 #define CU(call)                                                                                      \
   do {                                                                                                \
@@ -550,6 +562,7 @@ int ls_icp_register(ls_ctx* ctx, const ls_icp_params* prm, const float* reading4
                     const float* ref_normals, int normals_stride, int m, const float T0[16], float T_out[16],
                     ls_icp_stats* stats, int32_t* opt_ids, float* opt_d2, float* opt_T_iter_hist) {
   if (!ctx) return LS_ERR_ARG;
+  BUSY_CHECK(ctx);
   if (!reading4 || !ref4 || !ref_normals || !T0 || !T_out || n < 0 || m < 0 || normals_stride < 3)
     return fail(ctx, LS_ERR_ARG, "bad argument");
   int rc = check_params(ctx, prm);
@@ -580,6 +593,7 @@ int ls_icp_register(ls_ctx* ctx, const ls_icp_params* prm, const float* reading4
 int ls_nn_query(ls_ctx* ctx, const ls_icp_params* prm, const float* reading4, int n, const float* ref4, int m,
                 const float T0[16], int32_t* ids, float* d2) {
   if (!ctx) return LS_ERR_ARG;
+  BUSY_CHECK(ctx);
   if (!reading4 || !ref4 || !T0 || !ids || !d2 || n < 0 || m < 0) return fail(ctx, LS_ERR_ARG, "bad argument");
   int rc = check_params(ctx, prm);
   if (rc) return rc;
@@ -617,6 +631,7 @@ int ls_nn_query(ls_ctx* ctx, const ls_icp_params* prm, const float* reading4, in
 int ls_transform_cloud(ls_ctx* ctx, const float T[16], const float* in4, const float* normals, int normals_stride,
                        int n, float* out4, float* out_normals3) {
   if (!ctx) return LS_ERR_ARG;
+  BUSY_CHECK(ctx);
   if (!T || !in4 || !out4 || n < 0 || (normals && normals_stride < 3) || (normals && !out_normals3))
     return fail(ctx, LS_ERR_ARG, "bad argument");
   if (n == 0) return LS_OK;
@@ -693,6 +708,7 @@ int ls_map_push_scan(ls_map* map, const float* features4, const float* normals, 
                      uint64_t* scan_id) {
   if (!map) return LS_ERR_ARG;
   ls_ctx* ctx = map->ctx;
+  BUSY_CHECK(ctx);
   if (!features4 || !normals || normals_stride < 3 || n < 0 || n > map->max_pts || !scan_id)
     return fail(ctx, LS_ERR_ARG, "bad argument (n=%d, max=%d)", n, map->max_pts);
   CU(cudaSetDevice(ctx->device));
@@ -797,6 +813,7 @@ int enqueue_normals(ls_ctx* ctx, Workspace* w, const float4* pts_dev, int n, int
 
 int ls_estimate_normals(ls_ctx* ctx, const float* features4, int n, int knn, float* out_normals3) {
   if (!ctx) return LS_ERR_ARG;
+  BUSY_CHECK(ctx);
   if (!features4 || !out_normals3 || n < 0 || knn < 3 || knn > LS_KNN_MAX) return fail(ctx, LS_ERR_ARG, "bad argument (3 <= knn <= %d)", LS_KNN_MAX);
   if (n == 0) return LS_OK;
   CU(cudaSetDevice(ctx->device));
@@ -815,6 +832,7 @@ int ls_estimate_normals(ls_ctx* ctx, const float* features4, int n, int knn, flo
 int ls_map_push_scan_estimate_normals(ls_map* map, const float* features4, int n, int knn, uint64_t* scan_id) {
   if (!map) return LS_ERR_ARG;
   ls_ctx* ctx = map->ctx;
+  BUSY_CHECK(ctx);
   if (!features4 || n < 0 || n > map->max_pts || !scan_id || knn < 3 || knn > LS_KNN_MAX)
     return fail(ctx, LS_ERR_ARG, "bad argument (n=%d, max=%d, 3 <= knn <= %d)", n, map->max_pts, LS_KNN_MAX);
   CU(cudaSetDevice(ctx->device));
@@ -849,6 +867,7 @@ int ls_icp_register_submap(ls_ctx* ctx, const ls_icp_params* prm, const ls_map* 
                            const uint64_t* part_ids, const float* T_parts, const float T0[16], float T_out[16],
                            ls_icp_stats* stats, int32_t* opt_ids, float* opt_d2, float* opt_T_iter_hist) {
   if (!ctx) return LS_ERR_ARG;
+  BUSY_CHECK(ctx);
   if (!map || map->ctx != ctx || !part_ids || !T_parts || !T0 || !T_out) return fail(ctx, LS_ERR_ARG, "bad argument");
   int rc = check_params(ctx, prm);
   if (rc) return rc;
@@ -879,6 +898,7 @@ int ls_icp_register_submaps(ls_ctx* ctx, const ls_icp_params* prm, const ls_map*
                             int n_reading_parts, const uint64_t* reading_part_ids, const float* T_reading_parts,
                             const float T0[16], float T_out[16], ls_icp_stats* stats) {
   if (!ctx) return LS_ERR_ARG;
+  BUSY_CHECK(ctx);
   if (!ref_map || ref_map->ctx != ctx || !reading_map || reading_map->ctx != ctx || !ref_part_ids || !T_ref_parts ||
       !reading_part_ids || !T_reading_parts || !T0 || !T_out)
     return fail(ctx, LS_ERR_ARG, "bad argument");
@@ -907,24 +927,25 @@ int ls_icp_register_submaps(ls_ctx* ctx, const ls_icp_params* prm, const ls_map*
 // Problem b stages on its own stream (assembly + hash build overlap across problems); the persistent kernel's
 // grid is split into `batch` CTA groups, each with its own barrier, so one problem's barrier / solve latency is
 // filled by the others' search.  Results are bit-identical to `batch` separate ls_icp_register_submap calls.
-int ls_icp_register_submap_batch(ls_ctx* ctx, const ls_icp_params* prm, const ls_map* map, int batch,
-                                 const uint64_t* reading_ids, const int* n_parts, const uint64_t* part_ids,
-                                 const float* T_parts, const float* T0s, float* T_outs, ls_icp_stats* stats, int* statuses) {
+int ls_icp_register_submap_batch_begin(ls_ctx* ctx, const ls_icp_params* prm, const ls_map* map, int batch,
+                                       const uint64_t* reading_ids, const int* n_parts, const uint64_t* part_ids,
+                                       const float* T_parts, const float* T0s) {
   if (!ctx) return LS_ERR_ARG;
-  if (!map || map->ctx != ctx || batch < 1 || batch > kMaxBatch || !reading_ids || !n_parts || !part_ids || !T_parts || !T0s ||
-      !T_outs || !statuses)
+  BUSY_CHECK(ctx);
+  if (!map || map->ctx != ctx || batch < 1 || batch > kMaxBatch || !reading_ids || !n_parts || !part_ids || !T_parts || !T0s)
     return fail(ctx, LS_ERR_ARG, "bad argument (1 <= batch <= %d)", kMaxBatch);
   int rc = check_params(ctx, prm);
   if (rc) return rc;
   CU(cudaSetDevice(ctx->device));
   if ((rc = ensure_workspaces(ctx, batch))) return rc;
   const Resolved r = resolve(prm);
-  std::vector<int> ns(batch);
+  ctx->pending_n.assign(batch, 0);
+  ctx->pending_T0.assign(T0s, T0s + 16 * (size_t)batch);
+  ctx->pending_prm = *prm;
   int n_max = 0, part_off = 0;
   for (int b = 0; b < batch; ++b) {
     Workspace* w = ctx->ws[b];
     const float* T0 = T0s + 16 * b;
-    std::memcpy(T_outs + 16 * b, T0, 16 * sizeof(float));
     const ls_scan_slot* rs = find_slot(map, reading_ids[b]);
     if (!rs) return fail(ctx, LS_ERR_STATE, "reading scan %llu is not resident", (unsigned long long)reading_ids[b]);
     Parts parts;
@@ -934,7 +955,7 @@ int ls_icp_register_submap_batch(ls_ctx* ctx, const ls_icp_params* prm, const ls
     part_off += n_parts[b];
     const int n = rs->n, m = parts.offset[n_parts[b]];
     if (n == 0 || m == 0) return fail(ctx, LS_ERR_ARG, "empty reading or reference in a batch (use the single call)");
-    ns[b] = n;
+    ctx->pending_n[b] = n;
     n_max = n > n_max ? n : n_max;
     if ((rc = ensure_capacity(ctx, w, n, m, r.max_cells, prm->max_iterations))) return rc;
     CU(cudaEventRecord(w->ev0, w->stream));
@@ -942,18 +963,44 @@ int ls_icp_register_submap_batch(ls_ctx* ctx, const ls_icp_params* prm, const ls
     if ((rc = prep_icp(ctx, w, prm, rs->pts, n, T0, false, false))) return rc;
   }
   if ((rc = launch_icp(ctx, prm, batch, n_max))) return rc;
+  ctx->pending_batch = batch;
+  ctx->pending = true;
+  return LS_OK;
+}
+
+int ls_icp_register_submap_batch_end(ls_ctx* ctx, float* T_outs, ls_icp_stats* stats, int* statuses) {
+  if (!ctx) return LS_ERR_ARG;
+  if (!ctx->pending) return fail(ctx, LS_ERR_STATE, "no batch in flight");
+  if (!T_outs || !statuses) return fail(ctx, LS_ERR_ARG, "bad argument");
+  ctx->pending = false;
+  const int batch = ctx->pending_batch;
+  std::memcpy(T_outs, ctx->pending_T0.data(), 16 * sizeof(float) * (size_t)batch);
+  CU(cudaSetDevice(ctx->device));
   CU(cudaStreamSynchronize(ctx->ws[0]->stream));
   for (int b = 0; b < batch; ++b) {
-    const int st = fetch_icp(ctx, ctx->ws[b], prm, ns[b], T0s + 16 * b, T_outs + 16 * b, stats ? stats + b : nullptr);
+    const int st = fetch_icp(ctx, ctx->ws[b], &ctx->pending_prm, ctx->pending_n[b], ctx->pending_T0.data() + 16 * b, T_outs + 16 * b,
+                             stats ? stats + b : nullptr);
     if (st < 0) return st;
     statuses[b] = st;
   }
   return LS_OK;
 }
 
+int ls_icp_register_submap_batch(ls_ctx* ctx, const ls_icp_params* prm, const ls_map* map, int batch,
+                                 const uint64_t* reading_ids, const int* n_parts, const uint64_t* part_ids,
+                                 const float* T_parts, const float* T0s, float* T_outs, ls_icp_stats* stats, int* statuses) {
+  if (!ctx) return LS_ERR_ARG;
+  if (!T_outs || !statuses) return fail(ctx, LS_ERR_ARG, "bad argument");
+  if (T0s && batch >= 1 && batch <= kMaxBatch) std::memcpy(T_outs, T0s, 16 * sizeof(float) * (size_t)batch);
+  const int rc = ls_icp_register_submap_batch_begin(ctx, prm, map, batch, reading_ids, n_parts, part_ids, T_parts, T0s);
+  if (rc != LS_OK) return rc;
+  return ls_icp_register_submap_batch_end(ctx, T_outs, stats, statuses);
+}
+
 int ls_map_assemble(ls_ctx* ctx, const ls_map* map, int n_parts, const uint64_t* part_ids, const float* T_parts,
                     float* out4, float* out_normals3, int* m_out) {
   if (!ctx) return LS_ERR_ARG;
+  BUSY_CHECK(ctx);
   if (!map || map->ctx != ctx || !part_ids || !T_parts || !out4 || !m_out) return fail(ctx, LS_ERR_ARG, "bad argument");
   Parts parts;
   int rc;

@@ -328,3 +328,33 @@ def test_async_scan_upload_is_ordered_before_its_consumers(gpu_ctx, scans, traj)
     again = ring.register(ids[3], ids[:3], Ts, T0, p)
     assert np.array_equal(again["T"], want["T"])
     ring.close()
+
+
+def test_batch_begin_end_equals_blocking_batch_and_guards_the_context(gpu_ctx, scans, traj):
+    """ls_icp_register_submap_batch_begin/_end: same bits as the blocking call; between the halves the context refuses
+    other work that needs its workspaces, while asynchronous uploads are allowed."""
+    import torch
+    import laser_slam_b200 as ls
+    truth, odom = traj
+    mp = gpu_ctx.create_map(8, 131072)
+    sid = [mp.push_scan(*scans[k]) for k in range(5)]
+    p = ls.default_params(max_iterations=6, use_differential=0)
+    problems = []
+    for ref, rd, ks in [(3, 4, [3, 2, 1]), (2, 3, [2, 1])]:
+        Ts = [np.eye(4, dtype=np.float32) if k == ref else (np.linalg.inv(truth[ref]) @ truth[k]).astype(np.float32) for k in ks]
+        problems.append((sid[rd], [sid[k] for k in ks], Ts, (np.linalg.inv(truth[ref]) @ odom[rd]).astype(np.float32)))
+    want = mp.register_batch(problems, p)
+    end = mp.begin_batch(problems, p)
+    f, n = torch.from_numpy(scans[5][0]).pin_memory(), torch.from_numpy(scans[5][1]).pin_memory()
+    extra = mp.push_scan_raw_async(f.data_ptr(), n.data_ptr(), 3, f.shape[0])      # allowed while the batch runs
+    with pytest.raises(ls.LsError):
+        mp.register(*problems[0], p)                                               # needs the busy workspaces
+    got = end()
+    for b in range(2):
+        assert got[b]["rc"] == 0 and np.array_equal(got[b]["T"], want[b]["T"])
+        assert got[b]["stats"].last_kept == want[b]["stats"].last_kept
+    mp.sync()
+    assert mp.scan_size(extra) == 131072
+    again = mp.register(*problems[0], p)                                            # the context is free again
+    assert np.array_equal(again["T"], want[0]["T"])
+    mp.close()
