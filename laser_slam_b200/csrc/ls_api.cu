@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/ls_b200.h"
@@ -28,6 +29,7 @@ struct Workspace {
   float* nrm_raw = nullptr;                               // raw normals staging
   size_t nrm_raw_cap = 0;
   int* pos = nullptr;
+  float4 *vq = nullptr, *vpts = nullptr;                   // certified candidate lists (ls_grid.cuh VLists)
   float* d2 = nullptr;
   int* ids = nullptr;
   float* d2_out = nullptr;
@@ -55,6 +57,8 @@ struct ls_ctx {
   std::vector<int> pending_n;
   std::vector<float> pending_T0;
   ls_icp_params pending_prm;
+  // ring slots (map, slot index) the in-flight batch reads: an asynchronous upload must not overwrite them
+  std::vector<std::pair<const ls_map*, int>> pending_slots;
 };
 constexpr int kMaxBatch = 16;
 
@@ -137,6 +141,8 @@ int ensure_capacity(ls_ctx* ctx, Workspace* w, int n, int m, int max_cells, int 
     if ((rc = dev_alloc(ctx, &w->rd, (size_t)cap))) return rc;
     if ((rc = dev_alloc(ctx, &w->pos, (size_t)cap))) return rc;
     if ((rc = dev_alloc(ctx, &w->d2, (size_t)cap))) return rc;
+    if ((rc = dev_alloc(ctx, &w->vq, (size_t)cap))) return rc;
+    if ((rc = dev_alloc(ctx, &w->vpts, (size_t)cap * LS_VK))) return rc;
     if ((rc = dev_alloc(ctx, &w->ids, (size_t)cap))) return rc;
     if ((rc = dev_alloc(ctx, &w->d2_out, (size_t)cap))) return rc;
     if ((rc = dev_alloc(ctx, &w->A.qkey, (size_t)cap))) return rc;
@@ -243,7 +249,9 @@ int enqueue_build(ls_ctx* ctx, Workspace* w, const Parts& parts, const Resolved&
 }
 
 int upload_normals(ls_ctx* ctx, Workspace* w, const float* normals, int stride, int n, float4* dst) {
-  const size_t need = (size_t)n * (size_t)(stride <= 8 ? stride : 3);
+  // the descriptor block may be addressed at a row offset (normals = descriptors.data() + row, stride = D): the last
+  // point's normal ends (n-1)*stride + 3 floats after `normals`, and nothing beyond that may be read
+  const size_t need = n > 0 ? (stride <= 8 ? (size_t)(n - 1) * (size_t)stride + 3 : (size_t)n * 3) : 0;
   if (need > w->nrm_raw_cap) {
     int rc;
     if ((rc = dev_alloc(ctx, &w->nrm_raw, need + 4096))) return rc;
@@ -297,6 +305,9 @@ int prep_icp(ls_ctx* ctx, Workspace* w, const ls_icp_params* prm, const float4* 
   hp.ids = w->ids;
   hp.d2_out = w->d2_out;
   hp.qperm = w->A.qperm;
+  hp.lists.vq = w->vq;
+  hp.lists.vpts = w->vpts;
+  hp.lists.n = n;
   hp.work = w->work;
   hp.T_hist = want_hist ? w->T_hist : nullptr;
   hp.want_matches = want_matches ? 1 : 0;
@@ -479,7 +490,7 @@ void free_workspace(Workspace* w) {
   if (w->stream) cudaStreamSynchronize(w->stream);
   void* bufs[] = {w->A.sub_pts, w->A.sub_nrm, w->A.srt_pts, w->A.srt_nrm, w->A.pkey, w->A.top, w->A.cnt0, w->A.tab1, w->A.cnt1,
                   w->A.tab1_cell, w->A.pyr, w->bs, w->reading, w->rd, w->ref_stage, w->ref_nrm_stage, w->nrm_raw, w->pos, w->d2,
-                  w->ids, w->work, w->T_hist, w->T0_dev, w->phase_ns, w->d2_out, w->A.qkey, w->A.qperm, w->A.rd_s,
+                  w->ids, w->vq, w->vpts, w->work, w->T_hist, w->T0_dev, w->phase_ns, w->d2_out, w->A.qkey, w->A.qperm, w->A.rd_s,
                   w->A.qtab_local, w->A.qtab_total, w->A.qtop_start};
   for (void* b : bufs)
     if (b) cudaFree(b);
@@ -745,14 +756,21 @@ int ls_map_push_scan_async(ls_map* map, const float* features4, const float* nor
   if (!features4 || !normals || normals_stride < 3 || normals_stride > 8 || n < 0 || n > map->max_pts || !scan_id)
     return fail(ctx, LS_ERR_ARG, "bad argument (n=%d, max=%d, 3 <= normals_stride <= 8)", n, map->max_pts);
   CU(cudaSetDevice(ctx->device));
+  // The slot this upload evicts must not be one the batch in flight (between _batch_begin and _batch_end) still reads:
+  // its assemble / reading kernels run on other streams and are not ordered against this copy.  Every other consumer
+  // of a slot is a synchronous call, so it has returned; uploads into the same slot are ordered by the upload stream.
+  const int slot_index = (int)(map->next_id % (uint64_t)map->capacity);
+  if (ctx->pending)
+    for (const auto& ps : ctx->pending_slots)
+      if (ps.first == map && ps.second == slot_index)
+        return fail(ctx, LS_ERR_STATE, "ring slot %d is read by the batch in flight (capacity %d too small for the scans in flight)",
+                    slot_index, map->capacity);
   const uint64_t id = map->next_id++;
   ls_scan_slot& s = map->slots[id % (uint64_t)map->capacity];
   s.used = false;
-  // a registration that still reads the evicted scan was synchronous, so it has returned; uploads into the same slot
-  // are ordered by the stream
   if (n > 0) {
     const int k = (int)(map->n_async++ % kStageRing);
-    const size_t need = (size_t)n * (size_t)normals_stride;
+    const size_t need = (size_t)(n - 1) * (size_t)normals_stride + 3;  // never read past the last normal
     if (!map->stage_free[k]) CU(cudaEventCreateWithFlags(&map->stage_free[k], cudaEventDisableTiming));
     else CU(cudaEventSynchronize(map->stage_free[k]));  // the upload that used this staging buffer 16 pushes ago
     if (need > map->stage_cap[k]) {
@@ -942,6 +960,27 @@ int ls_icp_register_submap_batch_begin(ls_ctx* ctx, const ls_icp_params* prm, co
   ctx->pending_n.assign(batch, 0);
   ctx->pending_T0.assign(T0s, T0s + 16 * (size_t)batch);
   ctx->pending_prm = *prm;
+  ctx->pending_slots.clear();
+  // validate every problem before anything is enqueued
+  {
+    int po = 0;
+    for (int b = 0; b < batch; ++b) {
+      if (n_parts[b] < 1 || n_parts[b] > kMaxParts) return fail(ctx, LS_ERR_ARG, "n_parts must be in [1,%d]", kMaxParts);
+      const ls_scan_slot* rs = find_slot(map, reading_ids[b]);
+      if (!rs) return fail(ctx, LS_ERR_STATE, "reading scan %llu is not resident", (unsigned long long)reading_ids[b]);
+      if (rs->n == 0) return fail(ctx, LS_ERR_ARG, "empty reading in a batch (use the single call)");
+      ctx->pending_slots.emplace_back(map, (int)(rs - map->slots.data()));
+      long long m = 0;
+      for (int p = 0; p < n_parts[b]; ++p) {
+        const ls_scan_slot* s = find_slot(map, part_ids[po + p]);
+        if (!s) return fail(ctx, LS_ERR_STATE, "scan %llu is not resident (evicted or never pushed)", (unsigned long long)part_ids[po + p]);
+        ctx->pending_slots.emplace_back(map, (int)(s - map->slots.data()));
+        m += s->n;
+      }
+      if (m == 0) return fail(ctx, LS_ERR_ARG, "empty reference in a batch (use the single call)");
+      po += n_parts[b];
+    }
+  }
   int n_max = 0, part_off = 0;
   for (int b = 0; b < batch; ++b) {
     Workspace* w = ctx->ws[b];
@@ -973,6 +1012,7 @@ int ls_icp_register_submap_batch_end(ls_ctx* ctx, float* T_outs, ls_icp_stats* s
   if (!ctx->pending) return fail(ctx, LS_ERR_STATE, "no batch in flight");
   if (!T_outs || !statuses) return fail(ctx, LS_ERR_ARG, "bad argument");
   ctx->pending = false;
+  ctx->pending_slots.clear();
   const int batch = ctx->pending_batch;
   std::memcpy(T_outs, ctx->pending_T0.data(), 16 * sizeof(float) * (size_t)batch);
   CU(cudaSetDevice(ctx->device));

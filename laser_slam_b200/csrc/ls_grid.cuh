@@ -33,6 +33,7 @@
 #include <cstring>
 
 #include <vector_types.h>
+#include <vector_functions.h>
 
 #include "ls_math.cuh"
 
@@ -90,6 +91,7 @@ struct Best {
       pos = p;
     }
   }
+  LS_HD void offer_pt(float d, const float4& c, int p);
 };
 
 // K nearest (K <= LS_KNN_MAX at run time), ascending by (d2, index); a candidate offered twice is kept once.
@@ -118,6 +120,7 @@ struct TopK {
     d[j] = dist;
     id[j] = i;
   }
+  LS_HD void offer_pt(float dist, const float4& c, int p);
 };
 
 // tests/sim instruments the query (candidates examined, table entries loaded) to tune H0/leaf_split
@@ -143,6 +146,8 @@ LS_HD Entry ld_entry(const Entry* e) {
 }
 LS_HD int f2i(float f) { return __float_as_int(f); }
 LS_HD float i2f(int i) { return __int_as_float(i); }
+LS_HD float4 ld_state4(const float4* p) { return __ldcg(p); }   // per-query state crosses CTAs: L2, never L1
+LS_HD void st_state4(float4* p, const float4 v) { __stcg(p, v); }
 LS_HD unsigned long long ld_mask(const unsigned long long* p) { return __ldg(p); }
 LS_HD int ctz64(unsigned long long m) { return __ffsll((long long)m) - 1; }
 #else
@@ -150,6 +155,8 @@ LS_HD float4 ld_pt(const float4* p) { LS_CNT_CAND(); return *p; }
 LS_HD Entry ld_entry(const Entry* e) { LS_CNT_ENTRY(); return *e; }
 LS_HD int f2i(float f) { int i; std::memcpy(&i, &f, 4); return i; }
 LS_HD float i2f(int i) { float f; std::memcpy(&f, &i, 4); return f; }
+LS_HD float4 ld_state4(const float4* p) { return *p; }
+LS_HD void st_state4(float4* p, const float4 v) { *p = v; }
 LS_HD unsigned long long ld_mask(const unsigned long long* p) { LS_CNT_ENTRY(); return *p; }
 LS_HD int ctz64(unsigned long long m) { return __builtin_ctzll(m); }
 #endif
@@ -182,9 +189,11 @@ LS_HD float ball_radius(float best_d2, float margin) { return sqrtf(best_d2) * 1
 
 // The candidate test (for Best: branch-free selects; a data-dependent branch per candidate was measured ~1.6x
 // slower).
+LS_HD void Best::offer_pt(float d, const float4& c, int p) { offer(d, f2i(c.w), p); }
+LS_HD void TopK::offer_pt(float dist, const float4& c, int p) { offer(dist, f2i(c.w), p); }
 template <class Acc>
 LS_HD void consider_pt(const float4 p, int pos, float qx, float qy, float qz, Acc& b) {
-  b.offer(dist2(qx, qy, qz, p.x, p.y, p.z), f2i(p.w), pos);
+  b.offer_pt(dist2(qx, qy, qz, p.x, p.y, p.z), p, pos);
 }
 template <class Acc>
 LS_HD void consider(const float4* pts, int pos, float qx, float qy, float qz, Acc& b) {
@@ -386,6 +395,114 @@ LS_HD Best nn_search(const Grid& g, const GridView& v, float qx, float qy, float
   ball_query(g, v, qx, qy, qz, b);
   if (b.pos < 0) { b.idx = -1; b.d2 = INFINITY; }
   return b;
+}
+
+// ---- certified candidate lists ("Verlet lists") ------------------------------------------------------------------
+// Between two ICP iterations a query moves by far less than the distance to its match, so the search result rarely
+// changes -- but "rarely" is not "never", and the contract is the EXACT nearest neighbour every iteration.  A list
+// makes the repeat provable: after a full search at position q0 the kernel also records EVERY map point within
+// R_v = |match| * ratio (capped by |match| + skin) of q0.  At a later position q (moved by delta = |q - q0|) any
+// point NOT in the list is farther than R_v - delta from q, hence: if the best listed candidate lies within
+// R_c = R_v - delta (minus rounding slack) it is the exact nearest neighbour -- ties included, since every point at
+// that distance is listed too; and if nothing lies within sqrt(cap) <= R_c the capped search provably finds nothing.
+// Otherwise the list is refused and the full search runs (and rebuilds the list).  The certificate only ever
+// replaces a search by its own proven result: correspondences are bit-identical with or without lists.
+//
+// Layout (per query i of n, in the kernel's rank order): vq[i] = {q0.x, q0.y, q0.z, bits}, bits = R_v with its low
+// 4 mantissa bits replaced by the candidate count (R_v is thereby rounded DOWN: conservative); bits == 0: no list.
+// vpts[k*n + i] = candidate k as {x, y, z, sorted position} -- structure of arrays, so a warp streams 512
+// contiguous bytes per k.  The original index (tie-break) is fetched from the sorted map only when two candidates
+// are exactly equidistant.
+#define LS_VK 8  // candidates per list; a ball holding more is not listed
+struct VLists {
+  float4* vq;
+  float4* vpts;
+  int n;  // stride between candidate planes
+};
+
+// All points within sqrt(r2) of the query, at most LS_VK of them: one more and the collection gives up (r2 turns
+// negative, which prunes every remaining cell and rejects every remaining candidate).
+struct Collector {
+  float r2;
+  int cnt;
+  float4* out;
+  int stride;
+  LS_HD float bound() const { return r2; }
+  LS_HD void offer_pt(float d, const float4& c, int p) {
+    if (d <= r2) {
+      if (cnt < LS_VK) st_state4(out + (size_t)cnt * stride, make_float4(c.x, c.y, c.z, i2f(p)));
+      else r2 = -1.0f;
+      ++cnt;
+    }
+  }
+};
+
+// Try to answer the capped query (qx,qy,qz) from list i, whose header `v` = vq[i] and first candidate `c0` =
+// vpts[i] the caller has already loaded (both addresses are known up front, so the common case -- a one-candidate
+// list -- costs a single round trip to memory).  true: `b` is exactly what nn_search(.., cap_d2) returns (b.pos < 0:
+// nothing within the cap; b.idx is NOT filled in) and cbest = the match's {x, y, z, sorted position}.  false: no valid
+// certificate, run the search.
+LS_HD bool vlist_query(const VLists& L, const float4* pts, int i, const float4 v, const float4 c0, float qx, float qy,
+                       float qz, float cap_d2, Best& b, float4& cbest) {
+  const unsigned int bits = (unsigned int)f2i(v.w);
+  if (bits == 0u) return false;
+  const int cnt = (int)(bits & 15u);
+  const float Rv = i2f((int)(bits & ~15u));
+  // rounding slack: fl(d2) carries < 4 ulp relative error, sqrtf is correctly rounded; 4e-6 dwarfs both
+  const float Rc = Rv * 0.999996f - sqrtf(dist2(qx, qy, qz, v.x, v.y, v.z)) * 1.000004f;
+  if (!(Rc > 0.0f)) return false;
+  b.d2 = cap_d2;
+  b.idx = INT_MAX;
+  b.pos = -1;
+  for (int k = 0; k < cnt; ++k) {
+    const float4 c = k == 0 ? c0 : ld_state4(L.vpts + (size_t)k * L.n + i);
+    const float d = dist2(qx, qy, qz, c.x, c.y, c.z);
+    const int cpos = f2i(c.w);
+    if (d < b.d2) {
+      b.d2 = d;
+      b.pos = cpos;
+      cbest = c;
+    } else if (d == b.d2) {
+      // exact tie (or d == cap): lowest original index wins, as in Best::offer; indices live in the sorted map
+      if (b.pos < 0 || f2i(ld_pt(pts + cpos).w) < f2i(ld_pt(pts + b.pos).w)) {
+        b.pos = cpos;
+        cbest = c;
+      }
+    }
+  }
+  // b.d2 == cap_d2 when nothing was accepted: then the certificate must cover the whole cap
+  return b.d2 * 1.00001f <= Rc * Rc;
+}
+
+// After a full search at (qx,qy,qz) whose answer was `found_d2` (or nothing within cap_d2): record every point within
+// R_v -- if that can pay off.  `motion` bounds how far the last ICP step moved this query; steps shrink geometrically,
+// so a list is only worth its second traversal when its margin (R_v minus the match distance) covers about twice
+// that.  A list that is not rebuilt is left as it is: it remains a true statement about its own q0.
+LS_HD void vlist_build(const Grid& g, const GridView& v, const VLists& L, int i, float qx, float qy, float qz, bool found,
+                       float found_d2, float cap_d2, float motion) {
+  float Rv;
+  if (found) {
+    const float want = sqrtf(found_d2);
+    const float margin = want * 0.5f + 1e-4f;
+    if (!(motion <= margin)) return;
+    Rv = want + fminf(margin, fmaxf(0.002f, 4.0f * motion));
+  } else {
+    const float want = sqrtf(cap_d2);  // the cap itself moves a little between iterations: 5 % head room
+    if (!(motion <= want * 0.125f)) return;
+    Rv = want * 1.05f + fminf(want * 0.25f, fmaxf(0.002f, 4.0f * motion));
+  }
+  if (!(Rv < 3.0e38f)) return;
+  Collector c;
+  c.r2 = Rv * Rv;
+  c.cnt = 0;
+  c.out = L.vpts + i;
+  c.stride = L.n;
+  ball_query(g, v, qx, qy, qz, c);
+  // every point with fl(d2) <= fl(Rv*Rv) is recorded; the stored radius is rounded down twice (1 ulp for the
+  // square's rounding, then the count bits).  More than LS_VK points: no list.
+  float4 head = make_float4(qx, qy, qz, 0.0f);
+  if (c.cnt <= LS_VK) head.w = i2f((int)((((unsigned int)f2i(Rv * 0.9999999f)) & ~15u) | (unsigned int)c.cnt));
+  st_state4(L.vq + i, head);
 }
 
 // Exact K nearest neighbours (ties: lower index first) by verified expanding balls: a round searches the ball of

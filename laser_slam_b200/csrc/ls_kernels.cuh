@@ -80,7 +80,7 @@ struct IcpParamsDev {
 struct IcpWork {
   unsigned int barrier;
   unsigned int pad0[31];
-  unsigned int hist[2][3][2048];
+  unsigned int hist[2][5][2048];  // per parity: radix levels 1-3, then the speculative copies of levels 2 and 3
   unsigned long long acc[2][32];
   unsigned int qctr[2];  // phase-A work counters (next unclaimed query), one per iteration parity
   float T_out[16];
@@ -102,6 +102,7 @@ struct IcpProblem {
   int* ids;             // original order, written by the final pass only
   float* d2_out;        // original order, written by the final pass only
   const uint32_t* qperm;  // rank -> original query index
+  VLists lists;           // certified candidate lists (ls_grid.cuh), rank order
   IcpWork* work;
   float* T_hist;  // max_iterations*16 floats or null
   int want_matches;  // 1: finish with an uncapped NN pass so ids/d2 hold every point's true match
@@ -802,33 +803,163 @@ __device__ __forceinline__ void block_select(const unsigned int* ghist, int nbin
   __syncthreads();
 }
 
-// Per-query state accessors.  With dynamic scheduling the state crosses CTAs (written by whichever warp claimed
-// the query, read by the static owner in phases B-D): then it goes through L2 (.cg), never through L1.
-template <bool CG, typename T>
-__device__ __forceinline__ T ld_state(const T* p) {
-  return CG ? __ldcg(p) : *p;
-}
-template <bool CG, typename T>
-__device__ __forceinline__ void st_state(T* p, T v) {
-  if (CG) __stcg(p, v);
-  else *p = v;
+// ---- phase A building blocks ------------------------------------------------------------------------------------
+// Per-query state (pos, d2, candidate lists) crosses CTAs -- it is written by whichever warp claimed the query in
+// phase A and read by the static owner of the query in the select / correction passes -- so it always goes through
+// L2 (.cg loads and stores), never through L1.
+
+// Per-CTA histograms of the trimmed-quantile select (3-level radix over the float bits of d2: 10 + 11 + 10 bits).
+// Level 1 is always built in phase A.  Levels 2 and 3 need the bin chosen at the level above -- which is only known
+// a grid-wide barrier later -- so phase A builds them SPECULATIVELY for the bins of the previous iteration's limit;
+// when the limit has moved by less than a bin (almost always once the registration settles) the whole select needs
+// no further pass and no further barrier.
+struct SelHists {
+  unsigned int h1[1024];  // key >> 21
+  unsigned int h2[2048];  // (key >> 10) & 2047 of the keys in the predicted level-1 bin
+  unsigned int h3[1024];  // key & 1023 of the keys under the predicted (level-1, level-2) prefix
+};
+constexpr unsigned int kNoPrediction = 0xffffffffu;
+
+// outcome of one query: remember the last real match as the next warm start, record d2, count it
+__device__ __forceinline__ void phase_a_record(const IcpProblem& P, int i, const Best& b, SelHists* H, unsigned int pred_bin1,
+                                               unsigned int pred_pref12) {
+  if (b.pos >= 0) __stcg(P.pos + i, b.pos);
+  const float d = b.pos >= 0 ? b.d2 : INFINITY;
+  __stcg(P.d2 + i, d);
+  const unsigned int key = __float_as_uint(d);
+  if (key <= 0x7f800000u) {  // non-negative, not NaN; +inf (no match inside the cap) -> bin 1020
+    atomicAdd(&H->h1[key >> 21], 1u);
+    if ((key >> 21) == pred_bin1) {
+      atomicAdd(&H->h2[(key >> 10) & 2047u], 1u);
+      if ((key >> 10) == pred_pref12) atomicAdd(&H->h3[key & 1023u], 1u);
+    }
+  }
 }
 
-// Phase A for one query: transform, (maybe) skip, search inside the cap, record the outcome.
-template <bool CG>
-__device__ __forceinline__ void phase_a_query(const Grid& g, const IcpProblem& P, const float* T_iter, int i, float cap,
-                                              unsigned int* hist_s) {
+// Point-to-plane terms of one pair (PointToPlaneErrorMinimizer): f = [s x n; n], e = (s - q) . n, every operation
+// individually rounded in this fixed order (oracle/icp_oracle.cpp).  The same function serves phase A and the
+// correction pass, so a pair added in one and removed in the other cancels exactly.
+__device__ __forceinline__ void residual_terms(float sx, float sy, float sz, const float4 q, const float4 nn, float* f, float& e) {
+  float u = sy * nn.z, v = sz * nn.y;
+  f[0] = u - v;
+  u = sz * nn.x; v = sx * nn.z;
+  f[1] = u - v;
+  u = sx * nn.y; v = sy * nn.x;
+  f[2] = u - v;
+  f[3] = nn.x; f[4] = nn.y; f[5] = nn.z;
+  const float dx = sx - q.x, dy = sy - q.y, dz = sz - q.z;
+  e = dx * nn.x;
+  float t = dy * nn.y;
+  e = e + t;
+  t = dz * nn.z;
+  e = e + t;
+}
+
+// Warp-collective (all 32 lanes, converged): add (sign = +1), remove (-1) or skip (0) each lane's pair in the
+// normal equations A = sum f f^T (21 unique entries), b = sum f e (6), count (1).  Every product is quantised to
+// 2^-22 and summed as int64 (REDUX over 21-bit limbs), so the result is exact and independent of any ordering;
+// lane 0 folds the warp's sums into the warp's slab in shared memory.
+__device__ __noinline__ void accumulate_warp(int sign, float f0, float f1, float f2, float f3, float f4, float f5, float e,
+                                             unsigned long long* slab) {
+  const float f[6] = {f0, f1, f2, f3, f4, f5};
+  const bool lane0 = (threadIdx.x & 31) == 0;
+  int k = 0;
+#pragma unroll
+  for (int rr = 0; rr < 6; ++rr)
+#pragma unroll
+    for (int cc = rr; cc < 6; ++cc, ++k) {
+      long long v = sign ? __float2ll_rn((f[rr] * f[cc]) * 4194304.0f) : 0ll;
+      if (sign < 0) v = -v;
+      const long long sm = warp_sum_ll(v);
+      if (lane0) slab[k] += (unsigned long long)sm;
+    }
+#pragma unroll
+  for (int rr = 0; rr < 6; ++rr) {
+    long long v = sign ? __float2ll_rn((f[rr] * e) * 4194304.0f) : 0ll;
+    if (sign < 0) v = -v;
+    const long long sm = warp_sum_ll(v);
+    if (lane0) slab[21 + rr] += (unsigned long long)sm;
+  }
+  const int plus = __popc(__ballot_sync(0xffffffffu, sign > 0)), minus = __popc(__ballot_sync(0xffffffffu, sign < 0));
+  if (lane0) slab[27] += (unsigned long long)(long long)(plus - minus);
+}
+
+// Warp-collective: lanes with sign != 0 contribute the pair (query at s, matched point q at sorted position pos).
+__device__ __forceinline__ void accumulate_pairs(const IcpProblem& P, int sign, float sx, float sy, float sz, const float4 q,
+                                                 int pos, unsigned long long* slab) {
+  if (__ballot_sync(0xffffffffu, sign != 0) == 0u) return;  // warp-uniform
+  float f[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, e = 0.f;
+  if (sign) residual_terms(sx, sy, sz, q, __ldg(P.nrm + pos), f, e);
+  accumulate_warp(sign, f[0], f[1], f[2], f[3], f[4], f[5], e, slab);
+}
+
+// Slow path of phase A: the search itself (warm-started, inside the cap), then -- from the second iteration on -- the
+// list that lets later iterations skip it (vlist_build decides whether it can pay off from how far the last step moved
+// this query: T_prev is the previous iteration's T_iter).  Not inlined: the search wants the whole register budget
+// for itself, not the caller's loop state spilled into its inner loops.  Returns {sorted position or -1, d2 bits}.
+__device__ __noinline__ int2 phase_a_search(const Grid* gp, const IcpProblem* Pp, const float* T_iter, const float* T_prev,
+                                            int i, float cap, SelHists* H, unsigned int pred_bin1, unsigned int pred_pref12) {
+  const Grid& g = *gp;
+  const IcpProblem& P = *Pp;
   const float4 r = __ldg(P.rd + i);
   float sx, sy, sz;
   xform_point(T_iter, r.x, r.y, r.z, sx, sy, sz);
-  const int warm = ld_state<CG>(P.pos + i);
+  const int warm = __ldcg(P.pos + i);
   const Best b = nn_search(g, P.view, sx, sy, sz, warm, cap);
-  if (b.pos >= 0) st_state<CG>(P.pos + i, b.pos);  // keep the last real match as the next warm start
-  st_state<CG>(P.d2 + i, b.d2);
-  const unsigned int key = __float_as_uint(b.d2);
-  if (key <= 0x7f800000u) atomicAdd(&hist_s[key >> 21], 1u);  // non-negative; +inf (no match in cap) -> bin 1020
+  phase_a_record(P, i, b, H, pred_bin1, pred_pref12);
+  if (T_prev) {
+    float px, py, pz;
+    xform_point(T_prev, r.x, r.y, r.z, px, py, pz);
+    vlist_build(g, P.view, P.lists, i, sx, sy, sz, b.pos >= 0, b.d2, cap, sqrtf(dist2(sx, sy, sz, px, py, pz)));
+  }
+  return make_int2(b.pos, __float_as_int(b.d2));
 }
 
+// After the loop, when the caller asked for correspondences: every point's true (uncapped) match under T.
+__device__ __noinline__ void final_match(const Grid* gp, const IcpProblem* Pp, const float* T, int i) {
+  const IcpProblem& P = *Pp;
+  const float4 r = __ldg(P.rd + i);
+  float sx, sy, sz;
+  xform_point(T, r.x, r.y, r.z, sx, sy, sz);
+  const Best b = nn_search(*gp, P.view, sx, sy, sz, __ldcg(P.pos + i), INFINITY);
+  const uint32_t orig = __ldg(P.qperm + i);
+  P.d2_out[orig] = b.d2;
+  P.ids[orig] = b.idx;
+}
+
+// CTA-wide: fold the per-warp slabs into the problem's accumulators (L2 atomics), leave the slabs zero.
+__device__ __forceinline__ void flush_slabs(unsigned long long (*acc_w)[28], unsigned long long* gacc) {
+  __syncthreads();
+  if (threadIdx.x < 28) {
+    unsigned long long t = 0ull;
+#pragma unroll
+    for (int w = 0; w < kIcpThreads / 32; ++w) {
+      t += acc_w[w][threadIdx.x];
+      acc_w[w][threadIdx.x] = 0ull;
+    }
+    if (t != 0ull) atomicAdd(&gacc[threadIdx.x], t);
+  }
+}
+
+__device__ __forceinline__ void flush_hist(const unsigned int* hs, int nbins, unsigned int* gh) {
+  for (int k = threadIdx.x; k < nbins; k += kIcpThreads) {
+    const unsigned int v = hs[k];
+    if (v) atomicAdd(&gh[k], v);
+  }
+}
+
+// One iteration, seen from one problem's group of CTAs (G of them, each owning a contiguous chunk of the queries for
+// the passes that read per-query state back):
+//   A   every query gets its match -- from its certified candidate list when that proves the answer, from the search
+//       otherwise -- and on the spot: its d2 enters the select histograms (all three radix levels, the lower two
+//       speculatively) and, when d2 <= the PREVIOUS iteration's limit, its pair enters the normal equations
+//   --  barrier
+//   S   every CTA resolves the trimmed limit from the histograms (a pass over d2 + a barrier per level only where
+//       the speculation missed), then corrects the normal equations for the queries between the previous and the
+//       actual limit: +pair / -pair, exact because the sums are integers
+//   --  barrier
+//   E   every CTA solves the 6x6 system, updates T_iter and runs the transformation checkers, identically
+// i.e. two grid-wide barriers per iteration once the limit moves by less than a histogram bin per iteration.
 __global__ void __launch_bounds__(kIcpThreads, kIcpCtasPerSm)
 icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParamsDev prm, int dynamic) {
   const int pi = blockIdx.x / ctas_per_problem;
@@ -840,13 +971,14 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
 
   __shared__ Grid g;
   __shared__ float T_iter[16], T_last[16];
-  __shared__ unsigned int hist_s[2048];
+  __shared__ SelHists hs;
   __shared__ unsigned long long acc_w[kIcpThreads / 32][28];
   __shared__ SelectOut sel;
   __shared__ unsigned int ws[kIcpThreads / 32];
   __shared__ double qh[kMaxSmooth + 2][4];
   __shared__ double th[kMaxSmooth + 2][3];
   __shared__ int flag_stop, flag_status;
+  __shared__ int miss_buf[kIcpThreads / 32][64];  // per-warp queue of queries whose list did not certify
 
   if (tid == 0) {
     g = P.bs->grid;
@@ -856,6 +988,7 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
     flag_stop = 0;
     flag_status = 0;
   }
+  if (tid < 28 * (kIcpThreads / 32)) acc_w[tid / 28][tid % 28] = 0ull;
   __syncthreads();
 
   // contiguous chunk of queries per CTA (spatially compact, coalesced)
@@ -864,12 +997,10 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
   chunk = (chunk + 31) & ~31;
   const int q_begin = min(n, cta * chunk), q_end = min(n, q_begin + chunk);
 
-  // Per-query state (pos, d2, miss) is written by whichever warp claimed the query in phase A and read by the
-  // static owner in phases B-D, i.e. it crosses CTAs: always accessed with .cg (L2) loads/stores, never through L1.
   for (int i = q_begin + tid; i < q_end; i += kIcpThreads) {
     __stcg(P.pos + i, -1);
+    __stcg(P.lists.vq + i, make_float4(0.f, 0.f, 0.f, 0.f));  // no list yet
   }
-  (void)lane;
 
   // Trim-aware search cap (squared metres).  TrimmedDistOutlierFilter keeps matches with d2 <= limit,
   // so a match only has to be exact if d2 <= limit; searching inside a ball of radius sqrt(cap) with
@@ -882,39 +1013,112 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
   int hist_count = 1;  // entries in qh/th
   int iter = 0, converged = 0, max_reached = 0, last_kept = 0;
   float last_limit = 0.f;
+  // what the previous iteration predicts for this one (uniform over the CTA, identical in every CTA)
+  unsigned int pred_bin1 = kNoPrediction, pred_pref12 = kNoPrediction;
+  float acc_limit = -1.0f;  // pairs with d2 <= acc_limit enter the normal equations in phase A (< 0: none do)
 
   for (;;) {
     const int par = iter & 1;
     LS_STAMP(0);
-    // ---------------- phase A: K2 nearest neighbour + level-1 histogram ----------------
-    for (int k = tid; k < 2048; k += kIcpThreads) hist_s[k] = 0u;
+    // ---------------- phase A ----------------
+    for (int k = tid; k < (int)(sizeof(SelHists) / 4); k += kIcpThreads) reinterpret_cast<unsigned int*>(&hs)[k] = 0u;
     __syncthreads();
-    if (dynamic) {
-      // Dynamic scheduling (several problems per launch): warps claim 32 consecutive queries at a time from the
-      // problem's counter, so every warp of the problem runs out of work at (almost) the same moment instead of
-      // parking at the barrier -- and starving the co-resident CTA of another problem -- while the slowest
-      // static chunk finishes.
+    {
+      // Every warp walks its share of the queries 32 at a time.  A query whose candidate list certifies the answer
+      // is done on the spot (one round trip of coalesced loads); the others are queued PER WARP and searched 32 at
+      // a time, so the expensive, divergent search always runs on full warps even when only a few percent of the
+      // queries need it.
+      const float* T_prev = iter >= 1 ? T_last : nullptr;  // lists are built from the second iteration on
+      unsigned long long* slab = acc_w[tid >> 5];
+      int* mq = miss_buf[tid >> 5];
+      int n_miss = 0;                    // warp-uniform
+      int next = q_begin + (tid & ~31);  // static schedule: this warp's next 32 queries
       for (;;) {
-        unsigned int base = 0;
-        if (lane == 0) base = atomicAdd(&W->qctr[par], 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= (unsigned int)n) break;
-        const int i = (int)base + lane;
-        if (i < n) phase_a_query<true>(g, P, T_iter, i, cap, hist_s);
+        int base;
+        if (dynamic) {
+          // Several problems per launch: warps claim 32 consecutive queries at a time from the problem's counter, so
+          // every warp of the problem runs out of work at (almost) the same moment instead of parking at the
+          // barrier -- and starving the co-resident CTA of another problem.
+          unsigned int bb = 0;
+          if (lane == 0) bb = atomicAdd(&W->qctr[par], 32u);
+          bb = __shfl_sync(0xffffffffu, bb, 0);
+          if (bb >= (unsigned int)n) break;
+          base = (int)bb;
+        } else {
+          if (next >= q_end) break;  // one problem owns the whole grid: contiguous chunk per CTA
+          base = next;
+          next += kIcpThreads;
+        }
+        const int i = base + lane;
+        const bool valid = i < (dynamic ? n : q_end);
+        bool hit = false;
+        Best b;
+        b.d2 = INFINITY; b.idx = INT_MAX; b.pos = -1;
+        float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+        if (valid) {
+          // reading point, list header, first candidate: three addresses known up front, one round trip
+          const float4 r = __ldg(P.rd + i);
+          const float4 v = __ldcg(P.lists.vq + i);
+          const float4 c0 = __ldcg(P.lists.vpts + i);
+          xform_point(T_iter, r.x, r.y, r.z, sx, sy, sz);
+          hit = vlist_query(P.lists, P.view.pts, i, v, c0, sx, sy, sz, cap, b, c);
+          if (hit) phase_a_record(P, i, b, &hs, pred_bin1, pred_pref12);
+        }
+        accumulate_pairs(P, (hit && b.pos >= 0 && b.d2 <= acc_limit) ? 1 : 0, sx, sy, sz, c, b.pos, slab);
+        const unsigned int mm = __ballot_sync(0xffffffffu, valid && !hit);
+        if (mm) {
+          if (valid && !hit) mq[n_miss + __popc(mm & ((1u << lane) - 1u))] = i;
+          n_miss += __popc(mm);
+          __syncwarp();
+          if (n_miss >= 32) {
+            n_miss -= 32;
+            const int j = mq[n_miss + lane];
+            __syncwarp();
+            const int2 res = phase_a_search(&g, &P, T_iter, T_prev, j, cap, &hs, pred_bin1, pred_pref12);
+            const bool keep = res.x >= 0 && __int_as_float(res.y) <= acc_limit;
+            if (__ballot_sync(0xffffffffu, keep)) {
+              float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (keep) {
+                const float4 r = __ldg(P.rd + j);
+                xform_point(T_iter, r.x, r.y, r.z, sx, sy, sz);
+                q = __ldg(P.view.pts + res.x);
+              }
+              accumulate_pairs(P, keep ? 1 : 0, sx, sy, sz, q, res.x, slab);
+            }
+          }
+        }
       }
-    } else {
-      // One problem owns the whole grid: one query per thread, state stays in the owning SM's L1.
-      for (int i = q_begin + tid; i < q_end; i += kIcpThreads) phase_a_query<false>(g, P, T_iter, i, cap, hist_s);
+      if (n_miss > 0) {  // warp-uniform: the last, partial batch of searches
+        __syncwarp();
+        const bool active = lane < n_miss;
+        const int j = active ? mq[lane] : 0;
+        int2 res = make_int2(-1, 0);
+        if (active) res = phase_a_search(&g, &P, T_iter, T_prev, j, cap, &hs, pred_bin1, pred_pref12);
+        __syncwarp();
+        const bool keep = active && res.x >= 0 && __int_as_float(res.y) <= acc_limit;
+        if (__ballot_sync(0xffffffffu, keep)) {
+          float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+          float sx = 0.f, sy = 0.f, sz = 0.f;
+          if (keep) {
+            const float4 r = __ldg(P.rd + j);
+            xform_point(T_iter, r.x, r.y, r.z, sx, sy, sz);
+            q = __ldg(P.view.pts + res.x);
+          }
+          accumulate_pairs(P, keep ? 1 : 0, sx, sy, sz, q, res.x, slab);
+        }
+      }
     }
-    __syncthreads();
-    for (int k = tid; k < 1024; k += kIcpThreads) {
-      const unsigned int v = hist_s[k];
-      if (v) atomicAdd(&W->hist[par][0][k], v);
+    flush_slabs(acc_w, W->acc[par]);  // (starts with a __syncthreads: every warp is done with phase A)
+    flush_hist(hs.h1, 1024, W->hist[par][0]);
+    if (pred_bin1 != kNoPrediction) {
+      flush_hist(hs.h2, 2048, W->hist[par][3]);
+      flush_hist(hs.h3, 1024, W->hist[par][4]);
     }
     problem_barrier(&W->barrier, G, epoch);
     LS_STAMP(1);
 
-    // ---------------- phase B: K3 select level 1, build level-2 histogram ----------------
+    // ---------------- select, level 1 ----------------
     block_select(W->hist[par][0], 1024, 0u, true, prm.trim_ratio, &sel, ws);
     if (sel.total == 0u) {  // no point at all -> ConvergenceError
       if (tid == 0) { flag_status = 1; if (cta == 0) W->fail_code = 1; }
@@ -931,115 +1135,77 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
       cap = cap < 64.0f ? cap * 16.0f : INFINITY;
       problem_barrier(&W->barrier, G, epoch);  // everyone has read the histogram
       if (cta == 0) {
-        for (int k = tid; k < 2048; k += kIcpThreads) W->hist[par][0][k] = 0u;
+        unsigned int* h = &W->hist[par][0][0];
+        for (int k = tid; k < 5 * 2048; k += kIcpThreads) h[k] = 0u;
+        if (tid < 32) W->acc[par][tid] = 0ull;
         if (tid == 0) W->qctr[par] = 0u;
       }
       problem_barrier(&W->barrier, G, epoch);
       continue;  // redo phase A of this iteration with the larger cap
     }
     const unsigned int bin1 = sel.bin, rem1 = sel.rem;
-    if (cta == 0) {  // clear the other parity's scratch for the next iteration
+    if (cta == 0) {  // clear the other parity's scratch for the next iteration (nobody touches it before the next barrier)
       unsigned int* h = &W->hist[par ^ 1][0][0];
-      for (int k = tid; k < 3 * 2048; k += kIcpThreads) h[k] = 0u;
+      for (int k = tid; k < 5 * 2048; k += kIcpThreads) h[k] = 0u;
       if (tid < 32) W->acc[par ^ 1][tid] = 0ull;
       if (tid == 0) W->qctr[par ^ 1] = 0u;
     }
-    for (int k = tid; k < 2048; k += kIcpThreads) hist_s[k] = 0u;
-    __syncthreads();
-    for (int i = q_begin + tid; i < q_end; i += kIcpThreads) {
-      const unsigned int key = __float_as_uint(dynamic ? __ldcg(P.d2 + i) : P.d2[i]);
-      if (key < 0x7f800000u && (key >> 21) == bin1) atomicAdd(&hist_s[(key >> 10) & 2047u], 1u);
+    // ---------------- level 2: from the speculative histogram, or a pass over d2 + barrier ----------------
+    const bool spec2 = bin1 == pred_bin1;
+    if (!spec2) {
+      for (int k = tid; k < 2048; k += kIcpThreads) hs.h2[k] = 0u;
+      __syncthreads();
+      for (int i = q_begin + tid; i < q_end; i += kIcpThreads) {
+        const unsigned int key = __float_as_uint(__ldcg(P.d2 + i));
+        if (key < 0x7f800000u && (key >> 21) == bin1) atomicAdd(&hs.h2[(key >> 10) & 2047u], 1u);
+      }
+      __syncthreads();
+      flush_hist(hs.h2, 2048, W->hist[par][1]);
+      problem_barrier(&W->barrier, G, epoch);
     }
-    __syncthreads();
-    for (int k = tid; k < 2048; k += kIcpThreads) {
-      const unsigned int v = hist_s[k];
-      if (v) atomicAdd(&W->hist[par][1][k], v);
-    }
-    problem_barrier(&W->barrier, G, epoch);
     LS_STAMP(2);
-
-    // ---------------- phase C: select level 2, build level-3 histogram ----------------
-    block_select(W->hist[par][1], 2048, rem1, false, 0.f, &sel, ws);
+    block_select(W->hist[par][spec2 ? 3 : 1], 2048, rem1, false, 0.f, &sel, ws);
     const unsigned int bin2 = sel.bin, rem2 = sel.rem;
-    for (int k = tid; k < 1024; k += kIcpThreads) hist_s[k] = 0u;
-    __syncthreads();
     const unsigned int prefix12 = (bin1 << 11) | bin2;
-    for (int i = q_begin + tid; i < q_end; i += kIcpThreads) {
-      const unsigned int key = __float_as_uint(dynamic ? __ldcg(P.d2 + i) : P.d2[i]);
-      if (key < 0x7f800000u && (key >> 10) == prefix12) atomicAdd(&hist_s[key & 1023u], 1u);
+    // ---------------- level 3 ----------------
+    const bool spec3 = spec2 && prefix12 == pred_pref12;
+    if (!spec3) {
+      for (int k = tid; k < 1024; k += kIcpThreads) hs.h3[k] = 0u;
+      __syncthreads();
+      for (int i = q_begin + tid; i < q_end; i += kIcpThreads) {
+        const unsigned int key = __float_as_uint(__ldcg(P.d2 + i));
+        if (key < 0x7f800000u && (key >> 10) == prefix12) atomicAdd(&hs.h3[key & 1023u], 1u);
+      }
+      __syncthreads();
+      flush_hist(hs.h3, 1024, W->hist[par][2]);
+      problem_barrier(&W->barrier, G, epoch);
     }
-    __syncthreads();
-    for (int k = tid; k < 1024; k += kIcpThreads) {
-      const unsigned int v = hist_s[k];
-      if (v) atomicAdd(&W->hist[par][2][k], v);
-    }
-    problem_barrier(&W->barrier, G, epoch);
     LS_STAMP(3);
-
-    // ---------------- phase D: K4 normal equations over matches with d2 <= limit ----------------
-    block_select(W->hist[par][2], 1024, rem2, false, 0.f, &sel, ws);
+    block_select(W->hist[par][spec3 ? 4 : 2], 1024, rem2, false, 0.f, &sel, ws);
     const float limit = __uint_as_float((prefix12 << 10) | sel.bin);
     cap = fmaxf(limit * 2.0f, 1e-12f);  // guess for the next iteration (verified there)
-    // One query per thread per pass (a CTA normally holds <= one query per thread): every product is
-    // quantised to 2^-22 and reduced across the warp at once (REDUX), so no per-thread accumulator array
-    // has to live in registers.  Integer sums are exact, hence independent of any ordering.
-    if (tid < 28 * (kIcpThreads / 32)) acc_w[tid / 28][tid % 28] = 0ull;
-    __syncthreads();
+
+    // ---------------- correction pass: pairs between the predicted and the actual limit ----------------
+    // Phase A added every pair with d2 <= acc_limit; the minimiser wants exactly those with d2 <= limit.
     for (int base = q_begin; base < q_end; base += kIcpThreads) {
       const int i = base + tid;
-      bool keep = false;
-      float f[6], e = 0.f;
-#pragma unroll
-      for (int k = 0; k < 6; ++k) f[k] = 0.f;
+      int sign = 0, pos = -1;
       if (i < q_end) {
-        const float d = dynamic ? __ldcg(P.d2 + i) : P.d2[i];
-        const int pos = dynamic ? __ldcg(P.pos + i) : P.pos[i];
-        if (d <= limit && pos >= 0) {
-          keep = true;
-          const float4 r = __ldg(P.rd + i);
-          float sx, sy, sz;
-          xform_point(T_iter, r.x, r.y, r.z, sx, sy, sz);
-          const float4 q = __ldg(P.view.pts + pos);
-          const float4 nn = __ldg(P.nrm + pos);
-          float u = sy * nn.z, v = sz * nn.y;
-          f[0] = u - v;
-          u = sz * nn.x; v = sx * nn.z;
-          f[1] = u - v;
-          u = sx * nn.y; v = sy * nn.x;
-          f[2] = u - v;
-          f[3] = nn.x; f[4] = nn.y; f[5] = nn.z;
-          const float dx = sx - q.x, dy = sy - q.y, dz = sz - q.z;
-          e = dx * nn.x;
-          float t = dy * nn.y;
-          e = e + t;
-          t = dz * nn.z;
-          e = e + t;
-        }
+        const float d = __ldcg(P.d2 + i);
+        pos = __ldcg(P.pos + i);
+        sign = ((d <= limit && pos >= 0) ? 1 : 0) - ((d <= acc_limit) ? 1 : 0);  // d2 is +inf where nothing was found
       }
-      const unsigned int kmask = __ballot_sync(0xffffffffu, keep);
-      if (kmask == 0u) continue;  // warp-uniform
-      int k = 0;
-#pragma unroll
-      for (int rr = 0; rr < 6; ++rr)
-#pragma unroll
-        for (int cc = rr; cc < 6; ++cc, ++k) {
-          const long long s = warp_sum_ll(keep ? __float2ll_rn((f[rr] * f[cc]) * 4194304.0f) : 0ll);
-          if (lane == 0) acc_w[tid >> 5][k] += (unsigned long long)s;
-        }
-#pragma unroll
-      for (int rr = 0; rr < 6; ++rr) {
-        const long long s = warp_sum_ll(keep ? __float2ll_rn((f[rr] * e) * 4194304.0f) : 0ll);
-        if (lane == 0) acc_w[tid >> 5][21 + rr] += (unsigned long long)s;
+      if (__ballot_sync(0xffffffffu, sign != 0) == 0u) continue;  // warp-uniform
+      float sx = 0.f, sy = 0.f, sz = 0.f;
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (sign) {
+        const float4 r = __ldg(P.rd + i);
+        xform_point(T_iter, r.x, r.y, r.z, sx, sy, sz);
+        q = __ldg(P.view.pts + pos);
       }
-      if (lane == 0) acc_w[tid >> 5][27] += (unsigned long long)__popc(kmask);
+      accumulate_pairs(P, sign, sx, sy, sz, q, pos, acc_w[tid >> 5]);
     }
-    __syncthreads();
-    if (tid < 28) {
-      unsigned long long t = 0ull;
-#pragma unroll
-      for (int w = 0; w < kIcpThreads / 32; ++w) t += acc_w[w][tid];
-      if (t != 0ull) atomicAdd(&W->acc[par][tid], t);
-    }
+    flush_slabs(acc_w, W->acc[par]);
     problem_barrier(&W->barrier, G, epoch);
     LS_STAMP(4);
 
@@ -1115,20 +1281,17 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
     __syncthreads();
     if (!flag_status) ++iter;  // every thread tracks the iteration count (parity, warm start)
     if (flag_stop) break;
+    // what this iteration predicts for the next: the select bins of its limit, and -- once the limit has stopped
+    // falling by large factors -- the limit itself as the threshold of phase A's accumulation
+    pred_bin1 = bin1;
+    pred_pref12 = prefix12;
+    acc_limit = iter >= 2 ? limit : -1.0f;
   }
 
   if (P.want_matches && !flag_status && iter > 0) {
     // The loop ended right after the update of T_iter; the matches reported are those of the LAST
     // iteration, i.e. of the reading under T_last.  Redo that query without a cap.
-    for (int i = q_begin + tid; i < q_end; i += kIcpThreads) {
-      const float4 r = __ldg(P.rd + i);
-      float sx, sy, sz;
-      xform_point(T_last, r.x, r.y, r.z, sx, sy, sz);
-      const Best b = nn_search(g, P.view, sx, sy, sz, __ldcg(P.pos + i), INFINITY);
-      const uint32_t orig = __ldg(P.qperm + i);
-      P.d2_out[orig] = b.d2;
-      P.ids[orig] = b.idx;
-    }
+    for (int i = q_begin + tid; i < q_end; i += kIcpThreads) final_match(&g, &P, T_last, i);
   }
 
   if (cta == 0 && tid == 0) {

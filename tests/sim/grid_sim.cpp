@@ -140,4 +140,53 @@ void sim_nn(const float* q3, int n, const float* refc3, int m, float cell, int m
     stats[5] = S.g.n_cells0;
   }
 }
+
+// Certified candidate lists over a sequence of poses: queries rd3 (n x 3) are moved by T_seq[t] (column-major 4x4,
+// n_iter of them); iteration t answers every query through vlist_query when its certificate holds and through
+// nn_search (+ vlist_build) otherwise, exactly as the ICP kernel's phase A does, and checks each answer against
+// nn_search alone.  caps[t] = capped-search radius^2 of iteration t, skin_w/skin_v[t] = motion bound of the last
+// step (|rotation vector|, |translation|).  Returns the number of answers that differ (must be 0);
+// hits[t] = queries answered from their list, overflow[t] = list builds refused (more than LS_VK points).
+int sim_vlists(const float* rd3, int n, const float* refc3, int m, float cell, int max_cells, int split, const float* T_seq,
+               int n_iter, const float* caps, const float* skin_w, const float* skin_v, int32_t* hits, int32_t* overflow,
+               int32_t* ids_last, float* d2_last) {
+  SimGrid S;
+  build(S, refc3, m, cell, max_cells, split);
+  ls::GridView v{S.top.data(), S.tab1.data(), S.pts.data(), S.pyr.data()};
+  std::vector<float4> vq(n, make_float4(0.f, 0.f, 0.f, 0.f)), vpts((size_t)LS_VK * n);
+  std::vector<int> warm(n, -1);
+  ls::VLists L{vq.data(), vpts.data(), n};
+  int bad = 0;
+  for (int t = 0; t < n_iter; ++t) {
+    const float* T = T_seq + 16 * t;
+    int h = 0, of = 0;
+    for (int i = 0; i < n; ++i) {
+      float qx, qy, qz;
+      ls::xform_point(T, rd3[3 * i], rd3[3 * i + 1], rd3[3 * i + 2], qx, qy, qz);
+      const ls::Best ref = ls::nn_search(S.g, v, qx, qy, qz, warm[i], caps[t]);
+      ls::Best b;
+      float4 cb = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ls::vlist_query(L, S.pts.data(), i, vq[i], vpts[i], qx, qy, qz, caps[t], b, cb)) {
+        ++h;
+        if (b.pos >= 0 && (ls::f2i(cb.w) != b.pos || cb.x != S.pts[b.pos].x || cb.y != S.pts[b.pos].y || cb.z != S.pts[b.pos].z)) ++bad;
+        if (b.pos >= 0) b.idx = ls::f2i(S.pts[b.pos].w);
+        else { b.idx = -1; b.d2 = INFINITY; }
+        if (b.pos != ref.pos || b.idx != ref.idx || !(b.d2 == ref.d2)) ++bad;
+      } else if (t >= 1) {
+        float px, py, pz;  // where the previous iteration had this query
+        ls::xform_point(T_seq + 16 * (t - 1), rd3[3 * i], rd3[3 * i + 1], rd3[3 * i + 2], px, py, pz);
+        const float motion = std::sqrt(ls::dist2(qx, qy, qz, px, py, pz));
+        (void)skin_w; (void)skin_v;
+        const float4 before = vq[i];
+        ls::vlist_build(S.g, v, L, i, qx, qy, qz, ref.pos >= 0, ref.d2, caps[t], motion);
+        if (ls::f2i(vq[i].w) == 0 && (before.x != vq[i].x || ls::f2i(before.w) != 0)) ++of;
+      }
+      if (ref.pos >= 0) warm[i] = ref.pos;
+      if (t == n_iter - 1) { ids_last[i] = ref.idx; d2_last[i] = ref.d2; }
+    }
+    if (hits) hits[t] = h;
+    if (overflow) overflow[t] = of;
+  }
+  return bad;
+}
 }

@@ -107,3 +107,72 @@ def test_sim_capped_search_is_exact_within_cap(sim, oracle_mod, small_pair):
             inside = db <= np.float32(cap)
             assert np.array_equal(ig[inside], ib[inside]) and np.array_equal(dg[inside], db[inside])
             assert (ig[~inside] == -1).all() and np.isinf(dg[~inside]).all()
+
+
+# ---- certified candidate lists (ls_grid.cuh vlist_query / vlist_build): answers must equal the plain search ------
+@pytest.fixture(scope="module")
+def sim_lists(sim):
+    L = ctypes.CDLL(SIM_LIB)
+    vp = ctypes.c_void_p
+    L.sim_vlists.restype = ctypes.c_int
+    L.sim_vlists.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int,
+                             vp, vp, vp, vp, vp, vp, vp]
+
+    def run(rd3, refc3, T_seq, caps, skin_w, skin_v, cell=1.0, split=32):
+        rd3 = np.ascontiguousarray(rd3, np.float32)
+        refc3 = np.ascontiguousarray(refc3, np.float32)
+        Tcm = np.ascontiguousarray(np.stack([np.asarray(T, np.float32).T.ravel() for T in T_seq]))   # column-major
+        K = len(T_seq)
+        caps, skin_w, skin_v = (np.ascontiguousarray(a, np.float32) for a in (caps, skin_w, skin_v))
+        hits, over = np.zeros(K, np.int32), np.zeros(K, np.int32)
+        ids, d2 = np.empty(len(rd3), np.int32), np.empty(len(rd3), np.float32)
+        bad = L.sim_vlists(rd3.ctypes.data, len(rd3), refc3.ctypes.data, len(refc3), cell, 1 << 22, split, Tcm.ctypes.data, K,
+                           caps.ctypes.data, skin_w.ctypes.data, skin_v.ctypes.data, hits.ctypes.data, over.ctypes.data,
+                           ids.ctypes.data, d2.ctypes.data)
+        return bad, hits, over, ids, d2
+    return run
+
+
+def _pose_sequence(T_hist):
+    """T_iter before every iteration (identity first) + the motion bound of the step that led to it."""
+    Ts = [np.eye(4, dtype=np.float32)] + [np.asarray(T, np.float32) for T in T_hist[:-1]]
+    w, v = [0.0], [0.0]
+    for a, b in zip(Ts[:-1], Ts[1:]):
+        S = b.astype(np.float64) @ np.linalg.inv(a.astype(np.float64))
+        w.append(float(np.arccos(np.clip((np.trace(S[:3, :3]) - 1) / 2, -1, 1))))
+        v.append(float(np.linalg.norm(S[:3, 3])))
+    return Ts, w, v
+
+
+def test_sim_lists_reproduce_the_search_over_an_icp_run(sim_lists, oracle_mod, small_pair):
+    """Every query of every iteration of a real ICP run: the list path and the plain search give the same match."""
+    o = oracle_mod
+    r = o.icp(small_pair["reading"], small_pair["ref"], small_pair["ref_normals"], small_pair["T0"],
+              o.default_params(max_iterations=20, use_differential=0), want_hist=True)
+    mu = o.mean(small_pair["ref"])
+    refc = (small_pair["ref"][:, :3] - mu).astype(np.float32)
+    Tpre = small_pair["T0"].copy()
+    Tpre[:3, 3] -= mu
+    rd = o.transform_points(Tpre, small_pair["reading"])[:, :3].copy()
+    Ts, w, v = _pose_sequence(r["T_iter_hist"])
+    for caps in ([0.25] + [0.02] * 19, [0.25] + [0.004] * 19, [np.inf] * 20):
+        bad, hits, over, ids, d2 = sim_lists(rd, refc, Ts, caps, w, v)
+        assert bad == 0
+        assert hits[0] == 0 and hits[-1] > 0.9 * len(rd), hits          # converged: almost every query is certified
+    assert np.array_equal(ids, r["ids_hist"][-1])                       # last iteration == the oracle's correspondences
+
+
+def test_sim_lists_ties_and_tiny_motions(sim_lists):
+    """Lattice + duplicates (exact ties inside the lists), queries drifting by fractions of the spacing."""
+    rng = np.random.default_rng(5)
+    g = np.stack(np.meshgrid(np.arange(10), np.arange(10), np.arange(4), indexing="ij"), -1).reshape(-1, 3).astype(np.float32) * 0.05
+    ref = np.concatenate([g, g[rng.permutation(len(g))[:100]]]).astype(np.float32)
+    q = np.concatenate([g + 0.025, g, rng.uniform(-0.1, 0.6, (400, 3)).astype(np.float32)]).astype(np.float32)
+    Ts = []
+    for t in range(12):
+        T = np.eye(4, dtype=np.float32)
+        T[:3, 3] = [0.0004 * t, -0.0002 * t, 0.0001 * (t % 3)]
+        Ts.append(T)
+    for cap in (np.inf, 0.01, 0.0007):
+        bad, hits, over, _, _ = sim_lists(q, ref, Ts, [cap] * 12, [0.0] * 12, [0.0005] * 12, cell=0.5, split=16)
+        assert bad == 0 and hits[1:].sum() > 0
