@@ -180,6 +180,7 @@ int ensure_capacity(ls_ctx* ctx, Workspace* w, int n, int m, int max_cells, int 
     if ((rc = dev_alloc(ctx, &w->A.top, (size_t)max_cells + 1))) return rc;
     if ((rc = dev_alloc(ctx, &w->A.cnt0, (size_t)max_cells + 1))) return rc;
     if ((rc = dev_alloc(ctx, &w->A.pyr, (size_t)max_cells / 2 + 4096))) return rc;
+    if ((rc = dev_alloc(ctx, &w->A.topmask, (size_t)max_cells + 1))) return rc;
     if ((rc = dev_alloc(ctx, &w->A.qtop_start, (size_t)max_cells + 1))) return rc;
     CU(cudaMemsetAsync(w->A.cnt0, 0, ((size_t)max_cells + 1) * sizeof(uint32_t), w->stream));
     w->cells_cap = max_cells;
@@ -297,6 +298,7 @@ int prep_icp(ls_ctx* ctx, Workspace* w, const ls_icp_params* prm, const float4* 
   hp.view.tab1 = w->A.tab1;
   hp.view.pts = w->A.srt_pts;
   hp.view.pyr = w->A.pyr;
+  hp.view.topmask = w->A.topmask;
   hp.nrm = w->A.srt_nrm;
   hp.rd = w->A.rd_s;
   hp.n = n;
@@ -348,7 +350,7 @@ int launch_icp(ls_ctx* ctx, const ls_icp_params* prm, int batch, int n_max) {
   int dynamic = batch > 1 ? 1 : 0;  // several problems: warps pull work from per-problem counters
   void* args[] = {(void*)&probs, (void*)&ctas, (void*)&dp, (void*)&dynamic};
   CU(cudaEventRecord(w0->ev_launch, w0->stream));
-  CU(cudaLaunchCooperativeKernel((void*)icp_kernel, dim3(ctas * batch), dim3(kIcpThreads), args, 0, w0->stream));
+  CU(cudaLaunchCooperativeKernel((void*)icp_kernel, dim3(ctas * batch), dim3(kIcpThreads), args, kIcpPairBytes, w0->stream));
   ++ctx->launches;
   CU(cudaEventRecord(w0->ev2, w0->stream));
   for (int b = 0; b < batch; ++b) {
@@ -489,7 +491,7 @@ void free_workspace(Workspace* w) {
   if (!w) return;
   if (w->stream) cudaStreamSynchronize(w->stream);
   void* bufs[] = {w->A.sub_pts, w->A.sub_nrm, w->A.srt_pts, w->A.srt_nrm, w->A.pkey, w->A.top, w->A.cnt0, w->A.tab1, w->A.cnt1,
-                  w->A.tab1_cell, w->A.pyr, w->bs, w->reading, w->rd, w->ref_stage, w->ref_nrm_stage, w->nrm_raw, w->pos, w->d2,
+                  w->A.tab1_cell, w->A.pyr, w->A.topmask, w->bs, w->reading, w->rd, w->ref_stage, w->ref_nrm_stage, w->nrm_raw, w->pos, w->d2,
                   w->ids, w->vq, w->vpts, w->work, w->T_hist, w->T0_dev, w->phase_ns, w->d2_out, w->A.qkey, w->A.qperm, w->A.rd_s,
                   w->A.qtab_local, w->A.qtab_total, w->A.qtop_start};
   for (void* b : bufs)
@@ -531,7 +533,8 @@ int ls_b200_init(int device, ls_ctx** out) {
   if (!prop.cooperativeLaunch) return bail(LS_ERR_CUDA);
   ctx->sm_count = prop.multiProcessorCount;
   int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, icp_kernel, kIcpThreads, 0) != cudaSuccess || occ < 1)
+  if (cudaFuncSetAttribute(icp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kIcpPairBytes) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, icp_kernel, kIcpThreads, kIcpPairBytes) != cudaSuccess || occ < 1)
     return bail(LS_ERR_CUDA);
   ctx->icp_ctas = occ * ctx->sm_count;
   if (ensure_workspaces(ctx, 1) != LS_OK) return bail(LS_ERR_NOMEM);
@@ -630,7 +633,7 @@ int ls_nn_query(ls_ctx* ctx, const ls_icp_params* prm, const float* reading4, in
   if ((rc = enqueue_build(ctx, w, parts, r, T0))) return rc;
   reading_kernel<<<blocks_for(n, 256, ctx->sm_count * 8), 256, 0, w->stream>>>(w->bs, w->reading, n, w->rd);
   LAUNCH_CHECK();
-  GridView v{w->A.top, w->A.tab1, w->A.srt_pts, w->A.pyr};
+  GridView v{w->A.top, w->A.tab1, w->A.srt_pts, w->A.pyr, w->A.topmask};
   nn_query_kernel<<<blocks_for(n, 256, ctx->sm_count * 8), 256, 0, w->stream>>>(w->bs, v, w->rd, n, w->ids, w->d2);
   LAUNCH_CHECK();
   CU(cudaMemcpyAsync(ids, w->ids, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, w->stream));
@@ -822,7 +825,7 @@ int enqueue_normals(ls_ctx* ctx, Workspace* w, const float4* pts_dev, int n, int
   parts.identity[0] = 1;
   const float I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
   if ((rc = enqueue_build(ctx, w, parts, r, I))) return rc;
-  GridView v{w->A.top, w->A.tab1, w->A.srt_pts, w->A.pyr};
+  GridView v{w->A.top, w->A.tab1, w->A.srt_pts, w->A.pyr, w->A.topmask};
   knn_normals_kernel<<<blocks_for(n, 128, ctx->sm_count * 16), 128, 0, w->stream>>>(w->bs, v, w->A.sub_pts, n, knn, nrm_out);
   LAUNCH_CHECK();
   return LS_OK;

@@ -75,6 +75,10 @@ struct GridView {
   const Entry* tab1;  // fine tables, LS_FB3 entries each (all leaves)
   const float4* pts;  // sorted {x,y,z,idx}
   const unsigned long long* pyr;  // occupancy masks, levels 1..n_pyr
+  // per level-0 cell that owns a fine table: bit (z*LS_FB + y) set iff row (z, y) of the table holds a point (LS_FB == 8:
+  // 64 rows).  Surfaces leave most rows of a table empty; the mask -- fetched together with the cell's entry, same
+  // index -- lets the ball query skip them without touching their entries.  Meaningless for other cells.
+  const unsigned long long* topmask;
 };
 
 // Accumulator of the traversal.  `bound()` is the squared distance beyond which a candidate cannot matter
@@ -149,6 +153,7 @@ LS_HD float i2f(int i) { return __int_as_float(i); }
 LS_HD float4 ld_state4(const float4* p) { return __ldcg(p); }   // per-query state crosses CTAs: L2, never L1
 LS_HD void st_state4(float4* p, const float4 v) { __stcg(p, v); }
 LS_HD unsigned long long ld_mask(const unsigned long long* p) { return __ldg(p); }
+LS_HD unsigned long long ld_rows(const unsigned long long* p) { return __ldg(p); }
 LS_HD int ctz64(unsigned long long m) { return __ffsll((long long)m) - 1; }
 #else
 LS_HD float4 ld_pt(const float4* p) { LS_CNT_CAND(); return *p; }
@@ -158,6 +163,7 @@ LS_HD float i2f(int i) { float f; std::memcpy(&f, &i, 4); return f; }
 LS_HD float4 ld_state4(const float4* p) { return *p; }
 LS_HD void st_state4(float4* p, const float4 v) { *p = v; }
 LS_HD unsigned long long ld_mask(const unsigned long long* p) { LS_CNT_ENTRY(); return *p; }
+LS_HD unsigned long long ld_rows(const unsigned long long* p) { return *p; }
 LS_HD int ctz64(unsigned long long m) { return __builtin_ctzll(m); }
 #endif
 
@@ -221,8 +227,8 @@ LS_HD void scan_range(const float4* pts, uint32_t a, uint32_t e, float qx, float
 // Points are sorted x-fastest, so for a row (z, y) the fine cells x0..x1 are ONE contiguous run
 // [start(z,y,x0), end(z,y,x1)): two entry loads, then a stream of candidates.
 template <class Acc>
-LS_HD void visit_fine(const Grid& g, const Entry* tab, float lox, float loy, float loz, const float4* pts,
-                      float qx, float qy, float qz, Acc& b) {
+LS_HD void visit_fine(const Grid& g, const Entry* tab, unsigned long long rows, float lox, float loy, float loz,
+                      const float4* pts, float qx, float qy, float qz, Acc& b) {
   const float R = ball_radius(b.bound(), g.margin);
   const int x0 = coord_sub(qx - R, lox, g.inv1), x1 = coord_sub(qx + R, lox, g.inv1);
   const int y0 = coord_sub(qy - R, loy, g.inv1), y1 = coord_sub(qy + R, loy, g.inv1);
@@ -233,6 +239,9 @@ LS_HD void visit_fine(const Grid& g, const Entry* tab, float lox, float loy, flo
     if (gz2 * LS_SHRINK > b.bound()) continue;
     const Entry* row = tab + (z * LS_FB + y0) * LS_FB;
     for (int y = y0; y <= y1; ++y, row += LS_FB) {
+#if LS_FB == 8
+      if (!((rows >> (z * LS_FB + y)) & 1ull)) continue;  // empty row
+#endif
       const float gy = gap(qy, cell_lo(loy, y, g.H1), cell_lo(loy, y + 1, g.H1), g.margin);
       const float lb = gy * gy + gz2;
       if (lb * LS_SHRINK > b.bound()) continue;
@@ -246,19 +255,22 @@ LS_HD void visit_fine(const Grid& g, const Entry* tab, float lox, float loy, flo
 
 // one level-0 cell (leaf scan or fine table)
 template <class Acc>
-LS_HD void visit_top_entry(const Grid& g, const GridView& v, const Entry e, float cx, float cy, float cz, float qx,
-                           float qy, float qz, Acc& b) {
+LS_HD void visit_top_entry(const Grid& g, const GridView& v, const Entry e, unsigned long long rows, float cx, float cy,
+                           float cz, float qx, float qy, float qz, Acc& b) {
   if (e.meta > 0) {
     scan_range(v.pts, e.start, e.start + (uint32_t)e.meta, qx, qy, qz, b);
   } else if (e.meta < 0) {
-    visit_fine(g, v.tab1 + (size_t)(~e.meta) * LS_FB3, cx, cy, cz, v.pts, qx, qy, qz, b);
+    visit_fine(g, v.tab1 + (size_t)(~e.meta) * LS_FB3, rows, cx, cy, cz, v.pts, qx, qy, qz, b);
   }
 }
 template <class Acc>
 LS_HD void visit_top_cell(const Grid& g, const GridView& v, int x, int y, int z, float cx, float cy, float cz, float qx,
                           float qy, float qz, Acc& b) {
   LS_CNT_STEP();
-  visit_top_entry(g, v, ld_entry(v.top + ((size_t)z * g.dim[1] + y) * g.dim[0] + x), cx, cy, cz, qx, qy, qz, b);
+  const size_t ci = ((size_t)z * g.dim[1] + y) * g.dim[0] + x;
+  const Entry e = ld_entry(v.top + ci);
+  const unsigned long long rows = ld_rows(v.topmask + ci);  // independent of the entry: one round trip for both
+  visit_top_entry(g, v, e, rows, cx, cy, cz, qx, qy, qz, b);
 }
 
 // ---- large balls: depth-first walk of the occupancy pyramid (empty space costs one mask load per
@@ -413,7 +425,23 @@ LS_HD Best nn_search(const Grid& g, const GridView& v, float qx, float qy, float
 // vpts[k*n + i] = candidate k as {x, y, z, sorted position} -- structure of arrays, so a warp streams 512
 // contiguous bytes per k.  The original index (tie-break) is fetched from the sorted map only when two candidates
 // are exactly equidistant.
+#ifndef LS_VK
 #define LS_VK 8  // candidates per list; a ball holding more is not listed
+#endif
+static_assert(LS_VK <= 15, "the list header keeps the candidate count in 4 bits");
+// tuning knobs of vlist_build (tests/sim sweeps them; results never depend on them)
+#ifndef LS_VL_ABS
+#define LS_VL_ABS 0.0f   // floor of the list margin [m]
+#endif
+#ifndef LS_VL_REL
+#define LS_VL_REL 0.5f   // cap of the list margin relative to the match distance
+#endif
+#ifndef LS_VL_SKIN
+#define LS_VL_SKIN 4.0f  // margin wanted = skin * (how far the last step moved the query)
+#endif
+#ifndef LS_VL_GATE
+#define LS_VL_GATE 1.0f  // build only if motion * gate <= margin
+#endif
 struct VLists {
   float4* vq;
   float4* vpts;
@@ -483,9 +511,9 @@ LS_HD void vlist_build(const Grid& g, const GridView& v, const VLists& L, int i,
   float Rv;
   if (found) {
     const float want = sqrtf(found_d2);
-    const float margin = want * 0.5f + 1e-4f;
-    if (!(motion <= margin)) return;
-    Rv = want + fminf(margin, fmaxf(0.002f, 4.0f * motion));
+    const float margin = fmaxf(want * LS_VL_REL, LS_VL_ABS) + 1e-4f;
+    if (!(motion * LS_VL_GATE <= margin)) return;
+    Rv = want + fminf(margin, fmaxf(0.002f, LS_VL_SKIN * motion));
   } else {
     const float want = sqrtf(cap_d2);  // the cap itself moves a little between iterations: 5 % head room
     if (!(motion <= want * 0.125f)) return;

@@ -60,6 +60,7 @@ struct BuildArrays {
   uint32_t* tab1_cell;   // level-0 cell of each fine table
   int tab_cap;
   unsigned long long* pyr;  // occupancy pyramid masks
+  unsigned long long* topmask;  // per level-0 cell with a table: non-empty rows (GridView::topmask)
   // query ordering (same keys as the map): rank -> query
   uint32_t* qkey;        // per query: tag | cell key
   uint32_t* qtop_start;  // per level-0 cell: first rank
@@ -433,6 +434,22 @@ __global__ void __launch_bounds__(256) tables_kernel(BuildState* bs, BuildArrays
       tab[threadIdx.x * per + k] = e;
       run += c[k];
     }
+#if LS_FB == 8
+    // non-empty rows: a row is 8 consecutive cells = 4 consecutive threads; warp w covers rows 8w .. 8w+7
+    const unsigned int occ = __ballot_sync(0xffffffffu, loc != 0u);
+    unsigned int rows8 = 0u;
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if ((occ >> (4 * r)) & 0xFu) rows8 |= 1u << r;
+    __syncthreads();  // ws was read above
+    if (lane == 0) ws[warp] = rows8;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long m = 0ull;
+      for (int w = 0; w < 8; ++w) m |= (unsigned long long)ws[w] << (8 * w);
+      A.topmask[A.tab1_cell[t]] = m;
+    }
+#endif
   }
 }
 
@@ -751,8 +768,20 @@ __device__ __forceinline__ void problem_barrier(unsigned int* ctr, unsigned int 
   if (threadIdx.x == 0) {
     epoch += n_ctas;
     red_release_inc(ctr);
+    unsigned int polls = 0;
+    unsigned long long t0 = 0ull;
     while (ld_relaxed_u32(ctr) < epoch) {
       __nanosleep(64);  // the polling thread shares its SM's issue slots with a CTA that is still working
+      // watchdog: a barrier that does not complete within seconds is a bug (or a launch that was not co-resident);
+      // fail the launch loudly instead of hanging the device
+      if ((++polls & 0x3fffu) == 0u) {
+        const unsigned long long now = globaltimer_ns();
+        if (t0 == 0ull) t0 = now;
+        else if (now - t0 > 8000000000ull) {
+          printf("[ls] icp_kernel barrier timeout: block %d waits for %u, counter %u\n", (int)blockIdx.x, epoch, ld_relaxed_u32(ctr));
+          __trap();
+        }
+      }
     }
   }
   __syncthreads();
@@ -855,50 +884,92 @@ __device__ __forceinline__ void residual_terms(float sx, float sy, float sz, con
   e = e + t;
 }
 
-// Warp-collective (all 32 lanes, converged): add (sign = +1), remove (-1) or skip (0) each lane's pair in the
-// normal equations A = sum f f^T (21 unique entries), b = sum f e (6), count (1).  Every product is quantised to
-// 2^-22 and summed as int64 (REDUX over 21-bit limbs), so the result is exact and independent of any ordering;
-// lane 0 folds the warp's sums into the warp's slab in shared memory.
-__device__ __noinline__ void accumulate_warp(int sign, float f0, float f1, float f2, float f3, float f4, float f5, float e,
-                                             unsigned long long* slab) {
-  const float f[6] = {f0, f1, f2, f3, f4, f5};
-  const bool lane0 = (threadIdx.x & 31) == 0;
-  int k = 0;
-#pragma unroll
-  for (int rr = 0; rr < 6; ++rr)
-#pragma unroll
-    for (int cc = rr; cc < 6; ++cc, ++k) {
-      long long v = sign ? __float2ll_rn((f[rr] * f[cc]) * 4194304.0f) : 0ll;
-      if (sign < 0) v = -v;
-      const long long sm = warp_sum_ll(v);
-      if (lane0) slab[k] += (unsigned long long)sm;
-    }
-#pragma unroll
-  for (int rr = 0; rr < 6; ++rr) {
-    long long v = sign ? __float2ll_rn((f[rr] * e) * 4194304.0f) : 0ll;
-    if (sign < 0) v = -v;
-    const long long sm = warp_sum_ll(v);
-    if (lane0) slab[21 + rr] += (unsigned long long)sm;
+// ---- normal equations: A = sum f f^T (21 unique entries), b = sum f e (6), number of pairs (1) -------------------
+// Every product is a float32 product quantised to 2^-22 and summed as int64 -- exact, hence independent of any
+// ordering (oracle/icp_oracle.cpp).  Pairs are not reduced across lanes as they come (that took 81 warp-wide integer
+// reductions per 32 queries): each warp queues the pairs that count as 8-float records {f0..f5, e, sign} in shared
+// memory and, whenever 32 are waiting, lane k walks all 32 records for ITS entry of the system -- 28 lanes, 28
+// private int64 sums held in registers for the whole pass, no cross-lane traffic at all.  A record with sign -1
+// removes a pair that an earlier pass added (same floats, same products: cancels exactly).
+constexpr int kPairSlots = 64;  // per warp: up to 31 waiting + 32 arriving
+constexpr int kIcpPairBytes = (kIcpThreads / 32) * kPairSlots * 8 * (int)sizeof(float);  // dynamic shared memory of icp_kernel
+__constant__ unsigned char kPairRow[32] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 5, 0, 1, 2, 3, 4, 5, 7, 7, 7, 7, 7};
+__constant__ unsigned char kPairCol[32] = {0, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5, 2, 3, 4, 5, 3, 4, 5, 4, 5, 5, 6, 6, 6, 6, 6, 6, 7, 7, 7, 7, 7};
+
+struct PairQueue {
+  float* recs;    // kPairSlots x 8 floats, shared memory, this warp's
+  int head, cnt;  // warp-uniform
+  long long acc;  // lane k < 28: its entry's running sum
+};
+
+// lanes 0..20: upper triangle of A; 21..26: b; 27: count (sign * sign quantised with scale 1); 28..31 idle copies of 27
+__device__ __noinline__ long long consume_pairs(const float* recs, int head, int count, long long acc) {
+  const int lane = threadIdx.x & 31;
+  const int ro = kPairRow[lane], co = kPairCol[lane];
+  const float scale = lane < 27 ? 4194304.0f : 1.0f;
+#pragma unroll 4
+  for (int j = 0; j < count; ++j) {
+    const float* r = recs + ((head + j) & (kPairSlots - 1)) * 8;
+    const float a = r[ro], b = r[co], sg = r[7];
+    long long v = __float2ll_rn((a * b) * scale);
+    if (sg < 0.f) v = -v;
+    acc += v;
   }
-  const int plus = __popc(__ballot_sync(0xffffffffu, sign > 0)), minus = __popc(__ballot_sync(0xffffffffu, sign < 0));
-  if (lane0) slab[27] += (unsigned long long)(long long)(plus - minus);
+  return acc;
 }
 
-// Warp-collective: lanes with sign != 0 contribute the pair (query at s, matched point q at sorted position pos).
-__device__ __forceinline__ void accumulate_pairs(const IcpProblem& P, int sign, float sx, float sy, float sz, const float4 q,
-                                                 int pos, unsigned long long* slab) {
-  if (__ballot_sync(0xffffffffu, sign != 0) == 0u) return;  // warp-uniform
-  float f[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, e = 0.f;
-  if (sign) residual_terms(sx, sy, sz, q, __ldg(P.nrm + pos), f, e);
-  accumulate_warp(sign, f[0], f[1], f[2], f[3], f[4], f[5], e, slab);
+// Warp-collective (all 32 lanes, converged): lanes with sign != 0 queue the pair (query at s, matched point q at sorted
+// position pos, its normal fetched here).
+template <int site>
+__device__ __forceinline__ void push_pairs(const IcpProblem& P, PairQueue& Q, int sign, float sx, float sy, float sz,
+                                           const float4 q, int pos) {
+  const unsigned int m = __ballot_sync(0xffffffffu, sign != 0);
+  if (m == 0u) return;  // warp-uniform
+#ifdef LS_DEBUG_PAIRS
+  if (sign && (pos < 0 || pos >= P.bs->grid.m)) {
+    printf("[ls] push_pairs: sign %d pos %d site %d block %d thread %d q.w %d\n", sign, pos, site, (int)blockIdx.x, (int)threadIdx.x, __float_as_int(q.w));
+    sign = 0;
+  }
+#endif
+  if (sign) {
+    float f[6], e;
+    residual_terms(sx, sy, sz, q, __ldg(P.nrm + pos), f, e);
+    const int slot = (Q.head + Q.cnt + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))) & (kPairSlots - 1);
+    float4* r = reinterpret_cast<float4*>(Q.recs + slot * 8);
+    r[0] = make_float4(f[0], f[1], f[2], f[3]);
+    r[1] = make_float4(f[4], f[5], e, (float)sign);
+  }
+  Q.cnt += __popc(m);
+  __syncwarp();
+  if (Q.cnt >= 32) {
+    Q.acc = consume_pairs(Q.recs, Q.head, 32, Q.acc);
+    Q.head = (Q.head + 32) & (kPairSlots - 1);
+    Q.cnt -= 32;
+    __syncwarp();
+  }
+}
+
+// end of a pass: consume what is waiting, hand the lane sums to the CTA (slab), start from zero
+__device__ __forceinline__ void drain_pairs(PairQueue& Q, unsigned long long* slab) {
+  if (Q.cnt > 0) {
+    Q.acc = consume_pairs(Q.recs, Q.head, Q.cnt, Q.acc);
+    Q.head = (Q.head + Q.cnt) & (kPairSlots - 1);
+    Q.cnt = 0;
+  }
+  const int lane = threadIdx.x & 31;
+  if (lane < 28) slab[lane] = (unsigned long long)Q.acc;
+  Q.acc = 0ll;
+  __syncwarp();
 }
 
 // Slow path of phase A: the search itself (warm-started, inside the cap), then -- from the second iteration on -- the
 // list that lets later iterations skip it (vlist_build decides whether it can pay off from how far the last step moved
 // this query: T_prev is the previous iteration's T_iter).  Not inlined: the search wants the whole register budget
-// for itself, not the caller's loop state spilled into its inner loops.  Returns {sorted position or -1, d2 bits}.
-__device__ __noinline__ int2 phase_a_search(const Grid* gp, const IcpProblem* Pp, const float* T_iter, const float* T_prev,
+// for itself, not the caller's loop state spilled into its inner loops.  Called by all 32 lanes (i < 0: nothing to do);
+// the outcome is left in the query's state (P.pos / P.d2), where the caller -- the same thread -- reads it back.
+__device__ __noinline__ void phase_a_search(const Grid* gp, const IcpProblem* Pp, const float* T_iter, const float* T_prev,
                                             int i, float cap, SelHists* H, unsigned int pred_bin1, unsigned int pred_pref12) {
+  if (i < 0) return;
   const Grid& g = *gp;
   const IcpProblem& P = *Pp;
   const float4 r = __ldg(P.rd + i);
@@ -912,11 +983,32 @@ __device__ __noinline__ int2 phase_a_search(const Grid* gp, const IcpProblem* Pp
     xform_point(T_prev, r.x, r.y, r.z, px, py, pz);
     vlist_build(g, P.view, P.lists, i, sx, sy, sz, b.pos >= 0, b.d2, cap, sqrtf(dist2(sx, sy, sz, px, py, pz)));
   }
-  return make_int2(b.pos, __float_as_int(b.d2));
+}
+
+// Warp-collective: the queries just searched (j < 0: none on this lane) whose match lies inside the accumulation
+// limit queue their pairs.  The match is read back from the query's state, written by this very thread.
+template <int site>
+__device__ __forceinline__ void push_searched(const IcpProblem& P, PairQueue& Q, const float* T_iter, int j, float acc_limit) {
+  if (!(acc_limit >= 0.0f)) return;  // uniform: nothing enters the normal equations during phase A
+  float d = INFINITY;
+  if (j >= 0) d = __ldcg(P.d2 + j);
+  const bool keep = d <= acc_limit;  // finite d2 <=> matched in this iteration, P.pos[j] is that match
+  if (__ballot_sync(0xffffffffu, keep) == 0u) return;
+  float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  int pos = -1;
+  if (keep) {
+    pos = __ldcg(P.pos + j);
+    const float4 r = __ldg(P.rd + j);
+    xform_point(T_iter, r.x, r.y, r.z, sx, sy, sz);
+    q = __ldg(P.view.pts + pos);
+  }
+  push_pairs<site>(P, Q, keep ? 1 : 0, sx, sy, sz, q, pos);
 }
 
 // After the loop, when the caller asked for correspondences: every point's true (uncapped) match under T.
 __device__ __noinline__ void final_match(const Grid* gp, const IcpProblem* Pp, const float* T, int i) {
+  if (i < 0) return;  // called by whole warps (a divergent call of a non-inlined function miscompiled once: never again)
   const IcpProblem& P = *Pp;
   const float4 r = __ldg(P.rd + i);
   float sx, sy, sz;
@@ -927,18 +1019,16 @@ __device__ __noinline__ void final_match(const Grid* gp, const IcpProblem* Pp, c
   P.ids[orig] = b.idx;
 }
 
-// CTA-wide: fold the per-warp slabs into the problem's accumulators (L2 atomics), leave the slabs zero.
+// CTA-wide: fold the warps' sums (drain_pairs) into the problem's accumulators (L2 atomics).
 __device__ __forceinline__ void flush_slabs(unsigned long long (*acc_w)[28], unsigned long long* gacc) {
   __syncthreads();
   if (threadIdx.x < 28) {
     unsigned long long t = 0ull;
 #pragma unroll
-    for (int w = 0; w < kIcpThreads / 32; ++w) {
-      t += acc_w[w][threadIdx.x];
-      acc_w[w][threadIdx.x] = 0ull;
-    }
+    for (int w = 0; w < kIcpThreads / 32; ++w) t += acc_w[w][threadIdx.x];
     if (t != 0ull) atomicAdd(&gacc[threadIdx.x], t);
   }
+  __syncthreads();  // the slabs may be rewritten
 }
 
 __device__ __forceinline__ void flush_hist(const unsigned int* hs, int nbins, unsigned int* gh) {
@@ -979,6 +1069,7 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
   __shared__ double th[kMaxSmooth + 2][3];
   __shared__ int flag_stop, flag_status;
   __shared__ int miss_buf[kIcpThreads / 32][64];  // per-warp queue of queries whose list did not certify
+  extern __shared__ __align__(16) float pair_buf[];  // kIcpPairBytes, dynamic: per-warp queues of pairs (PairQueue)
 
   if (tid == 0) {
     g = P.bs->grid;
@@ -988,8 +1079,12 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
     flag_stop = 0;
     flag_status = 0;
   }
-  if (tid < 28 * (kIcpThreads / 32)) acc_w[tid / 28][tid % 28] = 0ull;
   __syncthreads();
+  PairQueue Q;
+  Q.recs = pair_buf + (tid >> 5) * (kPairSlots * 8);
+  Q.head = 0;
+  Q.cnt = 0;
+  Q.acc = 0ll;
 
   // contiguous chunk of queries per CTA (spatially compact, coalesced)
   const int n = P.n;
@@ -1004,10 +1099,13 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
 
   // Trim-aware search cap (squared metres).  TrimmedDistOutlierFilter keeps matches with d2 <= limit,
   // so a match only has to be exact if d2 <= limit; searching inside a ball of radius sqrt(cap) with
-  // cap >= limit finds exactly those.  cap is a GUESS (first iteration: 0.25 m^2, then 2x the previous
-  // limit) that is VERIFIED every iteration: points without a match inside the cap are counted in the
-  // +inf histogram bin, and if the quantile lands in that bin the search is redone with a larger cap.
-  float cap = 0.25f;
+  // cap >= limit finds exactly those.  cap is a GUESS (first iteration: 0.04 m^2; second: half the first limit;
+  // then twice the previous limit) that is VERIFIED every iteration: points without a match inside
+  // the cap are counted in the +inf histogram bin, and if the quantile lands in that bin the queries that found
+  // nothing -- only those: a match found inside a smaller cap is the nearest neighbour under any cap -- are
+  // searched again with a 4x larger cap (`redo` counts these rounds).
+  float cap = 0.04f;
+  int redo = 0;
   unsigned int epoch = 0;
   problem_barrier(&W->barrier, G, epoch);  // the state initialised above is read by other CTAs
   int hist_count = 1;  // entries in qh/th
@@ -1029,7 +1127,6 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
       // a time, so the expensive, divergent search always runs on full warps even when only a few percent of the
       // queries need it.
       const float* T_prev = iter >= 1 ? T_last : nullptr;  // lists are built from the second iteration on
-      unsigned long long* slab = acc_w[tid >> 5];
       int* mq = miss_buf[tid >> 5];
       int n_miss = 0;                    // warp-uniform
       int next = q_begin + (tid & ~31);  // static schedule: this warp's next 32 queries
@@ -1050,7 +1147,8 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
           next += kIcpThreads;
         }
         const int i = base + lane;
-        const bool valid = i < (dynamic ? n : q_end);
+        bool valid = i < (dynamic ? n : q_end);
+        if (redo && valid) valid = !(__ldcg(P.d2 + i) < INFINITY);  // matched in an earlier round of this iteration: final
         bool hit = false;
         Best b;
         b.d2 = INFINITY; b.idx = INT_MAX; b.pos = -1;
@@ -1065,7 +1163,7 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
           hit = vlist_query(P.lists, P.view.pts, i, v, c0, sx, sy, sz, cap, b, c);
           if (hit) phase_a_record(P, i, b, &hs, pred_bin1, pred_pref12);
         }
-        accumulate_pairs(P, (hit && b.pos >= 0 && b.d2 <= acc_limit) ? 1 : 0, sx, sy, sz, c, b.pos, slab);
+        push_pairs<0>(P, Q, (hit && b.pos >= 0 && b.d2 <= acc_limit) ? 1 : 0, sx, sy, sz, c, b.pos);
         const unsigned int mm = __ballot_sync(0xffffffffu, valid && !hit);
         if (mm) {
           if (valid && !hit) mq[n_miss + __popc(mm & ((1u << lane) - 1u))] = i;
@@ -1075,40 +1173,20 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
             n_miss -= 32;
             const int j = mq[n_miss + lane];
             __syncwarp();
-            const int2 res = phase_a_search(&g, &P, T_iter, T_prev, j, cap, &hs, pred_bin1, pred_pref12);
-            const bool keep = res.x >= 0 && __int_as_float(res.y) <= acc_limit;
-            if (__ballot_sync(0xffffffffu, keep)) {
-              float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (keep) {
-                const float4 r = __ldg(P.rd + j);
-                xform_point(T_iter, r.x, r.y, r.z, sx, sy, sz);
-                q = __ldg(P.view.pts + res.x);
-              }
-              accumulate_pairs(P, keep ? 1 : 0, sx, sy, sz, q, res.x, slab);
-            }
+            phase_a_search(&g, &P, T_iter, T_prev, j, cap, &hs, pred_bin1, pred_pref12);
+            push_searched<1>(P, Q, T_iter, j, acc_limit);
           }
         }
       }
       if (n_miss > 0) {  // warp-uniform: the last, partial batch of searches
         __syncwarp();
-        const bool active = lane < n_miss;
-        const int j = active ? mq[lane] : 0;
-        int2 res = make_int2(-1, 0);
-        if (active) res = phase_a_search(&g, &P, T_iter, T_prev, j, cap, &hs, pred_bin1, pred_pref12);
+        const int j = lane < n_miss ? mq[lane] : -1;
+        phase_a_search(&g, &P, T_iter, T_prev, j, cap, &hs, pred_bin1, pred_pref12);
         __syncwarp();
-        const bool keep = active && res.x >= 0 && __int_as_float(res.y) <= acc_limit;
-        if (__ballot_sync(0xffffffffu, keep)) {
-          float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-          float sx = 0.f, sy = 0.f, sz = 0.f;
-          if (keep) {
-            const float4 r = __ldg(P.rd + j);
-            xform_point(T_iter, r.x, r.y, r.z, sx, sy, sz);
-            q = __ldg(P.view.pts + res.x);
-          }
-          accumulate_pairs(P, keep ? 1 : 0, sx, sy, sz, q, res.x, slab);
-        }
+        push_searched<2>(P, Q, T_iter, j, acc_limit);
       }
     }
+    drain_pairs(Q, acc_w[tid >> 5]);
     flush_slabs(acc_w, W->acc[par]);  // (starts with a __syncthreads: every warp is done with phase A)
     flush_hist(hs.h1, 1024, W->hist[par][0]);
     if (pred_bin1 != kNoPrediction) {
@@ -1132,16 +1210,15 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
         __syncthreads();
         break;
       }
-      cap = cap < 64.0f ? cap * 16.0f : INFINITY;
+      cap = cap < 64.0f ? cap * 4.0f : INFINITY;
+      ++redo;
       problem_barrier(&W->barrier, G, epoch);  // everyone has read the histogram
-      if (cta == 0) {
-        unsigned int* h = &W->hist[par][0][0];
-        for (int k = tid; k < 5 * 2048; k += kIcpThreads) h[k] = 0u;
-        if (tid < 32) W->acc[par][tid] = 0ull;
-        if (tid == 0) W->qctr[par] = 0u;
+      if (cta == 0 && tid == 0) {
+        W->hist[par][0][1020] = 0u;  // the unmatched queries are counted again; everything else stands
+        W->qctr[par] = 0u;
       }
       problem_barrier(&W->barrier, G, epoch);
-      continue;  // redo phase A of this iteration with the larger cap
+      continue;  // phase A again, for the queries without a match, with the larger cap
     }
     const unsigned int bin1 = sel.bin, rem1 = sel.rem;
     if (cta == 0) {  // clear the other parity's scratch for the next iteration (nobody touches it before the next barrier)
@@ -1183,7 +1260,11 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
     LS_STAMP(3);
     block_select(W->hist[par][spec3 ? 4 : 2], 1024, rem2, false, 0.f, &sel, ws);
     const float limit = __uint_as_float((prefix12 << 10) | sel.bin);
-    cap = fmaxf(limit * 2.0f, 1e-12f);  // guess for the next iteration (verified there)
+    // guess for the next iteration (verified there): the first step removes most of the initial misalignment, so the
+    // limit drops sharply once and then settles -- a guess that turns out too small costs one more round for the
+    // unmatched queries only
+    cap = fmaxf(limit * (iter == 0 ? 0.5f : 2.0f), 1e-12f);
+    redo = 0;
 
     // ---------------- correction pass: pairs between the predicted and the actual limit ----------------
     // Phase A added every pair with d2 <= acc_limit; the minimiser wants exactly those with d2 <= limit.
@@ -1203,8 +1284,9 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
         xform_point(T_iter, r.x, r.y, r.z, sx, sy, sz);
         q = __ldg(P.view.pts + pos);
       }
-      accumulate_pairs(P, sign, sx, sy, sz, q, pos, acc_w[tid >> 5]);
+      push_pairs<3>(P, Q, sign, sx, sy, sz, q, pos);
     }
+    drain_pairs(Q, acc_w[tid >> 5]);
     flush_slabs(acc_w, W->acc[par]);
     problem_barrier(&W->barrier, G, epoch);
     LS_STAMP(4);
@@ -1291,7 +1373,7 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
   if (P.want_matches && !flag_status && iter > 0) {
     // The loop ended right after the update of T_iter; the matches reported are those of the LAST
     // iteration, i.e. of the reading under T_last.  Redo that query without a cap.
-    for (int i = q_begin + tid; i < q_end; i += kIcpThreads) final_match(&g, &P, T_last, i);
+    for (int base = q_begin; base < q_end; base += kIcpThreads) final_match(&g, &P, T_last, base + tid < q_end ? base + tid : -1);
   }
 
   if (cta == 0 && tid == 0) {

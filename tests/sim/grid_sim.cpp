@@ -19,7 +19,7 @@ struct SimGrid {
   ls::Grid g;
   std::vector<ls::Entry> top, tab1;
   std::vector<float4> pts;
-  std::vector<unsigned long long> pyr;
+  std::vector<unsigned long long> pyr, topmask;
 };
 
 void build(SimGrid& S, const float* refc3, int m, float cell, int max_cells, int split) {
@@ -82,6 +82,11 @@ void build(SimGrid& S, const float* refc3, int m, float cell, int max_cells, int
     }
   }
   S.g.n_tab1 = n1;
+  S.topmask.assign(g.n_cells0, 0ull);
+  for (int c = 0; c < g.n_cells0; ++c)
+    if (tabidx0[c] >= 0)
+      for (int f = 0; f < LS_FB3; ++f)
+        if (cnt1[(size_t)tabidx0[c] * LS_FB3 + f] > 0 && LS_FB == 8) S.topmask[c] |= 1ull << (f / LS_FB);
   // occupancy pyramid
   S.pyr.assign(g.n_pyr_cells, 0ull);
   for (int l = 1; l <= g.n_pyr; ++l) {
@@ -115,7 +120,7 @@ void sim_nn(const float* q3, int n, const float* refc3, int m, float cell, int m
   build(S, refc3, m, cell, max_cells, split);
   std::vector<int> pos_of(m);
   for (int i = 0; i < m; ++i) pos_of[ls::f2i(S.pts[i].w)] = i;
-  ls::GridView v{S.top.data(), S.tab1.data(), S.pts.data(), S.pyr.data()};
+  ls::GridView v{S.top.data(), S.tab1.data(), S.pts.data(), S.pyr.data(), S.topmask.data()};
   long long cand = 0, ent = 0, cmax = 0;
   for (int i = 0; i < n; ++i) {
     ls::ls_sim_cand = 0;
@@ -152,14 +157,14 @@ int sim_vlists(const float* rd3, int n, const float* refc3, int m, float cell, i
                int32_t* ids_last, float* d2_last) {
   SimGrid S;
   build(S, refc3, m, cell, max_cells, split);
-  ls::GridView v{S.top.data(), S.tab1.data(), S.pts.data(), S.pyr.data()};
+  ls::GridView v{S.top.data(), S.tab1.data(), S.pts.data(), S.pyr.data(), S.topmask.data()};
   std::vector<float4> vq(n, make_float4(0.f, 0.f, 0.f, 0.f)), vpts((size_t)LS_VK * n);
   std::vector<int> warm(n, -1);
   ls::VLists L{vq.data(), vpts.data(), n};
   int bad = 0;
   for (int t = 0; t < n_iter; ++t) {
     const float* T = T_seq + 16 * t;
-    int h = 0, of = 0;
+    int h = 0, of = 0, of_builds = 0;
     for (int i = 0; i < n; ++i) {
       float qx, qy, qz;
       ls::xform_point(T, rd3[3 * i], rd3[3 * i + 1], rd3[3 * i + 2], qx, qy, qz);
@@ -180,12 +185,13 @@ int sim_vlists(const float* rd3, int n, const float* refc3, int m, float cell, i
         const float4 before = vq[i];
         ls::vlist_build(S.g, v, L, i, qx, qy, qz, ref.pos >= 0, ref.d2, caps[t], motion);
         if (ls::f2i(vq[i].w) == 0 && (before.x != vq[i].x || ls::f2i(before.w) != 0)) ++of;
+        if (before.x != vq[i].x || before.y != vq[i].y || before.w != vq[i].w) ++of_builds;
       }
       if (ref.pos >= 0) warm[i] = ref.pos;
       if (t == n_iter - 1) { ids_last[i] = ref.idx; d2_last[i] = ref.d2; }
     }
     if (hits) hits[t] = h;
-    if (overflow) overflow[t] = of;
+    if (overflow) overflow[t] = of | (of_builds << 12);  // low 12 bits: refused builds (saturating use in tests is fine), rest: builds
   }
   return bad;
 }
