@@ -37,6 +37,8 @@ struct Workspace {
   float* T_hist = nullptr;
   unsigned long long* phase_ns = nullptr;  // debug (LS_PHASE_TIMING=1)
   float* T0_dev = nullptr;
+  BuildJob* job_host = nullptr;  // pinned; this workspace's slot of the context's job array
+  BuildJob* job_dev = nullptr;
   IcpWork* h_work = nullptr;  // pinned host mirrors of the small results
   Grid* h_grid = nullptr;
   IcpProblem hp;              // host copy of this problem's descriptor
@@ -51,6 +53,9 @@ struct ls_ctx {
   std::vector<Workspace*> ws;
   IcpProblem* probs_dev = nullptr;   // [kMaxBatch]
   IcpProblem* probs_host = nullptr;  // pinned
+  BuildJob* jobs_dev = nullptr;      // [kMaxBatch]: workspace b stages its build in slot b
+  BuildJob* jobs_host = nullptr;     // pinned
+  IcpWork* work_pool = nullptr;      // [kMaxBatch] contiguous, so one memset clears a whole batch
   // a batch between ls_icp_register_submap_batch_begin and _end: the workspaces are busy
   bool pending = false;
   int pending_batch = 0;
@@ -60,7 +65,7 @@ struct ls_ctx {
   // ring slots (map, slot index) the in-flight batch reads: an asynchronous upload must not overwrite them
   std::vector<std::pair<const ls_map*, int>> pending_slots;
 };
-constexpr int kMaxBatch = 16;
+constexpr int kMaxBatch = 32;
 
 struct ls_scan_slot {
   float4* pts = nullptr;
@@ -217,36 +222,78 @@ int check_params(ls_ctx* ctx, const ls_icp_params* p) {
   return LS_OK;
 }
 
-// Build the spatial hash over the sub-map described by `parts` (device pointers), then pre-transform
-// the reading.  Everything is enqueued on w->stream; nothing synchronises.
-int enqueue_build(ls_ctx* ctx, Workspace* w, const Parts& parts, const Resolved& r, const float* T0_host) {
-  const int m = parts.offset[parts.n_parts];
-  reset_build_kernel<<<1, 32, 0, w->stream>>>(w->bs);
+// Stage workspace w's build job (pinned host slot): the sub-map `parts` (device pointers), the initial guess, and --
+// when the registration follows -- the reading.
+void fill_job(Workspace* w, const Parts& parts, const float* T0_host, const float4* reading_dev, int n) {
+  BuildJob& J = *w->job_host;
+  J.parts = parts;
+  J.bs = w->bs;
+  J.A = w->A;
+  J.m = parts.offset[parts.n_parts];
+  J.n = n;
+  J.reading = reading_dev;
+  J.rd = w->rd;
+  std::memcpy(J.T0, T0_host, sizeof(J.T0));
+}
+
+// The spatial hash of `batch` staged jobs (slots jobs_dev[0..batch)): every phase is ONE launch serving all of them
+// (grid.y = job).  Enqueued on `st`; nothing synchronises.
+int launch_build(ls_ctx* ctx, const BuildJob* jobs_dev, int batch, int m_max, const Resolved& r, cudaStream_t st) {
+  const unsigned int B = (unsigned int)batch;
+  const int cap = batch > 1 ? ctx->sm_count * 2 : ctx->sm_count * 8;  // blocks per job: the jobs fill the machine together
+  const int pb = blocks_for(m_max, 256, cap);
+  reset_build_kernel<<<dim3(1, B), 32, 0, st>>>(jobs_dev);
   LAUNCH_CHECK();
-  CU(cudaMemcpyAsync(w->T0_dev, T0_host, 16 * sizeof(float), cudaMemcpyHostToDevice, w->stream));
-  const int pb = blocks_for(m, 256, ctx->sm_count * 8);
-  assemble_kernel<<<pb, 256, 0, w->stream>>>(parts, w->A.sub_pts, w->A.sub_nrm, w->bs);
+  assemble_kernel<<<dim3(pb, B), 256, 0, st>>>(jobs_dev);
   LAUNCH_CHECK();
-  setup_kernel<<<1, 32, 0, w->stream>>>(w->bs, m, r.cell, r.max_cells, r.split, w->T0_dev);
+  setup_kernel<<<dim3(1, B), 32, 0, st>>>(jobs_dev, r.cell, r.max_cells, r.split);
   LAUNCH_CHECK();
-  count0_kernel<<<pb, 256, 0, w->stream>>>(w->bs, w->A, m);
+  count0_kernel<<<dim3(pb, B), 256, 0, st>>>(jobs_dev);
   LAUNCH_CHECK();
   const int tiles = (r.max_cells + kScanTile - 1) / kScanTile;
-  scan_reduce_kernel<<<tiles, kScanThreads, 0, w->stream>>>(w->bs, w->A.cnt0);
+  scan_reduce_kernel<<<dim3(tiles, B), kScanThreads, 0, st>>>(jobs_dev);
   LAUNCH_CHECK();
-  scan_apply_kernel<<<tiles, kScanThreads, 0, w->stream>>>(w->bs, w->A);
+  scan_apply_kernel<<<dim3(tiles, B), kScanThreads, 0, st>>>(jobs_dev);
   LAUNCH_CHECK();
-  pyramid1_kernel<<<blocks_for(r.max_cells / 16 + 1, 256, ctx->sm_count * 4), 256, 0, w->stream>>>(w->bs, w->A);
+  pyramid1_kernel<<<dim3(blocks_for(r.max_cells / 16 + 1, 256, batch > 1 ? ctx->sm_count : ctx->sm_count * 4), B), 256, 0, st>>>(jobs_dev);
   LAUNCH_CHECK();
-  pyramid_up_kernel<<<1, 1024, 0, w->stream>>>(w->bs, w->A);
+  pyramid_up_kernel<<<dim3(1, B), 1024, 0, st>>>(jobs_dev);
   LAUNCH_CHECK();
-  count1_kernel<<<pb, 256, 0, w->stream>>>(w->bs, w->A, m);
+  count1_kernel<<<dim3(pb, B), 256, 0, st>>>(jobs_dev);
   LAUNCH_CHECK();
-  tables_kernel<<<ctx->sm_count * 8, 256, 0, w->stream>>>(w->bs, w->A);
+  tables_kernel<<<dim3(cap, B), 256, 0, st>>>(jobs_dev);
   LAUNCH_CHECK();
-  scatter_kernel<<<pb, 256, 0, w->stream>>>(w->A, m);
+  scatter_kernel<<<dim3(pb, B), 256, 0, st>>>(jobs_dev);
   LAUNCH_CHECK();
   return LS_OK;
+}
+
+// R' = T_refMean_dataIn * R for every staged job, then the readings are ordered by their map's cell keys (q_count_kernel).
+int launch_reading_sort(ls_ctx* ctx, const BuildJob* jobs_dev, int batch, int n_max, const Resolved& r, cudaStream_t st) {
+  const unsigned int B = (unsigned int)batch;
+  const int cap = batch > 1 ? ctx->sm_count * 2 : ctx->sm_count * 8;
+  const int qb = blocks_for(n_max, 256, cap);
+  const int scan_tiles = (r.max_cells + kScanTile - 1) / kScanTile;
+  reading_kernel<<<dim3(qb, B), 256, 0, st>>>(jobs_dev);
+  LAUNCH_CHECK();
+  q_count_kernel<<<dim3(qb, B), 256, 0, st>>>(jobs_dev);
+  LAUNCH_CHECK();
+  q_tables_kernel<<<dim3(cap, B), 256, 0, st>>>(jobs_dev);
+  LAUNCH_CHECK();
+  q_scan_reduce_kernel<<<dim3(scan_tiles, B), kScanThreads, 0, st>>>(jobs_dev);
+  LAUNCH_CHECK();
+  q_scan_apply_kernel<<<dim3(scan_tiles, B), kScanThreads, 0, st>>>(jobs_dev);
+  LAUNCH_CHECK();
+  q_scatter_kernel<<<dim3(qb, B), 256, 0, st>>>(jobs_dev);
+  LAUNCH_CHECK();
+  return LS_OK;
+}
+
+// Single problem on workspace w: stage the job (the reading may follow in prep_icp), upload it, build.
+int enqueue_build(ls_ctx* ctx, Workspace* w, const Parts& parts, const Resolved& r, const float* T0_host) {
+  fill_job(w, parts, T0_host, nullptr, 0);
+  CU(cudaMemcpyAsync(w->job_dev, w->job_host, sizeof(BuildJob), cudaMemcpyHostToDevice, w->stream));
+  return launch_build(ctx, w->job_dev, 1, w->job_host->m, r, w->stream);
 }
 
 int upload_normals(ls_ctx* ctx, Workspace* w, const float* normals, int stride, int n, float4* dst) {
@@ -271,27 +318,9 @@ int upload_normals(ls_ctx* ctx, Workspace* w, const float* normals, int stride, 
   return LS_OK;
 }
 
-// Stage one problem for the persistent ICP kernel: pre-transform the reading, clear the scratch, fill the
-// problem descriptor.  Enqueued on the workspace's stream; nothing synchronises.
-int prep_icp(ls_ctx* ctx, Workspace* w, const ls_icp_params* prm, const float4* reading_dev, int n, const float T0[16],
-             bool want_matches, bool want_hist) {
-  const int scan_tiles = (resolve(prm).max_cells + kScanTile - 1) / kScanTile;
-  const int qb = blocks_for(n, 256, ctx->sm_count * 8);
-  reading_kernel<<<qb, 256, 0, w->stream>>>(w->bs, reading_dev, n, w->rd);
-  LAUNCH_CHECK();
-  // order the queries by the map's cell keys (see q_count_kernel)
-  q_count_kernel<<<qb, 256, 0, w->stream>>>(w->bs, w->A, w->rd, n);
-  LAUNCH_CHECK();
-  q_tables_kernel<<<ctx->sm_count * 8, 256, 0, w->stream>>>(w->bs, w->A);
-  LAUNCH_CHECK();
-  q_scan_reduce_kernel<<<scan_tiles, kScanThreads, 0, w->stream>>>(w->bs, w->A);
-  LAUNCH_CHECK();
-  q_scan_apply_kernel<<<scan_tiles, kScanThreads, 0, w->stream>>>(w->bs, w->A);
-  LAUNCH_CHECK();
-  q_scatter_kernel<<<qb, 256, 0, w->stream>>>(w->A, w->rd, n);
-  LAUNCH_CHECK();
-  CU(cudaEventRecord(w->ev1, w->stream));
-  CU(cudaMemsetAsync(w->work, 0, sizeof(IcpWork), w->stream));
+// Fill workspace w's problem descriptor for the persistent ICP kernel (host side only).
+int fill_problem(ls_ctx* ctx, Workspace* w, const ls_icp_params* prm, int n, const float T0[16], bool want_matches,
+                 bool want_hist) {
   IcpProblem& hp = w->hp;
   hp.bs = w->bs;
   hp.view.top = w->A.top;
@@ -322,6 +351,20 @@ int prep_icp(ls_ctx* ctx, Workspace* w, const ls_icp_params* prm, const float4* 
   hp.phase_ns = want_phase ? w->phase_ns : nullptr;
   std::memcpy(hp.T0, T0, sizeof(hp.T0));
   return LS_OK;
+}
+
+// Single problem: stage the reading in the job built by enqueue_build, sort it, clear the scratch, fill the descriptor.
+// Enqueued on the workspace's stream; nothing synchronises.
+int prep_icp(ls_ctx* ctx, Workspace* w, const ls_icp_params* prm, const float4* reading_dev, int n, const float T0[16],
+             bool want_matches, bool want_hist) {
+  w->job_host->reading = reading_dev;
+  w->job_host->n = n;
+  CU(cudaMemcpyAsync(w->job_dev, w->job_host, sizeof(BuildJob), cudaMemcpyHostToDevice, w->stream));
+  int rc;
+  if ((rc = launch_reading_sort(ctx, w->job_dev, 1, n, resolve(prm), w->stream))) return rc;
+  CU(cudaEventRecord(w->ev1, w->stream));
+  CU(cudaMemsetAsync(w->work, 0, sizeof(IcpWork), w->stream));
+  return fill_problem(ctx, w, prm, n, T0, want_matches, want_hist);
 }
 
 // One cooperative launch over `batch` staged problems (workspaces 0..batch-1): the grid is partitioned into
@@ -366,7 +409,7 @@ int launch_icp(ls_ctx* ctx, const ls_icp_params* prm, int batch, int n_max) {
 
 // After launch_icp + a synchronise of workspace 0's stream: unpack one problem's results.
 int fetch_icp(ls_ctx* ctx, Workspace* w, const ls_icp_params* prm, int n, const float T0[16], float T_out[16],
-              ls_icp_stats* stats) {
+              ls_icp_stats* stats, bool batch_timing = false) {
   const IcpWork& wk = *w->h_work;
   if (getenv("LS_PHASE_TIMING") && w->phase_ns) {
     std::vector<unsigned long long> ph((size_t)prm->max_iterations * 6);
@@ -391,8 +434,9 @@ int fetch_icp(ls_ctx* ctx, Workspace* w, const ls_icp_params* prm, int n, const 
     stats->last_limit = wk.last_limit;
     stats->used_ratio = n > 0 ? (float)wk.last_kept / (float)n : 0.f;
     float ms = 0.f, bms = 0.f, kms = 0.f;
-    cudaEventElapsedTime(&ms, w->ev0, ctx->ws[0]->ev2);  // staging of this problem .. end of the (shared) ICP launch
-    cudaEventElapsedTime(&bms, w->ev0, w->ev1);
+    const Workspace* tw = batch_timing ? ctx->ws[0] : w;  // a batch is staged and built as one: its timing is shared
+    cudaEventElapsedTime(&ms, tw->ev0, ctx->ws[0]->ev2);  // staging .. end of the (shared) ICP launch
+    cudaEventElapsedTime(&bms, tw->ev0, tw->ev1);
     cudaEventElapsedTime(&kms, ctx->ws[0]->ev_launch, ctx->ws[0]->ev2);
     stats->device_ms = ms;
     stats->build_ms = bms;
@@ -474,13 +518,15 @@ extern "C" {
 int ls_b200_version(void) { return LS_VERSION; }
 
 namespace {
-Workspace* new_workspace() {
+Workspace* new_workspace(ls_ctx* ctx, int index) {
   Workspace* w = new Workspace();
+  w->work = ctx->work_pool + index;
+  w->job_dev = ctx->jobs_dev + index;
+  w->job_host = ctx->jobs_host + index;
   bool ok = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreate(&w->ev0) == cudaSuccess && cudaEventCreate(&w->ev1) == cudaSuccess &&
             cudaEventCreate(&w->ev2) == cudaSuccess && cudaEventCreate(&w->ev_launch) == cudaSuccess &&
             cudaMalloc((void**)&w->bs, sizeof(BuildState)) == cudaSuccess &&
-            cudaMalloc((void**)&w->work, sizeof(IcpWork)) == cudaSuccess &&
             cudaMalloc((void**)&w->T0_dev, 64 * sizeof(float)) == cudaSuccess &&
             cudaMallocHost((void**)&w->h_work, sizeof(IcpWork)) == cudaSuccess &&
             cudaMallocHost((void**)&w->h_grid, sizeof(Grid)) == cudaSuccess;
@@ -492,7 +538,7 @@ void free_workspace(Workspace* w) {
   if (w->stream) cudaStreamSynchronize(w->stream);
   void* bufs[] = {w->A.sub_pts, w->A.sub_nrm, w->A.srt_pts, w->A.srt_nrm, w->A.pkey, w->A.top, w->A.cnt0, w->A.tab1, w->A.cnt1,
                   w->A.tab1_cell, w->A.pyr, w->A.topmask, w->bs, w->reading, w->rd, w->ref_stage, w->ref_nrm_stage, w->nrm_raw, w->pos, w->d2,
-                  w->ids, w->vq, w->vpts, w->work, w->T_hist, w->T0_dev, w->phase_ns, w->d2_out, w->A.qkey, w->A.qperm, w->A.rd_s,
+                  w->ids, w->vq, w->vpts, w->T_hist, w->T0_dev, w->phase_ns, w->d2_out, w->A.qkey, w->A.qperm, w->A.rd_s,
                   w->A.qtab_local, w->A.qtab_total, w->A.qtop_start};
   for (void* b : bufs)
     if (b) cudaFree(b);
@@ -507,7 +553,7 @@ void free_workspace(Workspace* w) {
 }
 int ensure_workspaces(ls_ctx* ctx, int count) {
   while ((int)ctx->ws.size() < count) {
-    Workspace* w = new_workspace();
+    Workspace* w = new_workspace(ctx, (int)ctx->ws.size());
     if (!w) return fail(ctx, LS_ERR_NOMEM, "workspace allocation failed");
     ctx->ws.push_back(w);
   }
@@ -537,9 +583,12 @@ int ls_b200_init(int device, ls_ctx** out) {
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, icp_kernel, kIcpThreads, kIcpPairBytes) != cudaSuccess || occ < 1)
     return bail(LS_ERR_CUDA);
   ctx->icp_ctas = occ * ctx->sm_count;
-  if (ensure_workspaces(ctx, 1) != LS_OK) return bail(LS_ERR_NOMEM);
   if (cudaMalloc((void**)&ctx->probs_dev, sizeof(IcpProblem) * kMaxBatch) != cudaSuccess) return bail(LS_ERR_NOMEM);
   if (cudaMallocHost((void**)&ctx->probs_host, sizeof(IcpProblem) * kMaxBatch) != cudaSuccess) return bail(LS_ERR_NOMEM);
+  if (cudaMalloc((void**)&ctx->jobs_dev, sizeof(BuildJob) * kMaxBatch) != cudaSuccess) return bail(LS_ERR_NOMEM);
+  if (cudaMallocHost((void**)&ctx->jobs_host, sizeof(BuildJob) * kMaxBatch) != cudaSuccess) return bail(LS_ERR_NOMEM);
+  if (cudaMalloc((void**)&ctx->work_pool, sizeof(IcpWork) * kMaxBatch) != cudaSuccess) return bail(LS_ERR_NOMEM);
+  if (ensure_workspaces(ctx, 1) != LS_OK) return bail(LS_ERR_NOMEM);
   *out = ctx;
   return LS_OK;
 }
@@ -550,6 +599,9 @@ void ls_b200_destroy(ls_ctx* ctx) {
   for (Workspace* w : ctx->ws) free_workspace(w);
   if (ctx->probs_dev) cudaFree(ctx->probs_dev);
   if (ctx->probs_host) cudaFreeHost(ctx->probs_host);
+  if (ctx->jobs_dev) cudaFree(ctx->jobs_dev);
+  if (ctx->jobs_host) cudaFreeHost(ctx->jobs_host);
+  if (ctx->work_pool) cudaFree(ctx->work_pool);
   delete ctx;
 }
 
@@ -631,7 +683,10 @@ int ls_nn_query(ls_ctx* ctx, const ls_icp_params* prm, const float* reading4, in
   parts.nrm[0] = w->ref_nrm_stage;
   parts.identity[0] = 1;
   if ((rc = enqueue_build(ctx, w, parts, r, T0))) return rc;
-  reading_kernel<<<blocks_for(n, 256, ctx->sm_count * 8), 256, 0, w->stream>>>(w->bs, w->reading, n, w->rd);
+  w->job_host->reading = w->reading;
+  w->job_host->n = n;
+  CU(cudaMemcpyAsync(w->job_dev, w->job_host, sizeof(BuildJob), cudaMemcpyHostToDevice, w->stream));
+  reading_kernel<<<dim3(blocks_for(n, 256, ctx->sm_count * 8), 1), 256, 0, w->stream>>>(w->job_dev);
   LAUNCH_CHECK();
   GridView v{w->A.top, w->A.tab1, w->A.srt_pts, w->A.pyr, w->A.topmask};
   nn_query_kernel<<<blocks_for(n, 256, ctx->sm_count * 8), 256, 0, w->stream>>>(w->bs, v, w->rd, n, w->ids, w->d2);
@@ -984,26 +1039,36 @@ int ls_icp_register_submap_batch_begin(ls_ctx* ctx, const ls_icp_params* prm, co
       po += n_parts[b];
     }
   }
-  int n_max = 0, part_off = 0;
+  // stage every problem's job on the host, then ONE upload and ONE launch per build phase for the whole batch
+  Workspace* w0 = ctx->ws[0];
+  int n_max = 0, m_max = 0, part_off = 0;
   for (int b = 0; b < batch; ++b) {
     Workspace* w = ctx->ws[b];
     const float* T0 = T0s + 16 * b;
     const ls_scan_slot* rs = find_slot(map, reading_ids[b]);
-    if (!rs) return fail(ctx, LS_ERR_STATE, "reading scan %llu is not resident", (unsigned long long)reading_ids[b]);
     Parts parts;
-    if ((rc = make_parts(ctx, map, n_parts[b], part_ids + part_off, T_parts + 16 * (size_t)part_off, &parts, w->stream)))
+    if ((rc = make_parts(ctx, map, n_parts[b], part_ids + part_off, T_parts + 16 * (size_t)part_off, &parts, w0->stream)))
       return rc;
-    if (wait_slot(rs, w->stream) != LS_OK) return fail(ctx, LS_ERR_CUDA, "cudaStreamWaitEvent failed");
+    if (wait_slot(rs, w0->stream) != LS_OK) return fail(ctx, LS_ERR_CUDA, "cudaStreamWaitEvent failed");
     part_off += n_parts[b];
     const int n = rs->n, m = parts.offset[n_parts[b]];
-    if (n == 0 || m == 0) return fail(ctx, LS_ERR_ARG, "empty reading or reference in a batch (use the single call)");
     ctx->pending_n[b] = n;
     n_max = n > n_max ? n : n_max;
+    m_max = m > m_max ? m : m_max;
     if ((rc = ensure_capacity(ctx, w, n, m, r.max_cells, prm->max_iterations))) return rc;
-    CU(cudaEventRecord(w->ev0, w->stream));
-    if ((rc = enqueue_build(ctx, w, parts, r, T0))) return rc;
-    if ((rc = prep_icp(ctx, w, prm, rs->pts, n, T0, false, false))) return rc;
+    fill_job(w, parts, T0, rs->pts, n);
+    if ((rc = fill_problem(ctx, w, prm, n, T0, false, false))) return rc;
   }
+  for (int b = 1; b < batch; ++b) {  // allocations / clears a workspace enqueued on its own stream come first
+    CU(cudaEventRecord(ctx->ws[b]->ev2, ctx->ws[b]->stream));
+    CU(cudaStreamWaitEvent(w0->stream, ctx->ws[b]->ev2, 0));
+  }
+  CU(cudaEventRecord(w0->ev0, w0->stream));
+  CU(cudaMemcpyAsync(ctx->jobs_dev, ctx->jobs_host, sizeof(BuildJob) * (size_t)batch, cudaMemcpyHostToDevice, w0->stream));
+  if ((rc = launch_build(ctx, ctx->jobs_dev, batch, m_max, r, w0->stream))) return rc;
+  if ((rc = launch_reading_sort(ctx, ctx->jobs_dev, batch, n_max, r, w0->stream))) return rc;
+  CU(cudaEventRecord(w0->ev1, w0->stream));
+  CU(cudaMemsetAsync(ctx->work_pool, 0, sizeof(IcpWork) * (size_t)batch, w0->stream));
   if ((rc = launch_icp(ctx, prm, batch, n_max))) return rc;
   ctx->pending_batch = batch;
   ctx->pending = true;
@@ -1022,7 +1087,7 @@ int ls_icp_register_submap_batch_end(ls_ctx* ctx, float* T_outs, ls_icp_stats* s
   CU(cudaStreamSynchronize(ctx->ws[0]->stream));
   for (int b = 0; b < batch; ++b) {
     const int st = fetch_icp(ctx, ctx->ws[b], &ctx->pending_prm, ctx->pending_n[b], ctx->pending_T0.data() + 16 * b, T_outs + 16 * b,
-                             stats ? stats + b : nullptr);
+                             stats ? stats + b : nullptr, true);
     if (st < 0) return st;
     statuses[b] = st;
   }
@@ -1054,10 +1119,12 @@ int ls_map_assemble(ls_ctx* ctx, const ls_map* map, int n_parts, const uint64_t*
   *m_out = m;
   if (m == 0) return LS_OK;
   if ((rc = ensure_capacity(ctx, w, 1, m, 64, 1))) return rc;
-  reset_build_kernel<<<1, 32, 0, w->stream>>>(w->bs);
+  const float I16[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  fill_job(w, parts, I16, nullptr, 0);
+  CU(cudaMemcpyAsync(w->job_dev, w->job_host, sizeof(BuildJob), cudaMemcpyHostToDevice, w->stream));
+  reset_build_kernel<<<dim3(1, 1), 32, 0, w->stream>>>(w->job_dev);
   LAUNCH_CHECK();
-  assemble_kernel<<<blocks_for(m, 256, ctx->sm_count * 8), 256, 0, w->stream>>>(parts, w->A.sub_pts, w->A.sub_nrm,
-                                                                                   w->bs);
+  assemble_kernel<<<dim3(blocks_for(m, 256, ctx->sm_count * 8), 1), 256, 0, w->stream>>>(w->job_dev);
   LAUNCH_CHECK();
   CU(cudaMemcpyAsync(out4, w->A.sub_pts, (size_t)m * sizeof(float4), cudaMemcpyDeviceToHost, w->stream));
   if (out_normals3) {

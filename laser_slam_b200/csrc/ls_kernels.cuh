@@ -70,6 +70,20 @@ struct BuildArrays {
   float4* rd_s;          // pre-transformed reading in rank order
 };
 
+// One map build (+ optional reading sort) of a launch: every build kernel takes an array of these and serves job
+// blockIdx.y, so a step that registers B scans issues each build phase ONCE for all B problems instead of B times
+// (a registration's build is a chain of ~17 short kernels: launched per problem it is bound by launch latency).
+struct BuildJob {
+  Parts parts;            // the sub-map: resident scans + per-scan transforms
+  BuildState* bs;
+  BuildArrays A;
+  int m;                  // map points (= parts.offset[parts.n_parts])
+  int n;                  // reading points (0: no reading)
+  const float4* reading;  // raw reading, device
+  float4* rd;             // reading pre-transformed by T_refMean_dataIn
+  float T0[16];           // initial guess (column-major)
+};
+
 struct IcpParamsDev {
   int max_iterations;
   float trim_ratio;
@@ -133,8 +147,12 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
 }
 
 // ---- K0: assemble + statistics -------------------------------------------------------------------
-__global__ void __launch_bounds__(256) assemble_kernel(const __grid_constant__ Parts parts, float4* __restrict__ sub_pts,
-                                                       float4* __restrict__ sub_nrm, BuildState* bs) {
+__global__ void __launch_bounds__(256) assemble_kernel(const BuildJob* __restrict__ jobs) {
+  const BuildJob& J = jobs[blockIdx.y];
+  const Parts& parts = J.parts;
+  float4* __restrict__ sub_pts = J.A.sub_pts;
+  float4* __restrict__ sub_nrm = J.A.sub_nrm;
+  BuildState* bs = J.bs;
   const int total = parts.offset[parts.n_parts];
   long long s0 = 0, s1 = 0, s2 = 0;
   float mn0 = INFINITY, mn1 = INFINITY, mn2 = INFINITY, mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY;
@@ -200,7 +218,8 @@ __global__ void expand_normals_kernel(const float* __restrict__ raw, int stride,
   }
 }
 
-__global__ void reset_build_kernel(BuildState* bs) {
+__global__ void reset_build_kernel(const BuildJob* __restrict__ jobs) {
+  BuildState* bs = jobs[blockIdx.y].bs;
   const int t = threadIdx.x;
   if (t < 3) {
     bs->sum[t] = 0ull;
@@ -210,9 +229,12 @@ __global__ void reset_build_kernel(BuildState* bs) {
 }
 
 // ---- K1a: mean, bounding box, grid geometry, T_pre -------------------------------------------------
-__global__ void setup_kernel(BuildState* bs, int m, float cell_size, int max_cells, int leaf_split,
-                             const float* __restrict__ T0 /* 16 floats, device */) {
+__global__ void setup_kernel(const BuildJob* __restrict__ jobs, float cell_size, int max_cells, int leaf_split) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const BuildJob& J = jobs[blockIdx.y];
+  BuildState* bs = J.bs;
+  const int m = J.m;
+  const float* T0 = J.T0;
   float mu[3], lo[3], hi[3];
   for (int a = 0; a < 3; ++a) {
     const long long s = (long long)bs->sum[a];
@@ -230,7 +252,11 @@ __global__ void setup_kernel(BuildState* bs, int m, float cell_size, int max_cel
 }
 
 // ---- K1b: centre + level-0 histogram --------------------------------------------------------------
-__global__ void __launch_bounds__(256) count0_kernel(const BuildState* __restrict__ bs, BuildArrays A, int m) {
+__global__ void __launch_bounds__(256) count0_kernel(const BuildJob* __restrict__ jobs) {
+  const BuildJob& J = jobs[blockIdx.y];
+  const BuildState* __restrict__ bs = J.bs;
+  const BuildArrays A = J.A;
+  const int m = J.m;
   __shared__ Grid g;
   if (threadIdx.x == 0) g = bs->grid;
   __syncthreads();
@@ -247,7 +273,9 @@ __global__ void __launch_bounds__(256) count0_kernel(const BuildState* __restric
 }
 
 // ---- K1c: exclusive scan of the level-0 histogram (two kernels, no spin-waits) ----------------------
-__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(BuildState* bs, const uint32_t* __restrict__ cnt0) {
+__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const BuildJob* __restrict__ jobs) {
+  BuildState* bs = jobs[blockIdx.y].bs;
+  const uint32_t* __restrict__ cnt0 = jobs[blockIdx.y].A.cnt0;
   const int n = bs->grid.n_cells0;
   const int base = blockIdx.x * kScanTile;
   if (base >= n) return;
@@ -267,7 +295,9 @@ __global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(BuildState* b
   }
 }
 
-__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(BuildState* bs, BuildArrays A) {
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const BuildJob* __restrict__ jobs) {
+  BuildState* bs = jobs[blockIdx.y].bs;
+  const BuildArrays A = jobs[blockIdx.y].A;
   const int n = bs->grid.n_cells0;
   const int base = blockIdx.x * kScanTile;
   if (base >= n) return;
@@ -353,7 +383,9 @@ __device__ __forceinline__ unsigned long long pyramid_mask(const Grid& g, int l,
   return mask;
 }
 
-__global__ void __launch_bounds__(256) pyramid1_kernel(const BuildState* __restrict__ bs, BuildArrays A) {
+__global__ void __launch_bounds__(256) pyramid1_kernel(const BuildJob* __restrict__ jobs) {
+  const BuildState* __restrict__ bs = jobs[blockIdx.y].bs;
+  const BuildArrays A = jobs[blockIdx.y].A;
   __shared__ Grid g;
   if (threadIdx.x == 0) g = bs->grid;
   __syncthreads();
@@ -365,7 +397,9 @@ __global__ void __launch_bounds__(256) pyramid1_kernel(const BuildState* __restr
   }
 }
 
-__global__ void __launch_bounds__(1024) pyramid_up_kernel(const BuildState* __restrict__ bs, BuildArrays A) {
+__global__ void __launch_bounds__(1024) pyramid_up_kernel(const BuildJob* __restrict__ jobs) {
+  const BuildState* __restrict__ bs = jobs[blockIdx.y].bs;
+  const BuildArrays A = jobs[blockIdx.y].A;
   __shared__ Grid g;
   if (threadIdx.x == 0) g = bs->grid;
   __syncthreads();
@@ -382,7 +416,10 @@ __global__ void __launch_bounds__(1024) pyramid_up_kernel(const BuildState* __re
 }
 
 // ---- K1d: level-1 histogram -------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) count1_kernel(const BuildState* __restrict__ bs, BuildArrays A, int m) {
+__global__ void __launch_bounds__(256) count1_kernel(const BuildJob* __restrict__ jobs) {
+  const BuildState* __restrict__ bs = jobs[blockIdx.y].bs;
+  const BuildArrays A = jobs[blockIdx.y].A;
+  const int m = jobs[blockIdx.y].m;
   __shared__ Grid g;
   if (threadIdx.x == 0) g = bs->grid;
   __syncthreads();
@@ -400,7 +437,9 @@ __global__ void __launch_bounds__(256) count1_kernel(const BuildState* __restric
 }
 
 // one CTA per fine table: exclusive scan of its LS_FB3 counts -> Entry{start, count}
-__global__ void __launch_bounds__(256) tables_kernel(BuildState* bs, BuildArrays A) {
+__global__ void __launch_bounds__(256) tables_kernel(const BuildJob* __restrict__ jobs) {
+  BuildState* bs = jobs[blockIdx.y].bs;
+  const BuildArrays A = jobs[blockIdx.y].A;
   const int n_tab = min(bs->grid.n_tab1, A.tab_cap);
   constexpr int per = LS_FB3 / 256;  // 2 (LS_FB 8) or 16 (LS_FB 16) consecutive cells per thread
   __shared__ unsigned int ws[8];
@@ -454,7 +493,9 @@ __global__ void __launch_bounds__(256) tables_kernel(BuildState* bs, BuildArrays
 }
 
 // ---- K1f: scatter into sorted order (the leaf histograms double as cursors and end at zero) ---------
-__global__ void __launch_bounds__(256) scatter_kernel(BuildArrays A, int m) {
+__global__ void __launch_bounds__(256) scatter_kernel(const BuildJob* __restrict__ jobs) {
+  const BuildArrays A = jobs[blockIdx.y].A;
+  const int m = jobs[blockIdx.y].m;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
     const uint32_t k = A.pkey[i];
     const uint32_t tag = k & ~kKeyMask, key = k & kKeyMask;
@@ -474,8 +515,11 @@ __global__ void __launch_bounds__(256) scatter_kernel(BuildArrays A, int m) {
 // lidar ring.  It is a counting sort that borrows the map's histogram arrays -- they are all zero again once the
 // map's scatter has run, and the cursors below return them to zero.  Results do not depend on the order: every
 // reduction of the ICP kernel is an exact integer sum.
-__global__ void __launch_bounds__(256) q_count_kernel(const BuildState* __restrict__ bs, BuildArrays A,
-                                                      const float4* __restrict__ rd, int n) {
+__global__ void __launch_bounds__(256) q_count_kernel(const BuildJob* __restrict__ jobs) {
+  const BuildState* __restrict__ bs = jobs[blockIdx.y].bs;
+  const BuildArrays A = jobs[blockIdx.y].A;
+  const float4* __restrict__ rd = jobs[blockIdx.y].rd;
+  const int n = jobs[blockIdx.y].n;
   __shared__ Grid g;
   if (threadIdx.x == 0) g = bs->grid;
   __syncthreads();
@@ -498,7 +542,9 @@ __global__ void __launch_bounds__(256) q_count_kernel(const BuildState* __restri
   }
 }
 
-__global__ void __launch_bounds__(256) q_tables_kernel(BuildState* bs, BuildArrays A) {
+__global__ void __launch_bounds__(256) q_tables_kernel(const BuildJob* __restrict__ jobs) {
+  BuildState* bs = jobs[blockIdx.y].bs;
+  const BuildArrays A = jobs[blockIdx.y].A;
   const int n_tab = min(bs->grid.n_tab1, A.tab_cap);
   constexpr int per = LS_FB3 / 256;
   __shared__ unsigned int ws[8];
@@ -539,7 +585,9 @@ __device__ __forceinline__ unsigned int q_cell_count(const BuildArrays& A, int c
   return e.meta < 0 ? A.qtab_total[~e.meta] : A.cnt0[c];
 }
 
-__global__ void __launch_bounds__(kScanThreads) q_scan_reduce_kernel(BuildState* bs, BuildArrays A) {
+__global__ void __launch_bounds__(kScanThreads) q_scan_reduce_kernel(const BuildJob* __restrict__ jobs) {
+  BuildState* bs = jobs[blockIdx.y].bs;
+  const BuildArrays A = jobs[blockIdx.y].A;
   const int n = bs->grid.n_cells0;
   const int base = blockIdx.x * kScanTile;
   if (base >= n) return;
@@ -559,7 +607,9 @@ __global__ void __launch_bounds__(kScanThreads) q_scan_reduce_kernel(BuildState*
   }
 }
 
-__global__ void __launch_bounds__(kScanThreads) q_scan_apply_kernel(BuildState* bs, BuildArrays A) {
+__global__ void __launch_bounds__(kScanThreads) q_scan_apply_kernel(const BuildJob* __restrict__ jobs) {
+  BuildState* bs = jobs[blockIdx.y].bs;
+  const BuildArrays A = jobs[blockIdx.y].A;
   const int n = bs->grid.n_cells0;
   const int base = blockIdx.x * kScanTile;
   if (base >= n) return;
@@ -603,7 +653,10 @@ __global__ void __launch_bounds__(kScanThreads) q_scan_apply_kernel(BuildState* 
   }
 }
 
-__global__ void __launch_bounds__(256) q_scatter_kernel(BuildArrays A, const float4* __restrict__ rd, int n) {
+__global__ void __launch_bounds__(256) q_scatter_kernel(const BuildJob* __restrict__ jobs) {
+  const BuildArrays A = jobs[blockIdx.y].A;
+  const float4* __restrict__ rd = jobs[blockIdx.y].rd;
+  const int n = jobs[blockIdx.y].n;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t k = A.qkey[i];
     uint32_t rank;
@@ -619,8 +672,11 @@ __global__ void __launch_bounds__(256) q_scatter_kernel(BuildArrays A, const flo
 }
 
 // ---- reading pre-transform: R' = T_refMean_dataIn * R ----------------------------------------------
-__global__ void __launch_bounds__(256) reading_kernel(const BuildState* __restrict__ bs, const float4* __restrict__ in,
-                                                      int n, float4* __restrict__ out) {
+__global__ void __launch_bounds__(256) reading_kernel(const BuildJob* __restrict__ jobs) {
+  const BuildState* __restrict__ bs = jobs[blockIdx.y].bs;
+  const float4* __restrict__ in = jobs[blockIdx.y].reading;
+  float4* __restrict__ out = jobs[blockIdx.y].rd;
+  const int n = jobs[blockIdx.y].n;
   __shared__ float T[16];
   if (threadIdx.x < 16) T[threadIdx.x] = bs->T_pre[threadIdx.x];
   __syncthreads();
