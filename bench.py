@@ -24,10 +24,27 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_SCAN, K_MAP, ITERS = 131072, 4, 30
-POOL = 24                         # scans per rank kept resident (96 MB of scans + ~70 MB workspace > L2)
-ALG_BYTES_ICP = 64 * N_SCAN * ITERS                       # 64 B per query per iteration
-ALG_BYTES_REG = 68 * (K_MAP * N_SCAN) + ALG_BYTES_ICP     # + 68 B per map point for ingest/index
+# BASELINE.json configs[1] (default) and configs[4] (--config 5): scan size, scans per map, ICP iterations, sensor
+WORKLOADS = {
+    2: dict(n_scan=131072, k_map=4, iters=30, sensor=0, pool=24, tracks=32,
+            name="configs[1]: scan-to-local-map ICP, 131072-pt scan vs 524288-pt rolling map (4 scans), 30 iterations",
+            metric="ICP registrations/s (131072-pt scan vs 524288-pt map, 30 iterations)"),
+    5: dict(n_scan=262144, k_map=8, iters=50, sensor=1, pool=14, tracks=8,
+            name="configs[4]: dense-sensor stress, 262144-pt scan (VLS-128-like) vs 2097152-pt map (8 scans), 50 iterations",
+            metric="ICP registrations/s (262144-pt scan vs 2097152-pt map, 50 iterations)"),
+}
+N_SCAN, K_MAP, ITERS, POOL, SENSOR = 131072, 4, 30, 24, 0   # set by select_workload()
+ALG_BYTES_ICP = ALG_BYTES_REG = 0
+
+
+def select_workload(cfg):
+    """Algorithmic bytes: 64 B per query per iteration + 68 B per map point for ingest/index."""
+    global N_SCAN, K_MAP, ITERS, POOL, SENSOR, ALG_BYTES_ICP, ALG_BYTES_REG
+    w = WORKLOADS[cfg]
+    N_SCAN, K_MAP, ITERS, POOL, SENSOR = w["n_scan"], w["k_map"], w["iters"], w["pool"], w["sensor"]
+    ALG_BYTES_ICP = 64 * N_SCAN * ITERS
+    ALG_BYTES_REG = 68 * (K_MAP * N_SCAN) + ALG_BYTES_ICP
+    return w
 
 
 def load_peaks():
@@ -94,8 +111,17 @@ class ClockSampler(threading.Thread):
 def make_pool(seq):
     from laser_slam_b200 import synth
     truth, odom = synth.trajectory(seq, POOL, y_start=-20.0)
-    scans = [synth.scan(truth[k], seq, k) for k in range(POOL)]
+    scans = [synth.scan(truth[k], seq, k, sensor=SENSOR) for k in range(POOL)]
     return truth, odom, scans
+
+
+def make_pools(seqs):
+    """One pool per sequence, generated on a few host threads (the generator is C++ behind ctypes: no GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from laser_slam_b200 import synth
+    synth.build()
+    with ThreadPoolExecutor(max_workers=min(16, usable_threads())) as ex:
+        return list(ex.map(make_pool, seqs))
 
 
 def walk(step):
@@ -144,7 +170,7 @@ def best_thread_count(oracle, reading, refp, refn, T0):
     return min(cands, key=lambda c: t1[(8, c)] - t1[(2, c)])
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, wl):
     """The reference arm: the CPU algorithm on the host cores (oracle port; kind == "port")."""
     if rank != 0:
         return
@@ -176,12 +202,11 @@ def run_reference(args, rank):
     dt = time.perf_counter() - t0
     val = args.steps / dt
     print(json.dumps({
-        "impl": "reference", "metric": "ICP registrations/s (131072-pt scan vs 524288-pt map, 30 iterations)",
+        "impl": "reference", "metric": wl["metric"],
         "value": val, "unit": "registrations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: scan-to-local-map ICP, 131072-pt scan vs 524288-pt rolling map (4 scans), 30 iterations",
-                   "pool_scans": POOL},
+        "config": {"workload": wl["name"], "pool_scans": POOL},
         "cpu_baseline": {"value": val, "unit": "registrations/s", "cores": threads, "kind": "port",
                          "sample": f"{args.steps} full registrations (sub-map assembly + kd-tree build + 30 ICP iterations), "
                                    f"query loop OpenMP over {threads} threads (fastest of the counts tried, "
@@ -193,22 +218,22 @@ def run_reference(args, rank):
 def cpu_baseline_sample():
     import oracle
     truth, odom, scans = make_pool(0)
-    hist = [0, 1, 2, 3, 4]
+    hist = list(range(K_MAP + 1))
     ref, ks, Ts = submap_parts(truth, hist)
     parts = [scans[k] if k == ref else oracle.transform_cloud(T, *scans[k]) for k, T in zip(ks, Ts)]
     refp = np.concatenate([p[0] for p in parts])
     refn = np.concatenate([p[1] for p in parts])
-    T0 = (np.linalg.inv(truth[ref]) @ odom[4]).astype(np.float32)
-    threads = best_thread_count(oracle, scans[4][0], refp, refn, T0)
+    T0 = (np.linalg.inv(truth[ref]) @ odom[K_MAP]).astype(np.float32)
+    threads = best_thread_count(oracle, scans[K_MAP][0], refp, refn, T0)
     out = {}
     for th, reps in ((threads, 4), (1, 1)) if threads > 1 else ((1, 3),):
         po = oracle.default_params(max_iterations=ITERS, use_differential=0, num_threads=th)
         t0 = time.perf_counter()
         for _ in range(reps):
-            oracle.icp(scans[4][0], refp, refn, T0, po)
+            oracle.icp(scans[K_MAP][0], refp, refn, T0, po)
         out[th] = reps / (time.perf_counter() - t0)
     return {"value": out[threads], "unit": "registrations/s", "cores": threads, "kind": "port",
-            "sample": f"oracle port (kd-tree 1-NN + nth_element trim + point-to-plane), 4 full config-2 registrations with the "
+            "sample": f"oracle port (kd-tree 1-NN + nth_element trim + point-to-plane), 4 full registrations of this workload with the "
                       f"query loop on {threads} OpenMP threads (fastest count, {usable_threads()} usable); "
                       f"single-thread (libpointmatcher default): {out[1]:.3f} registrations/s"}
 
@@ -219,13 +244,26 @@ def main():
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--tracks", type=int, default=8, help="independent sequences (tracks) hosted per GPU, batched per launch")
+    ap.add_argument("--tracks", type=int, default=0, help="independent sequences (tracks) hosted per GPU, batched per "
+                    "launch (default: 32 for config 2, 8 for config 5)")
+    ap.add_argument("--config", type=int, default=2, choices=(2, 3, 4, 5),
+                    help="BASELINE.json workload: 2 scan-to-map ICP (default, the headline metric), 3 batched trajectories "
+                         "feeding the shared estimator, 4 pose-graph solve, 5 dense-sensor stress")
     args = ap.parse_args()
+    if args.config == 4:
+        import bench_posegraph
+        return bench_posegraph.main(args)
+    if args.config == 3:
+        import bench_trajectory
+        return bench_trajectory.main(args)
+    wl = select_workload(args.config)
+    if args.tracks <= 0:
+        args.tracks = wl["tracks"]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, wl)
         return
     args.warmup = max(args.warmup, 3)
 
@@ -241,7 +279,7 @@ def main():
     seq_base = int(os.environ.get('LS_BENCH_SEQ_BASE', '0'))   # diagnostic: run another rank's tracks on this one
     # every rank drives the SAME B synthetic sequences: per-GPU work is then identical by construction (the cost of a
     # registration varies by +-25 % with where along the street the vehicle is), which is what weak scaling assumes
-    tracks = [make_pool(seq_base + t) for t in range(B)]
+    tracks = make_pools([seq_base + t for t in range(B)])
     prm = ls.default_params(max_iterations=ITERS, use_differential=0)
     feats = [[torch.from_numpy(s[0]).pin_memory() for s in tr[2]] for tr in tracks]   # pinned host staging
     nrms = [[torch.from_numpy(s[1]).pin_memory() for s in tr[2]] for tr in tracks]
@@ -326,6 +364,23 @@ def main():
     truth_rel = np.linalg.inv(tracks[0][0][ref]) @ tracks[0][0][idx]
     pose_err = float(np.abs(ls.from_colmajor(last[0])[:3, 3] - truth_rel[:3, 3]).max())
 
+    # parity of what was just timed, outside the clock: one problem of the last batched step against the oracle
+    parity = None
+    if rank == 0:
+        import oracle
+        tchk = (n_total - 1) % B
+        idx_c, ref_c, ks_c, Ts_c, T0_c = staged[tchk][n_total - 1]
+        sc = tracks[tchk][2]
+        parts_c = [sc[k] if k == ref_c else oracle.transform_cloud(T, *sc[k]) for k, T in zip(ks_c, Ts_c)]
+        r = oracle.icp(sc[idx_c][0], np.concatenate([p_[0] for p_ in parts_c]), np.concatenate([p_[1] for p_ in parts_c]), T0_c,
+                       oracle.default_params(max_iterations=ITERS, use_differential=0, num_threads=usable_threads()))
+        got = ls.from_colmajor(last[tchk])
+        parity = {"problem": f"track {tchk}, last timed step ({B} registrations in that launch)",
+                  "final_transform_bit_equal_to_oracle": bool(np.array_equal(got, r["T"])),
+                  "max_abs_diff": float(np.abs(got - r["T"]).max())}
+        if not parity["final_transform_bit_equal_to_oracle"]:
+            raise RuntimeError(f"bench: the timed batched launch disagrees with the oracle: {parity}")
+
     # single-stream latency (one track, one registration per launch), a few steps
     lat = []
     for s in range(min(20, n_total)):
@@ -335,7 +390,7 @@ def main():
 
     # ------------------------------------------------------------------ end-to-end arm (host buffers)
     # every step uploads the new scan of every track from pinned host memory, then registers the batch
-    mp2 = ctx.create_map(B * 16, N_SCAN)   # ring: every track keeps its last K_MAP+1 scans resident with slack
+    mp2 = ctx.create_map(B * (2 * K_MAP + 8), N_SCAN)   # ring: every track keeps its last K_MAP+1 scans resident with slack
     sid2 = [dict() for _ in range(B)]
     for t in range(B):
         for s in range(K_MAP + 1):
@@ -356,7 +411,7 @@ def main():
             idx, ref, ks, Ts, T0 = staged[t][s]
             probs.append((sid2[t][idx], [sid2[t][k] for k in ks], Ts, T0))
         end = mp2.begin_batch(probs, prm)   # stage + launch step s, returns at once
-        upload(s + 1)   # new ids in ring slots last used 16 pushes per track ago: nothing step s reads is overwritten
+        upload(s + 1)   # new ids land in ring slots last used >= K_MAP+1 steps ago (the library refuses anything else)
         out = end()                                                                                            # wait; D2H of T + stats
         if world > 1:
             share_pose_delta(out[0]["T"])
@@ -388,7 +443,7 @@ def main():
     # ncu DRAM bytes of one launch of the same shape (8 registrations per launch has its own capture: eight maps do
     # not fit L2 together, one does)
     traffic, traffic_note = None, None
-    for fname, regs in (("r1_icp_kernel_batch8_summary.json", 8), ("r1_icp_kernel_summary.json", 1)):
+    for fname, regs in ((f"r2_icp_kernel_cfg{args.config}_batch{B}_summary.json", B),):
         prof = os.path.join(ROOT, "profiles", fname)
         if regs == B and os.path.exists(prof):
             try:
@@ -396,7 +451,7 @@ def main():
                 traffic_note = f"ncu dram__bytes_read+write of one launch with {regs} registration(s) (profiles/{fname})"
             except Exception:
                 traffic = None
-    roof = {"bound": "hbm", "kernel": f"ls::icp_kernel (persistent: NN query + trimmed select + normal equations, 30 iterations, "
+    roof = {"bound": "hbm", "kernel": f"ls::icp_kernel (persistent: NN query + trimmed select + normal equations, {ITERS} iterations, "
                                       f"{B} registrations per launch)",
             "achieved": B * ALG_BYTES_ICP / t_icp / 1e9, "peak": peak, "unit": "GB/s",
             "frac": B * ALG_BYTES_ICP / t_icp / 1e9 / peak,
@@ -406,11 +461,11 @@ def main():
                              "achieved": B * ALG_BYTES_REG / t_dev / 1e9, "frac": B * ALG_BYTES_REG / t_dev / 1e9 / peak}}
     cpu = cpu_baseline_sample() if args.gpus == 1 else None
     out = {
-        "metric": "ICP registrations/s (131072-pt scan vs 524288-pt map, 30 iterations)",
+        "metric": wl["metric"],
         "value": world * B * args.steps / t_res, "unit": "registrations/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: scan-to-local-map ICP, 131072-pt scan vs 524288-pt rolling map (4 scans), 30 iterations",
+        "config": {"workload": wl["name"],
                    "tracks_per_gpu": B, "registrations_per_step": world * B,
                    "concurrency": f"{B} independent sequences (tracks) per GPU (the same {B} synthetic sequences on every rank, so "
                                   f"per-GPU work is identical); one step registers the next scan of every track in one "
@@ -419,7 +474,7 @@ def main():
                    "l2": f"inputs larger than L2: {B * POOL} resident scans/rank cycled ({B * POOL * N_SCAN * 32 / 1e6:.0f} MB) "
                          f"+ {B} x ~170 MB workspaces",
                    "collective": "none on the data path; one 32 B/rank NCCL all-gather of pose records per step when n_gpus > 1",
-                   "final_pose_err_vs_truth_m": pose_err},
+                   "final_pose_err_vs_truth_m": pose_err, "parity_check": parity},
         "e2e": {"value": world * B * args.steps / t_e2e, "unit": "registrations/s",
                 "h2d_bytes_per_step": B * (N_SCAN * 16 + N_SCAN * 12 + 16 * 4 * (K_MAP + 1) + 8 * (K_MAP + 1)),
                 "d2h_bytes_per_step": B * (216 + 212),   # per registration: result block of the ICP scratch + grid header

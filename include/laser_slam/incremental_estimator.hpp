@@ -16,6 +16,7 @@ namespace laser_slam {
 
 class IncrementalEstimator {
  public:
+  IncrementalEstimator() {}
   explicit IncrementalEstimator(const EstimatorParams& parameters, unsigned int n_laser_slam_workers = 1u);
   ~IncrementalEstimator();
   IncrementalEstimator(const IncrementalEstimator&) = delete;
@@ -35,18 +36,32 @@ class IncrementalEstimator {
   gtsam::Values registerPrior(const gtsam::NonlinearFactorGraph& new_factors, const gtsam::Values& new_values,
                               const unsigned int worker_id);
 
+  // (new) One scan callback of SEVERAL workers at once: poses[i] / scans[i] belong to worker worker_ids[i].  Equivalent to
+  // calling getLaserTrack(worker_ids[i])->processPoseAndLaserScan(...) for every i (reference
+  // laser_slam_ros/src/laser_slam_worker.cpp:133,158), but the scan-to-sub-map registrations of the step run as ONE
+  // batched launch on the estimator's device context (ls_icp_register_submap_batch): the tracks are independent, so
+  // the results are the same bits.  Outputs are indexed like the inputs.
+  void processPosesAndLaserScans(const std::vector<unsigned int>& worker_ids, const std::vector<Pose>& poses,
+                                 const std::vector<LaserScan>& scans, std::vector<gtsam::NonlinearFactorGraph>* new_factors,
+                                 std::vector<gtsam::Values>* new_values, std::vector<bool>* is_prior);
+  ls_ctx* trackContext() const { return track_ctx_; }
+
   const ls_pg_stats& getLastSolveStats() const { return last_stats_; }
 
  private:
   gtsam::Values updateGraph(const gtsam::NonlinearFactorGraph& factors, const gtsam::Values& values,
                             const std::vector<uint64_t>& remove, std::vector<uint64_t>* new_indices);
-  unsigned int n_laser_slam_workers_;
+  unsigned int n_laser_slam_workers_ = 0u;
   mutable std::recursive_mutex full_class_mutex_;
   std::vector<std::shared_ptr<LaserTrack> > laser_tracks_;
   ls_pg* graph_ = nullptr;
+  // device side of the lidar odometry, shared by all tracks so that one launch can serve them all
+  ls_ctx* track_ctx_ = nullptr;
+  ls_map* track_ring_ = nullptr;
+  int track_ring_capacity_ = 0, track_ring_max_pts_ = 0;
   ls_ctx* icp_ctx_ = nullptr;  // loop-closure ICP (sub-map <-> sub-map)
   ls_icp_params icp_params_;
-  gtsam::NoiseModel loop_closure_noise_model_, first_association_noise_model_;
+  gtsam::noiseModel::Base::shared_ptr loop_closure_noise_model_, first_association_noise_model_;
   std::unordered_map<unsigned int, size_t> factor_indices_to_remove_;
   std::vector<std::vector<unsigned int> > linked_workers_;
   EstimatorParams params_;

@@ -17,6 +17,10 @@ namespace laser_slam {
 class LaserTrack {
  public:
   explicit LaserTrack(const LaserTrackParams& parameters, unsigned int laser_track_id = 0u);
+  // (new) a track hosted by an IncrementalEstimator: context and scan ring belong to the estimator and are shared by
+  // all of its tracks, so that their registrations can be served by ONE batched launch (ls_icp_register_submap_batch).
+  LaserTrack(const LaserTrackParams& parameters, unsigned int laser_track_id, ls_ctx* shared_ctx, ls_map** shared_ring,
+             int* shared_ring_capacity, int* shared_ring_max_pts, int ring_slots_per_track);
   ~LaserTrack();
   LaserTrack(const LaserTrack&) = delete;
   LaserTrack& operator=(const LaserTrack&) = delete;
@@ -42,14 +46,18 @@ class LaserTrack {
 
   void appendPriorFactors(const curves::Time& prior_time_ns, gtsam::NonlinearFactorGraph* graph) const;
   void appendOdometryFactors(const curves::Time& optimization_min_time_ns, const curves::Time& optimization_max_time_ns,
-                             const gtsam::NoiseModel& noise_model, gtsam::NonlinearFactorGraph* graph) const;
+                             gtsam::noiseModel::Base::shared_ptr noise_model, gtsam::NonlinearFactorGraph* graph) const;
   void appendICPFactors(const curves::Time& optimization_min_time_ns, const curves::Time& optimization_max_time_ns,
-                        const gtsam::NoiseModel& noise_model, gtsam::NonlinearFactorGraph* graph) const;
+                        gtsam::noiseModel::Base::shared_ptr noise_model, gtsam::NonlinearFactorGraph* graph) const;
   void appendLoopClosureFactors(const curves::Time& optimization_min_time_ns, const curves::Time& optimization_max_time_ns,
-                                const gtsam::NoiseModel& noise_model, gtsam::NonlinearFactorGraph* graph) const;
+                                gtsam::noiseModel::Base::shared_ptr noise_model, gtsam::NonlinearFactorGraph* graph) const;
 
-  void initializeGTSAMValues(const std::vector<Key>& keys, gtsam::Values* values) const;
+  void initializeGTSAMValues(const gtsam::KeySet& keys, gtsam::Values* values) const;
   void updateFromGTSAMValues(const gtsam::Values& values);
+  // gtsam::Marginals(factor_graph, values).marginalCovariance(key) for every node of the trajectory
+  // (reference laser_track.cpp:421-429): one device pass (ls_pg_marginals) instead of one elimination per key
+  void updateCovariancesFromGTSAMValues(const gtsam::NonlinearFactorGraph& factor_graph, const gtsam::Values& values);
+  void printTrajectory() const;
 
   size_t getNumScans() const;
   Pose findNearestPose(const Time& timestamp_ns) const;
@@ -58,10 +66,36 @@ class LaserTrack {
   // ls_map_destroy) and described by (ids, 16 floats per part), ready for ls_icp_register_submaps.
   void stageSubMapAroundTime(const curves::Time& time_ns, const unsigned int sub_maps_radius, ls_ctx* ctx, ls_map** ring_out,
                              std::vector<uint64_t>* ids_out, std::vector<float>* T_parts_out) const;
-  Key getValueKey(const curves::Time& time_ns) const;  // the leaf of trajectory_.getValueExpression(time)
+  gtsam::Expression<SE3> getValueExpression(const curves::Time& time_ns) const;  // leaf expression of the node at time_ns
+  Key getValueKey(const curves::Time& time_ns) const;                            // its key
   SE3 evaluate(const curves::Time& time_ns) const;
   void getScanMatchingTimes(std::map<Time, double>* scan_matching_times) const;
   void saveTrajectory(const std::string& filename) const;
+
+  // (new) processPoseAndLaserScan in two halves around the registration, so that a host of several tracks can run the
+  // registrations of one step as a batch: begin...() does everything up to and including the staging of the
+  // scan-to-sub-map problem (reference laser_track.cpp:122-206, 466-491) and describes it in `pending` (active == false:
+  // first scan of the track, or ICP factors disabled); the caller registers it -- alone through ls_icp_register_submap
+  // or together with other tracks' problems -- and hands the outcome to end...(), which stores the RelativePose and
+  // emits factors and values (reference :493-519, 208-230).
+  struct PendingIcp {
+    bool active = false;
+    uint64_t reading_id = 0;
+    std::vector<uint64_t> part_ids;
+    std::vector<float> T_parts;  // 16 floats per part
+    PointMatcher::TransformationParameters T0;
+    RelativePose icp_transformation;
+    // (internal) carried from begin to end
+    RelativePose relative_measurement;
+    LaserScan scan;
+    bool first = false;
+    Pose pose;
+    double t_start_ms = 0.0;
+  };
+  void beginPoseAndLaserScan(const Pose& pose, const LaserScan& in_scan, PendingIcp* pending);
+  void endPoseAndLaserScan(PendingIcp* pending, int rc, const float* T_out16, const ls_icp_stats* stats,
+                           gtsam::NonlinearFactorGraph* newFactors, gtsam::Values* newValues, bool* is_prior);
+  const ls_icp_params& icpParams() const { return icp_params_; }
 
   // (new) ICP results and run statistics, for tests and the bench
   const RelativePoseVector& getIcpTransformations() const { return icp_transformations_; }
@@ -71,10 +105,13 @@ class LaserTrack {
 
  private:
   struct Node { SE3 value; Key key; };
-  ls_factor makeRelativeMeasurementFactor(const RelativePose& m, const gtsam::NoiseModel& noise, bool fix_first_node = false) const;
-  ls_factor makeMeasurementFactor(const Pose& pose_measurement, const gtsam::NoiseModel& noise) const;
-  void computeICPTransformations();
-  void localScanToSubMap();
+  gtsam::ExpressionFactor<SE3> makeRelativeMeasurementFactor(const RelativePose& relative_pose_measurement,
+                                                             gtsam::noiseModel::Base::shared_ptr noise_model,
+                                                             const bool fix_first_node = false) const;
+  gtsam::ExpressionFactor<SE3> makeMeasurementFactor(const Pose& pose_measurement, gtsam::noiseModel::Base::shared_ptr noise_model) const;
+  void stageLocalScanToSubMap(PendingIcp* pending);
+  void finishLocalScanToSubMap(const PendingIcp& pending, int rc, const float* T_out16);
+  void ensureRing(size_t max_pts);
   const Pose& findPose(const Time& timestamp_ns) const;
   Pose& findPose(const Time& timestamp_ns);
   Key extendTrajectory(const Time& timestamp_ns, const SE3& value);
@@ -92,15 +129,21 @@ class LaserTrack {
   std::map<Time, Node> trajectory_;  // curves::DiscreteSE3Curve: time -> (value, key)
   mutable std::recursive_mutex full_laser_track_mutex_;
   std::vector<Covariance> covariances_;
-  gtsam::NoiseModel prior_noise_model_, odometry_noise_model_, icp_noise_model_;
+  gtsam::noiseModel::Base::shared_ptr prior_noise_model_, odometry_noise_model_, icp_noise_model_;
   std::map<Time, double> scan_matching_times_;
   LaserTrackParams params_;
   ls_icp_params icp_params_;
   ls_icp_stats last_icp_stats_;
   // device side
   ls_ctx* ctx_ = nullptr;
-  ls_map* map_ = nullptr;
-  int map_capacity_ = 0, map_max_pts_ = 0;
+  bool owns_ctx_ = true;
+  // the ring: the track's own, or the host's (then these point into the IncrementalEstimator)
+  ls_map* own_map_ = nullptr;
+  int own_capacity_ = 0, own_max_pts_ = 0;
+  ls_map** map_p_ = &own_map_;
+  int* map_capacity_p_ = &own_capacity_;
+  int* map_max_pts_p_ = &own_max_pts_;
+  int ring_slots_per_track_ = 0;  // shared ring: slots every track may count on
   mutable std::map<size_t, uint64_t> resident_;  // scan index -> device scan id
   static constexpr double kDistanceBetweenPriorPoses_m = 100.0;
 };

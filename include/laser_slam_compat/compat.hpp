@@ -7,10 +7,16 @@
 #define LASER_SLAM_COMPAT_HPP_
 
 #include <array>
+#include <cctype>
 #include <cmath>
+#include <cstdlib>
 #include <cstdint>
 #include <cstring>
+#include <istream>
 #include <map>
+#include <memory>
+#include <set>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -161,12 +167,29 @@ struct PointMatcher {
     std::string text;
     size_t span;
   };
+  // column-major dynamic matrix with the few Eigen members laser_slam touches (rows(), cols(), data(), (r,c))
+  struct Matrix {
+    std::vector<T> v;
+    size_t nrows = 0;
+    Matrix() {}
+    Matrix(size_t r, size_t c) : v(r * c), nrows(r) {}
+    size_t rows() const { return nrows; }
+    size_t cols() const { return nrows ? v.size() / nrows : 0; }
+    size_t size() const { return v.size(); }
+    T* data() { return v.data(); }
+    const T* data() const { return v.data(); }
+    T& operator()(size_t r, size_t c) { return v[c * nrows + r]; }
+    T operator()(size_t r, size_t c) const { return v[c * nrows + r]; }
+    void resize(size_t r, size_t c) { nrows = r; v.resize(r * c); }
+    void assign(size_t r, const T* first, const T* last) { nrows = r; v.assign(first, last); }
+    void append(const Matrix& o) { v.insert(v.end(), o.v.begin(), o.v.end()); }
+  };
   struct DataPoints {
-    std::vector<T> features;     // 4 x N, column-major: x,y,z,1 per point
-    std::vector<T> descriptors;  // D x N, column-major
+    Matrix features;     // 4 x N, column-major: x,y,z,1 per point
+    Matrix descriptors;  // D x N, column-major
     std::vector<Label> featureLabels, descriptorLabels;
     size_t descriptorDim = 0;
-    size_t getNbPoints() const { return features.size() / 4; }
+    size_t getNbPoints() const { return features.cols(); }
     bool descriptorExists(const std::string& name) const {
       for (const auto& l : descriptorLabels)
         if (l.text == name) return true;
@@ -184,23 +207,188 @@ struct PointMatcher {
     void concatenate(const DataPoints& o) {
       if (getNbPoints() == 0) { *this = o; return; }
       if (o.descriptorDim != descriptorDim) throw std::runtime_error("DataPoints::concatenate: descriptor mismatch");
-      features.insert(features.end(), o.features.begin(), o.features.end());
-      descriptors.insert(descriptors.end(), o.descriptors.begin(), o.descriptors.end());
+      features.append(o.features);
+      descriptors.append(o.descriptors);
+    }
+    // (re)place a descriptor block of `span` rows (the SurfaceNormal filters add "normals" this way)
+    void setDescriptor(const std::string& name, size_t span, const T* block /* span x N */) {
+      const size_t n = getNbPoints();
+      if (descriptorExists(name)) {
+        const size_t off = (size_t)descriptorOffset(name);
+        for (size_t i = 0; i < n; ++i)
+          for (size_t r = 0; r < span; ++r) descriptors(off + r, i) = block[i * span + r];
+        return;
+      }
+      Matrix nd(descriptorDim + span, n);
+      for (size_t i = 0; i < n; ++i) {
+        for (size_t r = 0; r < descriptorDim; ++r) nd(r, i) = descriptors(r, i);
+        for (size_t r = 0; r < span; ++r) nd(descriptorDim + r, i) = block[i * span + r];
+      }
+      descriptors = nd;
+      descriptorLabels.push_back({name, span});
+      descriptorDim += span;
     }
     // convenience: cloud with a 3-row "normals" descriptor
     static DataPoints fromArrays(const T* feat4, const T* normals3, size_t n) {
       DataPoints d;
-      d.features.assign(feat4, feat4 + 4 * n);
+      d.features.assign(4, feat4, feat4 + 4 * n);
       d.featureLabels = {{"x", 1}, {"y", 1}, {"z", 1}, {"pad", 1}};
       if (normals3) {
-        d.descriptors.assign(normals3, normals3 + 3 * n);
+        d.descriptors.assign(3, normals3, normals3 + 3 * n);
         d.descriptorLabels = {{"normals", 3}};
         d.descriptorDim = 3;
       }
       return d;
     }
   };
+  // One device context per process for the stand-ins below (the LaserTrack / IncrementalEstimator classes own theirs).
+  static ls_ctx* sharedContext() {
+    static ls_ctx* ctx = nullptr;
+    if (!ctx && ls_b200_init(0, &ctx) != LS_OK) throw std::runtime_error("ls_b200_init failed: no usable CUDA device");
+    return ctx;
+  }
+
+  // PointMatcher<T>::Transformation (reference laser_slam/src/laser_track.cpp:33,265,485; common.hpp:140-147):
+  // RigidTransformation::compute / checkParameters / correctParameters.
+  struct Transformation {
+    DataPoints compute(const DataPoints& in, const TransformationParameters& Tr) const {
+      DataPoints out = in;
+      const int off = in.descriptorOffset("normals");
+      const size_t n = in.getNbPoints();
+      std::vector<T> nrm(3 * (n ? n : 1));
+      const int rc = ls_transform_cloud(sharedContext(), Tr.data(), in.features.data(), off >= 0 ? in.descriptors.data() + off : nullptr,
+                                        (int)in.descriptorDim, (int)n, out.features.data(), off >= 0 ? nrm.data() : nullptr);
+      if (rc != LS_OK) throw std::runtime_error(std::string("ls_transform_cloud: ") + ls_b200_last_error(sharedContext()));
+      if (off >= 0) out.setDescriptor("normals", 3, nrm.data());
+      return out;
+    }
+    bool checkParameters(const TransformationParameters& Tr) const { return ls_check_rigid(Tr.data()) != 0; }
+    TransformationParameters correctParameters(const TransformationParameters& Tr) const {
+      TransformationParameters o;
+      ls_correct_rigid(Tr.data(), o.data());
+      return o;
+    }
+  };
+  struct TransformationRegistrarT {
+    std::shared_ptr<Transformation> create(const std::string& name) const {
+      if (name != "RigidTransformation") throw std::runtime_error("Transformation '" + name + "' is not available");
+      return std::make_shared<Transformation>();
+    }
+  };
+  TransformationRegistrarT TransformationRegistrar;
+  static PointMatcher& get() {
+    static PointMatcher instance;
+    return instance;
+  }
+
+  // PointMatcher<T>::DataPointsFilters (reference laser_track.cpp:22-30,146): the filter chain of a YAML list.  Built
+  // here: SurfaceNormalDataPointsFilter / SamplingSurfaceNormalDataPointsFilter {knn} (normals on the device, exact
+  // k-NN: ls_estimate_normals), RandomSamplingDataPointsFilter {prob} (counter-based hash of the point index instead
+  // of libc rand(): reproducible), anything else throws.
+  struct DataPointsFilters {
+    struct Filter { std::string name; int knn = 10; double prob = 1.0; };
+    std::vector<Filter> filters;
+    DataPointsFilters() {}
+    explicit DataPointsFilters(std::istream& in) {
+      std::string line;
+      while (std::getline(in, line)) {
+        const size_t hash = line.find('#');
+        if (hash != std::string::npos) line = line.substr(0, hash);
+        size_t a = line.find_first_not_of(" \t-");
+        if (a == std::string::npos) continue;
+        line = line.substr(a);
+        const size_t colon = line.find(':');
+        std::string key = colon == std::string::npos ? line : line.substr(0, colon);
+        std::string val = colon == std::string::npos ? "" : line.substr(colon + 1);
+        while (!key.empty() && isspace((unsigned char)key.back())) key.pop_back();
+        if (key.find("DataPointsFilter") != std::string::npos) {
+          Filter f;
+          f.name = key;
+          filters.push_back(f);
+        } else if (!filters.empty() && !val.empty()) {
+          if (key == "knn") filters.back().knn = std::atoi(val.c_str());
+          if (key == "prob" || key == "ratio") filters.back().prob = std::atof(val.c_str());
+        }
+      }
+    }
+    void apply(DataPoints& cloud) const {
+      for (const Filter& f : filters) {
+        if (f.name == "SurfaceNormalDataPointsFilter" || f.name == "SamplingSurfaceNormalDataPointsFilter") {
+          const size_t n = cloud.getNbPoints();
+          std::vector<T> nrm(3 * (n ? n : 1));
+          const int rc = ls_estimate_normals(sharedContext(), cloud.features.data(), (int)n, f.knn < 3 ? 3 : (f.knn > 16 ? 16 : f.knn), nrm.data());
+          if (rc != LS_OK) throw std::runtime_error(std::string("ls_estimate_normals: ") + ls_b200_last_error(sharedContext()));
+          cloud.setDescriptor("normals", 3, nrm.data());
+          if (f.name == "SamplingSurfaceNormalDataPointsFilter" && f.prob < 1.0) subsample(cloud, f.prob, 0x5a17u);
+        } else if (f.name == "RandomSamplingDataPointsFilter") {
+          subsample(cloud, f.prob, 0x7e11u);
+        } else {
+          throw std::runtime_error("DataPointsFilter '" + f.name + "' is not available");
+        }
+      }
+    }
+    // keep point i iff hash(i, salt) / 2^32 < prob (ls_keep_point: the same rule as the device-side sampler)
+    static void subsample(DataPoints& cloud, double prob, uint32_t salt) {
+      const size_t n = cloud.getNbPoints(), D = cloud.descriptorDim;
+      Matrix f(4, 0), d(D, 0);
+      for (size_t i = 0; i < n; ++i) {
+        if (!ls_keep_point((uint32_t)i, salt, (float)prob)) continue;
+        for (size_t r = 0; r < 4; ++r) f.v.push_back(cloud.features(r, i));
+        for (size_t r = 0; r < D; ++r) d.v.push_back(cloud.descriptors(r, i));
+      }
+      cloud.features = f;
+      cloud.descriptors = d;
+    }
+  };
+
+  // PointMatcher<T>::ICP (reference laser_track.cpp:14-21,496; incremental_estimator.cpp:52-60,108): loadFromYaml /
+  // setDefault / compute(reading, reference, T0) -> ls_icp_params_from_yaml / ls_icp_register.  The reference cloud
+  // must carry a "normals" descriptor (PointToPlaneErrorMinimizer asserts the same upstream).
+  struct ICP {
+    ls_icp_params params;
+    ls_icp_stats last_stats;
+    ICP() { setDefault(); }
+    void setDefault() {  // ICPChainBase::setDefault() values
+      ls_icp_default_params(&params);
+      params.trim_ratio = 0.85f;
+      params.min_diff_rot = 0.001f;
+      params.min_diff_trans = 0.001f;
+      params.smooth_length = 3;
+    }
+    void loadFromYaml(std::istream& in) {
+      std::stringstream ss;
+      ss << in.rdbuf();
+      if (ls_icp_params_from_yaml(ss.str().c_str(), &params) != LS_OK) throw std::runtime_error("unsupported ICP chain");
+    }
+    // readingDataPointsFilters / referenceDataPointsFilters of the chain (icp_default.yaml:1-7) run inside compute(), as in
+    // libpointmatcher's ICP::compute: deterministic sampling of the reading, normals (+ sampling) of the reference.
+    TransformationParameters compute(const DataPoints& reading_in, const DataPoints& reference_in, const TransformationParameters& T0) {
+      DataPoints reading = reading_in, reference = reference_in;
+      if (params.reading_sampling_prob < 1.0f) DataPointsFilters::subsample(reading, params.reading_sampling_prob, 0x7e11u);
+      if (params.reference_normals_knn > 0) {
+        typename DataPointsFilters::Filter f;
+        f.name = "SamplingSurfaceNormalDataPointsFilter";
+        f.knn = params.reference_normals_knn;
+        f.prob = params.reference_sampling_ratio;
+        DataPointsFilters chain;
+        chain.filters.push_back(f);
+        chain.apply(reference);
+      }
+      const int off = reference.descriptorOffset("normals");
+      if (off < 0) throw std::runtime_error("PointToPlaneErrorMinimizer: the reference has no 'normals' descriptor");
+      TransformationParameters out = T0;
+      const int rc = ls_icp_register(sharedContext(), &params, reading.features.data(), (int)reading.getNbPoints(),
+                                     reference.features.data(), reference.descriptors.data() + off, (int)reference.descriptorDim,
+                                     (int)reference.getNbPoints(), T0.data(), out.data(), &last_stats, nullptr, nullptr, nullptr);
+      if (rc == LS_ERR_CONVERGENCE) throw ConvergenceError(ls_b200_last_error(sharedContext()));
+      if (rc != LS_OK) throw std::runtime_error(std::string("ls_icp_register: ") + ls_b200_last_error(sharedContext()));
+      return out;
+    }
+  };
 };
+#ifndef REG
+#define REG(name) name##Registrar  // libpointmatcher: PointMatcher::get().REG(Transformation).create("RigidTransformation")
+#endif
 
 // ------------------------------------------------------------------------------------------------ gtsam
 namespace gtsam {
@@ -212,6 +400,14 @@ typedef uint64_t Key;
 class NonlinearFactorGraph {
  public:
   void push_back(const ls_factor& f) { factors_.push_back(f); }
+  std::set<Key> keys() const {
+    std::set<Key> k;
+    for (const ls_factor& f : factors_) {
+      if (f.type == LS_FACTOR_PRIOR || !f.fix_a) k.insert(f.key_a);
+      if (f.type == LS_FACTOR_BETWEEN) k.insert(f.key_b);
+    }
+    return k;
+  }
   bool empty() const { return factors_.empty(); }
   size_t size() const { return factors_.size(); }
   void clear() { factors_.clear(); }
@@ -240,12 +436,231 @@ class Values {
   std::map<Key, SE3> v_;
 };
 
-// noiseModel::Diagonal::Sigmas / Robust::Create(Cauchy(1), Diagonal)
-struct NoiseModel {
-  std::array<double, 6> sigmas;
-  bool cauchy;
+typedef std::set<Key> KeySet;
+
+// noiseModel::Diagonal::Sigmas / Robust::Create(mEstimator::Cauchy::Create(1), Diagonal)  (reference laser_track.cpp:37-64)
+namespace noiseModel {
+struct Base {
+  typedef std::shared_ptr<Base> shared_ptr;
+  std::array<double, 6> sigmas{{1, 1, 1, 1, 1, 1}};
+  bool cauchy = false;
+};
+struct Diagonal {
+  typedef std::shared_ptr<Base> shared_ptr;
+  template <typename V>
+  static shared_ptr Sigmas(const V& v) {
+    shared_ptr m = std::make_shared<Base>();
+    for (int i = 0; i < 6; ++i) m->sigmas[i] = (double)v[i];
+    return m;
+  }
+};
+namespace mEstimator {
+struct Cauchy {
+  typedef std::shared_ptr<Cauchy> shared_ptr;
+  double k = 1.0;
+  static shared_ptr Create(double k) {
+    if (k != 1.0) throw std::runtime_error("only Cauchy(1) is built (reference laser_track.cpp:41,50)");
+    return std::make_shared<Cauchy>();
+  }
+};
+}  // namespace mEstimator
+struct Robust {
+  static Base::shared_ptr Create(const mEstimator::Cauchy::shared_ptr&, const Base::shared_ptr& base) {
+    Base::shared_ptr m = std::make_shared<Base>(*base);
+    m->cauchy = true;
+    return m;
+  }
+};
+}  // namespace noiseModel
+typedef noiseModel::Base NoiseModel;
+
+// Expression<SE3> as laser_slam builds them (reference laser_track.cpp:431-458, incremental_estimator.cpp:117-125):
+// a trajectory leaf (key), a constant, inverse(leaf | constant), compose(inverse(a), b).  Nothing else is needed by
+// ExpressionFactor<SE3>, whose two shapes are the prior Local(meas, T(key)) and the relative pose
+// Local(meas, T(a)^-1 T(b)).
+template <typename T>
+class Expression {
+ public:
+  enum Form { kLeaf, kConstant, kInverse, kBetween };
+  Expression() {}
+  explicit Expression(Key k) : form_(kLeaf), key_b_(k) {}
+  explicit Expression(const T& value) : form_(kConstant), const_a_(value) {}
+  Form form() const { return form_; }
+  Key keyA() const { return key_a_; }
+  Key keyB() const { return key_b_; }
+  bool aIsConstant() const { return a_const_; }
+  const T& constant() const { return const_a_; }
+  std::set<Key> keys() const {
+    std::set<Key> k;
+    if (form_ == kLeaf || form_ == kInverse) { if (!(form_ == kInverse && a_const_)) k.insert(key_b_); }
+    if (form_ == kBetween) { if (!a_const_) k.insert(key_a_); k.insert(key_b_); }
+    return k;
+  }
+  static Expression inverseOf(const Expression& e) {
+    if (e.form_ != kLeaf && e.form_ != kConstant) throw std::logic_error("inverse() of a composite expression is not built");
+    Expression r = e;
+    r.form_ = kInverse;
+    r.a_const_ = e.form_ == kConstant;
+    return r;
+  }
+  static Expression composeOf(const Expression& a_inv, const Expression& b) {
+    if (a_inv.form_ != kInverse || b.form_ != kLeaf) throw std::logic_error("compose(): only inverse(a) * leaf(b) is built");
+    Expression r;
+    r.form_ = kBetween;
+    r.a_const_ = a_inv.a_const_;
+    r.const_a_ = a_inv.const_a_;
+    r.key_a_ = a_inv.key_b_;
+    r.key_b_ = b.key_b_;
+    return r;
+  }
+
+ private:
+  Form form_ = kLeaf;
+  Key key_a_ = 0, key_b_ = 0;
+  bool a_const_ = false;
+  T const_a_;
+};
+
+template <typename T>
+class ExpressionFactor {
+ public:
+  ExpressionFactor(const noiseModel::Base::shared_ptr& noise, const T& measured, const Expression<T>& e) {
+    std::memset(&f_, 0, sizeof(f_));
+    f_.robust = noise->cauchy ? 1 : 0;
+    for (int i = 0; i < 6; ++i) f_.sigma[i] = noise->sigmas[i];
+    measured.toArray7(f_.meas);
+    f_.fixed_a[0] = 1.0;
+    if (e.form() == Expression<T>::kLeaf) {
+      f_.type = LS_FACTOR_PRIOR;
+      f_.key_a = f_.key_b = e.keyB();
+    } else if (e.form() == Expression<T>::kBetween) {
+      f_.type = LS_FACTOR_BETWEEN;
+      f_.key_a = e.keyA();
+      f_.key_b = e.keyB();
+      if (e.aIsConstant()) {
+        f_.fix_a = 1;
+        e.constant().toArray7(f_.fixed_a);
+      }
+    } else {
+      throw std::logic_error("ExpressionFactor: unsupported expression");
+    }
+  }
+  const ls_factor& record() const { return f_; }
+  operator const ls_factor&() const { return f_; }
+
+ private:
+  ls_factor f_;
+};
+
+// gtsam::Marginals(graph, values).marginalCovariance(key) (reference laser_track.cpp:421-429): a device pose graph is
+// built from the factors and values, and ls_pg_marginals returns the 6x6 block of the inverse Hessian.
+class Marginals {
+ public:
+  typedef std::array<double, 36> Matrix6;  // row-major
+  Marginals(const NonlinearFactorGraph& graph, const Values& values) {
+    if (ls_pg_create(0, &pg_) != LS_OK) throw std::runtime_error("ls_pg_create failed");
+    std::vector<Key> keys;
+    std::vector<double> poses;
+    for (const auto& kv : values) {
+      keys.push_back(kv.first);
+      double a[7];
+      kv.second.toArray7(a);
+      poses.insert(poses.end(), a, a + 7);
+    }
+    std::vector<uint32_t> tracks(keys.size());
+    for (size_t i = 0; i < keys.size(); ++i) tracks[i] = (uint32_t)(keys[i] >> 48);  // LaserTrack keys carry the track id
+    if (ls_pg_add_poses(pg_, keys.data(), tracks.data(), poses.data(), (int)keys.size()) != LS_OK ||
+        ls_pg_add_factors(pg_, graph.factors().data(), (int)graph.size(), nullptr) != LS_OK) {
+      const std::string e = ls_pg_last_error(pg_);
+      ls_pg_destroy(pg_);
+      throw std::runtime_error("Marginals: " + e);
+    }
+  }
+  ~Marginals() { if (pg_) ls_pg_destroy(pg_); }
+  Marginals(const Marginals&) = delete;
+  Marginals& operator=(const Marginals&) = delete;
+  Matrix6 marginalCovariance(Key key) const {
+    Matrix6 c;
+    if (ls_pg_marginals(pg_, &key, 1, c.data()) != LS_OK) throw std::runtime_error(std::string("Marginals: ") + ls_pg_last_error(pg_));
+    return c;
+  }
+  std::vector<Matrix6> marginalCovariances(const std::vector<Key>& keys) const {  // one device pass for many keys
+    std::vector<Matrix6> c(keys.size());
+    if (!keys.empty() && ls_pg_marginals(pg_, keys.data(), (int)keys.size(), c[0].data()) != LS_OK)
+      throw std::runtime_error(std::string("Marginals: ") + ls_pg_last_error(pg_));
+    return c;
+  }
+
+ private:
+  ls_pg* pg_ = nullptr;
+};
+
+// gtsam::ISAM2 as IncrementalEstimator drives it (reference incremental_estimator.cpp:17-20,156-161,258-264,272-289):
+// update(new factors, new values[, remove indices]) / update() run ONE Gauss-Newton pass over the whole device graph each,
+// calculateEstimate() returns every value.
+struct ISAM2Params {
+  void setRelinearizeSkip(int) {}
+  void setRelinearizeThreshold(double) {}
+};
+struct ISAM2Result {
+  std::vector<size_t> newFactorsIndices;
+  ls_pg_stats stats;
+  void print(const std::string& = "") const {}
+};
+class ISAM2 {
+ public:
+  explicit ISAM2(const ISAM2Params& = ISAM2Params()) {
+    if (ls_pg_create(0, &pg_) != LS_OK) throw std::runtime_error("ls_pg_create failed");
+  }
+  ~ISAM2() { if (pg_) ls_pg_destroy(pg_); }
+  ISAM2(const ISAM2&) = delete;
+  ISAM2& operator=(const ISAM2&) = delete;
+  ISAM2Result update(const NonlinearFactorGraph& new_factors = NonlinearFactorGraph(), const Values& new_values = Values(),
+                     const std::vector<size_t>& remove_factor_indices = std::vector<size_t>()) {
+    ISAM2Result r;
+    std::vector<Key> keys;
+    std::vector<double> poses;
+    std::vector<uint32_t> tracks;
+    for (const auto& kv : new_values) {
+      keys.push_back(kv.first);
+      tracks.push_back((uint32_t)(kv.first >> 48));
+      double a[7];
+      kv.second.toArray7(a);
+      poses.insert(poses.end(), a, a + 7);
+    }
+    std::vector<uint64_t> idx(new_factors.size() ? new_factors.size() : 1), rem(remove_factor_indices.begin(), remove_factor_indices.end());
+    if ((!keys.empty() && ls_pg_add_poses(pg_, keys.data(), tracks.data(), poses.data(), (int)keys.size()) != LS_OK) ||
+        (!rem.empty() && ls_pg_remove_factors(pg_, rem.data(), (int)rem.size()) != LS_OK) ||
+        (new_factors.size() && ls_pg_add_factors(pg_, new_factors.factors().data(), (int)new_factors.size(), idx.data()) != LS_OK) ||
+        ls_pg_optimize(pg_, 1, &r.stats) < 0)
+      throw std::runtime_error(std::string("ISAM2::update: ") + ls_pg_last_error(pg_));
+    r.newFactorsIndices.assign(idx.begin(), idx.begin() + new_factors.size());
+    return r;
+  }
+  Values calculateEstimate() const {
+    int n = ls_pg_num_poses(pg_);
+    std::vector<Key> keys((size_t)(n > 0 ? n : 1));
+    std::vector<double> poses(7 * (size_t)(n > 0 ? n : 1));
+    ls_pg_get_poses(pg_, keys.data(), poses.data(), &n);
+    Values v;
+    for (int i = 0; i < n; ++i) v.insert(keys[i], Values::SE3::fromArray7(&poses[7 * (size_t)i]));
+    return v;
+  }
+
+ private:
+  ls_pg* pg_ = nullptr;
 };
 
 }  // namespace gtsam
+
+// kindr::minimal::inverse / compose on expressions (minkindr_gtsam; reference laser_track.cpp:442-448)
+namespace kindr {
+namespace minimal {
+template <typename T>
+gtsam::Expression<T> inverse(const gtsam::Expression<T>& e) { return gtsam::Expression<T>::inverseOf(e); }
+template <typename T>
+gtsam::Expression<T> compose(const gtsam::Expression<T>& a, const gtsam::Expression<T>& b) { return gtsam::Expression<T>::composeOf(a, b); }
+}  // namespace minimal
+}  // namespace kindr
 
 #endif  // LASER_SLAM_COMPAT_HPP_

@@ -52,6 +52,13 @@ typedef struct ls_icp_params {
   float cell_size;      /* level-0 cell edge [m]; <= 0 -> 1.0 */
   int leaf_split;       /* subdivide cells holding more points; <= 0 -> 32 (min 16) */
   int max_cells;        /* cap on level-0 cells; <= 0 -> 4194304 */
+  /* The DataPointsFilters sections of the chain (icp_default.yaml:1-7).  ls_icp_params_from_yaml reports them here; the
+   * registration entry points do NOT apply them -- they take clouds as given, normals included -- the caller does, with
+   * ls_keep_point / ls_estimate_normals (what PointMatcher::ICP::compute in include/laser_slam_compat/compat.hpp does). */
+  float reading_sampling_prob;    /* readingDataPointsFilters: RandomSamplingDataPointsFilter.prob; 1 = absent */
+  int reference_normals_knn;      /* referenceDataPointsFilters: (Sampling)SurfaceNormalDataPointsFilter.knn; 0 = absent */
+  float reference_sampling_ratio; /* its ratio (SamplingSurfaceNormal keeps that fraction); 1 = absent */
+  int unapplied_modules;          /* YAML modules present that the registration itself does not run (the filter sections above) */
 } ls_icp_params;
 
 typedef struct ls_icp_stats {
@@ -80,9 +87,16 @@ uint64_t ls_b200_launch_count(const ls_ctx* ctx);
 /* icp_.setDefault()-like defaults, but with the values of icp_default.yaml:9-27
  * (replaces PointMatcher::ICP::loadFromYaml at laser_slam/src/laser_track.cpp:14-21). */
 void ls_icp_default_params(ls_icp_params* p);
-/* Parse the keys of icp_default.yaml this path honours out of a YAML text; unknown modules are
- * ignored, unsupported matcher / minimiser names return LS_ERR_ARG. */
+/* Parse the keys of icp_default.yaml this path honours out of a YAML text; unsupported matcher / minimiser / outlier
+ * filter names return LS_ERR_ARG; reading / reference DataPointsFilters are reported in the params (see the struct:
+ * `unapplied_modules` counts them) because they run upstream of the registration; inspector / logger are ignored. */
 int ls_icp_params_from_yaml(const char* yaml_text, ls_icp_params* p);
+
+/* Deterministic stand-in for RandomSamplingDataPointsFilter's `rand() / RAND_MAX < prob`
+ * (laser_slam/configurations/icp_default.yaml:1-3; libpointmatcher draws from the process-global libc generator, which is
+ * not reproducible): point `index` of a cloud is kept iff hash32(index, salt) < prob * 2^32, a counter-based rule that
+ * host, device and oracle evaluate identically.  Returns 1 (keep) or 0. */
+int ls_keep_point(uint32_t index, uint32_t salt, float prob);
 
 /* ---- one-shot registration ----------------------------------------------------------------------
  * Replaces PointMatcher::ICP::compute(reading, reference, T0) at
@@ -237,6 +251,11 @@ int ls_pg_remove_factors(ls_pg* pg, const uint64_t* indices, int n);
 /* gn_iters Gauss-Newton iterations over the whole graph on the device (3 = one estimate() call:
  * update(new) + update() + update(), incremental_estimator.cpp:156-159). */
 int ls_pg_optimize(ls_pg* pg, int gn_iters, ls_pg_stats* stats);
+/* gtsam::Marginals(graph, values).marginalCovariance(key) for each of keys[0..n)
+ * (LaserTrack::updateCovariancesFromGTSAMValues, laser_slam/src/laser_track.cpp:421-429): the 6x6 block of the inverse
+ * Gauss-Newton Hessian at the CURRENT estimate (robust factors at their current Cauchy weights), tangent order
+ * [translation; rotation], row-major, 36 doubles per key. */
+int ls_pg_marginals(ls_pg* pg, const uint64_t* keys, int n, double* out_cov36);
 /* isam2.calculateEstimate(): all keys and poses (either pointer may be NULL); *n = number of poses. */
 int ls_pg_get_poses(const ls_pg* pg, uint64_t* out_keys, double* out_poses7, int* n);
 

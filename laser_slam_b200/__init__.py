@@ -30,7 +30,9 @@ class IcpParams(ctypes.Structure):
     _fields_ = [("max_iterations", ctypes.c_int), ("trim_ratio", ctypes.c_float),
                 ("use_differential", ctypes.c_int), ("min_diff_rot", ctypes.c_float),
                 ("min_diff_trans", ctypes.c_float), ("smooth_length", ctypes.c_int),
-                ("cell_size", ctypes.c_float), ("leaf_split", ctypes.c_int), ("max_cells", ctypes.c_int)]
+                ("cell_size", ctypes.c_float), ("leaf_split", ctypes.c_int), ("max_cells", ctypes.c_int),
+                ("reading_sampling_prob", ctypes.c_float), ("reference_normals_knn", ctypes.c_int),
+                ("reference_sampling_ratio", ctypes.c_float), ("unapplied_modules", ctypes.c_int)]
 
 
 class IcpStats(ctypes.Structure):
@@ -120,6 +122,8 @@ def lib():
         L.ls_pg_remove_factors.argtypes = [vp, vp, ci]
         L.ls_pg_optimize.argtypes = [vp, ci, ctypes.POINTER(PgStats)]
         L.ls_pg_get_poses.argtypes = [vp, vp, vp, ctypes.POINTER(ci)]
+        L.ls_pg_marginals.argtypes = [vp, vp, ci, vp]
+        L.ls_keep_point.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_float]
         _lib = L
     return _lib
 
@@ -138,6 +142,31 @@ def params_from_yaml(text):
     if rc != 0:
         raise LsError(f"unsupported ICP chain configuration (rc={rc})")
     return p
+
+
+def keep_mask(n, salt, prob):
+    """ls_keep_point for indices 0..n-1: the deterministic RandomSamplingDataPointsFilter rule (host side of the C ABI)."""
+    f = lib().ls_keep_point
+    return np.fromiter((f(i, salt, prob) for i in range(n)), dtype=bool, count=n)
+
+
+READING_SALT, REFERENCE_SALT = 0x7e11, 0x5a17   # the salts PointMatcher::DataPointsFilters uses (compat.hpp)
+
+
+def apply_chain_filters(ctx, reading4, ref4, ref_normals3, params):
+    """The reading / reference DataPointsFilters of an ICP chain (icp_default.yaml:1-7) as PointMatcher::ICP::compute runs
+    them before matching, in their deterministic form: RandomSampling of the reading (ls_keep_point), surface normals of
+    the reference on the device (ls_estimate_normals, exact k-NN) and its sampling.  Returns (reading, ref, ref_normals)."""
+    reading4 = np.ascontiguousarray(reading4, np.float32)
+    ref4 = np.ascontiguousarray(ref4, np.float32)
+    if params.reading_sampling_prob < 1.0:
+        reading4 = np.ascontiguousarray(reading4[keep_mask(len(reading4), READING_SALT, params.reading_sampling_prob)])
+    if params.reference_normals_knn > 0:
+        ref_normals3 = ctx.estimate_normals(ref4, knn=max(3, min(16, params.reference_normals_knn)))
+        if params.reference_sampling_ratio < 1.0:
+            keep = keep_mask(len(ref4), REFERENCE_SALT, params.reference_sampling_ratio)
+            ref4, ref_normals3 = np.ascontiguousarray(ref4[keep]), np.ascontiguousarray(ref_normals3[keep])
+    return reading4, ref4, ref_normals3
 
 
 def colmajor(T):
@@ -509,6 +538,13 @@ class PoseGraph:
         st = PgStats()
         self._check(lib().ls_pg_optimize(self._h, gn_iters, ctypes.byref(st)))
         return st
+
+    def marginals(self, keys):
+        """gtsam::Marginals::marginalCovariance per key at the current estimate: (len(keys), 6, 6), [translation; rotation]."""
+        k = np.ascontiguousarray(keys, np.uint64)
+        cov = np.zeros((max(len(k), 1), 6, 6), np.float64)
+        self._check(lib().ls_pg_marginals(self._h, k.ctypes.data, len(k), cov.ctypes.data))
+        return cov[:len(k)]
 
     def poses(self):
         n = ctypes.c_int(lib().ls_pg_num_poses(self._h))

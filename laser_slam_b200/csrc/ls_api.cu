@@ -619,6 +619,10 @@ void ls_icp_default_params(ls_icp_params* p) {
   p->cell_size = 0.f;
   p->leaf_split = 0;
   p->max_cells = 0;
+  p->reading_sampling_prob = 1.0f;
+  p->reference_normals_knn = 0;
+  p->reference_sampling_ratio = 1.0f;
+  p->unapplied_modules = 0;
 }
 
 int ls_check_rigid(const float T[16]) { return check_rigid(T); }

@@ -206,7 +206,7 @@ __global__ void pg_assemble_kernel(int P, const int* __restrict__ inc_ptr, const
 // ---------------------------------------------------------------- K6a: block-tridiagonal Cholesky, thread per track
 __global__ void pg_chain_factor_kernel(int n_tracks, const int* __restrict__ track_begin, const double* __restrict__ D,
                                        const double* __restrict__ Bsub, double* __restrict__ Ld, double* __restrict__ Ls,
-                                       int* fail) {
+                                       double* __restrict__ Ldi /* 6 per pose: 1 / diag(Ld) */, int* fail) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_tracks) return;
   double Lprev[36];
@@ -244,6 +244,7 @@ __global__ void pg_chain_factor_kernel(int n_tracks, const int* __restrict__ tra
       }
     }
     for (int i = 0; i < 36; ++i) { Ld[36 * (size_t)k + i] = L[i]; Ls[36 * (size_t)k + i] = S[i]; Lprev[i] = L[i]; }
+    for (int i = 0; i < 6; ++i) Ldi[6 * (size_t)k + i] = 1.0 / L[6 * i + i];  // the sweeps multiply instead of dividing
   }
 }
 
@@ -252,7 +253,7 @@ __global__ void pg_chain_factor_kernel(int n_tracks, const int* __restrict__ tra
 __global__ void pg_chain_solve_kernel(int P, int ncol, const FactorDev* __restrict__ fac, const int* __restrict__ extra_fac,
                                       const double* __restrict__ Ja, const double* __restrict__ Jb,
                                       const double* __restrict__ g, const double* __restrict__ Ld,
-                                      const double* __restrict__ Ls, double* __restrict__ Z) {
+                                      const double* __restrict__ Ls, const double* __restrict__ Ldi, double* __restrict__ Z) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncol) return;
   int ia = -2, ib = -2, row = 0;
@@ -266,7 +267,11 @@ __global__ void pg_chain_solve_kernel(int P, int ncol, const FactorDev* __restri
     jb = Jb + 36 * (size_t)f + 6 * row;
   }
   double y[6] = {0, 0, 0, 0, 0, 0};
-  for (int k = 0; k < P; ++k) {  // forward: y_k = Ld_k^-1 (b_k - Ls_k y_{k-1});  Ls_k == 0 at the start of a track
+  // a border column is zero above its first pose: so is its forward solution (the gradient column starts at 0)
+  const int kstart = c == 0 ? 0 : (ia >= 0 && ia < ib ? ia : ib);
+  for (int k = 0; k < kstart; ++k)
+    for (int i = 0; i < 6; ++i) Z[((size_t)k * 6 + i) * ncol + c] = 0.0;
+  for (int k = kstart; k < P; ++k) {  // forward: y_k = Ld_k^-1 (b_k - Ls_k y_{k-1});  Ls_k == 0 at the start of a track
     double b[6];
     for (int i = 0; i < 6; ++i) b[i] = (c == 0) ? -g[6 * (size_t)k + i] : (k == ia ? ja[i] : 0.0) + (k == ib ? jb[i] : 0.0);
     const double* S = Ls + 36 * (size_t)k;
@@ -276,10 +281,11 @@ __global__ void pg_chain_solve_kernel(int P, int ncol, const FactorDev* __restri
       for (int m = 0; m < 6; ++m) s += S[6 * i + m] * y[m];
       b[i] -= s;
     }
+    const double* Li = Ldi + 6 * (size_t)k;
     for (int i = 0; i < 6; ++i) {
       double v = b[i];
       for (int m = 0; m < i; ++m) v -= L[6 * i + m] * b[m];
-      b[i] = v / L[6 * i + i];
+      b[i] = v * Li[i];
     }
     for (int i = 0; i < 6; ++i) { y[i] = b[i]; Z[((size_t)k * 6 + i) * ncol + c] = b[i]; }
   }
@@ -296,10 +302,11 @@ __global__ void pg_chain_solve_kernel(int P, int ncol, const FactorDev* __restri
       }
     }
     const double* L = Ld + 36 * (size_t)k;
+    const double* Li = Ldi + 6 * (size_t)k;
     for (int i = 5; i >= 0; --i) {
       double v = b[i];
       for (int m = i + 1; m < 6; ++m) v -= L[6 * m + i] * b[m];
-      b[i] = v / L[6 * i + i];
+      b[i] = v * Li[i];
     }
     for (int i = 0; i < 6; ++i) { x[i] = b[i]; Z[((size_t)k * 6 + i) * ncol + c] = b[i]; }
   }
@@ -433,6 +440,113 @@ __global__ void pg_update_kernel(int P, int ncol, const double* __restrict__ Z, 
   for (int i = 0; i < 4; ++i) X[i] = o[i] * n;
 }
 
+// ---------------------------------------------------------------- marginal covariances (gtsam::Marginals)
+// Sigma_kk = (H^-1)_kk at the current estimate, for a chunk of requested poses.  Column c = 6*q + j is the unit vector
+// e_(pose[q], j): X = H_c^-1 E by the chain sweeps (restricted to the pose's own track), then the border correction
+// through the same Woodbury identity as the update: Sigma = X - Z S^-1 (U X), of which only the 6x6 block of rows
+// pose[q] is wanted.  X layout as Z: X[(k*6+i)*ncol + c].
+__global__ void pg_chain_solve_unit_kernel(int ncol, const int* __restrict__ qpos, const int* __restrict__ track_begin_of,
+                                           const int* __restrict__ track_end_of, const double* __restrict__ Ld,
+                                           const double* __restrict__ Ls, const double* __restrict__ Ldi, double* __restrict__ X) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncol) return;
+  const int kp = qpos[c / 6], comp = c % 6;
+  const int k0 = track_begin_of[c / 6], k1 = track_end_of[c / 6];
+  double y[6] = {0, 0, 0, 0, 0, 0};
+  for (int k = kp; k < k1; ++k) {  // forward (zero before kp)
+    double b[6];
+    for (int i = 0; i < 6; ++i) b[i] = (k == kp && i == comp) ? 1.0 : 0.0;
+    const double* S = Ls + 36 * (size_t)k;
+    const double* L = Ld + 36 * (size_t)k;
+    if (k > kp)
+      for (int i = 0; i < 6; ++i) {
+        double s = 0.0;
+        for (int m = 0; m < 6; ++m) s += S[6 * i + m] * y[m];
+        b[i] -= s;
+      }
+    const double* Li = Ldi + 6 * (size_t)k;
+    for (int i = 0; i < 6; ++i) {
+      double v = b[i];
+      for (int m = 0; m < i; ++m) v -= L[6 * i + m] * b[m];
+      b[i] = v * Li[i];
+    }
+    for (int i = 0; i < 6; ++i) { y[i] = b[i]; X[((size_t)k * 6 + i) * ncol + c] = b[i]; }
+  }
+  double x[6] = {0, 0, 0, 0, 0, 0};
+  for (int k = k1 - 1; k >= k0; --k) {  // backward over the whole track
+    double b[6];
+    for (int i = 0; i < 6; ++i) b[i] = k >= kp ? X[((size_t)k * 6 + i) * ncol + c] : 0.0;
+    if (k + 1 < k1) {
+      const double* S = Ls + 36 * (size_t)(k + 1);
+      for (int i = 0; i < 6; ++i) {
+        double s = 0.0;
+        for (int m = 0; m < 6; ++m) s += S[6 * m + i] * x[m];
+        b[i] -= s;
+      }
+    }
+    const double* L = Ld + 36 * (size_t)k;
+    const double* Li = Ldi + 6 * (size_t)k;
+    for (int i = 5; i >= 0; --i) {
+      double v = b[i];
+      for (int m = i + 1; m < 6; ++m) v -= L[6 * m + i] * b[m];
+      b[i] = v * Li[i];
+    }
+    for (int i = 0; i < 6; ++i) { x[i] = b[i]; X[((size_t)k * 6 + i) * ncol + c] = b[i]; }
+  }
+}
+
+// T = U X for the border rows (n of them, padded to n16 with zeros): T[row*ncol + c].  X is zero outside the column's track.
+__global__ void pg_border_rhs_kernel(int n, int n16, int ncol, const FactorDev* __restrict__ fac, const int* __restrict__ extra_fac,
+                                     const double* __restrict__ Ja, const double* __restrict__ Jb, const int* __restrict__ tb,
+                                     const int* __restrict__ te, const double* __restrict__ X, double* __restrict__ T) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int rowi = blockIdx.y;
+  if (c >= ncol || rowi >= n16) return;
+  double v = 0.0;
+  if (rowi < n) {
+    const int f = extra_fac[rowi / 6], rr = rowi % 6;
+    const int ia = fac[f].ia, ib = fac[f].ib;
+    const int k0 = tb[c / 6], k1 = te[c / 6];
+    const double* ja = Ja + 36 * (size_t)f + 6 * rr;
+    const double* jb = Jb + 36 * (size_t)f + 6 * rr;
+    if (ia >= k0 && ia < k1)
+      for (int i = 0; i < 6; ++i) v += ja[i] * X[((size_t)ia * 6 + i) * ncol + c];
+    if (ib >= k0 && ib < k1)
+      for (int i = 0; i < 6; ++i) v += jb[i] * X[((size_t)ib * 6 + i) * ncol + c];
+  }
+  T[(size_t)rowi * ncol + c] = v;
+}
+
+// many right-hand sides against the dense factor (thread per column; W[row*ncol + c], coalesced across the threads)
+__global__ void dense_solve_multi_kernel(int n16, int ncol, const double* __restrict__ A, double* __restrict__ W) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncol) return;
+  for (int j = 0; j < n16; ++j) {
+    double v = W[(size_t)j * ncol + c];
+    for (int m = 0; m < j; ++m) v -= A[(size_t)j * n16 + m] * W[(size_t)m * ncol + c];
+    W[(size_t)j * ncol + c] = v / A[(size_t)j * n16 + j];
+  }
+  for (int j = n16 - 1; j >= 0; --j) {
+    double v = W[(size_t)j * ncol + c];
+    for (int m = j + 1; m < n16; ++m) v -= A[(size_t)m * n16 + j] * W[(size_t)m * ncol + c];
+    W[(size_t)j * ncol + c] = v / A[(size_t)j * n16 + j];
+  }
+}
+
+// cov[q][i][j] = X[(pose q, i)][6q + j] - sum_r Z[(pose q, i)][1 + r] * W[r][6q + j]
+__global__ void pg_marginal_block_kernel(int nq, int ncol, int n, int ncolZ, const int* __restrict__ qpos,
+                                         const double* __restrict__ X, const double* __restrict__ Z, const double* __restrict__ W,
+                                         double* __restrict__ cov) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nq * 36) return;
+  const int q = e / 36, i = (e % 36) / 6, j = e % 6;
+  const int kp = qpos[q], c = 6 * q + j;
+  double v = X[((size_t)kp * 6 + i) * ncol + c];
+  const double* zr = Z + ((size_t)kp * 6 + i) * ncolZ + 1;
+  for (int r = 0; r < n; ++r) v -= zr[r] * W[(size_t)r * ncol + c];
+  cov[e] = v;
+}
+
 struct HostFactor {
   ls_factor f;
   bool active;
@@ -455,10 +569,15 @@ struct ls_pg {
   size_t capF = 0, capP = 0, capZ = 0, capS = 0, capInc = 0, capE = 0;
   FactorDev* d_fac = nullptr;
   double *d_poses = nullptr, *d_Ja = nullptr, *d_Jb = nullptr, *d_r = nullptr, *d_D = nullptr, *d_B = nullptr,
-         *d_g = nullptr, *d_Ld = nullptr, *d_Ls = nullptr, *d_Z = nullptr, *d_S = nullptr, *d_rhs = nullptr, *d_cost = nullptr;
+         *d_g = nullptr, *d_Ld = nullptr, *d_Ls = nullptr, *d_Ldi = nullptr, *d_Z = nullptr, *d_S = nullptr, *d_rhs = nullptr, *d_cost = nullptr;
   int *d_inc_ptr = nullptr, *d_inc_fac = nullptr, *d_extra = nullptr, *d_track_begin = nullptr, *d_fail = nullptr,
       *d_damp = nullptr;
   unsigned long long* d_dmax = nullptr;
+  // marginals scratch
+  size_t capX = 0, capW = 0, capQ = 0;
+  double *d_X = nullptr, *d_W = nullptr, *d_cov = nullptr;
+  int *d_qpos = nullptr, *d_qtb = nullptr, *d_qte = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
 };
 
 namespace {
@@ -496,9 +615,12 @@ int ls_pg_create(int device, ls_pg** out) {
   pg->device = device;
   cudaSetDevice(device);
   if (cudaStreamCreateWithFlags(&pg->stream, cudaStreamNonBlocking) != cudaSuccess) { delete pg; return LS_ERR_CUDA; }
-  cudaMalloc((void**)&pg->d_cost, sizeof(double));
-  cudaMalloc((void**)&pg->d_fail, sizeof(int));
-  cudaMalloc((void**)&pg->d_dmax, sizeof(unsigned long long));
+  if (cudaMalloc((void**)&pg->d_cost, sizeof(double)) != cudaSuccess || cudaMalloc((void**)&pg->d_fail, sizeof(int)) != cudaSuccess ||
+      cudaMalloc((void**)&pg->d_dmax, sizeof(unsigned long long)) != cudaSuccess || cudaEventCreate(&pg->e0) != cudaSuccess ||
+      cudaEventCreate(&pg->e1) != cudaSuccess) {
+    ls_pg_destroy(pg);
+    return LS_ERR_NOMEM;
+  }
   *out = pg;
   return LS_OK;
 }
@@ -507,11 +629,13 @@ void ls_pg_destroy(ls_pg* pg) {
   if (!pg) return;
   cudaSetDevice(pg->device);
   if (pg->stream) cudaStreamSynchronize(pg->stream);
-  void* bufs[] = {pg->d_fac, pg->d_poses, pg->d_Ja, pg->d_Jb, pg->d_r, pg->d_D, pg->d_B, pg->d_g, pg->d_Ld, pg->d_Ls, pg->d_Z,
+  void* bufs[] = {pg->d_fac, pg->d_poses, pg->d_Ja, pg->d_Jb, pg->d_r, pg->d_D, pg->d_B, pg->d_g, pg->d_Ld, pg->d_Ls, pg->d_Ldi, pg->d_Z,
                   pg->d_S, pg->d_rhs, pg->d_cost, pg->d_inc_ptr, pg->d_inc_fac, pg->d_extra, pg->d_track_begin, pg->d_fail,
-                  pg->d_dmax, pg->d_damp};
+                  pg->d_dmax, pg->d_damp, pg->d_X, pg->d_W, pg->d_cov, pg->d_qpos, pg->d_qtb, pg->d_qte};
   for (void* b : bufs)
     if (b) cudaFree(b);
+  if (pg->e0) cudaEventDestroy(pg->e0);
+  if (pg->e1) cudaEventDestroy(pg->e1);
   if (pg->stream) cudaStreamDestroy(pg->stream);
   delete pg;
 }
@@ -577,11 +701,15 @@ int ls_pg_get_poses(const ls_pg* pg, uint64_t* out_keys, double* out_poses7, int
   return LS_OK;
 }
 
-int ls_pg_optimize(ls_pg* pg, int gn_iters, ls_pg_stats* stats) {
-  if (!pg || gn_iters < 0) return pg_fail(pg, LS_ERR_ARG, "bad argument");
+}  // extern "C"
+
+namespace {
+// gn_iters Gauss-Newton iterations, then -- when n_mk > 0 -- the marginal covariances of the poses mkeys[0..n_mk) at
+// the resulting estimate (one more linearisation, no update).
+int pg_run(ls_pg* pg, int gn_iters, ls_pg_stats* stats, const uint64_t* mkeys, int n_mk, double* cov_out) {
   if (stats) std::memset(stats, 0, sizeof(*stats));
   const int P = (int)pg->keys.size();
-  if (P == 0 || gn_iters == 0) return LS_OK;
+  if (P == 0 || (gn_iters == 0 && n_mk == 0)) return LS_OK;
   PGCU(cudaSetDevice(pg->device));
   // ---- ordering: track by track, insertion order inside a track (= time order in laser_slam)
   std::map<uint32_t, std::vector<int>> by_track;
@@ -682,7 +810,7 @@ int ls_pg_optimize(ls_pg* pg, int gn_iters, ls_pg_stats* stats) {
   if ((size_t)P > pg->capP) {
     const size_t cap = (size_t)P + P / 4 + 64;
     if ((rc = grow(pg, &pg->d_poses, cap * 7)) || (rc = grow(pg, &pg->d_D, cap * 36)) || (rc = grow(pg, &pg->d_B, cap * 36)) ||
-        (rc = grow(pg, &pg->d_g, cap * 6)) || (rc = grow(pg, &pg->d_Ld, cap * 36)) || (rc = grow(pg, &pg->d_Ls, cap * 36)) ||
+        (rc = grow(pg, &pg->d_g, cap * 6)) || (rc = grow(pg, &pg->d_Ld, cap * 36)) || (rc = grow(pg, &pg->d_Ls, cap * 36)) || (rc = grow(pg, &pg->d_Ldi, cap * 6)) ||
         (rc = grow(pg, &pg->d_inc_ptr, cap + 1)) || (rc = grow(pg, &pg->d_track_begin, cap + 1)) ||
         (rc = grow(pg, &pg->d_damp, cap + 1)))
       return rc;
@@ -715,21 +843,21 @@ int ls_pg_optimize(ls_pg* pg, int gn_iters, ls_pg_stats* stats) {
   PGCU(cudaMemcpyAsync(pg->d_track_begin, track_begin.data(), track_begin.size() * sizeof(int), cudaMemcpyHostToDevice, st));
   PGCU(cudaMemcpyAsync(pg->d_damp, damp.data(), (size_t)P * sizeof(int), cudaMemcpyHostToDevice, st));
   PGCU(cudaMemsetAsync(pg->d_fail, 0, sizeof(int), st));
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0);
-  cudaEventCreate(&e1);
+  cudaEvent_t e0 = pg->e0, e1 = pg->e1;
   cudaEventRecord(e0, st);
   double cost_first = 0.0, cost_last = 0.0, dmax_last = 0.0;
-  for (int it = 0; it < gn_iters; ++it) {
+  const int n_pass = gn_iters + (n_mk > 0 ? 1 : 0);  // the last pass of a marginals request only linearises and factors
+  for (int it = 0; it < n_pass; ++it) {
+    const bool update = it < gn_iters;
     PGCU(cudaMemsetAsync(pg->d_cost, 0, sizeof(double), st));
     PGCU(cudaMemsetAsync(pg->d_dmax, 0, sizeof(unsigned long long), st));
     pg_linearize_kernel<<<(F + 127) / 128, 128, 0, st>>>(F, pg->d_fac, pg->d_poses, pg->d_Ja, pg->d_Jb, pg->d_r, pg->d_cost);
     pg_assemble_kernel<<<(P + 127) / 128, 128, 0, st>>>(P, pg->d_inc_ptr, pg->d_inc_fac, pg->d_fac, pg->d_Ja, pg->d_Jb, pg->d_r,
                                                         pg->d_damp, pg->d_D, pg->d_B, pg->d_g);
     pg_chain_factor_kernel<<<(n_tracks + 31) / 32, 32, 0, st>>>(n_tracks, pg->d_track_begin, pg->d_D, pg->d_B, pg->d_Ld, pg->d_Ls,
-                                                                pg->d_fail);
+                                                                pg->d_Ldi, pg->d_fail);
     pg_chain_solve_kernel<<<(ncol + 63) / 64, 64, 0, st>>>(P, ncol, pg->d_fac, pg->d_extra, pg->d_Ja, pg->d_Jb, pg->d_g, pg->d_Ld,
-                                                           pg->d_Ls, pg->d_Z);
+                                                           pg->d_Ls, pg->d_Ldi, pg->d_Z);
     pg->launches += 4;
     if (E) {
       pg_border_kernel<<<dim3((n16 + 1 + 127) / 128, n16), 128, 0, st>>>(n, n16, ncol, pg->d_fac, pg->d_extra, pg->d_Ja, pg->d_Jb,
@@ -741,9 +869,12 @@ int ls_pg_optimize(ls_pg* pg, int gn_iters, ls_pg_stats* stats) {
         if (rem > 0) dense_update_kernel<<<dim3(rem, rem), dim3(NB, NB), 0, st>>>(n16, p, pg->d_S);
         pg->launches += rem > 0 ? 2 : 1;
       }
-      dense_solve_kernel<<<1, 1024, 0, st>>>(n16, pg->d_S, pg->d_rhs);
-      ++pg->launches;
+      if (update) {
+        dense_solve_kernel<<<1, 1024, 0, st>>>(n16, pg->d_S, pg->d_rhs);
+        ++pg->launches;
+      }
     }
+    if (!update) break;
     pg_update_kernel<<<(P * 32 + 255) / 256, 256, 0, st>>>(P, ncol, pg->d_Z, pg->d_rhs, pg->d_poses, pg->d_dmax);
     ++pg->launches;
     if (it == 0 || it == gn_iters - 1) {
@@ -757,6 +888,48 @@ int ls_pg_optimize(ls_pg* pg, int gn_iters, ls_pg_stats* stats) {
       std::memcpy(&dmax_last, &dm, sizeof(double));
     }
   }
+  // ---- marginal covariances at the estimate just linearised: chunks of requested poses
+  if (n_mk > 0) {
+    constexpr int kChunk = 64;
+    std::vector<int> qpos(n_mk), qtb(n_mk), qte(n_mk);
+    for (int q = 0; q < n_mk; ++q) {
+      auto it = pg->key_index.find(mkeys[q]);
+      if (it == pg->key_index.end()) return pg_fail(pg, LS_ERR_ARG, "marginal of an unknown key");
+      qpos[q] = pos_of[it->second];
+      qtb[q] = track_begin[track_of_pos[qpos[q]]];
+      qte[q] = track_begin[track_of_pos[qpos[q]] + 1];
+    }
+    const int ncm = 6 * kChunk;
+    const size_t needX = (size_t)P * 6 * ncm, needW = (size_t)(n16 > 0 ? n16 : 1) * ncm;
+    if (needX > pg->capX) { if ((rc = grow(pg, &pg->d_X, needX))) return rc; pg->capX = needX; }
+    if (needW > pg->capW) { if ((rc = grow(pg, &pg->d_W, needW))) return rc; pg->capW = needW; }
+    if ((size_t)n_mk > pg->capQ) {
+      const size_t cap = (size_t)n_mk + 64;
+      if ((rc = grow(pg, &pg->d_qpos, cap)) || (rc = grow(pg, &pg->d_qtb, cap)) || (rc = grow(pg, &pg->d_qte, cap)) ||
+          (rc = grow(pg, &pg->d_cov, cap * 36)))
+        return rc;
+      pg->capQ = cap;
+    }
+    PGCU(cudaMemcpyAsync(pg->d_qpos, qpos.data(), (size_t)n_mk * sizeof(int), cudaMemcpyHostToDevice, st));
+    PGCU(cudaMemcpyAsync(pg->d_qtb, qtb.data(), (size_t)n_mk * sizeof(int), cudaMemcpyHostToDevice, st));
+    PGCU(cudaMemcpyAsync(pg->d_qte, qte.data(), (size_t)n_mk * sizeof(int), cudaMemcpyHostToDevice, st));
+    for (int q0 = 0; q0 < n_mk; q0 += kChunk) {
+      const int nq = n_mk - q0 < kChunk ? n_mk - q0 : kChunk, nc = 6 * nq;
+      PGCU(cudaMemsetAsync(pg->d_X, 0, (size_t)P * 6 * nc * sizeof(double), st));
+      pg_chain_solve_unit_kernel<<<(nc + 63) / 64, 64, 0, st>>>(nc, pg->d_qpos + q0, pg->d_qtb + q0, pg->d_qte + q0, pg->d_Ld, pg->d_Ls, pg->d_Ldi, pg->d_X);
+      ++pg->launches;
+      if (E) {
+        pg_border_rhs_kernel<<<dim3((nc + 127) / 128, n16), 128, 0, st>>>(n, n16, nc, pg->d_fac, pg->d_extra, pg->d_Ja, pg->d_Jb,
+                                                                          pg->d_qtb + q0, pg->d_qte + q0, pg->d_X, pg->d_W);
+        dense_solve_multi_kernel<<<(nc + 63) / 64, 64, 0, st>>>(n16, nc, pg->d_S, pg->d_W);
+        pg->launches += 2;
+      }
+      pg_marginal_block_kernel<<<(nq * 36 + 127) / 128, 128, 0, st>>>(nq, nc, E ? n : 0, ncol, pg->d_qpos + q0, pg->d_X, pg->d_Z,
+                                                                      pg->d_W, pg->d_cov + 36 * (size_t)q0);
+      ++pg->launches;
+    }
+    PGCU(cudaMemcpyAsync(cov_out, pg->d_cov, (size_t)n_mk * 36 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  }
   cudaEventRecord(e1, st);
   int fail = 0;
   PGCU(cudaMemcpyAsync(&fail, pg->d_fail, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -765,8 +938,6 @@ int ls_pg_optimize(ls_pg* pg, int gn_iters, ls_pg_stats* stats) {
   PGCU(cudaGetLastError());
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e0, e1);
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   if (fail) return pg_fail(pg, LS_ERR_CONVERGENCE, "chain block not positive definite (under-constrained graph)");
   for (int k = 0; k < P; ++k)
     for (int i = 0; i < 7; ++i)
@@ -783,6 +954,20 @@ int ls_pg_optimize(ls_pg* pg, int gn_iters, ls_pg_stats* stats) {
     stats->device_ms = ms;
   }
   return LS_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int ls_pg_optimize(ls_pg* pg, int gn_iters, ls_pg_stats* stats) {
+  if (!pg || gn_iters < 0) return pg_fail(pg, LS_ERR_ARG, "bad argument");
+  return pg_run(pg, gn_iters, stats, nullptr, 0, nullptr);
+}
+
+int ls_pg_marginals(ls_pg* pg, const uint64_t* keys, int n, double* out_cov36) {
+  if (!pg || !keys || !out_cov36 || n < 0) return pg_fail(pg, LS_ERR_ARG, "bad argument");
+  if (n == 0) return LS_OK;
+  return pg_run(pg, 0, nullptr, keys, n, out_cov36);
 }
 
 }  // extern "C"

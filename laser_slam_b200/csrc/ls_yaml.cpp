@@ -22,6 +22,17 @@ std::string trim(const std::string& s) {
 
 }  // namespace
 
+// hash32: two rounds of a multiply-xorshift mixer over (index, salt); the oracle restates it (oracle/__init__.py keep_mask)
+extern "C" int ls_keep_point(uint32_t index, uint32_t salt, float prob) {
+  if (!(prob < 1.0f)) return 1;
+  if (!(prob > 0.0f)) return 0;
+  uint32_t h = index * 0x9E3779B1u + salt * 0x85EBCA77u + 0x165667B1u;
+  h ^= h >> 15; h *= 0x2C1B3C6Du;
+  h ^= h >> 12; h *= 0x297A2D39u;
+  h ^= h >> 15;
+  return (double)h < (double)prob * 4294967296.0 ? 1 : 0;
+}
+
 extern "C" int ls_icp_params_from_yaml(const char* yaml_text, ls_icp_params* p) {
   if (!yaml_text || !p) return LS_ERR_ARG;
   ls_icp_default_params(p);
@@ -64,12 +75,26 @@ extern "C" int ls_icp_params_from_yaml(const char* yaml_text, ls_icp_params* p) 
         if (module != "TrimmedDistOutlierFilter") return LS_ERR_ARG;
         saw_trim = true;
       }
+      if (section == "readingDataPointsFilters" || section == "referenceDataPointsFilters") {
+        ++p->unapplied_modules;  // reported, applied by the caller (ls_keep_point / ls_estimate_normals)
+        if (section == "referenceDataPointsFilters" && module.find("SurfaceNormal") != std::string::npos && p->reference_normals_knn == 0)
+          p->reference_normals_knn = 5;  // libpointmatcher's default knn of the surface-normal filters
+      }
       if (module == "CounterTransformationChecker") saw_counter = true;
       if (module == "DifferentialTransformationChecker") saw_diff = true;
       continue;
     }
     if (val.empty()) continue;
     const double num = std::atof(val.c_str());
+    if (section == "readingDataPointsFilters" || section == "referenceDataPointsFilters") {
+      const bool reading = section == "readingDataPointsFilters";
+      if (module == "RandomSamplingDataPointsFilter" && key == "prob" && reading) p->reading_sampling_prob = (float)num;
+      if ((module == "SamplingSurfaceNormalDataPointsFilter" || module == "SurfaceNormalDataPointsFilter") && !reading) {
+        if (key == "knn") p->reference_normals_knn = (int)num;
+        if (key == "ratio") p->reference_sampling_ratio = (float)num;
+      }
+      continue;
+    }
     if (module == "KDTreeMatcher") {
       if (key == "knn" && (int)num != 1) return LS_ERR_ARG;         // only 1-NN is built
       if (key == "epsilon" && num != 0.0) return LS_ERR_ARG;        // only the exact search is built

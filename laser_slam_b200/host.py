@@ -28,6 +28,7 @@ def lib():
         L.lsh_last_error.restype = ctypes.c_char_p
         L.lsh_step.argtypes = [vp, ci, i64, vp, vp, vp, ci, vp, ctypes.POINTER(IcpStats)]
         L.lsh_loop_closure.argtypes = [vp, ci, i64, ci, i64, vp]
+        L.lsh_step_batch.argtypes = [vp, ci, vp, vp, vp, vp, vp, vp, ci, vp, vp]
         L.lsh_trajectory.argtypes = [vp, ci, vp, vp, ci]
         L.lsh_num_scans.argtypes = [vp, ci]
         L.lsh_build_submap.argtypes = [vp, ci, i64, ci, vp, vp, ci]
@@ -75,6 +76,24 @@ class Estimator:
         self._check(lib().lsh_step(self._h, worker, int(time_ns), p.ctypes.data, f.ctypes.data, nr.ctypes.data, f.shape[0],
                                    out.ctypes.data, ctypes.byref(st)))
         return out, st
+
+    def step_batch(self, workers, times_ns, poses7, feat_ptrs, nrm_ptrs, ns, with_estimator=True):
+        """The scan callbacks of several workers at once: one batched launch registers them all
+        (IncrementalEstimator::processPosesAndLaserScans).  feat_ptrs / nrm_ptrs: host addresses of each worker's
+        4xN features and 3xN normals.  Returns (icp T_a_b (len,7), list of IcpStats)."""
+        k = len(workers)
+        w = np.ascontiguousarray(workers, np.int32)
+        t = np.ascontiguousarray(times_ns, np.int64)
+        p = np.ascontiguousarray(poses7, np.float64).reshape(k, 7)
+        fp = (ctypes.c_void_p * k)(*[int(a) for a in feat_ptrs])
+        npp = (ctypes.c_void_p * k)(*[int(a) for a in nrm_ptrs])
+        nn = np.ascontiguousarray(ns, np.int32)
+        out = np.zeros((k, 7), np.float64)
+        st = (IcpStats * k)()
+        self._check(lib().lsh_step_batch(self._h, k, w.ctypes.data, t.ctypes.data, p.ctypes.data, ctypes.cast(fp, ctypes.c_void_p),
+                                         ctypes.cast(npp, ctypes.c_void_p), nn.ctypes.data, int(with_estimator), out.ctypes.data,
+                                         ctypes.cast(st, ctypes.c_void_p)))
+        return out, list(st)
 
     def loop_closure(self, track_a, time_a, track_b, time_b, w_T_a_b7):
         p = np.ascontiguousarray(w_T_a_b7, np.float64)

@@ -4,6 +4,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <vector>
 
 #include "laser_slam/incremental_estimator.hpp"
 
@@ -80,6 +81,45 @@ int lsh_step(void* hv, int worker, int64_t time_ns, const double* pose7, const f
       T.toArray7(out_icp7);
     }
     if (out_stats) *out_stats = track->getLastIcpStats();
+    return LS_OK;
+  });
+}
+
+// The scan callbacks of `n_workers` workers at once (IncrementalEstimator::processPosesAndLaserScans: one batched
+// launch for all registrations), each followed by registerPrior / estimate and updateFromGTSAMValues exactly as
+// lsh_step does.  pose7: 7 doubles per worker; feat4 / normals3: per-worker host pointers; n: points per worker.
+// out_icp7 (may be NULL): 7 doubles per worker.  with_estimator == 0 skips the pose-graph update (odometry only).
+int lsh_step_batch(void* hv, int n_workers, const int* workers, const int64_t* times_ns, const double* pose7, const float* const* feat4,
+                   const float* const* normals3, const int* n, int with_estimator, double* out_icp7, ls_icp_stats* out_stats) {
+  Handle* h = static_cast<Handle*>(hv);
+  return guarded(h, [&]() {
+    std::vector<unsigned int> ids;
+    std::vector<Pose> poses((size_t)n_workers);
+    std::vector<LaserScan> scans((size_t)n_workers);
+    for (int i = 0; i < n_workers; ++i) {
+      ids.push_back((unsigned int)workers[i]);
+      poses[i].T_w = SE3::fromArray7(pose7 + 7 * (size_t)i);
+      poses[i].time_ns = times_ns[i];
+      scans[i].scan = DataPoints::fromArrays(feat4[i], normals3[i], (size_t)n[i]);
+      scans[i].time_ns = times_ns[i];
+    }
+    std::vector<gtsam::NonlinearFactorGraph> nf;
+    std::vector<gtsam::Values> nv;
+    std::vector<bool> prior;
+    h->est->processPosesAndLaserScans(ids, poses, scans, &nf, &nv, &prior);
+    for (int i = 0; i < n_workers; ++i) {
+      std::shared_ptr<LaserTrack> track = h->est->getLaserTrack(ids[i]);
+      if (with_estimator) {
+        gtsam::Values result = prior[i] ? h->est->registerPrior(nf[i], nv[i], ids[i]) : h->est->estimate(nf[i], nv[i], times_ns[i]);
+        track->updateFromGTSAMValues(result);
+      }
+      if (out_icp7) {
+        SE3 T;
+        if (!track->getIcpTransformations().empty() && !prior[i]) T = track->getIcpTransformations().back().T_a_b;
+        T.toArray7(out_icp7 + 7 * (size_t)i);
+      }
+      if (out_stats) out_stats[i] = track->getLastIcpStats();
+    }
     return LS_OK;
   });
 }

@@ -24,10 +24,20 @@ IncrementalEstimator::IncrementalEstimator(const EstimatorParams& parameters, un
   std::memset(&last_stats_, 0, sizeof(last_stats_));
   if (ls_pg_create(params_.laser_track_params.cuda_device, &graph_) != LS_OK)
     throw std::runtime_error("ls_pg_create failed: no usable CUDA device (no CPU fallback)");
+  // all tracks live on one device context and share one scan ring (every track may count on nscan_in_sub_map + 4
+  // slots), so that processPosesAndLaserScans can register them in one batched launch
+  if (ls_b200_init(params_.laser_track_params.cuda_device, &track_ctx_) != LS_OK)
+    throw std::runtime_error("ls_b200_init failed: no usable CUDA device (no CPU fallback)");
+  const int slots = std::max(8, params_.laser_track_params.nscan_in_sub_map + 4);
+  track_ring_capacity_ = slots * (int)std::max(1u, n_laser_slam_workers_);
   for (unsigned int i = 0u; i < n_laser_slam_workers_; ++i)
-    laser_tracks_.push_back(std::make_shared<LaserTrack>(params_.laser_track_params, i));
-  loop_closure_noise_model_ = gtsam::NoiseModel{params_.loop_closure_noise_model, params_.add_m_estimator_on_loop_closures};
-  first_association_noise_model_ = gtsam::NoiseModel{{{0.05, 0.05, 0.05, 0.015, 0.015, 0.015}}, false};  // reference :40-48
+    laser_tracks_.push_back(std::make_shared<LaserTrack>(params_.laser_track_params, i, track_ctx_, &track_ring_,
+                                                         &track_ring_capacity_, &track_ring_max_pts_, slots));
+  using namespace gtsam::noiseModel;
+  loop_closure_noise_model_ = Diagonal::Sigmas(params_.loop_closure_noise_model);
+  if (params_.add_m_estimator_on_loop_closures)
+    loop_closure_noise_model_ = Robust::Create(mEstimator::Cauchy::Create(1), loop_closure_noise_model_);
+  first_association_noise_model_ = Diagonal::Sigmas(std::array<double, 6>{{0.05, 0.05, 0.05, 0.015, 0.015, 0.015}});  // reference :40-48
   // same chain as the lidar odometry (reference :50-60)
   ls_icp_default_params(&icp_params_);
   std::ifstream ifs(params_.laser_track_params.icp_configuration_file.c_str());
@@ -44,8 +54,69 @@ IncrementalEstimator::IncrementalEstimator(const EstimatorParams& parameters, un
 
 IncrementalEstimator::~IncrementalEstimator() {
   laser_tracks_.clear();
+  if (track_ring_) ls_map_destroy(track_ring_);
+  if (track_ctx_) ls_b200_destroy(track_ctx_);
   if (icp_ctx_) ls_b200_destroy(icp_ctx_);
   if (graph_) ls_pg_destroy(graph_);
+}
+
+// (new) the scan callbacks of several workers, registrations batched (see the header)
+void IncrementalEstimator::processPosesAndLaserScans(const std::vector<unsigned int>& worker_ids, const std::vector<Pose>& poses,
+                                                     const std::vector<LaserScan>& scans,
+                                                     std::vector<gtsam::NonlinearFactorGraph>* new_factors,
+                                                     std::vector<gtsam::Values>* new_values, std::vector<bool>* is_prior) {
+  std::lock_guard<std::recursive_mutex> lock(full_class_mutex_);
+  const size_t n = worker_ids.size();
+  LS_CHECK(poses.size() == n && scans.size() == n, "one pose and one scan per worker");
+  LS_CHECK(new_factors != NULL && new_values != NULL && is_prior != NULL, "null output");
+  new_factors->assign(n, gtsam::NonlinearFactorGraph());
+  new_values->assign(n, gtsam::Values());
+  is_prior->assign(n, false);
+  std::vector<LaserTrack::PendingIcp> pending(n);
+  std::vector<size_t> active;
+  for (size_t i = 0; i < n; ++i) {
+    LS_CHECK(worker_ids[i] < laser_tracks_.size(), "bad worker id");
+    for (size_t j = 0; j < i; ++j) LS_CHECK(worker_ids[j] != worker_ids[i], "a worker may appear once per step");
+    laser_tracks_[worker_ids[i]]->beginPoseAndLaserScan(poses[i], scans[i], &pending[i]);
+    if (pending[i].active) active.push_back(i);
+  }
+  // a scan uploaded by a later track may have evicted an earlier track's scan from the shared ring only if the ring
+  // were too small for one step: it holds nscan_in_sub_map + 4 slots per track
+  std::vector<float> T_outs(16 * std::max<size_t>(active.size(), 1));
+  std::vector<ls_icp_stats> stats(std::max<size_t>(active.size(), 1));
+  std::vector<int> statuses(std::max<size_t>(active.size(), 1), LS_OK);
+  constexpr size_t kMaxBatch = 32;  // ls_icp_register_submap_batch's limit
+  for (size_t b0 = 0; b0 < active.size(); b0 += kMaxBatch) {
+    const size_t nb = std::min(kMaxBatch, active.size() - b0);
+    std::vector<uint64_t> reading_ids, part_ids;
+    std::vector<int> n_parts;
+    std::vector<float> T_parts, T0s;
+    for (size_t k = 0; k < nb; ++k) {
+      const LaserTrack::PendingIcp& p = pending[active[b0 + k]];
+      reading_ids.push_back(p.reading_id);
+      n_parts.push_back((int)p.part_ids.size());
+      part_ids.insert(part_ids.end(), p.part_ids.begin(), p.part_ids.end());
+      T_parts.insert(T_parts.end(), p.T_parts.begin(), p.T_parts.end());
+      T0s.insert(T0s.end(), p.T0.data(), p.T0.data() + 16);
+    }
+    const ls_icp_params& prm = laser_tracks_[worker_ids[active[b0]]]->icpParams();
+    const int rc = ls_icp_register_submap_batch(track_ctx_, &prm, track_ring_, (int)nb, reading_ids.data(), n_parts.data(),
+                                                part_ids.data(), T_parts.data(), T0s.data(), T_outs.data() + 16 * b0,
+                                                stats.data() + b0, statuses.data() + b0);
+    if (rc < 0) throw std::runtime_error(std::string("ls_icp_register_submap_batch: ") + ls_b200_last_error(track_ctx_));
+  }
+  size_t a = 0;
+  for (size_t i = 0; i < n; ++i) {
+    bool prior = false;
+    if (pending[i].active) {
+      laser_tracks_[worker_ids[i]]->endPoseAndLaserScan(&pending[i], statuses[a], T_outs.data() + 16 * a, &stats[a],
+                                                        &(*new_factors)[i], &(*new_values)[i], &prior);
+      ++a;
+    } else {
+      laser_tracks_[worker_ids[i]]->endPoseAndLaserScan(&pending[i], LS_OK, NULL, NULL, &(*new_factors)[i], &(*new_values)[i], &prior);
+    }
+    (*is_prior)[i] = prior;
+  }
 }
 
 // reference :63-149
@@ -96,17 +167,14 @@ void IncrementalEstimator::processLoopClosure(const RelativePose& loop_closure) 
 
   // loop-closure factor, once with the loop-closure noise and once with the looser "first association" noise
   // (reference :117-133)
-  auto make = [&](const gtsam::NoiseModel& noise) {
-    ls_factor f;
-    std::memset(&f, 0, sizeof(f));
-    f.type = LS_FACTOR_BETWEEN;
-    f.robust = noise.cauchy ? 1 : 0;
-    f.key_a = track_a.getValueKey(updated.time_a_ns);
-    f.key_b = track_b.getValueKey(updated.time_b_ns);
-    updated.T_a_b.toArray7(f.meas);
-    for (int i = 0; i < 6; ++i) f.sigma[i] = noise.sigmas[i];
-    SE3().toArray7(f.fixed_a);
-    return f;
+  // reference :117-125: ExpressionFactor over inverse(T_w_a) * T_w_b, both trajectory leaves
+  auto make = [&](const gtsam::noiseModel::Base::shared_ptr& noise) {
+    using gtsam::Expression;
+    Expression<SE3> T_w_b(track_b.getValueExpression(updated.time_b_ns));
+    Expression<SE3> T_w_a(track_a.getValueExpression(updated.time_a_ns));
+    Expression<SE3> T_a_w(kindr::minimal::inverse(T_w_a));
+    Expression<SE3> relative(kindr::minimal::compose(T_a_w, T_w_b));
+    return gtsam::ExpressionFactor<SE3>(noise, updated.T_a_b, relative);
   };
   gtsam::NonlinearFactorGraph new_factors, new_associations_factors;
   new_factors.push_back(make(loop_closure_noise_model_));

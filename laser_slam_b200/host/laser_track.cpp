@@ -8,6 +8,7 @@
 
 #include <atomic>
 #include <chrono>
+#include <cstdio>
 #include <fstream>
 #include <sstream>
 #include <stdexcept>
@@ -43,6 +44,10 @@ void throwOnError(ls_ctx* ctx, int rc, const char* what) {
 
 // reference laser_track.cpp:10-65
 LaserTrack::LaserTrack(const LaserTrackParams& parameters, unsigned int laser_track_id)
+    : LaserTrack(parameters, laser_track_id, nullptr, nullptr, nullptr, nullptr, 0) {}
+
+LaserTrack::LaserTrack(const LaserTrackParams& parameters, unsigned int laser_track_id, ls_ctx* shared_ctx, ls_map** shared_ring,
+                       int* shared_ring_capacity, int* shared_ring_max_pts, int ring_slots_per_track)
     : laser_track_id_(laser_track_id), params_(parameters) {
   // ICP chain: the YAML the reference hands to icp_.loadFromYaml, or libpointmatcher's setDefault() values
   //  when the file cannot be opened (reference :14-21).
@@ -61,17 +66,29 @@ LaserTrack::LaserTrack(const LaserTrackParams& parameters, unsigned int laser_tr
   if (!params_.icp_input_filters_file.empty() && readFile(params_.icp_input_filters_file).empty())
     throw std::runtime_error("Could not open ICP input filters configuration file.");
   // noise models (reference :36-64)
-  odometry_noise_model_ = gtsam::NoiseModel{params_.odometry_noise_model, params_.add_m_estimator_on_odom};
-  icp_noise_model_ = gtsam::NoiseModel{params_.icp_noise_model, params_.add_m_estimator_on_icp};
-  prior_noise_model_ = gtsam::NoiseModel{{{1e-7, 1e-7, 1e-7, 1e-7, 1e-7, 1e-7}}, false};
+  using namespace gtsam::noiseModel;
+  odometry_noise_model_ = Diagonal::Sigmas(params_.odometry_noise_model);
+  if (params_.add_m_estimator_on_odom) odometry_noise_model_ = Robust::Create(mEstimator::Cauchy::Create(1), odometry_noise_model_);
+  icp_noise_model_ = Diagonal::Sigmas(params_.icp_noise_model);
+  if (params_.add_m_estimator_on_icp) icp_noise_model_ = Robust::Create(mEstimator::Cauchy::Create(1), icp_noise_model_);
+  prior_noise_model_ = Diagonal::Sigmas(std::array<double, 6>{{1e-7, 1e-7, 1e-7, 1e-7, 1e-7, 1e-7}});
   std::memset(&last_icp_stats_, 0, sizeof(last_icp_stats_));
-  const int rc = ls_b200_init(params_.cuda_device, &ctx_);
-  if (rc != LS_OK) throw std::runtime_error("ls_b200_init failed: no usable CUDA device (no CPU fallback)");
+  if (shared_ctx) {
+    ctx_ = shared_ctx;
+    owns_ctx_ = false;
+    map_p_ = shared_ring;
+    map_capacity_p_ = shared_ring_capacity;
+    map_max_pts_p_ = shared_ring_max_pts;
+    ring_slots_per_track_ = ring_slots_per_track;
+  } else {
+    const int rc = ls_b200_init(params_.cuda_device, &ctx_);
+    if (rc != LS_OK) throw std::runtime_error("ls_b200_init failed: no usable CUDA device (no CPU fallback)");
+  }
 }
 
 LaserTrack::~LaserTrack() {
-  if (map_) ls_map_destroy(map_);
-  if (ctx_) ls_b200_destroy(ctx_);
+  if (own_map_) ls_map_destroy(own_map_);
+  if (ctx_ && owns_ctx_) ls_b200_destroy(ctx_);
 }
 
 // reference :67-73
@@ -93,20 +110,68 @@ void LaserTrack::processLaserScan(const LaserScan& in_scan) {
 void LaserTrack::processPoseAndLaserScan(const Pose& pose, const LaserScan& in_scan, gtsam::NonlinearFactorGraph* newFactors,
                                          gtsam::Values* newValues, bool* is_prior) {
   std::lock_guard<std::recursive_mutex> lock(full_laser_track_mutex_);
-  const auto t_start = std::chrono::steady_clock::now();
   if (newFactors != NULL) LS_CHECK(newFactors->empty(), "newFactors must be empty on entry");
-  if (newValues != NULL) newValues->clear();
-  LS_CHECK(in_scan.scan.descriptorExists("normals"), "scans must carry a 'normals' descriptor");
+  PendingIcp pending;
+  beginPoseAndLaserScan(pose, in_scan, &pending);
+  int rc = LS_OK;
+  PointMatcher::TransformationParameters icp_solution = pending.T0;
+  ls_icp_stats stats;
+  std::memset(&stats, 0, sizeof(stats));
+  if (pending.active)  // icp_.compute(reading, sub_map, T0) (reference :496)
+    rc = ls_icp_register_submap(ctx_, &icp_params_, *map_p_, pending.reading_id, (int)pending.part_ids.size(),
+                                pending.part_ids.data(), pending.T_parts.data(), pending.T0.data(), icp_solution.data(), &stats,
+                                NULL, NULL, NULL);
+  endPoseAndLaserScan(&pending, rc, icp_solution.data(), &stats, newFactors, newValues, is_prior);
+}
 
-  LaserScan scan = in_scan;  // the reference copies too (:143); filters would run on the copy
+// reference :122-206 and, through computeICPTransformations (:460-464), localScanToSubMap up to the ICP call (:466-491)
+void LaserTrack::beginPoseAndLaserScan(const Pose& pose, const LaserScan& in_scan, PendingIcp* pending) {
+  std::lock_guard<std::recursive_mutex> lock(full_laser_track_mutex_);
+  LS_CHECK(pending != NULL, "null pending");
+  *pending = PendingIcp();
+  pending->t_start_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  LS_CHECK(in_scan.scan.descriptorExists("normals"), "scans must carry a 'normals' descriptor");
+  pending->pose = pose;
+  LaserScan& scan = pending->scan;
+  scan = in_scan;  // the reference copies too (:143); filters would run on the copy
   pose_measurements_.push_back(pose);
 
   if (trajectory_.empty()) {
+    pending->first = true;
     scan.key = extendTrajectory(scan.time_ns, findPose(scan.time_ns).T_w);
     findPose(scan.time_ns).key = scan.key;
     laser_scans_.push_back(scan);
+    return;
+  }
+  const Time t_last = trajectory_.rbegin()->first;
+  const SE3 last_pose_measurement = findPose(t_last).T_w;
+  const SE3 new_pose_measurement = findPose(scan.time_ns).T_w;
+  RelativePose& relative_measurement = pending->relative_measurement;
+  relative_measurement.T_a_b = last_pose_measurement.inverse() * new_pose_measurement;
+  relative_measurement.time_a_ns = t_last;
+  relative_measurement.key_a = findPose(t_last).key;
+  relative_measurement.time_b_ns = scan.time_ns;
+  relative_measurement.track_id_a = relative_measurement.track_id_b = laser_track_id_;
+  // extend the trajectory by odometry (reference :192)
+  scan.key = extendTrajectory(scan.time_ns, trajectory_.rbegin()->second.value * relative_measurement.T_a_b);
+  findPose(scan.time_ns).key = scan.key;
+  laser_scans_.push_back(scan);
+  relative_measurement.key_b = scan.key;
+  odometry_measurements_.push_back(relative_measurement);
+  if (params_.use_icp_factors && getNumScans() > 1u) stageLocalScanToSubMap(pending);  // computeICPTransformations (:460-464)
+}
+
+// reference :493-519 (rest of localScanToSubMap) and :208-230 (factor and value emission)
+void LaserTrack::endPoseAndLaserScan(PendingIcp* pending, int rc, const float* T_out16, const ls_icp_stats* stats,
+                                     gtsam::NonlinearFactorGraph* newFactors, gtsam::Values* newValues, bool* is_prior) {
+  std::lock_guard<std::recursive_mutex> lock(full_laser_track_mutex_);
+  LS_CHECK(pending != NULL, "null pending");
+  if (newFactors != NULL) LS_CHECK(newFactors->empty(), "newFactors must be empty on entry");
+  if (newValues != NULL) newValues->clear();
+  const LaserScan& scan = pending->scan;
+  if (pending->first) {
     if (newFactors != NULL) {
-      Pose prior_pose = pose;
+      Pose prior_pose = pending->pose;
       prior_pose.key = scan.key;
       prior_pose.time_ns = scan.time_ns;
       if (params_.force_priors)  // reference :165-169
@@ -115,32 +180,20 @@ void LaserTrack::processPoseAndLaserScan(const Pose& pose, const LaserScan& in_s
     }
     if (is_prior != NULL) *is_prior = true;
   } else {
-    const Time t_last = trajectory_.rbegin()->first;
-    const SE3 last_pose_measurement = findPose(t_last).T_w;
-    const SE3 new_pose_measurement = findPose(scan.time_ns).T_w;
-    RelativePose relative_measurement;
-    relative_measurement.T_a_b = last_pose_measurement.inverse() * new_pose_measurement;
-    relative_measurement.time_a_ns = t_last;
-    relative_measurement.key_a = findPose(t_last).key;
-    relative_measurement.time_b_ns = scan.time_ns;
-    relative_measurement.track_id_a = relative_measurement.track_id_b = laser_track_id_;
-    // extend the trajectory by odometry (reference :192)
-    scan.key = extendTrajectory(scan.time_ns, trajectory_.rbegin()->second.value * relative_measurement.T_a_b);
-    findPose(scan.time_ns).key = scan.key;
-    laser_scans_.push_back(scan);
-    relative_measurement.key_b = scan.key;
-    odometry_measurements_.push_back(relative_measurement);
-    if (params_.use_icp_factors) computeICPTransformations();
-    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();
-    scan_matching_times_.emplace(scan.time_ns, ms);
+    if (pending->active) {
+      if (stats) last_icp_stats_ = *stats;
+      finishLocalScanToSubMap(*pending, rc, T_out16);
+    }
+    const double now_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    scan_matching_times_.emplace(scan.time_ns, now_ms - pending->t_start_ms);
     if (newFactors != NULL) {
-      if (params_.use_odom_factors) newFactors->push_back(makeRelativeMeasurementFactor(relative_measurement, odometry_noise_model_));
+      if (params_.use_odom_factors) newFactors->push_back(makeRelativeMeasurementFactor(pending->relative_measurement, odometry_noise_model_));
       if (params_.use_icp_factors && !icp_transformations_.empty())
         newFactors->push_back(makeRelativeMeasurementFactor(icp_transformations_.back(), icp_noise_model_));
     }
     if (is_prior != NULL) *is_prior = false;
   }
-  if (newValues != NULL) newValues->insert(scan.key, pose.T_w);  // reference :228-230
+  if (newValues != NULL) newValues->insert(scan.key, pending->pose.T_w);  // reference :228-230
 }
 
 void LaserTrack::getLastPointCloud(DataPoints* out_point_cloud) const {  // stub in the reference too (:233-237)
@@ -234,7 +287,7 @@ void LaserTrack::appendPriorFactors(const Time& prior_time_ns, gtsam::NonlinearF
   graph->push_back(makeMeasurementFactor(p, prior_noise_model_));
 }
 // reference :346-361
-void LaserTrack::appendOdometryFactors(const Time& tmin, const Time& tmax, const gtsam::NoiseModel& noise,
+void LaserTrack::appendOdometryFactors(const Time& tmin, const Time& tmax, gtsam::noiseModel::Base::shared_ptr noise,
                                        gtsam::NonlinearFactorGraph* graph) const {
   std::lock_guard<std::recursive_mutex> lock(full_laser_track_mutex_);
   LS_CHECK(graph != NULL, "null graph");
@@ -253,7 +306,7 @@ void appendWindowed(const RelativePoseVector& v, const Time& tmin, const Time& t
 }
 }  // namespace
 // reference :363-384
-void LaserTrack::appendICPFactors(const Time& tmin, const Time& tmax, const gtsam::NoiseModel& noise,
+void LaserTrack::appendICPFactors(const Time& tmin, const Time& tmax, gtsam::noiseModel::Base::shared_ptr noise,
                                   gtsam::NonlinearFactorGraph* graph) const {
   std::lock_guard<std::recursive_mutex> lock(full_laser_track_mutex_);
   LS_CHECK(graph != NULL, "null graph");
@@ -261,7 +314,7 @@ void LaserTrack::appendICPFactors(const Time& tmin, const Time& tmax, const gtsa
                  [&](const RelativePose& m, bool fix) { return makeRelativeMeasurementFactor(m, noise, fix); });
 }
 // reference :386-409
-void LaserTrack::appendLoopClosureFactors(const Time& tmin, const Time& tmax, const gtsam::NoiseModel& noise,
+void LaserTrack::appendLoopClosureFactors(const Time& tmin, const Time& tmax, gtsam::noiseModel::Base::shared_ptr noise,
                                           gtsam::NonlinearFactorGraph* graph) const {
   std::lock_guard<std::recursive_mutex> lock(full_laser_track_mutex_);
   LS_CHECK(graph != NULL, "null graph");
@@ -270,12 +323,11 @@ void LaserTrack::appendLoopClosureFactors(const Time& tmin, const Time& tmax, co
 }
 
 // reference :411-419
-void LaserTrack::initializeGTSAMValues(const std::vector<Key>& keys, gtsam::Values* values) const {
+void LaserTrack::initializeGTSAMValues(const gtsam::KeySet& keys, gtsam::Values* values) const {
   std::lock_guard<std::recursive_mutex> lock(full_laser_track_mutex_);
   LS_CHECK(values != NULL, "null values");
   for (const auto& kv : trajectory_)
-    for (Key k : keys)
-      if (kv.second.key == k && !values->exists(k)) values->insert(k, kv.second.value);
+    if (keys.count(kv.second.key) && !values->exists(kv.second.key)) values->insert(kv.second.key, kv.second.value);
 }
 void LaserTrack::updateFromGTSAMValues(const gtsam::Values& values) {
   std::lock_guard<std::recursive_mutex> lock(full_laser_track_mutex_);
@@ -283,74 +335,88 @@ void LaserTrack::updateFromGTSAMValues(const gtsam::Values& values) {
     if (values.exists(kv.second.key)) kv.second.value = values.at(kv.second.key);
 }
 
-// reference :431-451
-ls_factor LaserTrack::makeRelativeMeasurementFactor(const RelativePose& m, const gtsam::NoiseModel& noise, bool fix_first_node) const {
-  ls_factor f;
-  std::memset(&f, 0, sizeof(f));
-  f.type = LS_FACTOR_BETWEEN;
-  f.robust = noise.cauchy ? 1 : 0;
-  f.fix_a = fix_first_node ? 1 : 0;
-  f.key_a = m.key_a;
-  f.key_b = m.key_b;
-  m.T_a_b.toArray7(f.meas);
-  for (int i = 0; i < 6; ++i) f.sigma[i] = noise.sigmas[i];
-  SE3 fixed;  // constant T_w_a when the first node is frozen (reference :440-444)
-  if (fix_first_node) fixed = evaluate(m.time_a_ns);
-  fixed.toArray7(f.fixed_a);
-  return f;
-}
-// reference :453-458
-ls_factor LaserTrack::makeMeasurementFactor(const Pose& pose_measurement, const gtsam::NoiseModel& noise) const {
-  ls_factor f;
-  std::memset(&f, 0, sizeof(f));
-  f.type = LS_FACTOR_PRIOR;
-  f.robust = noise.cauchy ? 1 : 0;
-  f.key_a = f.key_b = getValueKey(pose_measurement.time_ns);
-  pose_measurement.T_w.toArray7(f.meas);
-  for (int i = 0; i < 6; ++i) f.sigma[i] = noise.sigmas[i];
-  SE3().toArray7(f.fixed_a);
-  return f;
+// reference :421-429
+void LaserTrack::updateCovariancesFromGTSAMValues(const gtsam::NonlinearFactorGraph& factor_graph, const gtsam::Values& values) {
+  std::lock_guard<std::recursive_mutex> lock(full_laser_track_mutex_);
+  gtsam::Marginals marginals(factor_graph, values);
+  std::vector<Key> keys;
+  for (const auto& kv : trajectory_)
+    if (values.exists(kv.second.key)) keys.push_back(kv.second.key);
+  const std::vector<gtsam::Marginals::Matrix6> cov = marginals.marginalCovariances(keys);
+  covariances_.clear();
+  for (const auto& c : cov) covariances_.push_back(Covariance(c.begin(), c.end()));
 }
 
-// reference :460-464
-void LaserTrack::computeICPTransformations() {
-  if (getNumScans() > 1u) localScanToSubMap();
+void LaserTrack::printTrajectory() const {  // reference laser_track.hpp:114-117 (trajectory_.print)
+  std::lock_guard<std::recursive_mutex> lock(full_laser_track_mutex_);
+  std::printf("Laser track trajectory (%zu nodes)\n", trajectory_.size());
+  for (const auto& kv : trajectory_) {
+    const SE3::Position& t = kv.second.value.getPosition();
+    const SO3& q = kv.second.value.getRotation();
+    std::printf("  t = %lld ns  key %llu  p = [%.6f %.6f %.6f]  q = [%.6f %.6f %.6f %.6f]\n", (long long)kv.first,
+                (unsigned long long)kv.second.key, t[0], t[1], t[2], q.w(), q.x(), q.y(), q.z());
+  }
+}
+
+// reference :431-451: T_a_b expression = inverse(T_w_a) * T_w_b with T_w_a a leaf or, when the first node is frozen, a constant
+gtsam::ExpressionFactor<SE3> LaserTrack::makeRelativeMeasurementFactor(const RelativePose& relative_pose_measurement,
+                                                                       gtsam::noiseModel::Base::shared_ptr noise_model,
+                                                                       const bool fix_first_node) const {
+  using gtsam::Expression;
+  Expression<SE3> T_w_b(relative_pose_measurement.key_b);
+  Expression<SE3> T_w_a(relative_pose_measurement.key_a);
+  if (fix_first_node) T_w_a = Expression<SE3>(evaluate(relative_pose_measurement.time_a_ns));  // constant (reference :440-444)
+  Expression<SE3> T_a_w(kindr::minimal::inverse(T_w_a));
+  Expression<SE3> relative(kindr::minimal::compose(T_a_w, T_w_b));
+  return gtsam::ExpressionFactor<SE3>(noise_model, relative_pose_measurement.T_a_b, relative);
+}
+// reference :453-458
+gtsam::ExpressionFactor<SE3> LaserTrack::makeMeasurementFactor(const Pose& pose_measurement,
+                                                               gtsam::noiseModel::Base::shared_ptr noise_model) const {
+  gtsam::Expression<SE3> T_w(getValueKey(pose_measurement.time_ns));
+  return gtsam::ExpressionFactor<SE3>(noise_model, pose_measurement.T_w, T_w);
 }
 
 uint64_t LaserTrack::residentScan(size_t index) const {
   auto it = resident_.find(index);
-  if (it != resident_.end() && ls_map_scan_size(map_, it->second) >= 0) return it->second;
+  if (it != resident_.end() && ls_map_scan_size(*map_p_, it->second) >= 0) return it->second;
   const DataPoints& c = laser_scans_[index].scan;
   const int off = c.descriptorOffset("normals");
   LS_CHECK(off >= 0, "scan without normals");
   uint64_t id = 0;
-  const int rc = ls_map_push_scan(map_, c.features.data(), c.descriptors.data() + off, (int)c.descriptorDim, (int)c.getNbPoints(), &id);
+  const int rc = ls_map_push_scan(*map_p_, c.features.data(), c.descriptors.data() + off, (int)c.descriptorDim, (int)c.getNbPoints(), &id);
   throwOnError(ctx_, rc, "ls_map_push_scan");
   resident_[index] = id;
   return id;
 }
 
-// reference :466-519
-void LaserTrack::localScanToSubMap() {
+// device ring large enough for the sub-map + the reading; (re)created when a larger scan shows up.  A track of its own
+// keeps nscan_in_sub_map + 3 slots; a hosted track shares its host's ring (ring_slots_per_track_ slots per track).
+void LaserTrack::ensureRing(size_t max_pts) {
+  const int want_cap = owns_ctx_ ? std::max(8, params_.nscan_in_sub_map + 3) : *map_capacity_p_;
+  if (!*map_p_ || (int)max_pts > *map_max_pts_p_ || want_cap > *map_capacity_p_) {
+    LS_CHECK(owns_ctx_ || !*map_p_, "a scan larger than the shared ring's slots arrived (the host sizes the ring from the first scans)");
+    if (*map_p_) ls_map_destroy(*map_p_);
+    *map_p_ = nullptr;
+    resident_.clear();
+    *map_max_pts_p_ = (int)(max_pts + max_pts / 4 + 1024);
+    *map_capacity_p_ = std::max(want_cap, 8);
+    throwOnError(ctx_, ls_map_create(ctx_, *map_capacity_p_, *map_max_pts_p_, map_p_), "ls_map_create");
+  }
+}
+
+// reference :466-491: the sub-map, the initial guess, the uploads -- everything before icp_.compute
+void LaserTrack::stageLocalScanToSubMap(PendingIcp* pending) {
   const size_t n = laser_scans_.size();
   const LaserScan& last_scan = laser_scans_[n - 1u];
-  RelativePose icp_transformation;
+  RelativePose& icp_transformation = pending->icp_transformation;
   icp_transformation.time_b_ns = last_scan.time_ns;
   icp_transformation.time_a_ns = laser_scans_[n - 2u].time_ns;
   icp_transformation.track_id_a = icp_transformation.track_id_b = laser_track_id_;
 
-  // device ring large enough for the sub-map + the reading; (re)created when a larger scan shows up
   size_t max_pts = 0;
   for (size_t i = (n > 16 ? n - 16 : 0); i < n; ++i) max_pts = std::max(max_pts, laser_scans_[i].scan.getNbPoints());
-  const int want_cap = std::max(8, params_.nscan_in_sub_map + 3);
-  if (!map_ || (int)max_pts > map_max_pts_ || want_cap > map_capacity_) {
-    if (map_) ls_map_destroy(map_);
-    map_ = nullptr;
-    resident_.clear();
-    map_max_pts_ = (int)(max_pts + max_pts / 4 + 1024);
-    map_capacity_ = want_cap;
-    throwOnError(ctx_, ls_map_create(ctx_, map_capacity_, map_max_pts_, &map_), "ls_map_create");
-  }
+  ensureRing(max_pts);
 
   // the last (nscan_in_sub_map - 1) scans expressed in the frame of the second-last scan (reference :474-486)
   const SE3 T_w_to_second_last_scan = evaluate(laser_scans_[n - 2u].time_ns);
@@ -366,24 +432,28 @@ void LaserTrack::localScanToSubMap() {
   }
   // initial guess from the trajectory (reference :488-491)
   const SE3 initial_guess = evaluate(icp_transformation.time_a_ns).inverse() * evaluate(icp_transformation.time_b_ns);
-  const PointMatcher::TransformationParameters T0 = toFloatMatrix(initial_guess);
-  PointMatcher::TransformationParameters icp_solution = T0;
+  pending->T0 = toFloatMatrix(initial_guess);
 
   // upload what is not resident yet (normally only the newest scan), reading last so it cannot evict a part
-  std::vector<uint64_t> part_ids;
-  for (size_t idx : part_index) part_ids.push_back(residentScan(idx));
-  const uint64_t reading_id = residentScan(n - 1u);
-  for (size_t k = 0; k < part_index.size(); ++k) part_ids[k] = residentScan(part_index[k]);
-  std::vector<float> T_flat;
-  for (const auto& T : part_T) T_flat.insert(T_flat.end(), T.data(), T.data() + 16);
+  pending->part_ids.clear();
+  for (size_t idx : part_index) pending->part_ids.push_back(residentScan(idx));
+  pending->reading_id = residentScan(n - 1u);
+  for (size_t k = 0; k < part_index.size(); ++k) pending->part_ids[k] = residentScan(part_index[k]);
+  pending->T_parts.clear();
+  for (const auto& T : part_T) pending->T_parts.insert(pending->T_parts.end(), T.data(), T.data() + 16);
+  pending->active = true;
+}
 
-  const int rc = ls_icp_register_submap(ctx_, &icp_params_, map_, reading_id, (int)part_ids.size(), part_ids.data(), T_flat.data(),
-                                        T0.data(), icp_solution.data(), &last_icp_stats_, NULL, NULL, NULL);
+// reference :493-519: ConvergenceError keeps the initial guess; the result becomes a RelativePose
+void LaserTrack::finishLocalScanToSubMap(const PendingIcp& pending, int rc, const float* T_out16) {
+  PointMatcher::TransformationParameters icp_solution = pending.T0;
   if (rc == LS_ERR_CONVERGENCE) {
-    icp_solution = T0;  // PointMatcher::ConvergenceError is swallowed: keep the initial guess (reference :495-502)
+    // PointMatcher::ConvergenceError is swallowed: keep the initial guess (reference :495-502)
   } else {
     throwOnError(ctx_, rc, "ls_icp_register_submap");
+    std::memcpy(icp_solution.data(), T_out16, 16 * sizeof(float));
   }
+  RelativePose icp_transformation = pending.icp_transformation;
   icp_transformation.T_a_b = convertTransformationMatrixToSE3(icp_solution);
   icp_transformation.key_a = findPose(icp_transformation.time_a_ns).key;
   icp_transformation.key_b = findPose(icp_transformation.time_b_ns).key;
@@ -420,6 +490,9 @@ size_t LaserTrack::scanIndexAtTime(const curves::Time& time_ns) const {  // refe
   for (size_t i = 0; i < laser_scans_.size(); ++i)
     if (laser_scans_[i].time_ns == time_ns) return i;
   throw std::logic_error("CHECK failed: Could not find the scan.");
+}
+gtsam::Expression<SE3> LaserTrack::getValueExpression(const curves::Time& time_ns) const {
+  return gtsam::Expression<SE3>(getValueKey(time_ns));  // exact node times only, as every caller in laser_slam uses it
 }
 Key LaserTrack::getValueKey(const curves::Time& time_ns) const {
   std::lock_guard<std::recursive_mutex> lock(full_laser_track_mutex_);

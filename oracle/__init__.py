@@ -192,6 +192,23 @@ def knn_normals(pts4, k=10, num_threads=1):
     return out
 
 
+def keep_mask(n, salt, prob):
+    """Deterministic stand-in for RandomSamplingDataPointsFilter (reference laser_slam/configurations/icp_default.yaml:1-3;
+    libpointmatcher draws `rand() / RAND_MAX < prob`, which no two processes reproduce): point i is kept iff
+    hash32(i, salt) < prob * 2^32.  [DEFINED] -- the same counter-based rule as ls_keep_point (include/ls_b200.h)."""
+    if not prob < 1.0:
+        return np.ones(n, bool)
+    if not prob > 0.0:
+        return np.zeros(n, bool)
+    i = np.arange(n, dtype=np.uint64)
+    M = np.uint64(0xFFFFFFFF)
+    h = (i * np.uint64(0x9E3779B1) + np.uint64(salt) * np.uint64(0x85EBCA77) + np.uint64(0x165667B1)) & M
+    h ^= h >> np.uint64(15); h = (h * np.uint64(0x2C1B3C6D)) & M
+    h ^= h >> np.uint64(12); h = (h * np.uint64(0x297A2D39)) & M
+    h ^= h >> np.uint64(15)
+    return h.astype(np.float64) < float(np.float32(prob)) * 4294967296.0
+
+
 def sincos(x):
     s = ctypes.c_double()
     c = ctypes.c_double()

@@ -229,6 +229,31 @@ def gauss_newton_step(factors, keys, poses, damp_keys=()):
     return retract(poses, delta), float(np.abs(delta).max()), cost
 
 
+def hessian(factors, keys, poses, damp_keys=()):
+    """Gauss-Newton Hessian J^T J (robust factors at their current Cauchy weights) as a dense matrix: small graphs only."""
+    r, Ja, Jb, ia, ib, cost = linearize(factors, keys, poses)
+    P = len(keys)
+    H = np.zeros((6 * P, 6 * P))
+    index = {int(k): i for i, k in enumerate(keys)}
+    for dk in damp_keys:
+        i = index[int(dk)]
+        H[6 * i + np.arange(6), 6 * i + np.arange(6)] += np.array([1.0] * 3 + [4.0] * 3)
+    for f in range(len(factors)):
+        nodes = [(ib[f], Jb[f])] + ([(ia[f], Ja[f])] if ia[f] >= 0 else [])
+        for (i, Ji) in nodes:
+            for (j, Jj) in nodes:
+                H[6 * i:6 * i + 6, 6 * j:6 * j + 6] += Ji.T @ Jj
+    return H
+
+
+def marginals(factors, keys, poses, query_keys, damp_keys=()):
+    """gtsam::Marginals(graph, values).marginalCovariance(key) (reference laser_slam/src/laser_track.cpp:421-429):
+    the 6x6 diagonal blocks of the inverse Hessian at `poses`, tangent order [translation; rotation]."""
+    C = np.linalg.inv(hessian(factors, keys, poses, damp_keys))
+    index = {int(k): i for i, k in enumerate(keys)}
+    return np.stack([C[6 * index[int(k)]:6 * index[int(k)] + 6, 6 * index[int(k)]:6 * index[int(k)] + 6] for k in query_keys])
+
+
 def optimize(factors, keys, poses, iters=3, tol=0.0, damp_keys=()):
     """`iters` Gauss-Newton iterations (3 = one IncrementalEstimator::estimate call).  Returns poses, history."""
     poses = np.asarray(poses, np.float64).copy()

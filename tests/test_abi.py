@@ -32,8 +32,7 @@ def test_header_symbols_are_exported(ls):
         assert hasattr(lib, s), f"{s} declared in include/ls_b200.h but not exported"
 
 
-def test_yaml_chain_reader(ls):
-    ref_yaml = """
+REF_YAML = """
 readingDataPointsFilters:
   - RandomSamplingDataPointsFilter:
       prob: 0.5
@@ -64,6 +63,10 @@ inspector:
 logger:
   NullLogger
 """
+
+
+def test_yaml_chain_reader(ls):
+    ref_yaml = REF_YAML
     p = ls.params_from_yaml(ref_yaml)
     assert (p.max_iterations, p.use_differential, p.smooth_length) == (40, 1, 4)
     assert abs(p.trim_ratio - 0.75) < 1e-7 and abs(p.min_diff_rot - 1e-3) < 1e-9 and abs(p.min_diff_trans - 1e-2) < 1e-9
@@ -115,3 +118,34 @@ def test_product_never_imports_the_oracle():
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", text, flags=re.M), f
                 assert not re.search(r"#\s*include\s*[\"<][^\">]*oracle", text), f
                 assert "libls_oracle" not in text and "lso_" not in text, f
+
+
+def test_yaml_reports_the_filter_sections_it_does_not_apply(ls):
+    """icp_default.yaml:1-7: the reading / reference DataPointsFilters are parsed and reported (they run upstream of the
+    registration: ls_keep_point, ls_estimate_normals), not silently dropped."""
+    p = ls.params_from_yaml(REF_YAML)
+    assert abs(p.reading_sampling_prob - 0.5) < 1e-7 and p.reference_normals_knn == 10
+    assert p.reference_sampling_ratio == 1.0 and p.unapplied_modules == 2
+    assert p.max_iterations == 40 and abs(p.trim_ratio - 0.75) < 1e-7 and p.use_differential == 1
+    q = ls.default_params()
+    assert q.reading_sampling_prob == 1.0 and q.reference_normals_knn == 0 and q.unapplied_modules == 0
+
+
+def test_keep_point_matches_the_oracle_rule(ls):
+    """ls_keep_point (deterministic RandomSamplingDataPointsFilter) == oracle.keep_mask, and keeps about `prob` of the points."""
+    import oracle
+    for salt, prob in ((ls.READING_SALT, 0.5), (ls.REFERENCE_SALT, 0.25), (3, 0.999), (4, 1.0), (5, 0.0)):
+        got = ls.keep_mask(20000, salt, prob)
+        want = oracle.keep_mask(20000, salt, prob)
+        assert np.array_equal(got, want)
+        assert abs(got.mean() - prob) < 0.02
+    assert not np.array_equal(ls.keep_mask(5000, 1, 0.5), ls.keep_mask(5000, 2, 0.5))
+
+
+def test_reference_call_sites_compile_against_the_headers():
+    """the members laser_slam_ros and laser_slam's own sources use compile against include/ (tests/compile)."""
+    import subprocess
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    r = subprocess.run([cxx, "-std=c++17", "-fsyntax-only", "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "compile", "reference_call_sites.cpp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

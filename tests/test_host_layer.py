@@ -131,3 +131,35 @@ def test_host_layer_needs_a_gpu():
     import laser_slam_b200 as ls
     with pytest.raises(ls.LsError, match="no usable CUDA device"):
         host.Estimator()
+
+
+@pytest.mark.gpu
+def test_batched_scan_callbacks_equal_one_callback_per_worker(synth_mod):
+    """IncrementalEstimator::processPosesAndLaserScans (all workers' registrations of a step in ONE batched launch on the
+    estimator's shared context and scan ring) gives every worker the same bits as calling
+    LaserTrack::processPoseAndLaserScan worker by worker (reference laser_slam_ros/src/laser_slam_worker.cpp:133,158)."""
+    from laser_slam_b200 import host
+    W, n_scans = 3, 6
+    data = []
+    for w in range(W):
+        truth, odom = synth_mod.trajectory(w, n_scans)
+        sc = [synth_mod.subsample(*synth_mod.scan(truth[k], w, k), 8) for k in range(n_scans)]
+        data.append((pg.se3_from_matrix(odom), sc))
+    one = host.Estimator(n_workers=W, nscan_in_sub_map=3)
+    bat = host.Estimator(n_workers=W, nscan_in_sub_map=3)
+    for k in range(n_scans):
+        ws = [w for w in range(W) if not (w == 2 and k == 0)]         # worker 2 starts one step late: mixed first / later scans
+        feats = [np.ascontiguousarray(data[w][1][k][0]) for w in ws]
+        nrms = [np.ascontiguousarray(data[w][1][k][1]) for w in ws]
+        icp_b, st_b = bat.step_batch(ws, [k * 100 for _ in ws], [data[w][0][k] for w in ws], [f.ctypes.data for f in feats],
+                                     [n.ctypes.data for n in nrms], [len(f) for f in feats])
+        for j, w in enumerate(ws):
+            icp_1, st_1 = one.step(w, k * 100, data[w][0][k], feats[j], nrms[j])
+            assert np.array_equal(icp_1, icp_b[j]), (k, w)
+            assert st_1.iterations == st_b[j].iterations and st_1.last_kept == st_b[j].last_kept
+    for w in range(W):
+        t1, p1 = one.trajectory(w)
+        t2, p2 = bat.trajectory(w)
+        assert np.array_equal(t1, t2) and np.abs(p1 - p2).max() < 1e-9       # same factors -> same estimate
+    one.close()
+    bat.close()

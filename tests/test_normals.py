@@ -72,3 +72,31 @@ def test_gpu_icp_with_estimated_normals(gpu_ctx, oracle_mod, scans, traj):
     pts, nrm = mp.assemble([sid[3]], [np.eye(4, dtype=np.float32)])
     assert np.array_equal(nrm, oracle_mod.knn_normals(scans[3][0], 10, num_threads=8))
     mp.close()
+
+
+@pytest.mark.gpu
+def test_default_chain_with_its_datapoints_filters_equals_oracle(gpu_ctx, oracle_mod, small_pair):
+    """The whole chain of icp_default.yaml:1-27 -- reading RandomSampling(0.5), reference SurfaceNormal(knn 10), KDTreeMatcher,
+    TrimmedDist(0.75), PointToPlane, Counter(40) + Differential -- in its deterministic form (ls_keep_point instead of
+    rand(), exact k-NN normals): GPU path == oracle restatement, bit for bit; and it differs from the unfiltered chain."""
+    import laser_slam_b200 as ls
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_abi import REF_YAML
+    p = ls.params_from_yaml(REF_YAML)
+    assert p.reading_sampling_prob == 0.5 and p.reference_normals_knn == 10
+    rd, ref, nrm = ls.apply_chain_filters(gpu_ctx, small_pair["reading"], small_pair["ref"], small_pair["ref_normals"], p)
+    o = oracle_mod
+    rd_o = small_pair["reading"][o.keep_mask(len(small_pair["reading"]), ls.READING_SALT, 0.5)]
+    nrm_o = o.knn_normals(small_pair["ref"], 10)
+    assert np.array_equal(rd, rd_o) and np.array_equal(nrm, nrm_o) and 0.45 < len(rd) / len(small_pair["reading"]) < 0.55
+    po = o.default_params(max_iterations=p.max_iterations, trim_ratio=p.trim_ratio, use_differential=p.use_differential,
+                          min_diff_rot=p.min_diff_rot, min_diff_trans=p.min_diff_trans, smooth_length=p.smooth_length)
+    r = o.icp(rd_o, small_pair["ref"], nrm_o, small_pair["T0"], po, want_hist=True)
+    g = gpu_ctx.icp_register(rd, ref, nrm, small_pair["T0"], p, want_ids=True, want_hist=True)
+    assert r["rc"] == 0 and g["rc"] == 0 and g["stats"].iterations == r["stats"].iterations
+    assert np.array_equal(g["T_iter_hist"], r["T_iter_hist"]) and np.array_equal(g["ids"], r["ids_hist"][-1])
+    assert np.array_equal(g["T"], r["T"])
+    plain = gpu_ctx.icp_register(small_pair["reading"], small_pair["ref"], small_pair["ref_normals"], small_pair["T0"], p)
+    assert not np.array_equal(plain["T"], g["T"])
+    assert np.abs(plain["T"][:3, 3] - g["T"][:3, 3]).max() < 0.05          # both land on the same registration

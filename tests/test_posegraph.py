@@ -242,3 +242,74 @@ def test_gpu_config4_full_size():
     assert np.abs(est[:, 4:] - ref[:, 4:]).max() < 1e-6
     assert np.abs(pg.so3_log(np.swapaxes(pg.quat_to_R(est[:, :4]), -1, -2) @ pg.quat_to_R(ref[:, :4]))).max() < 1e-7
     g.close()
+
+
+def test_oracle_marginals_match_sampling_free_identities():
+    """Oracle self-check: the prior alone fixes the first pose's covariance; along a chain the covariance grows."""
+    rng = np.random.default_rng(11)
+    keys = np.arange(5, dtype=np.uint64) + 3
+    poses = np.stack([rand_pose(rng) for _ in range(5)])
+    sig0 = np.array([0.1, 0.2, 0.3, 0.01, 0.02, 0.03])
+    fac = [pg.make_factor(pg.PRIOR, keys[0], 0, poses[0], sig0)]
+    sig = [0.05] * 3 + [0.01] * 3
+    for k in range(1, 5):
+        fac.append(pg.make_factor(pg.BETWEEN, keys[k - 1], keys[k], pg.se3_compose(pg.se3_inverse(poses[k - 1]), poses[k]), sig))
+    C = pg.marginals(fac, keys, poses, keys)
+    R0 = pg.quat_to_R(poses[0, :4])        # the prior's translation residual lives in the measured pose's frame
+    want0 = np.zeros((6, 6))
+    want0[:3, :3] = R0 @ np.diag(sig0[:3] ** 2) @ R0.T
+    want0[3:, 3:] = np.diag(sig0[3:] ** 2)
+    assert np.allclose(C[0], want0, rtol=1e-9, atol=1e-15)
+    # an independent route to the same blocks: eliminate every other pose (Schur complement), invert what is left
+    H = pg.hessian(fac, keys, poses)
+    for q in range(5):
+        keep = np.arange(6 * q, 6 * q + 6)
+        rest = np.setdiff1d(np.arange(30), keep)
+        schur = H[np.ix_(keep, keep)] - H[np.ix_(keep, rest)] @ np.linalg.solve(H[np.ix_(rest, rest)], H[np.ix_(rest, keep)])
+        assert np.allclose(np.linalg.inv(schur), C[q], rtol=1e-7, atol=1e-14)
+
+
+@pytest.mark.gpu
+def test_gpu_marginal_covariances_match_the_inverse_hessian():
+    """ls_pg_marginals (LaserTrack::updateCovariancesFromGTSAMValues -> gtsam::Marginals::marginalCovariance, reference
+    laser_slam/src/laser_track.cpp:421-429) against numpy.linalg.inv of the oracle's Hessian at the same estimate:
+    chain + loop closures (border correction), several tracks, more keys than one chunk."""
+    import laser_slam_b200 as ls
+    keys, init, factors, truth = pg.make_config4(n_poses=300, n_lc=12, lap=100, seed=5)
+    g, _ = build_gpu_graph(ls, keys, init, factors)
+    g.optimize(4)
+    k2, est = g.poses()
+    want = pg.marginals(factors, keys, est, keys)
+    got = g.marginals(keys)                              # 300 keys: five chunks of 64
+    scale = np.abs(want).max(axis=(1, 2), keepdims=True)
+    assert np.abs(got - want).max() < 1e-9 * max(1.0, np.abs(want).max())
+    assert (np.abs(got - want) / scale).max() < 1e-6
+    assert np.allclose(got, np.swapaxes(got, 1, 2), atol=1e-12)          # symmetric
+    assert (np.linalg.eigvalsh(got) > 0).all()                            # positive definite
+    sub = keys[[250, 3, 77]]
+    assert np.allclose(g.marginals(sub), want[[250, 3, 77]], rtol=1e-6, atol=1e-15)
+    k3, est3 = g.poses()
+    assert np.array_equal(est3, est)                                      # asking for marginals does not move the estimate
+    g.close()
+    # no loop closures, three tracks
+    rng = np.random.default_rng(6)
+    sig = [0.005] * 3 + [0.0015] * 3
+    keys, init, tracks, factors = [], [], [], []
+    for t in range(3):
+        pose = rand_pose(rng, 20.0, 0.3)
+        for k in range(40):
+            key = 1000 * (t + 1) + k
+            keys.append(key); tracks.append(t)
+            if k == 0:
+                factors.append(pg.make_factor(pg.PRIOR, key, 0, pose, [1e-3] * 6))
+            else:
+                rel = rand_pose(rng, 0.5, 0.04)
+                factors.append(pg.make_factor(pg.BETWEEN, key - 1, key, rel, sig))
+                pose = pg.se3_compose(pose, rel)
+            init.append(pose)
+    keys = np.array(keys, np.uint64); init = np.stack(init)
+    g, _ = build_gpu_graph(ls, keys, init, factors, np.array(tracks))
+    got = g.marginals(keys)
+    want = pg.marginals(factors, keys, init, keys)
+    assert (np.abs(got - want) / np.abs(want).max(axis=(1, 2), keepdims=True)).max() < 1e-6
+    g.close()
