@@ -429,6 +429,53 @@ def main():
     t_e2e = time.perf_counter() - t0
     clocks = sampler.summary()
 
+    # ------------------------------------------------------------------ the same through the C++ host layer
+    # laser_slam::IncrementalEstimator::processPosesAndLaserScans (libls_host.so): what laser_slam_ros would call.  Host
+    # clouds arrive as DataPoints (pageable std::vector storage, copied into the track as the reference does), every
+    # track's scan is uploaded by LaserTrack::residentScan and the B registrations of a step run as one batched launch.
+    host_arm = None
+    if not os.environ.get("LS_BENCH_NO_HOST_ARM"):
+        import tempfile
+        from laser_slam_b200 import host as lsh
+        with tempfile.NamedTemporaryFile("w", suffix=".yaml", delete=False) as f:
+            f.write("matcher:\n  KDTreeMatcher:\n    knn: 1\noutlierFilters:\n  - TrimmedDistOutlierFilter:\n      ratio: 0.75\n"
+                    "errorMinimizer:\n  PointToPlaneErrorMinimizer\ntransformationCheckers:\n  - CounterTransformationChecker:\n"
+                    f"      maxIterationCount: {ITERS}\n")
+            yaml_path = f.name
+        est = lsh.Estimator(n_workers=B, nscan_in_sub_map=K_MAP, use_icp_factors=True, use_odom_factors=True, robust_icp=True,
+                            device=local, icp_yaml_path=yaml_path)
+
+        def pose7(T):
+            q = np.empty(4)
+            R = T[:3, :3]
+            q[0] = 0.5 * np.sqrt(max(1e-12, 1.0 + np.trace(R)))
+            q[1:] = np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]]) / (4.0 * q[0])
+            return np.concatenate([q / np.linalg.norm(q), T[:3, 3]])
+
+        def step_host(s):
+            idxs = [walk(s) for _ in range(B)]
+            return est.step_batch(list(range(B)), [s * 100_000_000] * B, [pose7(tracks[t][1][idxs[t]]) for t in range(B)],
+                                  [feats[t][idxs[t]].data_ptr() for t in range(B)], [nrms[t][idxs[t]].data_ptr() for t in range(B)],
+                                  [N_SCAN] * B, with_estimator=False)
+
+        n_host = max(3, min(args.steps, 10))
+        w_host = K_MAP + 2
+        for s in range(w_host):
+            step_host(s)
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(w_host, w_host + n_host):
+            icp7, hstats = step_host(s)
+        barrier()
+        t_host = time.perf_counter() - t0
+        t_host, = lsd.max_over_ranks([t_host], device=local)
+        host_arm = {"value": world * B * n_host / t_host, "unit": "registrations/s", "steps": n_host,
+                    "api": "laser_slam::IncrementalEstimator::processPosesAndLaserScans over libls_host.so: DataPoints in, "
+                           "RelativePose out; uploads are synchronous copies from pageable DataPoints storage inside the call",
+                    "iterations": int(hstats[0].iterations)}
+        est.close()
+        os.unlink(yaml_path)
+
     # ------------------------------------------------------------------ reduce over ranks (max time)
     t_res, t_e2e = lsd.max_over_ranks([t_res, t_e2e], device=local)
     exchange.close()
@@ -479,7 +526,8 @@ def main():
                 "h2d_bytes_per_step": B * (N_SCAN * 16 + N_SCAN * 12 + 16 * 4 * (K_MAP + 1) + 8 * (K_MAP + 1)),
                 "d2h_bytes_per_step": B * (216 + 212),   # per registration: result block of the ICP scratch + grid header
                 "pipeline": "the scans of step s+1 are uploaded (ls_map_push_scan_async, own stream) while step s is "
-                            "registered; every timed step issues one full set of uploads and reads its results back"},
+                            "registered; every timed step issues one full set of uploads and reads its results back",
+                "host_layer": host_arm},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
     }
     if cpu:

@@ -87,7 +87,8 @@ class LaserTrack {
     RelativePose icp_transformation;
     // (internal) carried from begin to end
     RelativePose relative_measurement;
-    LaserScan scan;
+    Key scan_key = 0;
+    Time scan_time_ns = 0;
     bool first = false;
     Pose pose;
     double t_start_ms = 0.0;

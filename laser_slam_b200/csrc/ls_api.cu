@@ -89,6 +89,9 @@ struct ls_map {
   size_t stage_cap[kStageRing] = {};
   cudaEvent_t stage_free[kStageRing] = {};
   uint64_t n_async = 0;
+  // pinned host staging of ls_map_push_scan (pageable caller memory is copied here, the DMA then runs behind the call)
+  float* host_stage[kStageRing] = {};
+  size_t host_stage_cap[kStageRing] = {};
 };
 
 namespace {
@@ -770,6 +773,7 @@ void ls_map_destroy(ls_map* map) {
     if (s.ready) cudaEventDestroy(s.ready);
   }
   for (int k = 0; k < kStageRing; ++k) {
+    if (map->host_stage[k]) cudaFreeHost(map->host_stage[k]);
     if (map->stage[k]) cudaFree(map->stage[k]);
     if (map->stage_free[k]) cudaEventDestroy(map->stage_free[k]);
   }
@@ -777,6 +781,10 @@ void ls_map_destroy(ls_map* map) {
   delete map;
 }
 
+// The caller's buffers (pageable in general: Eigen / std::vector storage of a DataPoints) are only valid during the
+// call, so they are copied into pinned staging memory owned by the map; the transfer to the device then runs on the
+// map's upload stream BEHIND the call, and consumers order themselves after it with the slot's event -- exactly the
+// asynchronous path, minus the caller's obligation to keep (and pin) its buffers.
 int ls_map_push_scan(ls_map* map, const float* features4, const float* normals, int normals_stride, int n,
                      uint64_t* scan_id) {
   if (!map) return LS_ERR_ARG;
@@ -785,26 +793,31 @@ int ls_map_push_scan(ls_map* map, const float* features4, const float* normals, 
   if (!features4 || !normals || normals_stride < 3 || n < 0 || n > map->max_pts || !scan_id)
     return fail(ctx, LS_ERR_ARG, "bad argument (n=%d, max=%d)", n, map->max_pts);
   CU(cudaSetDevice(ctx->device));
-  Workspace* w = ctx->ws[0];
-  const uint64_t id = map->next_id++;
-  ls_scan_slot& s = map->slots[id % (uint64_t)map->capacity];
-  s.used = false;
-  if (s.async) {  // an earlier asynchronous upload into this slot must not land after this one
-    CU(cudaEventSynchronize(s.ready));
-    s.async = false;
+  if (n == 0) return ls_map_push_scan_async(map, features4, normals, normals_stride > 8 ? 3 : normals_stride, 0, scan_id);
+  const int k = (int)(map->n_async % kStageRing);  // the slot of the staging rings the asynchronous push below will take
+  if (map->stage_free[k]) CU(cudaEventSynchronize(map->stage_free[k]));  // the upload that used this staging slot last
+  const int stride = normals_stride <= 8 ? normals_stride : 3;
+  const size_t nf = (size_t)n * 4, nn = (size_t)(n - 1) * (size_t)stride + 3;
+  if (nf + nn > map->host_stage_cap[k]) {
+    if (map->host_stage[k]) CU(cudaFreeHost(map->host_stage[k]));
+    map->host_stage[k] = nullptr;
+    map->host_stage_cap[k] = 0;
+    if (cudaMallocHost((void**)&map->host_stage[k], (nf + nn + 1024) * sizeof(float)) != cudaSuccess)
+      return fail(ctx, LS_ERR_NOMEM, "pinned staging allocation failed");
+    map->host_stage_cap[k] = nf + nn + 1024;
   }
-  if (n > 0) {
-    CU(cudaMemcpyAsync(s.pts, features4, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, w->stream));
-    int rc = upload_normals(ctx, w, normals, normals_stride, n, s.nrm);
-    if (rc) return rc;
-    // the staging buffer for normals is reused by the next upload: wait for the expand kernel
-    CU(cudaStreamSynchronize(w->stream));
+  float* hf = map->host_stage[k];
+  float* hn = hf + nf;
+  std::memcpy(hf, features4, nf * sizeof(float));
+  if (normals_stride <= 8) {
+    std::memcpy(hn, normals, nn * sizeof(float));  // never past the last normal (the block may start at a row offset)
+  } else {
+    for (int i = 0; i < n; ++i) {
+      const float* r = normals + (size_t)i * (size_t)normals_stride;
+      hn[3 * (size_t)i] = r[0]; hn[3 * (size_t)i + 1] = r[1]; hn[3 * (size_t)i + 2] = r[2];
+    }
   }
-  s.n = n;
-  s.id = id;
-  s.used = true;
-  *scan_id = id;
-  return LS_OK;
+  return ls_map_push_scan_async(map, hf, hn, stride, n, scan_id);
 }
 
 // Asynchronous variant: everything is enqueued on the map's own upload stream and the call returns; the host buffers

@@ -125,3 +125,86 @@ def max_over_ranks(values, device=None):
     t = torch.tensor(values, dtype=torch.float64, device=("cuda" if device is not None else "cpu"))
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return [float(v) for v in t]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The shared estimator fed from the gathered records (the reference has ONE iSAM2 for all tracks,
+# reference laser_slam/include/laser_slam/incremental_estimator.hpp:67; here every rank keeps a replica and feeds it the
+# same records in the same order, so the replicas stay identical without any further exchange).
+ICP_SIGMAS = [0.005] * 3 + [0.0015] * 3          # reference laser_slam_ros/config/config_example.yaml:4-6
+PRIOR_SIGMAS = [1e-7] * 6                        # reference laser_slam/src/laser_track.cpp:56-64
+
+
+def record_pose7(rec):
+    """Record delta (translation, rotation vector) -> {qw,qx,qy,qz,tx,ty,tz}, the pose layout of the C ABI."""
+    d = np.asarray(rec["delta"], np.float64)
+    th = float(np.linalg.norm(d[3:]))
+    if th < 1e-12:
+        q = np.array([1.0, 0.5 * d[3], 0.5 * d[4], 0.5 * d[5]])
+    else:
+        q = np.concatenate([[np.cos(0.5 * th)], np.sin(0.5 * th) / th * d[3:]])
+    return np.concatenate([q / np.linalg.norm(q), d[:3]])
+
+
+def _compose7(a, b):
+    qa, qb = a[:4], b[:4]
+    q = np.array([qa[0] * qb[0] - qa[1] * qb[1] - qa[2] * qb[2] - qa[3] * qb[3],
+                  qa[0] * qb[1] + qa[1] * qb[0] + qa[2] * qb[3] - qa[3] * qb[2],
+                  qa[0] * qb[2] - qa[1] * qb[3] + qa[2] * qb[0] + qa[3] * qb[1],
+                  qa[0] * qb[3] + qa[1] * qb[2] - qa[2] * qb[1] + qa[3] * qb[0]])
+    w, x, y, z = qa
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                  [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                  [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+    return np.concatenate([q / np.linalg.norm(q), R @ b[4:] + a[4:]])
+
+
+class ReplicatedGraph:
+    """Host mirror of the replicated pose graph: `feed(records)` turns one step's gathered records into new nodes and
+    factors -- track t's first record anchors it with a prior at (0, 100 t, 0) (reference laser_track.cpp:163-172,
+    force_priors), every later one adds the node `previous * delta` and a Cauchy ICP BetweenFactor (reference
+    laser_track.cpp:431-451) -- and hands them to `sink` (an ls PoseGraph on the GPU; None just keeps the lists, which
+    is what the CPU tests compare across ranks).  Records with status != 0 still extend the track (the reference keeps
+    the odometry guess, laser_track.cpp:495-502)."""
+
+    def __init__(self, world, sink=None):
+        self.world, self.sink = world, sink
+        self.keys, self.poses, self.factors, self.tracks = [], [], [], []
+        self.last = [None] * world        # (key, pose7) of every track's newest node
+        self.count = [0] * world
+
+    @staticmethod
+    def key(track, index):
+        return (int(track) << 48) | int(index)
+
+    def feed(self, records):
+        new_keys, new_poses, new_tracks, new_factors = [], [], [], []
+        for t in range(self.world):
+            rec = records[t]
+            k = self.key(t, self.count[t])
+            if self.last[t] is None:
+                pose = np.array([1.0, 0, 0, 0, 0.0, 100.0 * t, 0.0])
+                new_factors.append(dict(type=0, key_a=k, key_b=k, meas=pose, sigma=PRIOR_SIGMAS))
+            else:
+                rel = record_pose7(rec)
+                pose = _compose7(self.last[t][1], rel)
+                new_factors.append(dict(type=1, key_a=self.last[t][0], key_b=k, meas=rel, sigma=ICP_SIGMAS, robust=1))
+            new_keys.append(k); new_poses.append(pose); new_tracks.append(t)
+            self.last[t] = (k, pose)
+            self.count[t] += 1
+        self.keys += new_keys; self.poses += new_poses; self.tracks += new_tracks; self.factors += new_factors
+        if self.sink is not None:
+            self.sink.add_poses(np.array(new_keys, np.uint64), np.stack(new_poses), np.array(new_tracks, np.uint32))
+            self.sink.add_factors(new_factors)
+
+    def digest(self):
+        """Bytes that are equal on two ranks iff their graphs are (keys, initial values, factor table)."""
+        import hashlib
+        h = hashlib.sha256()
+        h.update(np.array(self.keys, np.uint64).tobytes())
+        h.update(np.stack(self.poses).tobytes() if self.poses else b"")
+        for f in self.factors:
+            h.update(np.array([f["type"], f.get("robust", 0)], np.int64).tobytes())
+            h.update(np.array([f["key_a"], f["key_b"]], np.uint64).tobytes())
+            h.update(np.asarray(f["meas"], np.float64).tobytes())
+        return h.hexdigest()

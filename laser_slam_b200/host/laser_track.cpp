@@ -132,15 +132,16 @@ void LaserTrack::beginPoseAndLaserScan(const Pose& pose, const LaserScan& in_sca
   pending->t_start_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
   LS_CHECK(in_scan.scan.descriptorExists("normals"), "scans must carry a 'normals' descriptor");
   pending->pose = pose;
-  LaserScan& scan = pending->scan;
-  scan = in_scan;  // the reference copies too (:143); filters would run on the copy
+  laser_scans_.push_back(in_scan);  // the one copy the track keeps (the reference copies twice, :143 and :197)
+  LaserScan& scan = laser_scans_.back();
   pose_measurements_.push_back(pose);
 
   if (trajectory_.empty()) {
     pending->first = true;
     scan.key = extendTrajectory(scan.time_ns, findPose(scan.time_ns).T_w);
     findPose(scan.time_ns).key = scan.key;
-    laser_scans_.push_back(scan);
+    pending->scan_key = scan.key;
+    pending->scan_time_ns = scan.time_ns;
     return;
   }
   const Time t_last = trajectory_.rbegin()->first;
@@ -155,7 +156,8 @@ void LaserTrack::beginPoseAndLaserScan(const Pose& pose, const LaserScan& in_sca
   // extend the trajectory by odometry (reference :192)
   scan.key = extendTrajectory(scan.time_ns, trajectory_.rbegin()->second.value * relative_measurement.T_a_b);
   findPose(scan.time_ns).key = scan.key;
-  laser_scans_.push_back(scan);
+  pending->scan_key = scan.key;
+  pending->scan_time_ns = scan.time_ns;
   relative_measurement.key_b = scan.key;
   odometry_measurements_.push_back(relative_measurement);
   if (params_.use_icp_factors && getNumScans() > 1u) stageLocalScanToSubMap(pending);  // computeICPTransformations (:460-464)
@@ -168,7 +170,7 @@ void LaserTrack::endPoseAndLaserScan(PendingIcp* pending, int rc, const float* T
   LS_CHECK(pending != NULL, "null pending");
   if (newFactors != NULL) LS_CHECK(newFactors->empty(), "newFactors must be empty on entry");
   if (newValues != NULL) newValues->clear();
-  const LaserScan& scan = pending->scan;
+  struct { Key key; Time time_ns; } scan{pending->scan_key, pending->scan_time_ns};
   if (pending->first) {
     if (newFactors != NULL) {
       Pose prior_pose = pending->pose;

@@ -82,3 +82,46 @@ def test_pose_record_layout():
     ex.post(rec)
     assert ex.collect()[0] == rec and ex.collect() is None
     assert lsd.shard(10, 1, 4) == [1, 5, 9]
+
+
+def _graph_worker(rank, world, port, out_dir):
+    """Every rank feeds its replica of the shared estimator from the gathered records; the replicas must be identical."""
+    import torch.distributed as dist
+    from laser_slam_b200 import dist as lsd
+    from oracle import posegraph_oracle as pg
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ex = lsd.Exchange(rank, world, device=None)
+    graph = lsd.ReplicatedGraph(world)
+    rng = np.random.default_rng(100 + rank)          # every rank only knows ITS track's registrations
+    for step in range(12):
+        T = np.eye(4)
+        T[:3, 3] = [0.8 + 0.01 * rng.normal(), 0.01 * rng.normal(), 0.0]
+        a = 0.02 * (rank + 1) + 0.001 * rng.normal()
+        T[:2, :2] = [[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]]
+        got = ex.collect()                            # split-phase: step s-1's records arrive while step s is posted
+        if got is not None:
+            graph.feed(got)
+        ex.post(lsd.pose_record(T, status=0, key=step))
+    graph.feed(ex.collect())
+    keys = np.array(graph.keys, np.uint64)
+    fac = [pg.make_factor(f["type"], f["key_a"], f["key_b"], f["meas"], f["sigma"], robust=f.get("robust", 0)) for f in graph.factors]
+    est, _ = pg.optimize(fac, keys, np.stack(graph.poses), iters=3)
+    np.savez(os.path.join(out_dir, f"g{rank}.npz"), digest=np.array(graph.digest()), est=est, keys=keys, n_fac=len(fac))
+    dist.destroy_process_group()
+
+
+def test_replicated_estimator_graphs_are_identical_across_ranks(tmp_path):
+    """BASELINE.json configs[2] / SURVEY.md §8e: the 32-byte records are all a rank needs to keep an exact replica of the
+    shared pose graph -- same keys, same initial values, same factors, hence the same estimate -- on every rank."""
+    import torch.multiprocessing as mp
+    world, port = 2, _free_port()
+    mp.spawn(_graph_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    g0, g1 = np.load(tmp_path / "g0.npz"), np.load(tmp_path / "g1.npz")
+    assert str(g0["digest"]) == str(g1["digest"])
+    assert np.array_equal(g0["keys"], g1["keys"]) and len(g0["keys"]) == 2 * 12 and int(g0["n_fac"]) == 2 * 12
+    assert np.array_equal(g0["est"], g1["est"])                      # identical graphs -> bit-identical estimates
+    track = g0["keys"] >> np.uint64(48)
+    assert sorted(set(track.tolist())) == [0, 1]
+    assert np.allclose(g0["est"][track == 1][0, 4:], [0, 100, 0], atol=1e-6)   # track 1 anchored at its prior
