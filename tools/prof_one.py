@@ -16,29 +16,32 @@ reps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 ctx = ls.Context(0)
 k0 = int(os.environ.get("LS_PROF_SCAN", "0"))
+SENSOR = int(os.environ.get("LS_PROF_SENSOR", "0"))   # 0 HDL-64 (131072 rays), 1 VLS-128 (262144 rays): config 5 with LS_PROF_K=8
+K = int(os.environ.get("LS_PROF_K", "4"))
 if "LS_PROF_Y" in os.environ or k0:
-    truth, odom = synth.trajectory(0, k0 + 8, y_start=float(os.environ.get("LS_PROF_Y", "-20")))
+    truth, odom = synth.trajectory(0, k0 + K + 4, y_start=float(os.environ.get("LS_PROF_Y", "-20")))
     truth, odom = truth[k0:], odom[k0:]
-    scans = [synth.scan(truth[k], 0, k0 + k) for k in range(5)]
+    scans = [synth.scan(truth[k], 0, k0 + k, sensor=SENSOR) for k in range(K + 1)]
 else:
-    truth, odom = synth.trajectory(0, 8)
-    scans = [synth.scan(truth[k], 0, k) for k in range(5)]
-mp = ctx.create_map(8, 131072)
-sid = [mp.push_scan(*scans[k]) for k in range(5)]
-Tparts = [np.eye(4, dtype=np.float32) if k == 3 else (np.linalg.inv(truth[3]) @ truth[k]).astype(np.float32) for k in [3, 2, 1, 0]]
-T0 = (np.linalg.inv(truth[3]) @ odom[4]).astype(np.float32)
+    truth, odom = synth.trajectory(0, K + 4)
+    scans = [synth.scan(truth[k], 0, k, sensor=SENSOR) for k in range(K + 1)]
+mp = ctx.create_map(K + 4, len(scans[0][0]))
+sid = [mp.push_scan(*scans[k]) for k in range(K + 1)]
+ref_order = [K - 1 - j for j in range(K)]
+Tparts = [np.eye(4, dtype=np.float32) if k == K - 1 else (np.linalg.inv(truth[K - 1]) @ truth[k]).astype(np.float32) for k in ref_order]
+T0 = (np.linalg.inv(truth[K - 1]) @ odom[K]).astype(np.float32)
 p = ls.default_params(max_iterations=iters, use_differential=0)
 for k in ("cell_size", "leaf_split"):
     if os.environ.get("LS_" + k.upper()):
         setattr(p, k, type(getattr(p, k))(float(os.environ["LS_" + k.upper()])))
 for rep in range(reps):
-    g = mp.register(sid[4], [sid[3], sid[2], sid[1], sid[0]], Tparts, T0, p)
+    g = mp.register(sid[K], [sid[k] for k in ref_order], Tparts, T0, p)
     print(f"rep {rep}: device {g['stats'].device_ms:.3f} ms build {g['stats'].build_ms:.3f} ms iters {g['stats'].iterations}")
 
 B = int(os.environ.get("LS_BATCH", "0"))
 if B:
     import time
-    probs = [(sid[4], [sid[3], sid[2], sid[1], sid[0]], Tparts, T0)] * B
+    probs = [(sid[K], [sid[k] for k in ref_order], Tparts, T0)] * B
     call = mp.prepare_batch(probs, p)
     for rep in range(reps + 1):
         t0 = time.perf_counter(); rc, statuses, touts, stats = call(); dt = time.perf_counter() - t0
