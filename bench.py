@@ -26,7 +26,7 @@ sys.path.insert(0, ROOT)
 
 # BASELINE.json configs[1] (default) and configs[4] (--config 5): scan size, scans per map, ICP iterations, sensor
 WORKLOADS = {
-    2: dict(n_scan=131072, k_map=4, iters=30, sensor=0, pool=24, tracks=32,
+    2: dict(n_scan=131072, k_map=4, iters=30, sensor=0, pool=24, tracks=74,
             name="configs[1]: scan-to-local-map ICP, 131072-pt scan vs 524288-pt rolling map (4 scans), 30 iterations",
             metric="ICP registrations/s (131072-pt scan vs 524288-pt map, 30 iterations)"),
     5: dict(n_scan=262144, k_map=8, iters=50, sensor=1, pool=14, tracks=8,
@@ -245,7 +245,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--tracks", type=int, default=0, help="independent sequences (tracks) hosted per GPU, batched per "
-                    "launch (default: 32 for config 2, 8 for config 5)")
+                    "launch (default: 74 for config 2 = 4 of the 296 co-resident CTAs each, 8 for config 5)")
     ap.add_argument("--config", type=int, default=2, choices=(2, 3, 4, 5),
                     help="BASELINE.json workload: 2 scan-to-map ICP (default, the headline metric), 3 batched trajectories "
                          "feeding the shared estimator, 4 pose-graph solve, 5 dense-sensor stress")

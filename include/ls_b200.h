@@ -172,7 +172,7 @@ int ls_icp_register_submap(ls_ctx* ctx, const ls_icp_params* prm, const ls_map* 
  * GPU: the reference's n_laser_slam_workers tracks, laser_slam/src/incremental_estimator.cpp:22-26).  Problem b
  * uses reading_ids[b], its n_parts[b] parts follow each other in part_ids / T_parts (16 floats per part),
  * T0s / T_outs hold 16 floats per problem, statuses[b] is LS_OK or LS_ERR_CONVERGENCE (then T_out == T0).
- * Results are bit-identical to separate ls_icp_register_submap calls.  1 <= batch <= 16. */
+ * Results are bit-identical to separate ls_icp_register_submap calls.  1 <= batch <= 80. */
 int ls_icp_register_submap_batch(ls_ctx* ctx, const ls_icp_params* prm, const ls_map* map, int batch,
                                  const uint64_t* reading_ids, const int* n_parts, const uint64_t* part_ids,
                                  const float* T_parts, const float* T0s, float* T_outs, ls_icp_stats* stats,
@@ -201,6 +201,24 @@ int ls_icp_register_submaps(ls_ctx* ctx, const ls_icp_params* prm, const ls_map*
  * out_normals3: 3*M floats (may be NULL); returns M through *m_out. */
 int ls_map_assemble(ls_ctx* ctx, const ls_map* map, int n_parts, const uint64_t* part_ids,
                     const float* T_parts, float* out4, float* out_normals3, int* m_out);
+
+/* ---- input side and map maintenance ---------------------------------------------------
+ * The steps laser_slam_ros runs on the CPU either side of the registration, on the device.  Host buffers in and out;
+ * `device` selects the GPU (no context needed).
+ *   ls_ingest_pointcloud2   sensor_msgs/PointCloud2 payload -> DataPoints features: x, y, z floats at byte offsets
+ *                           off_* inside records of point_step bytes -> {x, y, z, 1}
+ *                           (laser_slam_ros/src/laser_slam_worker.cpp:125, pcl::fromROSMsg + conversion)
+ *   ls_filter_cylinder      applyCylindricalFilter (laser_slam_ros/include/laser_slam_ros/common.hpp:194-223, used by
+ *                           LaserSlamWorker::getFilteredMap, laser_slam_worker.cpp:415-488): keeps the points inside
+ *                           (remove_points_inside == 0: d_xy^2 <= r^2 and |dz| <= h/2) or outside (>= on either) the
+ *                           cylinder, in input order; out4 holds up to n points, *n_out the number kept
+ *   ls_voxel_grid           pcl::VoxelGrid as getFilteredMap uses it (laser_slam_worker.cpp:434-441): one centroid per
+ *                           occupied voxel of edge leaf_size, voxels in ascending cell-index order (x fastest); the
+ *                           centroid is the exact mean of the voxel's points (fixed-point sums), rounded once */
+int ls_ingest_pointcloud2(int device, const void* data, int point_step, int off_x, int off_y, int off_z, int n, float* out4);
+int ls_filter_cylinder(int device, const float* in4, int n, const double center[3], double radius_m, double height_m,
+                       int remove_points_inside, float* out4, int* n_out);
+int ls_voxel_grid(int device, const float* in4, int n, const float leaf_size[3], float* out4, int* n_out);
 
 /* ---- pose graph ------------------------------------------------------------------------------------
  * Replaces gtsam::ISAM2 as IncrementalEstimator uses it (laser_slam/src/incremental_estimator.cpp:17-20,

@@ -124,6 +124,9 @@ def lib():
         L.ls_pg_get_poses.argtypes = [vp, vp, vp, ctypes.POINTER(ci)]
         L.ls_pg_marginals.argtypes = [vp, vp, ci, vp]
         L.ls_keep_point.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_float]
+        L.ls_ingest_pointcloud2.argtypes = [ci, vp, ci, ci, ci, ci, ci, vp]
+        L.ls_filter_cylinder.argtypes = [ci, vp, ci, vp, ctypes.c_double, ctypes.c_double, ci, vp, ctypes.POINTER(ci)]
+        L.ls_voxel_grid.argtypes = [ci, vp, ci, vp, vp, ctypes.POINTER(ci)]
         _lib = L
     return _lib
 
@@ -151,6 +154,40 @@ def keep_mask(n, salt, prob):
 
 
 READING_SALT, REFERENCE_SALT = 0x7e11, 0x5a17   # the salts PointMatcher::DataPointsFilters uses (compat.hpp)
+
+
+def _rc(rc, what):
+    if rc != 0:
+        raise LsError(f"{what}: rc={rc}")
+
+
+def ingest_pointcloud2(data, point_step, off_x, off_y, off_z, n, device=0):
+    """sensor_msgs/PointCloud2 payload (bytes / uint8 array) -> (n,4) float32 features {x,y,z,1} on the device."""
+    buf = np.frombuffer(data, np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data.view(np.uint8))
+    out = np.empty((max(n, 1), 4), np.float32)
+    _rc(lib().ls_ingest_pointcloud2(device, buf.ctypes.data, point_step, off_x, off_y, off_z, n, out.ctypes.data), "ls_ingest_pointcloud2")
+    return out[:n]
+
+
+def filter_cylinder(pts4, center, radius_m, height_m, remove_points_inside=False, device=0):
+    """applyCylindricalFilter (reference laser_slam_ros/include/laser_slam_ros/common.hpp:194-223) on the device."""
+    p = np.ascontiguousarray(pts4, np.float32)
+    c = np.ascontiguousarray(center, np.float64)
+    out = np.empty((max(len(p), 1), 4), np.float32)
+    n = ctypes.c_int(0)
+    _rc(lib().ls_filter_cylinder(device, p.ctypes.data, len(p), c.ctypes.data, float(radius_m), float(height_m),
+                                 int(bool(remove_points_inside)), out.ctypes.data, ctypes.byref(n)), "ls_filter_cylinder")
+    return out[:n.value].copy()
+
+
+def voxel_grid(pts4, leaf_size, device=0):
+    """pcl::VoxelGrid centroids (reference laser_slam_ros/src/laser_slam_worker.cpp:434-441) on the device."""
+    p = np.ascontiguousarray(pts4, np.float32)
+    leaf = np.ascontiguousarray(np.broadcast_to(np.asarray(leaf_size, np.float32), (3,)), np.float32)
+    out = np.empty((max(len(p), 1), 4), np.float32)
+    n = ctypes.c_int(0)
+    _rc(lib().ls_voxel_grid(device, p.ctypes.data, len(p), leaf.ctypes.data, out.ctypes.data, ctypes.byref(n)), "ls_voxel_grid")
+    return out[:n.value].copy()
 
 
 def apply_chain_filters(ctx, reading4, ref4, ref_normals3, params):

@@ -65,7 +65,7 @@ struct ls_ctx {
   // ring slots (map, slot index) the in-flight batch reads: an asynchronous upload must not overwrite them
   std::vector<std::pair<const ls_map*, int>> pending_slots;
 };
-constexpr int kMaxBatch = 32;
+constexpr int kMaxBatch = 80;
 
 struct ls_scan_slot {
   float4* pts = nullptr;

@@ -85,7 +85,7 @@ void IncrementalEstimator::processPosesAndLaserScans(const std::vector<unsigned 
   std::vector<float> T_outs(16 * std::max<size_t>(active.size(), 1));
   std::vector<ls_icp_stats> stats(std::max<size_t>(active.size(), 1));
   std::vector<int> statuses(std::max<size_t>(active.size(), 1), LS_OK);
-  constexpr size_t kMaxBatch = 32;  // ls_icp_register_submap_batch's limit
+  constexpr size_t kMaxBatch = 80;  // ls_icp_register_submap_batch's limit
   for (size_t b0 = 0; b0 < active.size(); b0 += kMaxBatch) {
     const size_t nb = std::min(kMaxBatch, active.size() - b0);
     std::vector<uint64_t> reading_ids, part_ids;

@@ -209,6 +209,44 @@ def keep_mask(n, salt, prob):
     return h.astype(np.float64) < float(np.float32(prob)) * 4294967296.0
 
 
+def filter_cylinder(pts4, center, radius_m, height_m, remove_points_inside=False):
+    """applyCylindricalFilter (reference laser_slam_ros/include/laser_slam_ros/common.hpp:194-223): double arithmetic on
+    float coordinates, <= / >= exactly as written there, input order kept."""
+    p = np.asarray(pts4, np.float32)
+    c = np.asarray(center, np.float64)
+    d2 = (p[:, 0].astype(np.float64) - c[0]) ** 2 + (p[:, 1].astype(np.float64) - c[1]) ** 2
+    dz = np.abs(p[:, 2].astype(np.float64) - c[2])
+    r2, hh = float(radius_m) ** 2, float(height_m) / 2.0
+    keep = ((d2 >= r2) | (dz >= hh)) if remove_points_inside else ((d2 <= r2) & (dz <= hh))
+    return p[keep].copy()
+
+
+def voxel_grid(pts4, leaf_size):
+    """pcl::VoxelGrid as LaserSlamWorker::getFilteredMap runs it (reference laser_slam_ros/src/laser_slam_worker.cpp:434-441):
+    cell = floor(p * (1 / leaf)) in float32, one output point per occupied cell, cells in ascending linear index (x fastest);
+    [DEFINED] the centroid is the exact mean (fixed point 2^-24) rounded once -- PCL's float running sum depends on the order."""
+    p = np.asarray(pts4, np.float32)
+    leaf = np.broadcast_to(np.asarray(leaf_size, np.float32), (3,))
+    inv = (np.float32(1.0) / leaf).astype(np.float32)
+    ok = np.isfinite(p[:, :3]).all(1)
+    q = p[ok]
+    if len(q) == 0:
+        return np.zeros((0, 4), np.float32)
+    ijk = np.floor(q[:, :3] * inv[None, :]).astype(np.int64)
+    mn = ijk.min(0)
+    dim = ijk.max(0) - mn + 1
+    key = (ijk[:, 0] - mn[0]) + (ijk[:, 1] - mn[1]) * dim[0] + (ijk[:, 2] - mn[2]) * dim[0] * dim[1]
+    order = np.argsort(key, kind="stable")
+    ks = key[order]
+    heads = np.flatnonzero(np.concatenate([[True], ks[1:] != ks[:-1]]))
+    fx = np.rint(q[order, :3].astype(np.float64) * 16777216.0).astype(np.int64)
+    sums = np.add.reduceat(fx, heads, axis=0)
+    cnt = np.diff(np.concatenate([heads, [len(ks)]]))
+    out = np.ones((len(heads), 4), np.float32)
+    out[:, :3] = (sums.astype(np.float64) / (cnt[:, None].astype(np.float64) * 16777216.0)).astype(np.float32)
+    return out
+
+
 def sincos(x):
     s = ctypes.c_double()
     c = ctypes.c_double()
