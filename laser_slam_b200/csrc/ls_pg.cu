@@ -312,6 +312,209 @@ __global__ void pg_chain_solve_kernel(int P, int ncol, const FactorDev* __restri
   }
 }
 
+
+// ---------------------------------------------------------------- K6a': block cyclic reduction of H_c
+// The sequential block sweeps above cost 2 x P dependent steps per right-hand side (75 ms per Gauss-Newton iteration at
+// 5000 poses and 1201 right-hand sides).  Odd-even (cyclic) reduction solves the same block-tridiagonal SPD system in
+// log2(P) levels, every level fully parallel over nodes and right-hand sides: level l (stride s = 2^l, nodes numbered
+// m = 1..P) eliminates the nodes m = s (mod 2s) into their neighbours m +- s, which keep a Schur complement and a coupling
+// of stride 2s; the back-substitution walks the levels down again.  Tracks are just zero couplings.
+//   Dc[m]      current diagonal block of node m (final once the node is eliminated)
+//   Di[m]      its inverse, formed at the node's elimination level
+//   Ll[l][j]   coupling H^(l)[m][m - s] of node m = j << l at level l  (the right coupling is the transpose of the right
+//              neighbour's left one: the matrix stays symmetric)
+__device__ __forceinline__ bool inv6_spd(const double* A, double* X) {  // X = A^-1 through Cholesky; false: not positive definite
+  double L[36];
+  for (int i = 0; i < 36; ++i) L[i] = 0.0;
+  for (int j = 0; j < 6; ++j) {
+    double s = A[6 * j + j];
+    for (int m = 0; m < j; ++m) s -= L[6 * j + m] * L[6 * j + m];
+    if (!(s > 0.0)) return false;
+    const double d = sqrt(s), id = 1.0 / d;
+    L[6 * j + j] = d;
+    for (int i = j + 1; i < 6; ++i) {
+      double v = A[6 * i + j];
+      for (int m = 0; m < j; ++m) v -= L[6 * i + m] * L[6 * j + m];
+      L[6 * i + j] = v * id;
+    }
+  }
+  for (int c = 0; c < 6; ++c) {  // solve L L^T x = e_c
+    double y[6];
+    for (int i = 0; i < 6; ++i) {
+      double v = (i == c) ? 1.0 : 0.0;
+      for (int m = 0; m < i; ++m) v -= L[6 * i + m] * y[m];
+      y[i] = v / L[6 * i + i];
+    }
+    for (int i = 5; i >= 0; --i) {
+      double v = y[i];
+      for (int m = i + 1; m < 6; ++m) v -= L[6 * m + i] * X[6 * m + c];
+      X[6 * i + c] = v / L[6 * i + i];
+    }
+  }
+  return true;
+}
+__device__ __forceinline__ void mm6(const double* A, const double* B, double* C) {  // C = A B
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) {
+      double s = 0.0;
+      for (int m = 0; m < 6; ++m) s += A[6 * i + m] * B[6 * m + j];
+      C[6 * i + j] = s;
+    }
+}
+__device__ __forceinline__ void mmt6(const double* A, const double* B, double* C) {  // C = A B^T
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) {
+      double s = 0.0;
+      for (int m = 0; m < 6; ++m) s += A[6 * i + m] * B[6 * j + m];
+      C[6 * i + j] = s;
+    }
+}
+__device__ __forceinline__ void mtm6(const double* A, const double* B, double* C) {  // C = A^T B
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) {
+      double s = 0.0;
+      for (int m = 0; m < 6; ++m) s += A[6 * m + i] * B[6 * m + j];
+      C[6 * i + j] = s;
+    }
+}
+
+__global__ void cr_init_kernel(int P, const double* __restrict__ D, const double* __restrict__ Bsub, double* __restrict__ Dc,
+                               double* __restrict__ L0) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= P) return;
+  for (int i = 0; i < 36; ++i) { Dc[36 * (size_t)k + i] = D[36 * (size_t)k + i]; L0[36 * (size_t)(k + 1) + i] = Bsub[36 * (size_t)k + i]; }
+}
+// nodes eliminated at this level: invert their (final) diagonal
+__global__ void cr_invert_kernel(int P, int s, const double* __restrict__ Dc, double* __restrict__ Di, int* fail) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long m = (long long)s + (long long)t * 2 * s;  // m = s (mod 2s)
+  if (m > P) return;
+  double X[36];
+  if (!inv6_spd(Dc + 36 * (size_t)(m - 1), X)) {
+    *fail = 1;
+    for (int i = 0; i < 36; ++i) X[i] = (i % 7 == 0) ? 1.0 : 0.0;
+  }
+  for (int i = 0; i < 36; ++i) Di[36 * (size_t)(m - 1) + i] = X[i];
+}
+// nodes kept at this level: Schur complement and the coupling of stride 2s
+__global__ void cr_reduce_kernel(int P, int s, int lshift, double* __restrict__ Dc, const double* __restrict__ Di,
+                                 const double* __restrict__ Lcur, double* __restrict__ Lnext) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long m = (long long)(t + 1) * 2 * s;  // m = 0 (mod 2s)
+  if (m > P) return;
+  double A[36], W[36], T[36];
+  for (int i = 0; i < 36; ++i) A[i] = Dc[36 * (size_t)(m - 1) + i];
+  const double* Lm = Lcur + 36 * (size_t)(m >> lshift);             // H[m][m-s]
+  mm6(Lm, Di + 36 * (size_t)(m - s - 1), W);                        // W = Lm Dinv[m-s]   (m - s >= s >= 1 always)
+  mmt6(W, Lm, T);
+  for (int i = 0; i < 36; ++i) A[i] -= T[i];
+  double* Ln = Lnext + 36 * (size_t)(m >> (lshift + 1));
+  if (m - 2 * s >= 1) {
+    mm6(W, Lcur + 36 * (size_t)((m - s) >> lshift), T);             // - W H[m-s][m-2s]
+    for (int i = 0; i < 36; ++i) Ln[i] = -T[i];
+  } else {
+    for (int i = 0; i < 36; ++i) Ln[i] = 0.0;
+  }
+  if (m + s <= P) {
+    const double* Lp = Lcur + 36 * (size_t)((m + s) >> lshift);     // H[m+s][m]
+    mtm6(Lp, Di + 36 * (size_t)(m + s - 1), W);                     // V = Lp^T Dinv[m+s]
+    mm6(W, Lp, T);
+    for (int i = 0; i < 36; ++i) A[i] -= T[i];
+  }
+  for (int i = 0; i < 36; ++i) Dc[36 * (size_t)(m - 1) + i] = A[i];
+}
+
+// right-hand sides: Z[(k*6+i)*ncol + c] = -g (c == 0) or the c-th column of U^T
+__global__ void cr_rhs_kernel(int P, int ncol, const FactorDev* __restrict__ fac, const int* __restrict__ extra_fac,
+                              const double* __restrict__ Ja, const double* __restrict__ Jb, const double* __restrict__ g,
+                              double* __restrict__ Z) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncol) return;
+  if (c == 0) {
+    for (int r = blockIdx.y; r < 6 * P; r += gridDim.y) Z[(size_t)r * ncol] = -g[r];
+    return;
+  }
+  if (blockIdx.y != 0) return;
+  const int f = extra_fac[(c - 1) / 6], row = (c - 1) % 6;
+  const int ia = fac[f].ia, ib = fac[f].ib;
+  for (int i = 0; i < 6; ++i) {
+    if (ia >= 0) Z[((size_t)ia * 6 + i) * ncol + c] = Ja[36 * (size_t)f + 6 * row + i];
+    Z[((size_t)ib * 6 + i) * ncol + c] = Jb[36 * (size_t)f + 6 * row + i];
+  }
+}
+// forward, eliminated nodes: t = Dinv b (in place)
+__global__ void cr_fwd_elim_kernel(int P, int s, int ncol, const double* __restrict__ Di, double* __restrict__ Z) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long m = (long long)s + (long long)blockIdx.y * 2 * s;
+  if (c >= ncol || m > P) return;
+  const double* X = Di + 36 * (size_t)(m - 1);
+  double b[6], t[6];
+  for (int i = 0; i < 6; ++i) b[i] = Z[((size_t)(m - 1) * 6 + i) * ncol + c];
+  for (int i = 0; i < 6; ++i) {
+    double v = 0.0;
+    for (int j = 0; j < 6; ++j) v += X[6 * i + j] * b[j];
+    t[i] = v;
+  }
+  for (int i = 0; i < 6; ++i) Z[((size_t)(m - 1) * 6 + i) * ncol + c] = t[i];
+}
+// forward, kept nodes: b -= H[m][m-s] t[m-s] + H[m][m+s] t[m+s]
+__global__ void cr_fwd_keep_kernel(int P, int s, int lshift, int ncol, const double* __restrict__ Lcur, double* __restrict__ Z) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long m = (long long)(blockIdx.y + 1) * 2 * s;
+  if (c >= ncol || m > P) return;
+  double b[6];
+  for (int i = 0; i < 6; ++i) b[i] = Z[((size_t)(m - 1) * 6 + i) * ncol + c];
+  {
+    const double* Lm = Lcur + 36 * (size_t)(m >> lshift);
+    double t[6];
+    for (int i = 0; i < 6; ++i) t[i] = Z[((size_t)(m - s - 1) * 6 + i) * ncol + c];
+    for (int i = 0; i < 6; ++i) {
+      double v = 0.0;
+      for (int j = 0; j < 6; ++j) v += Lm[6 * i + j] * t[j];
+      b[i] -= v;
+    }
+  }
+  if (m + s <= P) {
+    const double* Lp = Lcur + 36 * (size_t)((m + s) >> lshift);
+    double t[6];
+    for (int i = 0; i < 6; ++i) t[i] = Z[((size_t)(m + s - 1) * 6 + i) * ncol + c];
+    for (int i = 0; i < 6; ++i) {
+      double v = 0.0;
+      for (int j = 0; j < 6; ++j) v += Lp[6 * j + i] * t[j];
+      b[i] -= v;
+    }
+  }
+  for (int i = 0; i < 6; ++i) Z[((size_t)(m - 1) * 6 + i) * ncol + c] = b[i];
+}
+// backward, nodes eliminated at this level: x = t - Dinv (H[m][m-s] x[m-s] + H[m][m+s] x[m+s])
+__global__ void cr_bwd_kernel(int P, int s, int lshift, int ncol, const double* __restrict__ Di, const double* __restrict__ Lcur,
+                              double* __restrict__ Z) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long m = (long long)s + (long long)blockIdx.y * 2 * s;
+  if (c >= ncol || m > P) return;
+  double r[6] = {0, 0, 0, 0, 0, 0};
+  if (m - s >= 1) {
+    const double* Lm = Lcur + 36 * (size_t)(m >> lshift);
+    double x[6];
+    for (int i = 0; i < 6; ++i) x[i] = Z[((size_t)(m - s - 1) * 6 + i) * ncol + c];
+    for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < 6; ++j) r[i] += Lm[6 * i + j] * x[j];
+  }
+  if (m + s <= P) {
+    const double* Lp = Lcur + 36 * (size_t)((m + s) >> lshift);
+    double x[6];
+    for (int i = 0; i < 6; ++i) x[i] = Z[((size_t)(m + s - 1) * 6 + i) * ncol + c];
+    for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < 6; ++j) r[i] += Lp[6 * j + i] * x[j];
+  }
+  const double* X = Di + 36 * (size_t)(m - 1);
+  for (int i = 0; i < 6; ++i) {
+    double v = 0.0;
+    for (int j = 0; j < 6; ++j) v += X[6 * i + j] * r[j];
+    Z[((size_t)(m - 1) * 6 + i) * ncol + c] -= v;
+  }
+}
+
 // ---------------------------------------------------------------- K6c: S = I + U Z (padded to n16), rhs = U y
 __global__ void pg_border_kernel(int n, int n16, int ncol, const FactorDev* __restrict__ fac,
                                  const int* __restrict__ extra_fac, const double* __restrict__ Ja,
@@ -576,6 +779,8 @@ struct ls_pg {
   // marginals scratch
   size_t capX = 0, capW = 0, capQ = 0;
   double *d_X = nullptr, *d_W = nullptr, *d_cov = nullptr;
+  double *d_Dc = nullptr, *d_Di = nullptr, *d_Ll = nullptr;  // cyclic reduction: current diagonals, inverses, per-level couplings
+  size_t capCR = 0;
   int *d_qpos = nullptr, *d_qtb = nullptr, *d_qte = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
 };
@@ -631,7 +836,7 @@ void ls_pg_destroy(ls_pg* pg) {
   if (pg->stream) cudaStreamSynchronize(pg->stream);
   void* bufs[] = {pg->d_fac, pg->d_poses, pg->d_Ja, pg->d_Jb, pg->d_r, pg->d_D, pg->d_B, pg->d_g, pg->d_Ld, pg->d_Ls, pg->d_Ldi, pg->d_Z,
                   pg->d_S, pg->d_rhs, pg->d_cost, pg->d_inc_ptr, pg->d_inc_fac, pg->d_extra, pg->d_track_begin, pg->d_fail,
-                  pg->d_dmax, pg->d_damp, pg->d_X, pg->d_W, pg->d_cov, pg->d_qpos, pg->d_qtb, pg->d_qte};
+                  pg->d_dmax, pg->d_damp, pg->d_X, pg->d_W, pg->d_cov, pg->d_qpos, pg->d_qtb, pg->d_qte, pg->d_Dc, pg->d_Di, pg->d_Ll};
   for (void* b : bufs)
     if (b) cudaFree(b);
   if (pg->e0) cudaEventDestroy(pg->e0);
@@ -816,6 +1021,22 @@ int pg_run(ls_pg* pg, int gn_iters, ls_pg_stats* stats, const uint64_t* mkeys, i
       return rc;
     pg->capP = cap;
   }
+  // cyclic-reduction levels: level l holds one coupling per node m = j << l, j = 1 .. P >> l
+  std::vector<size_t> lvl_off;
+  size_t lvl_total = 0;
+  int n_levels = 0;
+  for (int l = 0; (1ll << l) <= (long long)P; ++l) {
+    lvl_off.push_back(lvl_total);
+    lvl_total += ((size_t)P >> l) + 1;
+    ++n_levels;
+  }
+  lvl_off.push_back(lvl_total);
+  lvl_total += 2;  // the "next level" slot the top level's (empty) reduction would write
+  if (lvl_total > pg->capCR || (size_t)P > pg->capCR) {
+    const size_t cap = lvl_total + lvl_total / 4 + 64;
+    if ((rc = grow(pg, &pg->d_Dc, cap * 36)) || (rc = grow(pg, &pg->d_Di, cap * 36)) || (rc = grow(pg, &pg->d_Ll, cap * 36))) return rc;
+    pg->capCR = cap;
+  }
   if (inc_fac.size() > pg->capInc) {
     if ((rc = grow(pg, &pg->d_inc_fac, inc_fac.size() * 2 + 64))) return rc;
     pg->capInc = inc_fac.size() * 2 + 64;
@@ -854,10 +1075,36 @@ int pg_run(ls_pg* pg, int gn_iters, ls_pg_stats* stats, const uint64_t* mkeys, i
     pg_linearize_kernel<<<(F + 127) / 128, 128, 0, st>>>(F, pg->d_fac, pg->d_poses, pg->d_Ja, pg->d_Jb, pg->d_r, pg->d_cost);
     pg_assemble_kernel<<<(P + 127) / 128, 128, 0, st>>>(P, pg->d_inc_ptr, pg->d_inc_fac, pg->d_fac, pg->d_Ja, pg->d_Jb, pg->d_r,
                                                         pg->d_damp, pg->d_D, pg->d_B, pg->d_g);
-    pg_chain_factor_kernel<<<(n_tracks + 31) / 32, 32, 0, st>>>(n_tracks, pg->d_track_begin, pg->d_D, pg->d_B, pg->d_Ld, pg->d_Ls,
-                                                                pg->d_Ldi, pg->d_fail);
-    pg_chain_solve_kernel<<<(ncol + 63) / 64, 64, 0, st>>>(P, ncol, pg->d_fac, pg->d_extra, pg->d_Ja, pg->d_Jb, pg->d_g, pg->d_Ld,
-                                                           pg->d_Ls, pg->d_Ldi, pg->d_Z);
+    // H_c^-1 [ -g | U^T ] by block cyclic reduction (K6a'): factor the levels, then every right-hand side through them
+    cr_init_kernel<<<(P + 127) / 128, 128, 0, st>>>(P, pg->d_D, pg->d_B, pg->d_Dc, pg->d_Ll + 36 * lvl_off[0]);
+    for (int l = 0; l < n_levels; ++l) {
+      const long long sl = 1ll << l;
+      const int n_elim = (int)((P - sl) / (2 * sl)) + 1, n_keep = (int)(P / (2 * sl));
+      cr_invert_kernel<<<(n_elim + 63) / 64, 64, 0, st>>>(P, (int)sl, pg->d_Dc, pg->d_Di, pg->d_fail);
+      if (n_keep > 0)
+        cr_reduce_kernel<<<(n_keep + 63) / 64, 64, 0, st>>>(P, (int)sl, l, pg->d_Dc, pg->d_Di, pg->d_Ll + 36 * lvl_off[l],
+                                                            pg->d_Ll + 36 * lvl_off[l + 1]);
+      pg->launches += n_keep > 0 ? 2 : 1;
+    }
+    PGCU(cudaMemsetAsync(pg->d_Z, 0, (size_t)P * 6 * ncol * sizeof(double), st));
+    cr_rhs_kernel<<<dim3((ncol + 127) / 128, 256), 128, 0, st>>>(P, ncol, pg->d_fac, pg->d_extra, pg->d_Ja, pg->d_Jb, pg->d_g, pg->d_Z);
+    for (int l = 0; l < n_levels; ++l) {
+      const long long sl = 1ll << l;
+      const int n_elim = (int)((P - sl) / (2 * sl)) + 1, n_keep = (int)(P / (2 * sl));
+      cr_fwd_elim_kernel<<<dim3((ncol + 127) / 128, n_elim), 128, 0, st>>>(P, (int)sl, ncol, pg->d_Di, pg->d_Z);
+      if (n_keep > 0)
+        cr_fwd_keep_kernel<<<dim3((ncol + 127) / 128, n_keep), 128, 0, st>>>(P, (int)sl, l, ncol, pg->d_Ll + 36 * lvl_off[l], pg->d_Z);
+      pg->launches += n_keep > 0 ? 2 : 1;
+    }
+    for (int l = n_levels - 1; l >= 0; --l) {
+      const long long sl = 1ll << l;
+      const int n_elim = (int)((P - sl) / (2 * sl)) + 1;
+      cr_bwd_kernel<<<dim3((ncol + 127) / 128, n_elim), 128, 0, st>>>(P, (int)sl, l, ncol, pg->d_Di, pg->d_Ll + 36 * lvl_off[l], pg->d_Z);
+      ++pg->launches;
+    }
+    if (!update)  // the marginals' unit right-hand sides still go through the sequential chain factor (restricted to one track)
+      pg_chain_factor_kernel<<<(n_tracks + 31) / 32, 32, 0, st>>>(n_tracks, pg->d_track_begin, pg->d_D, pg->d_B, pg->d_Ld, pg->d_Ls,
+                                                                  pg->d_Ldi, pg->d_fail);
     pg->launches += 4;
     if (E) {
       pg_border_kernel<<<dim3((n16 + 1 + 127) / 128, n16), 128, 0, st>>>(n, n16, ncol, pg->d_fac, pg->d_extra, pg->d_Ja, pg->d_Jb,
