@@ -107,10 +107,10 @@ def main(args):
                 "h2d_bytes_per_step": int(P * 56 + F * 232 + P * 12), "d2h_bytes_per_step": int(P * 56),
                 "note": "ls_pg_set_poses + ls_pg_optimize(3): host graph -> device tables, solve, all poses back"},
         "gpu_launches": int(launches), "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "pg_chain_solve_kernel (block-tridiagonal sweeps, one thread per right-hand side)",
+        "roofline": {"bound": "hbm", "kernel": "cr_fwd_keep_kernel / cr_bwd_kernel (block cyclic reduction of the chain Hessian over all right-hand sides)",
                      "achieved": alg_bytes / (t_dev / args.steps) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": alg_bytes / (t_dev / args.steps) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-                     "note": "latency-bound sequential block sweeps, not HBM-bound (SURVEY.md §8d): the fraction is for completeness"},
+                     "note": "launch- and level-latency bound (about 300 short launches per estimate), not HBM-bound (SURVEY.md §8d): the fraction is for completeness"},
         "cpu_baseline": {"value": 1.0 / t_cpu3, "unit": "solves/s", "cores": 1, "kind": "port",
                          "sample": "oracle/posegraph_oracle.py optimize(iters=3) on the same graph: scipy.sparse assembly + "
                                    "spsolve (SuperLU), one run"},

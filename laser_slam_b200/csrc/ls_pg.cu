@@ -10,9 +10,10 @@
 // between consecutive poses) plus a few loop closures.  Poses are ordered track by track, so
 //   H = H_c + U^T U,   H_c block-tridiagonal (chain + priors),   U = whitened Jacobians of the "extra" factors
 // and the update solves H d = -g exactly through the Woodbury identity:
-//   y = H_c^-1 (-g),  Z = H_c^-1 U^T,  (I + U Z) w = U y,  d = y - Z w.
+//   y = H_c^-1 (-g),  Z = H_c^-1 U^T,  (I + U Z) w = U y,  d = y - Z w,
+// with H_c^-1 applied to all 6 #LC + 1 right-hand sides at once by block cyclic reduction (log2 P parallel levels).
 // All arithmetic is float64; every sum has a fixed order (deterministic).  Not HBM-bound (a few MB per iteration,
-// SURVEY.md §8d): the cost is the sequential block sweep, so the kernels favour simplicity.
+// SURVEY.md §8d): the cost is latency -- kernel launches and dependent levels -- not bandwidth.
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -203,116 +204,6 @@ __global__ void pg_assemble_kernel(int P, const int* __restrict__ inc_ptr, const
   for (int i = 0; i < 6; ++i) g[6 * (size_t)k + i] = gg[i];
 }
 
-// ---------------------------------------------------------------- K6a: block-tridiagonal Cholesky, thread per track
-__global__ void pg_chain_factor_kernel(int n_tracks, const int* __restrict__ track_begin, const double* __restrict__ D,
-                                       const double* __restrict__ Bsub, double* __restrict__ Ld, double* __restrict__ Ls,
-                                       double* __restrict__ Ldi /* 6 per pose: 1 / diag(Ld) */, int* fail) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_tracks) return;
-  double Lprev[36];
-  for (int i = 0; i < 36; ++i) Lprev[i] = 0.0;
-  for (int k = track_begin[t]; k < track_begin[t + 1]; ++k) {
-    double A[36], L[36], S[36];
-    const bool first = (k == track_begin[t]);
-    // S = L_{k,k-1} = B_k * Ld_{k-1}^-T   (row i: solve Ld_{k-1} s_i = b_i)
-    for (int i = 0; i < 36; ++i) S[i] = 0.0;
-    if (!first) {
-      for (int i = 0; i < 6; ++i)
-        for (int j = 0; j < 6; ++j) {
-          double v = Bsub[36 * (size_t)k + 6 * i + j];
-          for (int m = 0; m < j; ++m) v -= S[6 * i + m] * Lprev[6 * j + m];
-          S[6 * i + j] = v / Lprev[6 * j + j];
-        }
-    }
-    for (int i = 0; i < 6; ++i)
-      for (int j = 0; j <= i; ++j) {
-        double v = D[36 * (size_t)k + 6 * i + j];
-        for (int m = 0; m < 6; ++m) v -= S[6 * i + m] * S[6 * j + m];
-        A[6 * i + j] = v;
-      }
-    for (int i = 0; i < 36; ++i) L[i] = 0.0;
-    for (int j = 0; j < 6; ++j) {
-      double s = A[6 * j + j];
-      for (int m = 0; m < j; ++m) s -= L[6 * j + m] * L[6 * j + m];
-      if (!(s > 0.0)) { *fail = 1; s = 1.0; }
-      const double dd = sqrt(s);
-      L[6 * j + j] = dd;
-      for (int i = j + 1; i < 6; ++i) {
-        double v = A[6 * i + j];
-        for (int m = 0; m < j; ++m) v -= L[6 * i + m] * L[6 * j + m];
-        L[6 * i + j] = v / dd;
-      }
-    }
-    for (int i = 0; i < 36; ++i) { Ld[36 * (size_t)k + i] = L[i]; Ls[36 * (size_t)k + i] = S[i]; Lprev[i] = L[i]; }
-    for (int i = 0; i < 6; ++i) Ldi[6 * (size_t)k + i] = 1.0 / L[6 * i + i];  // the sweeps multiply instead of dividing
-  }
-}
-
-// ---------------------------------------------------------------- K6b: H_c^-1 [ -g | U^T ], thread per column
-// Z layout: Z[(k*6+i)*ncol + c]  (column index fastest => coalesced across the threads of this kernel)
-__global__ void pg_chain_solve_kernel(int P, int ncol, const FactorDev* __restrict__ fac, const int* __restrict__ extra_fac,
-                                      const double* __restrict__ Ja, const double* __restrict__ Jb,
-                                      const double* __restrict__ g, const double* __restrict__ Ld,
-                                      const double* __restrict__ Ls, const double* __restrict__ Ldi, double* __restrict__ Z) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ncol) return;
-  int ia = -2, ib = -2, row = 0;
-  const double *ja = nullptr, *jb = nullptr;
-  if (c > 0) {
-    const int f = extra_fac[(c - 1) / 6];
-    row = (c - 1) % 6;
-    ia = fac[f].ia;
-    ib = fac[f].ib;
-    ja = Ja + 36 * (size_t)f + 6 * row;
-    jb = Jb + 36 * (size_t)f + 6 * row;
-  }
-  double y[6] = {0, 0, 0, 0, 0, 0};
-  // a border column is zero above its first pose: so is its forward solution (the gradient column starts at 0)
-  const int kstart = c == 0 ? 0 : (ia >= 0 && ia < ib ? ia : ib);
-  for (int k = 0; k < kstart; ++k)
-    for (int i = 0; i < 6; ++i) Z[((size_t)k * 6 + i) * ncol + c] = 0.0;
-  for (int k = kstart; k < P; ++k) {  // forward: y_k = Ld_k^-1 (b_k - Ls_k y_{k-1});  Ls_k == 0 at the start of a track
-    double b[6];
-    for (int i = 0; i < 6; ++i) b[i] = (c == 0) ? -g[6 * (size_t)k + i] : (k == ia ? ja[i] : 0.0) + (k == ib ? jb[i] : 0.0);
-    const double* S = Ls + 36 * (size_t)k;
-    const double* L = Ld + 36 * (size_t)k;
-    for (int i = 0; i < 6; ++i) {
-      double s = 0.0;
-      for (int m = 0; m < 6; ++m) s += S[6 * i + m] * y[m];
-      b[i] -= s;
-    }
-    const double* Li = Ldi + 6 * (size_t)k;
-    for (int i = 0; i < 6; ++i) {
-      double v = b[i];
-      for (int m = 0; m < i; ++m) v -= L[6 * i + m] * b[m];
-      b[i] = v * Li[i];
-    }
-    for (int i = 0; i < 6; ++i) { y[i] = b[i]; Z[((size_t)k * 6 + i) * ncol + c] = b[i]; }
-  }
-  double x[6] = {0, 0, 0, 0, 0, 0};
-  for (int k = P - 1; k >= 0; --k) {  // backward: x_k = Ld_k^-T (y_k - Ls_{k+1}^T x_{k+1})
-    double b[6];
-    for (int i = 0; i < 6; ++i) b[i] = Z[((size_t)k * 6 + i) * ncol + c];
-    if (k + 1 < P) {
-      const double* S = Ls + 36 * (size_t)(k + 1);
-      for (int i = 0; i < 6; ++i) {
-        double s = 0.0;
-        for (int m = 0; m < 6; ++m) s += S[6 * m + i] * x[m];
-        b[i] -= s;
-      }
-    }
-    const double* L = Ld + 36 * (size_t)k;
-    const double* Li = Ldi + 6 * (size_t)k;
-    for (int i = 5; i >= 0; --i) {
-      double v = b[i];
-      for (int m = i + 1; m < 6; ++m) v -= L[6 * m + i] * b[m];
-      b[i] = v * Li[i];
-    }
-    for (int i = 0; i < 6; ++i) { x[i] = b[i]; Z[((size_t)k * 6 + i) * ncol + c] = b[i]; }
-  }
-}
-
-
 // ---------------------------------------------------------------- K6a': block cyclic reduction of H_c
 // The sequential block sweeps above cost 2 x P dependent steps per right-hand side (75 ms per Gauss-Newton iteration at
 // 5000 poses and 1201 right-hand sides).  Odd-even (cyclic) reduction solves the same block-tridiagonal SPD system in
@@ -441,6 +332,11 @@ __global__ void cr_rhs_kernel(int P, int ncol, const FactorDev* __restrict__ fac
     if (ia >= 0) Z[((size_t)ia * 6 + i) * ncol + c] = Ja[36 * (size_t)f + 6 * row + i];
     Z[((size_t)ib * 6 + i) * ncol + c] = Jb[36 * (size_t)f + 6 * row + i];
   }
+}
+// unit right-hand sides of the marginals: column c = e_(pose[c / 6], c % 6)
+__global__ void cr_unit_rhs_kernel(int ncol, const int* __restrict__ qpos, double* __restrict__ X) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < ncol) X[((size_t)qpos[c / 6] * 6 + c % 6) * ncol + c] = 1.0;
 }
 // forward, eliminated nodes: t = Dinv b (in place)
 __global__ void cr_fwd_elim_kernel(int P, int s, int ncol, const double* __restrict__ Di, double* __restrict__ Z) {
@@ -645,59 +541,9 @@ __global__ void pg_update_kernel(int P, int ncol, const double* __restrict__ Z, 
 
 // ---------------------------------------------------------------- marginal covariances (gtsam::Marginals)
 // Sigma_kk = (H^-1)_kk at the current estimate, for a chunk of requested poses.  Column c = 6*q + j is the unit vector
-// e_(pose[q], j): X = H_c^-1 E by the chain sweeps (restricted to the pose's own track), then the border correction
+// e_(pose[q], j): X = H_c^-1 E through the cyclic-reduction levels (cr_unit_rhs_kernel + cr_solve), then the border correction
 // through the same Woodbury identity as the update: Sigma = X - Z S^-1 (U X), of which only the 6x6 block of rows
 // pose[q] is wanted.  X layout as Z: X[(k*6+i)*ncol + c].
-__global__ void pg_chain_solve_unit_kernel(int ncol, const int* __restrict__ qpos, const int* __restrict__ track_begin_of,
-                                           const int* __restrict__ track_end_of, const double* __restrict__ Ld,
-                                           const double* __restrict__ Ls, const double* __restrict__ Ldi, double* __restrict__ X) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ncol) return;
-  const int kp = qpos[c / 6], comp = c % 6;
-  const int k0 = track_begin_of[c / 6], k1 = track_end_of[c / 6];
-  double y[6] = {0, 0, 0, 0, 0, 0};
-  for (int k = kp; k < k1; ++k) {  // forward (zero before kp)
-    double b[6];
-    for (int i = 0; i < 6; ++i) b[i] = (k == kp && i == comp) ? 1.0 : 0.0;
-    const double* S = Ls + 36 * (size_t)k;
-    const double* L = Ld + 36 * (size_t)k;
-    if (k > kp)
-      for (int i = 0; i < 6; ++i) {
-        double s = 0.0;
-        for (int m = 0; m < 6; ++m) s += S[6 * i + m] * y[m];
-        b[i] -= s;
-      }
-    const double* Li = Ldi + 6 * (size_t)k;
-    for (int i = 0; i < 6; ++i) {
-      double v = b[i];
-      for (int m = 0; m < i; ++m) v -= L[6 * i + m] * b[m];
-      b[i] = v * Li[i];
-    }
-    for (int i = 0; i < 6; ++i) { y[i] = b[i]; X[((size_t)k * 6 + i) * ncol + c] = b[i]; }
-  }
-  double x[6] = {0, 0, 0, 0, 0, 0};
-  for (int k = k1 - 1; k >= k0; --k) {  // backward over the whole track
-    double b[6];
-    for (int i = 0; i < 6; ++i) b[i] = k >= kp ? X[((size_t)k * 6 + i) * ncol + c] : 0.0;
-    if (k + 1 < k1) {
-      const double* S = Ls + 36 * (size_t)(k + 1);
-      for (int i = 0; i < 6; ++i) {
-        double s = 0.0;
-        for (int m = 0; m < 6; ++m) s += S[6 * m + i] * x[m];
-        b[i] -= s;
-      }
-    }
-    const double* L = Ld + 36 * (size_t)k;
-    const double* Li = Ldi + 6 * (size_t)k;
-    for (int i = 5; i >= 0; --i) {
-      double v = b[i];
-      for (int m = i + 1; m < 6; ++m) v -= L[6 * m + i] * b[m];
-      b[i] = v * Li[i];
-    }
-    for (int i = 0; i < 6; ++i) { x[i] = b[i]; X[((size_t)k * 6 + i) * ncol + c] = b[i]; }
-  }
-}
-
 // T = U X for the border rows (n of them, padded to n16 with zeros): T[row*ncol + c].  X is zero outside the column's track.
 __global__ void pg_border_rhs_kernel(int n, int n16, int ncol, const FactorDev* __restrict__ fac, const int* __restrict__ extra_fac,
                                      const double* __restrict__ Ja, const double* __restrict__ Jb, const int* __restrict__ tb,
@@ -772,7 +618,7 @@ struct ls_pg {
   size_t capF = 0, capP = 0, capZ = 0, capS = 0, capInc = 0, capE = 0;
   FactorDev* d_fac = nullptr;
   double *d_poses = nullptr, *d_Ja = nullptr, *d_Jb = nullptr, *d_r = nullptr, *d_D = nullptr, *d_B = nullptr,
-         *d_g = nullptr, *d_Ld = nullptr, *d_Ls = nullptr, *d_Ldi = nullptr, *d_Z = nullptr, *d_S = nullptr, *d_rhs = nullptr, *d_cost = nullptr;
+         *d_g = nullptr, *d_Z = nullptr, *d_S = nullptr, *d_rhs = nullptr, *d_cost = nullptr;
   int *d_inc_ptr = nullptr, *d_inc_fac = nullptr, *d_extra = nullptr, *d_track_begin = nullptr, *d_fail = nullptr,
       *d_damp = nullptr;
   unsigned long long* d_dmax = nullptr;
@@ -834,7 +680,7 @@ void ls_pg_destroy(ls_pg* pg) {
   if (!pg) return;
   cudaSetDevice(pg->device);
   if (pg->stream) cudaStreamSynchronize(pg->stream);
-  void* bufs[] = {pg->d_fac, pg->d_poses, pg->d_Ja, pg->d_Jb, pg->d_r, pg->d_D, pg->d_B, pg->d_g, pg->d_Ld, pg->d_Ls, pg->d_Ldi, pg->d_Z,
+  void* bufs[] = {pg->d_fac, pg->d_poses, pg->d_Ja, pg->d_Jb, pg->d_r, pg->d_D, pg->d_B, pg->d_g, pg->d_Z,
                   pg->d_S, pg->d_rhs, pg->d_cost, pg->d_inc_ptr, pg->d_inc_fac, pg->d_extra, pg->d_track_begin, pg->d_fail,
                   pg->d_dmax, pg->d_damp, pg->d_X, pg->d_W, pg->d_cov, pg->d_qpos, pg->d_qtb, pg->d_qte, pg->d_Dc, pg->d_Di, pg->d_Ll};
   for (void* b : bufs)
@@ -1015,7 +861,7 @@ int pg_run(ls_pg* pg, int gn_iters, ls_pg_stats* stats, const uint64_t* mkeys, i
   if ((size_t)P > pg->capP) {
     const size_t cap = (size_t)P + P / 4 + 64;
     if ((rc = grow(pg, &pg->d_poses, cap * 7)) || (rc = grow(pg, &pg->d_D, cap * 36)) || (rc = grow(pg, &pg->d_B, cap * 36)) ||
-        (rc = grow(pg, &pg->d_g, cap * 6)) || (rc = grow(pg, &pg->d_Ld, cap * 36)) || (rc = grow(pg, &pg->d_Ls, cap * 36)) || (rc = grow(pg, &pg->d_Ldi, cap * 6)) ||
+        (rc = grow(pg, &pg->d_g, cap * 6)) ||
         (rc = grow(pg, &pg->d_inc_ptr, cap + 1)) || (rc = grow(pg, &pg->d_track_begin, cap + 1)) ||
         (rc = grow(pg, &pg->d_damp, cap + 1)))
       return rc;
@@ -1067,6 +913,23 @@ int pg_run(ls_pg* pg, int gn_iters, ls_pg_stats* stats, const uint64_t* mkeys, i
   cudaEvent_t e0 = pg->e0, e1 = pg->e1;
   cudaEventRecord(e0, st);
   double cost_first = 0.0, cost_last = 0.0, dmax_last = 0.0;
+  // every right-hand side of `buf` (6P x ncols, column index fastest) through the factored levels, in place
+  auto cr_solve = [&](double* buf, int ncols) {
+    for (int l = 0; l < n_levels; ++l) {
+      const long long sl = 1ll << l;
+      const int n_elim = (int)((P - sl) / (2 * sl)) + 1, n_keep = (int)(P / (2 * sl));
+      cr_fwd_elim_kernel<<<dim3((ncols + 127) / 128, n_elim), 128, 0, st>>>(P, (int)sl, ncols, pg->d_Di, buf);
+      if (n_keep > 0)
+        cr_fwd_keep_kernel<<<dim3((ncols + 127) / 128, n_keep), 128, 0, st>>>(P, (int)sl, l, ncols, pg->d_Ll + 36 * lvl_off[l], buf);
+      pg->launches += n_keep > 0 ? 2 : 1;
+    }
+    for (int l = n_levels - 1; l >= 0; --l) {
+      const long long sl = 1ll << l;
+      const int n_elim = (int)((P - sl) / (2 * sl)) + 1;
+      cr_bwd_kernel<<<dim3((ncols + 127) / 128, n_elim), 128, 0, st>>>(P, (int)sl, l, ncols, pg->d_Di, pg->d_Ll + 36 * lvl_off[l], buf);
+      ++pg->launches;
+    }
+  };
   const int n_pass = gn_iters + (n_mk > 0 ? 1 : 0);  // the last pass of a marginals request only linearises and factors
   for (int it = 0; it < n_pass; ++it) {
     const bool update = it < gn_iters;
@@ -1088,23 +951,7 @@ int pg_run(ls_pg* pg, int gn_iters, ls_pg_stats* stats, const uint64_t* mkeys, i
     }
     PGCU(cudaMemsetAsync(pg->d_Z, 0, (size_t)P * 6 * ncol * sizeof(double), st));
     cr_rhs_kernel<<<dim3((ncol + 127) / 128, 256), 128, 0, st>>>(P, ncol, pg->d_fac, pg->d_extra, pg->d_Ja, pg->d_Jb, pg->d_g, pg->d_Z);
-    for (int l = 0; l < n_levels; ++l) {
-      const long long sl = 1ll << l;
-      const int n_elim = (int)((P - sl) / (2 * sl)) + 1, n_keep = (int)(P / (2 * sl));
-      cr_fwd_elim_kernel<<<dim3((ncol + 127) / 128, n_elim), 128, 0, st>>>(P, (int)sl, ncol, pg->d_Di, pg->d_Z);
-      if (n_keep > 0)
-        cr_fwd_keep_kernel<<<dim3((ncol + 127) / 128, n_keep), 128, 0, st>>>(P, (int)sl, l, ncol, pg->d_Ll + 36 * lvl_off[l], pg->d_Z);
-      pg->launches += n_keep > 0 ? 2 : 1;
-    }
-    for (int l = n_levels - 1; l >= 0; --l) {
-      const long long sl = 1ll << l;
-      const int n_elim = (int)((P - sl) / (2 * sl)) + 1;
-      cr_bwd_kernel<<<dim3((ncol + 127) / 128, n_elim), 128, 0, st>>>(P, (int)sl, l, ncol, pg->d_Di, pg->d_Ll + 36 * lvl_off[l], pg->d_Z);
-      ++pg->launches;
-    }
-    if (!update)  // the marginals' unit right-hand sides still go through the sequential chain factor (restricted to one track)
-      pg_chain_factor_kernel<<<(n_tracks + 31) / 32, 32, 0, st>>>(n_tracks, pg->d_track_begin, pg->d_D, pg->d_B, pg->d_Ld, pg->d_Ls,
-                                                                  pg->d_Ldi, pg->d_fail);
+    cr_solve(pg->d_Z, ncol);
     pg->launches += 4;
     if (E) {
       pg_border_kernel<<<dim3((n16 + 1 + 127) / 128, n16), 128, 0, st>>>(n, n16, ncol, pg->d_fac, pg->d_extra, pg->d_Ja, pg->d_Jb,
@@ -1163,8 +1010,9 @@ int pg_run(ls_pg* pg, int gn_iters, ls_pg_stats* stats, const uint64_t* mkeys, i
     for (int q0 = 0; q0 < n_mk; q0 += kChunk) {
       const int nq = n_mk - q0 < kChunk ? n_mk - q0 : kChunk, nc = 6 * nq;
       PGCU(cudaMemsetAsync(pg->d_X, 0, (size_t)P * 6 * nc * sizeof(double), st));
-      pg_chain_solve_unit_kernel<<<(nc + 63) / 64, 64, 0, st>>>(nc, pg->d_qpos + q0, pg->d_qtb + q0, pg->d_qte + q0, pg->d_Ld, pg->d_Ls, pg->d_Ldi, pg->d_X);
+      cr_unit_rhs_kernel<<<(nc + 127) / 128, 128, 0, st>>>(nc, pg->d_qpos + q0, pg->d_X);
       ++pg->launches;
+      cr_solve(pg->d_X, nc);
       if (E) {
         pg_border_rhs_kernel<<<dim3((nc + 127) / 128, n16), 128, 0, st>>>(n, n16, nc, pg->d_fac, pg->d_extra, pg->d_Ja, pg->d_Jb,
                                                                           pg->d_qtb + q0, pg->d_qte + q0, pg->d_X, pg->d_W);
