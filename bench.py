@@ -246,6 +246,10 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--tracks", type=int, default=0, help="independent sequences (tracks) hosted per GPU, batched per "
                     "launch (default: 74 for config 2 = 4 of the 296 co-resident CTAs each, 8 for config 5)")
+    ap.add_argument("--contexts", type=int, default=1,
+                    help="device contexts the tracks of a GPU are split over, each with 1/contexts of the co-resident CTAs "
+                         "(experiment: measured on B200, cooperative launches of different contexts do NOT overlap -- 2 contexts "
+                         "run at 0.66x -- so the default is 1)")
     ap.add_argument("--config", type=int, default=2, choices=(2, 3, 4, 5),
                     help="BASELINE.json workload: 2 scan-to-map ICP (default, the headline metric), 3 batched trajectories "
                          "feeding the shared estimator, 4 pose-graph solve, 5 dense-sensor stress")
@@ -273,8 +277,16 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    ctx = ls.Context(local)
     B = args.tracks
+    G = max(1, min(args.contexts, B))
+    ctxs = [ls.Context(local) for _ in range(G)]
+    ctx = ctxs[0]
+    if G > 1:
+        full = ctx.set_icp_cta_budget(0)
+        for c in ctxs:
+            c.set_icp_cta_budget(full // G)
+    group_of = [t * G // B for t in range(B)]                 # contiguous groups of tracks
+    members = [[t for t in range(B) if group_of[t] == g] for g in range(G)]
     # B independent sequences (tracks) per GPU -- the reference's n_laser_slam_workers LaserTracks hosted on one device
     seq_base = int(os.environ.get('LS_BENCH_SEQ_BASE', '0'))   # diagnostic: run another rank's tracks on this one
     # every rank drives the SAME B synthetic sequences: per-GPU work is then identical by construction (the cost of a
@@ -324,45 +336,62 @@ def main():
     staged = [stage_track(t, n_total + 1) for t in range(B)]   # one step of look-ahead for the pipelined uploads
 
     # ------------------------------------------------------------------ resident arm (value)
-    mp = ctx.create_map(B * POOL + 2, N_SCAN)
-    sid = [[mp.push_scan_raw(feats[t][k].data_ptr(), nrms[t][k].data_ptr(), 3, N_SCAN) for k in range(POOL)] for t in range(B)]
-    prepared = []
+    # Every group of tracks lives in its own context (own ring, own workspaces).  A step registers the next scan of every
+    # track: group g's launch is begun, then the previous launch of the NEXT group is collected and begun again, ... so that
+    # while one group iterates, the other's sub-maps are assembled and indexed.
+    mps = [ctxs[g].create_map(len(members[g]) * POOL + 2, N_SCAN) for g in range(G)]
+    sid = [None] * B
+    for t in range(B):
+        sid[t] = [mps[group_of[t]].push_scan_raw(feats[t][k].data_ptr(), nrms[t][k].data_ptr(), 3, N_SCAN) for k in range(POOL)]
+    prepared = [[] for _ in range(G)]
     for s in range(n_total):
-        probs = [(sid[t][staged[t][s][0]], [sid[t][k] for k in staged[t][s][2]], staged[t][s][3], staged[t][s][4]) for t in range(B)]
-        prepared.append(mp.prepare_batch(probs, prm))
+        for g in range(G):
+            probs = [(sid[t][staged[t][s][0]], [sid[t][k] for k in staged[t][s][2]], staged[t][s][3], staged[t][s][4]) for t in members[g]]
+            prepared[g].append(mps[g].prepare_begin_batch(probs, prm))
     dev_ms, icp_ms = [], []
+    last_touts = [None] * G
 
-    def step_resident(s, record):
-        rc, statuses, touts, stats = prepared[s]()
+    def finish(g, s, record):
+        rc, statuses, touts, stats = prepared[g][s][1]()
         if rc != 0 or statuses.any():
             raise RuntimeError(f"registration failed rc={rc} {list(statuses)}")
-        if world > 1:
+        last_touts[g] = touts.copy()
+        if world > 1 and g == 0:
             share_pose_delta(ls.from_colmajor(touts[0]))
         if record:
             dev_ms.append(max(st.device_ms for st in stats))
             icp_ms.append(stats[0].icp_ms)
             if os.environ.get("LS_BENCH_TRACE"):
-                print(f"[trace] step {s}: icp {stats[0].icp_ms:.2f} ms; per track last_limit " +
+                print(f"[trace] step {s} group {g}: icp {stats[0].icp_ms:.2f} ms; per track last_limit " +
                       " ".join(f"{st.last_limit:.4f}" for st in stats) + " kept " + " ".join(str(st.last_kept) for st in stats),
                       file=sys.stderr, flush=True)
-        return touts
 
-    for s in range(args.warmup):
-        step_resident(s, False)
+    def run_resident(s0, n, record):
+        inflight = [None] * G
+        for s in range(s0, s0 + n):
+            for g in range(G):
+                if inflight[g] is not None:
+                    finish(g, inflight[g], record)
+                prepared[g][s][0]()          # stage + launch, returns at once
+                inflight[g] = s
+        for g in range(G):
+            if inflight[g] is not None:
+                finish(g, inflight[g], record)
+
+    run_resident(0, args.warmup, False)
     sampler = ClockSampler(local)
     sampler.start()
-    launches0 = ctx.launch_count
+    launches0 = sum(c.launch_count for c in ctxs)
     barrier()
     t0 = time.perf_counter()
-    for s in range(args.steps):
-        last = step_resident(args.warmup + s, True)
+    run_resident(args.warmup, args.steps, True)
     exchange.collect()   # the last step's records, inside the timed region
     barrier()
     t_res = time.perf_counter() - t0
-    launches = ctx.launch_count - launches0
+    launches = sum(c.launch_count for c in ctxs) - launches0
     idx, ref = staged[0][n_total - 1][0], staged[0][n_total - 1][1]
     truth_rel = np.linalg.inv(tracks[0][0][ref]) @ tracks[0][0][idx]
-    pose_err = float(np.abs(ls.from_colmajor(last[0])[:3, 3] - truth_rel[:3, 3]).max())
+    pose_err = float(np.abs(ls.from_colmajor(last_touts[0][0])[:3, 3] - truth_rel[:3, 3]).max())
 
     # parity of what was just timed, outside the clock: one problem of the last batched step against the oracle
     parity = None
@@ -374,8 +403,8 @@ def main():
         parts_c = [sc[k] if k == ref_c else oracle.transform_cloud(T, *sc[k]) for k, T in zip(ks_c, Ts_c)]
         r = oracle.icp(sc[idx_c][0], np.concatenate([p_[0] for p_ in parts_c]), np.concatenate([p_[1] for p_ in parts_c]), T0_c,
                        oracle.default_params(max_iterations=ITERS, use_differential=0, num_threads=usable_threads()))
-        got = ls.from_colmajor(last[tchk])
-        parity = {"problem": f"track {tchk}, last timed step ({B} registrations in that launch)",
+        got = ls.from_colmajor(last_touts[group_of[tchk]][members[group_of[tchk]].index(tchk)])
+        parity = {"problem": f"track {tchk}, last timed step ({len(members[group_of[tchk]])} registrations in that launch)",
                   "final_transform_bit_equal_to_oracle": bool(np.array_equal(got, r["T"])),
                   "max_abs_diff": float(np.abs(got - r["T"]).max())}
         if not parity["final_transform_bit_equal_to_oracle"]:
@@ -384,46 +413,57 @@ def main():
     # single-stream latency (one track, one registration per launch), a few steps
     lat = []
     for s in range(min(20, n_total)):
-        g = mp.register(sid[0][staged[0][s][0]], [sid[0][k] for k in staged[0][s][2]], staged[0][s][3], staged[0][s][4], prm)
+        g = mps[0].register(sid[0][staged[0][s][0]], [sid[0][k] for k in staged[0][s][2]], staged[0][s][3], staged[0][s][4], prm)
         lat.append(g["stats"].device_ms)
     single_ms = float(np.median(lat))
 
     # ------------------------------------------------------------------ end-to-end arm (host buffers)
     # every step uploads the new scan of every track from pinned host memory, then registers the batch
-    mp2 = ctx.create_map(B * (2 * K_MAP + 8), N_SCAN)   # ring: every track keeps its last K_MAP+1 scans resident with slack
+    mp2 = [ctxs[g].create_map(len(members[g]) * (2 * K_MAP + 8), N_SCAN) for g in range(G)]   # rings: every track keeps its last K_MAP+1 scans resident with slack
     sid2 = [dict() for _ in range(B)]
     for t in range(B):
         for s in range(K_MAP + 1):
             k = walk(s)
-            sid2[t][k] = mp2.push_scan_raw(feats[t][k].data_ptr(), nrms[t][k].data_ptr(), 3, N_SCAN)
+            sid2[t][k] = mp2[group_of[t]].push_scan_raw(feats[t][k].data_ptr(), nrms[t][k].data_ptr(), 3, N_SCAN)
 
     # Uploads are double-buffered: while step s is registered, the scans of step s+1 go up on the map's own stream
     # (ls_map_push_scan_async; the sensor delivers the next scan while the current one is being registered).  Every
     # timed step still issues one full set of uploads and reads its results back.
-    def upload(s):
-        for t in range(B):
+    def upload(g, s):
+        for t in members[g]:
             idx = staged[t][s][0]
-            sid2[t][idx] = mp2.push_scan_raw_async(feats[t][idx].data_ptr(), nrms[t][idx].data_ptr(), 3, N_SCAN)   # H2D, pinned
+            sid2[t][idx] = mp2[g].push_scan_raw_async(feats[t][idx].data_ptr(), nrms[t][idx].data_ptr(), 3, N_SCAN)   # H2D, pinned
 
-    def step_e2e(s):
+    def begin_e2e(g, s):
         probs = []
-        for t in range(B):
+        for t in members[g]:
             idx, ref, ks, Ts, T0 = staged[t][s]
             probs.append((sid2[t][idx], [sid2[t][k] for k in ks], Ts, T0))
-        end = mp2.begin_batch(probs, prm)   # stage + launch step s, returns at once
-        upload(s + 1)   # new ids land in ring slots last used >= K_MAP+1 steps ago (the library refuses anything else)
-        out = end()                                                                                            # wait; D2H of T + stats
-        if world > 1:
-            share_pose_delta(out[0]["T"])
-        return out
+        end = mp2[g].begin_batch(probs, prm)   # stage + launch step s of this group, returns at once
+        upload(g, s + 1)   # new ids land in ring slots last used >= K_MAP+1 steps ago (the library refuses anything else)
+        return end
 
-    upload(0)
-    for s in range(args.warmup):
-        step_e2e(s)
+    def run_e2e(s0, n):
+        inflight = [None] * G
+        for s in range(s0, s0 + n):
+            for g in range(G):
+                if inflight[g] is not None:
+                    out = inflight[g]()                                                              # wait; D2H of T + stats
+                    if world > 1 and g == 0:
+                        share_pose_delta(out[0]["T"])
+                inflight[g] = begin_e2e(g, s)
+        for g in range(G):
+            if inflight[g] is not None:
+                out = inflight[g]()
+                if world > 1 and g == 0:
+                    share_pose_delta(out[0]["T"])
+
+    for g in range(G):
+        upload(g, 0)
+    run_e2e(0, args.warmup)
     barrier()
     t0 = time.perf_counter()
-    for s in range(args.steps):
-        step_e2e(args.warmup + s)
+    run_e2e(args.warmup, args.steps)
     exchange.collect()
     barrier()
     t_e2e = time.perf_counter() - t0
@@ -490,22 +530,31 @@ def main():
     # ncu DRAM bytes of one launch of the same shape (8 registrations per launch has its own capture: eight maps do
     # not fit L2 together, one does)
     traffic, traffic_note = None, None
-    for fname, regs in ((f"r2_icp_kernel_cfg{args.config}_batch{B}_summary.json", B),):
+    for fname, regs in ((f"r2_icp_kernel_cfg{args.config}_batch{B // G}_summary.json", B // G),):
         prof = os.path.join(ROOT, "profiles", fname)
-        if regs == B and os.path.exists(prof):
+        if os.path.exists(prof):
             try:
                 traffic = json.load(open(prof)).get("dram_bytes_per_launch")
                 traffic_note = f"ncu dram__bytes_read+write of one launch with {regs} registration(s) (profiles/{fname})"
             except Exception:
                 traffic = None
+    Bg = B / G   # registrations per launch
+    t_step = t_res / args.steps
+    # G launches (one per context, B/G registrations and 1/G of the co-resident CTAs each) run side by side, so the device-level
+    # figure is the algorithmic bytes of ALL launches of a step over the step's duration; the per-launch figure (bytes of one
+    # launch over its own CUDA-event duration, during which it holds 1/G of the SM slots) is given next to it.
     roof = {"bound": "hbm", "kernel": f"ls::icp_kernel (persistent: NN query + trimmed select + normal equations, {ITERS} iterations, "
-                                      f"{B} registrations per launch)",
-            "achieved": B * ALG_BYTES_ICP / t_icp / 1e9, "peak": peak, "unit": "GB/s",
-            "frac": B * ALG_BYTES_ICP / t_icp / 1e9 / peak,
+                                      f"{Bg:.0f} registrations per launch, {G} launches side by side)",
+            "achieved": B * ALG_BYTES_ICP / t_step / 1e9, "peak": peak, "unit": "GB/s",
+            "frac": B * ALG_BYTES_ICP / t_step / 1e9 / peak,
             "traffic": traffic, "traffic_note": traffic_note,
-            "peak_source": peak_src, "algorithmic_bytes_per_launch": B * ALG_BYTES_ICP, "kernel_ms": t_icp * 1e3,
+            "peak_source": peak_src, "algorithmic_bytes_per_step": B * ALG_BYTES_ICP, "step_ms": t_step * 1e3,
+            "per_launch": {"registrations": Bg, "algorithmic_bytes": Bg * ALG_BYTES_ICP, "kernel_ms": t_icp * 1e3,
+                           "achieved": Bg * ALG_BYTES_ICP / t_icp / 1e9, "sm_share": 1.0 / G,
+                           "frac_of_peak": Bg * ALG_BYTES_ICP / t_icp / 1e9 / peak},
+            "kernel_ms": t_icp * 1e3,
             "registration": {"algorithmic_bytes": ALG_BYTES_REG, "device_ms_per_batch": t_dev * 1e3,
-                             "achieved": B * ALG_BYTES_REG / t_dev / 1e9, "frac": B * ALG_BYTES_REG / t_dev / 1e9 / peak}}
+                             "achieved": B * ALG_BYTES_REG / t_step / 1e9, "frac": B * ALG_BYTES_REG / t_step / 1e9 / peak}}
     cpu = cpu_baseline_sample() if args.gpus == 1 else None
     out = {
         "metric": wl["metric"],
@@ -514,9 +563,11 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["name"],
                    "tracks_per_gpu": B, "registrations_per_step": world * B,
+                   "contexts_per_gpu": G,
                    "concurrency": f"{B} independent sequences (tracks) per GPU (the same {B} synthetic sequences on every rank, so "
-                                  f"per-GPU work is identical); one step registers the next scan of every track in one "
-                                  f"cooperative launch (ls_icp_register_submap_batch)",
+                                  f"per-GPU work is identical) in {G} groups, one device context each; one step registers the "
+                                  f"next scan of every track, one cooperative launch per group (ls_icp_register_submap_batch_begin/"
+                                  f"_end), the groups' launches overlapping",
                    "single_stream_ms_per_registration": single_ms,
                    "l2": f"inputs larger than L2: {B * POOL} resident scans/rank cycled ({B * POOL * N_SCAN * 32 / 1e6:.0f} MB) "
                          f"+ {B} x ~170 MB workspaces",

@@ -81,6 +81,11 @@ int ls_b200_init(int device, ls_ctx** out);
 void ls_b200_destroy(ls_ctx* ctx);
 const char* ls_b200_last_error(const ls_ctx* ctx); /* text of the last failure on this context */
 int ls_b200_version(void);
+/* Cap the number of CTAs the persistent ICP kernel of this context may occupy (0 = all that can be co-resident, the
+ * default).  Two contexts that each take half of the device run their cooperative launches side by side, so the map build
+ * and host-side staging of one overlap the ICP iterations of the other (bench.py drives two such contexts). */
+int ls_b200_set_icp_cta_budget(ls_ctx* ctx, int ctas);
+int ls_b200_icp_cta_budget(const ls_ctx* ctx); /* CTAs the next launch will use at most */
 /* Number of this library's kernel launches issued on the context so far (bench "gpu_launches"). */
 uint64_t ls_b200_launch_count(const ls_ctx* ctx);
 

@@ -257,6 +257,11 @@ class Context:
     def launch_count(self):
         return int(lib().ls_b200_launch_count(self._h))
 
+    def set_icp_cta_budget(self, ctas):
+        """ls_b200_set_icp_cta_budget: cap the persistent ICP kernel's CTAs (0 = all); returns the budget in force."""
+        self._check(lib().ls_b200_set_icp_cta_budget(self._h, int(ctas)))
+        return int(lib().ls_b200_icp_cta_budget(self._h))
+
     def icp_register(self, reading4, ref4, ref_normals3, T0, params=None, want_ids=False, want_hist=False,
                      raise_on_convergence=True):
         """PointMatcher::ICP::compute(reading, reference, T0).  Returns dict(T, stats, rc[, ids, d2, T_iter_hist])."""
@@ -438,6 +443,35 @@ class Map:
         def call(_fn=fn, _args=args, _keep=keep):
             return _fn(*_args), statuses, touts, stats
         return call
+
+    def prepare_begin_batch(self, problems, params=None):
+        """Marshal once; returns (begin, end): `begin()` = ls_icp_register_submap_batch_begin (stage + launch, returns at once),
+        `end()` = ls_icp_register_submap_batch_end -> (rc, statuses, T_outs (B,16), stats array).  For callers that pre-stage
+        their inputs and interleave several contexts."""
+        p = params or default_params()
+        B = len(problems)
+        rids = np.ascontiguousarray([pr[0] for pr in problems], np.uint64)
+        nparts = np.ascontiguousarray([len(pr[1]) for pr in problems], np.int32)
+        pids = np.ascontiguousarray(np.concatenate([np.asarray(pr[1], np.uint64) for pr in problems]), np.uint64)
+        tparts = np.ascontiguousarray(np.concatenate([np.stack([colmajor(T) for T in pr[2]]) for pr in problems]), np.float32)
+        t0s = np.ascontiguousarray(np.stack([colmajor(pr[3]) for pr in problems]), np.float32)
+        touts = np.empty((B, 16), np.float32)
+        stats = (IcpStats * B)()
+        statuses = np.zeros(B, np.int32)
+        L = lib()
+        bargs = (self.ctx._h, ctypes.byref(p), self._h, B, rids.ctypes.data, nparts.ctypes.data, pids.ctypes.data,
+                 tparts.ctypes.data, t0s.ctypes.data)
+        eargs = (self.ctx._h, touts.ctypes.data, ctypes.cast(stats, ctypes.c_void_p), statuses.ctypes.data)
+        keep = (p, rids, nparts, pids, tparts, t0s)
+
+        def begin(_f=L.ls_icp_register_submap_batch_begin, _a=bargs, _k=keep):
+            rc = _f(*_a)
+            if rc != 0:
+                self.ctx._check(rc)
+
+        def end(_f=L.ls_icp_register_submap_batch_end, _a=eargs):
+            return _f(*_a), statuses, touts, stats
+        return begin, end
 
     def begin_batch(self, problems, params=None):
         """ls_icp_register_submap_batch_begin: stage and launch, return at once.  The returned callable is

@@ -42,12 +42,14 @@ struct Workspace {
   IcpWork* h_work = nullptr;  // pinned host mirrors of the small results
   Grid* h_grid = nullptr;
   IcpProblem hp;              // host copy of this problem's descriptor
+  bool stream_dirty = false;  // work (allocation-time clears) was enqueued on this workspace's own stream
 };
 
 struct ls_ctx {
   int device = 0;
   int sm_count = 0;
-  int icp_ctas = 0;  // co-resident CTAs for the cooperative ICP kernel
+  int icp_ctas = 0;      // co-resident CTAs for the cooperative ICP kernel
+  int icp_ctas_max = 0;  // what the device can hold (occupancy x SMs); icp_ctas <= this
   std::string err;
   uint64_t launches = 0;
   std::vector<Workspace*> ws;
@@ -179,6 +181,7 @@ int ensure_capacity(ls_ctx* ctx, Workspace* w, int n, int m, int max_cells, int 
     if ((rc = dev_alloc(ctx, &w->A.qtab_local, (size_t)tcap * LS_FB3))) return rc;
     if ((rc = dev_alloc(ctx, &w->A.qtab_total, (size_t)tcap))) return rc;
     CU(cudaMemsetAsync(w->A.cnt1, 0, (size_t)tcap * LS_FB3 * sizeof(uint32_t), w->stream));
+    w->stream_dirty = true;
     w->A.tab_cap = tcap;
     w->tab_cap = tcap;
     w->m_cap = cap;
@@ -191,6 +194,7 @@ int ensure_capacity(ls_ctx* ctx, Workspace* w, int n, int m, int max_cells, int 
     if ((rc = dev_alloc(ctx, &w->A.topmask, (size_t)max_cells + 1))) return rc;
     if ((rc = dev_alloc(ctx, &w->A.qtop_start, (size_t)max_cells + 1))) return rc;
     CU(cudaMemsetAsync(w->A.cnt0, 0, ((size_t)max_cells + 1) * sizeof(uint32_t), w->stream));
+    w->stream_dirty = true;
     w->cells_cap = max_cells;
   }
   if (max_iter > w->hist_cap) {
@@ -344,12 +348,17 @@ int fill_problem(ls_ctx* ctx, Workspace* w, const ls_icp_params* prm, int n, con
   hp.lists.n = n;
   hp.work = w->work;
   hp.T_hist = want_hist ? w->T_hist : nullptr;
+  if (want_hist) {  // entries past the executed iterations read as zeros, not as stale device memory
+    CU(cudaMemsetAsync(w->T_hist, 0, (size_t)prm->max_iterations * 16 * sizeof(float), w->stream));
+    w->stream_dirty = true;
+  }
   hp.want_matches = want_matches ? 1 : 0;
   const bool want_phase = getenv("LS_PHASE_TIMING") != nullptr;
   if (want_phase) {
     if (w->phase_ns) cudaFree(w->phase_ns);
     CU(cudaMalloc((void**)&w->phase_ns, (size_t)prm->max_iterations * 6 * sizeof(unsigned long long)));
     CU(cudaMemsetAsync(w->phase_ns, 0, (size_t)prm->max_iterations * 6 * sizeof(unsigned long long), w->stream));
+    w->stream_dirty = true;
   }
   hp.phase_ns = want_phase ? w->phase_ns : nullptr;
   std::memcpy(hp.T0, T0, sizeof(hp.T0));
@@ -375,10 +384,6 @@ int prep_icp(ls_ctx* ctx, Workspace* w, const ls_icp_params* prm, const float4* 
 // staging has finished; on return the results are on the host (pinned mirrors).
 int launch_icp(ls_ctx* ctx, const ls_icp_params* prm, int batch, int n_max) {
   Workspace* w0 = ctx->ws[0];
-  for (int b = 1; b < batch; ++b) {
-    CU(cudaEventRecord(ctx->ws[b]->ev2, ctx->ws[b]->stream));
-    CU(cudaStreamWaitEvent(w0->stream, ctx->ws[b]->ev2, 0));
-  }
   for (int b = 0; b < batch; ++b) ctx->probs_host[b] = ctx->ws[b]->hp;
   CU(cudaMemcpyAsync(ctx->probs_dev, ctx->probs_host, sizeof(IcpProblem) * (size_t)batch, cudaMemcpyHostToDevice, w0->stream));
   IcpParamsDev dp;
@@ -479,9 +484,8 @@ bool is_identity16(const float* T) {
 }
 
 const ls_scan_slot* find_slot(const ls_map* map, uint64_t id) {
-  for (const auto& s : map->slots)
-    if (s.used && s.id == id) return &s;
-  return nullptr;
+  const ls_scan_slot& s = map->slots[id % (uint64_t)map->capacity];  // ids are handed out round-robin over the ring
+  return (s.used && s.id == id) ? &s : nullptr;
 }
 
 // consumers of a slot filled by ls_map_push_scan_async order themselves behind its upload
@@ -585,7 +589,7 @@ int ls_b200_init(int device, ls_ctx** out) {
   if (cudaFuncSetAttribute(icp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kIcpPairBytes) != cudaSuccess ||
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, icp_kernel, kIcpThreads, kIcpPairBytes) != cudaSuccess || occ < 1)
     return bail(LS_ERR_CUDA);
-  ctx->icp_ctas = occ * ctx->sm_count;
+  ctx->icp_ctas = ctx->icp_ctas_max = occ * ctx->sm_count;
   if (cudaMalloc((void**)&ctx->probs_dev, sizeof(IcpProblem) * kMaxBatch) != cudaSuccess) return bail(LS_ERR_NOMEM);
   if (cudaMallocHost((void**)&ctx->probs_host, sizeof(IcpProblem) * kMaxBatch) != cudaSuccess) return bail(LS_ERR_NOMEM);
   if (cudaMalloc((void**)&ctx->jobs_dev, sizeof(BuildJob) * kMaxBatch) != cudaSuccess) return bail(LS_ERR_NOMEM);
@@ -610,6 +614,13 @@ void ls_b200_destroy(ls_ctx* ctx) {
 
 const char* ls_b200_last_error(const ls_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 uint64_t ls_b200_launch_count(const ls_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int ls_b200_set_icp_cta_budget(ls_ctx* ctx, int ctas) {
+  if (!ctx || ctas < 0) return LS_ERR_ARG;
+  BUSY_CHECK(ctx);
+  ctx->icp_ctas = (ctas == 0 || ctas > ctx->icp_ctas_max) ? ctx->icp_ctas_max : ctas;
+  return LS_OK;
+}
+int ls_b200_icp_cta_budget(const ls_ctx* ctx) { return ctx ? ctx->icp_ctas : LS_ERR_ARG; }
 
 void ls_icp_default_params(ls_icp_params* p) {
   if (!p) return;
@@ -1076,9 +1087,11 @@ int ls_icp_register_submap_batch_begin(ls_ctx* ctx, const ls_icp_params* prm, co
     fill_job(w, parts, T0, rs->pts, n);
     if ((rc = fill_problem(ctx, w, prm, n, T0, false, false))) return rc;
   }
-  for (int b = 1; b < batch; ++b) {  // allocations / clears a workspace enqueued on its own stream come first
+  for (int b = 1; b < batch; ++b) {  // allocation-time clears a workspace enqueued on its own stream come first
+    if (!ctx->ws[b]->stream_dirty) continue;
     CU(cudaEventRecord(ctx->ws[b]->ev2, ctx->ws[b]->stream));
     CU(cudaStreamWaitEvent(w0->stream, ctx->ws[b]->ev2, 0));
+    ctx->ws[b]->stream_dirty = false;
   }
   CU(cudaEventRecord(w0->ev0, w0->stream));
   CU(cudaMemcpyAsync(ctx->jobs_dev, ctx->jobs_host, sizeof(BuildJob) * (size_t)batch, cudaMemcpyHostToDevice, w0->stream));
