@@ -58,6 +58,10 @@ struct ls_ctx {
   BuildJob* jobs_dev = nullptr;      // [kMaxBatch]: workspace b stages its build in slot b
   BuildJob* jobs_host = nullptr;     // pinned
   IcpWork* work_pool = nullptr;      // [kMaxBatch] contiguous, so one memset clears a whole batch
+  // query-sharded registration: three rotating exchange scratches in the hosting rank's memory (peer-mapped elsewhere)
+  IcpWork* xwork = nullptr;
+  bool xwork_owner = false;
+  uint64_t xseq = 0;  // sharded registrations issued so far (every shard counts the same calls)
   // a batch between ls_icp_register_submap_batch_begin and _end: the workspaces are busy
   bool pending = false;
   int pending_batch = 0;
@@ -347,6 +351,11 @@ int fill_problem(ls_ctx* ctx, Workspace* w, const ls_icp_params* prm, int n, con
   hp.lists.vpts = w->vpts;
   hp.lists.n = n;
   hp.work = w->work;
+  hp.xwork = nullptr;
+  hp.xwork_clear = nullptr;
+  hp.shard_rank = 0;
+  hp.shard_count = 1;
+  hp.barrier_ctas = 0u;
   hp.T_hist = want_hist ? w->T_hist : nullptr;
   if (want_hist) {  // entries past the executed iterations read as zeros, not as stale device memory
     CU(cudaMemsetAsync(w->T_hist, 0, (size_t)prm->max_iterations * 16 * sizeof(float), w->stream));
@@ -609,6 +618,7 @@ void ls_b200_destroy(ls_ctx* ctx) {
   if (ctx->jobs_dev) cudaFree(ctx->jobs_dev);
   if (ctx->jobs_host) cudaFreeHost(ctx->jobs_host);
   if (ctx->work_pool) cudaFree(ctx->work_pool);
+  ls_shard_exchange_close(ctx);
   delete ctx;
 }
 
@@ -991,6 +1001,110 @@ int ls_icp_register_submap(ls_ctx* ctx, const ls_icp_params* prm, const ls_map* 
   CU(cudaEventRecord(w->ev0, w->stream));
   if ((rc = enqueue_build(ctx, w, parts, r, T0))) return rc;
   return run_icp(ctx, prm, rs->pts, n, T0, T_out, stats, opt_ids, opt_d2, opt_T_iter_hist, m);
+}
+
+// ---- query-sharded registration -------------------------------------------------------------
+// ONE registration whose reading is split over the GPUs of a node.  Every shard holds the whole map (the build is
+// replicated: it is 54 us) and a contiguous range of the cell-sorted reading; per iteration the shards meet in the select
+// histograms, the 28 normal-equation sums and the barrier counter of one exchange scratch that lives in shard 0's
+// memory and is peer-mapped (CUDA IPC, NVLink) by the others -- system-scope atomics and loads issued from inside the
+// persistent kernel, no collective call and no host involvement per iteration.  All the sums are integers, so the
+// result is bit-identical to the unsharded registration whatever the number of shards.
+int ls_shard_exchange_create(ls_ctx* ctx, unsigned char handle[LS_IPC_HANDLE_BYTES]) {
+  if (!ctx || !handle) return LS_ERR_ARG;
+  BUSY_CHECK(ctx);
+  static_assert(sizeof(cudaIpcMemHandle_t) <= LS_IPC_HANDLE_BYTES, "handle size");
+  CU(cudaSetDevice(ctx->device));
+  ls_shard_exchange_close(ctx);
+  CU(cudaMalloc((void**)&ctx->xwork, 3 * sizeof(IcpWork)));
+  ctx->xwork_owner = true;
+  ctx->xseq = 0;
+  CU(cudaMemset(ctx->xwork, 0, 3 * sizeof(IcpWork)));
+  CU(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, ctx->xwork));
+  std::memset(handle, 0, LS_IPC_HANDLE_BYTES);
+  std::memcpy(handle, &h, sizeof(h));
+  return LS_OK;
+}
+
+int ls_shard_exchange_open(ls_ctx* ctx, const unsigned char handle[LS_IPC_HANDLE_BYTES]) {
+  if (!ctx || !handle) return LS_ERR_ARG;
+  BUSY_CHECK(ctx);
+  CU(cudaSetDevice(ctx->device));
+  ls_shard_exchange_close(ctx);
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, sizeof(h));
+  void* p = nullptr;
+  CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  ctx->xwork = static_cast<IcpWork*>(p);
+  ctx->xwork_owner = false;
+  ctx->xseq = 0;
+  return LS_OK;
+}
+
+void ls_shard_exchange_close(ls_ctx* ctx) {
+  if (!ctx || !ctx->xwork) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->xwork_owner) cudaFree(ctx->xwork);
+  else cudaIpcCloseMemHandle(ctx->xwork);
+  ctx->xwork = nullptr;
+}
+
+int ls_icp_register_submap_sharded(ls_ctx* ctx, const ls_icp_params* prm, const ls_map* map, uint64_t reading_id, int n_parts,
+                                   const uint64_t* part_ids, const float* T_parts, const float T0[16], int shard_rank,
+                                   int shard_count, float T_out[16], ls_icp_stats* stats) {
+  if (!ctx) return LS_ERR_ARG;
+  BUSY_CHECK(ctx);
+  if (!map || map->ctx != ctx || !part_ids || !T_parts || !T0 || !T_out) return fail(ctx, LS_ERR_ARG, "bad argument");
+  if (shard_count < 1 || shard_count > 64 || shard_rank < 0 || shard_rank >= shard_count)
+    return fail(ctx, LS_ERR_ARG, "shard %d of %d", shard_rank, shard_count);
+  if (!ctx->xwork) return fail(ctx, LS_ERR_STATE, "no exchange buffer: ls_shard_exchange_create / _open first");
+  if ((shard_rank == 0) != ctx->xwork_owner) return fail(ctx, LS_ERR_STATE, "the exchange buffer lives on shard 0");
+  int rc = check_params(ctx, prm);
+  if (rc) return rc;
+  std::memcpy(T_out, T0, 16 * sizeof(float));
+  if (stats) std::memset(stats, 0, sizeof(*stats));
+  const ls_scan_slot* rs = find_slot(map, reading_id);
+  if (!rs) return fail(ctx, LS_ERR_STATE, "reading scan %llu is not resident", (unsigned long long)reading_id);
+  Parts parts;
+  CU(cudaSetDevice(ctx->device));
+  Workspace* w = ctx->ws[0];
+  if ((rc = make_parts(ctx, map, n_parts, part_ids, T_parts, &parts, w->stream))) return rc;
+  if (wait_slot(rs, w->stream) != LS_OK) return fail(ctx, LS_ERR_CUDA, "cudaStreamWaitEvent failed");
+  const int n = rs->n, m = parts.offset[n_parts];
+  if (n == 0 || m == 0) return fail(ctx, LS_ERR_CONVERGENCE, "empty reading or reference");
+  if (n < 32 * shard_count) return fail(ctx, LS_ERR_ARG, "reading of %d points is too small for %d shards", n, shard_count);
+  const Resolved r = resolve(prm);
+  if ((rc = ensure_capacity(ctx, w, n, m, r.max_cells, prm->max_iterations))) return rc;
+  CU(cudaEventRecord(w->ev0, w->stream));
+  if ((rc = enqueue_build(ctx, w, parts, r, T0))) return rc;
+  if ((rc = prep_icp(ctx, w, prm, rs->pts, n, T0, false, false))) return rc;
+  // this shard's range of the cell-sorted reading (whole warps), and everybody's CTA counts for the barrier
+  auto cut = [&](int s) { return (int)(((long long)n * s / shard_count) & ~31ll); };
+  unsigned int total_ctas = 0;
+  for (int s = 0; s < shard_count; ++s) {
+    const int ns = (s + 1 == shard_count ? n : cut(s + 1)) - cut(s);
+    total_ctas += (unsigned int)std::min(ctx->icp_ctas, (ns + 31) / 32);
+  }
+  const int q0 = cut(shard_rank), q1 = shard_rank + 1 == shard_count ? n : cut(shard_rank + 1);
+  IcpProblem& hp = w->hp;
+  hp.rd += q0;
+  hp.qperm += q0;
+  hp.pos += q0;
+  hp.d2 += q0;
+  hp.lists.vq += q0;
+  hp.lists.vpts += q0;  // the candidate slots keep their stride (lists.n = n)
+  hp.n = q1 - q0;
+  hp.xwork = ctx->xwork + (ctx->xseq % 3);
+  hp.xwork_clear = ctx->xwork + ((ctx->xseq + 1) % 3);
+  hp.shard_rank = shard_rank;
+  hp.shard_count = shard_count;
+  hp.barrier_ctas = total_ctas;
+  ++ctx->xseq;
+  if ((rc = launch_icp(ctx, prm, 1, q1 - q0))) return rc;
+  CU(cudaStreamSynchronize(w->stream));
+  return fetch_icp(ctx, w, prm, n, T0, T_out, stats);
 }
 
 // Sub-map <-> sub-map registration with both clouds assembled on the device (the loop-closure ICP of

@@ -119,6 +119,14 @@ struct IcpProblem {
   const uint32_t* qperm;  // rank -> original query index
   VLists lists;           // certified candidate lists (ls_grid.cuh), rank order
   IcpWork* work;
+  // Query-sharded registration (one registration, its queries split over several GPUs): the select histograms, the
+  // normal-equation sums and the barrier live in ONE IcpWork that every GPU's CTAs reach over NVLink (peer-mapped
+  // memory of the hosting rank); everything else -- per-query state, work counters, results -- stays local.
+  // null: not sharded, `work` serves both purposes.
+  IcpWork* xwork;
+  IcpWork* xwork_clear;          // shard 0 zeroes this one (the exchange scratch of the registration after this) on entry
+  int shard_rank, shard_count;   // shard_count <= 1: not sharded
+  unsigned int barrier_ctas;     // CTAs of ALL shards taking part in the barrier (sharded only)
   float* T_hist;  // max_iterations*16 floats or null
   int want_matches;  // 1: finish with an uncapped NN pass so ids/d2 hold every point's true match
   unsigned long long* phase_ns;  // debug: max_iterations*6 globaltimer stamps (CTA 0) or null
@@ -810,6 +818,25 @@ __device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int* p) {
 __device__ __forceinline__ void red_release_inc(unsigned int* p) {
   asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
 }
+// system-scope flavours for the exchange buffer of a query-sharded registration (peer memory over NVLink)
+__device__ __forceinline__ unsigned int ld_relaxed_sys_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_sys_inc(unsigned int* p) {
+  asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
+// reads of the exchange scratch: L2 of this GPU, or the hosting GPU's memory when sharded
+__device__ __forceinline__ unsigned int ld_xchg_u32(const unsigned int* p, bool xg) { return xg ? ld_relaxed_sys_u32(p) : __ldcg(p); }
+__device__ __forceinline__ unsigned long long ld_xchg_u64(const unsigned long long* p, bool xg) {
+  return xg ? ld_relaxed_sys_u64(p) : __ldcg(p);
+}
 
 // All CTAs of one problem.  `epoch` is the number of arrivals expected so far (kept in a register).
 //
@@ -819,14 +846,15 @@ __device__ __forceinline__ void red_release_inc(unsigned int* p) {
 // atomic or read back with ld.global.cg, i.e. served by L2, the point of coherence; per-query state
 // (pos/d2/ids) is only ever touched by its owning thread.  So the arrive is a release (prior writes are
 // performed at L2 before the counter moves) and the wait is a relaxed poll: L1 keeps the read-only map.
-__device__ __forceinline__ void problem_barrier(unsigned int* ctr, unsigned int n_ctas, unsigned int& epoch) {
+__device__ __forceinline__ void problem_barrier(unsigned int* ctr, unsigned int n_ctas, unsigned int& epoch, bool xg = false) {
   __syncthreads();
   if (threadIdx.x == 0) {
     epoch += n_ctas;
-    red_release_inc(ctr);
+    if (xg) red_release_sys_inc(ctr);
+    else red_release_inc(ctr);
     unsigned int polls = 0;
     unsigned long long t0 = 0ull;
-    while (ld_relaxed_u32(ctr) < epoch) {
+    while ((xg ? ld_relaxed_sys_u32(ctr) : ld_relaxed_u32(ctr)) < epoch) {
       __nanosleep(64);  // the polling thread shares its SM's issue slots with a CTA that is still working
       // watchdog: a barrier that does not complete within seconds is a bug (or a launch that was not co-resident);
       // fail the launch loudly instead of hanging the device
@@ -850,11 +878,11 @@ struct SelectOut {
 // Block-wide: find the histogram bin holding the element of 0-based rank k.
 // If `first` the rank is derived from the total: k = (unsigned)((float)total * ratio), clamped.
 __device__ __forceinline__ void block_select(const unsigned int* ghist, int nbins, unsigned int k, bool first,
-                                             float ratio, SelectOut* out, unsigned int* ws) {
+                                             float ratio, SelectOut* out, unsigned int* ws, bool xg = false) {
   const int per = nbins / kIcpThreads;
   unsigned int c[2048 / kIcpThreads], loc = 0;
   for (int j = 0; j < per; ++j) {
-    c[j] = __ldcg(ghist + threadIdx.x * per + j);
+    c[j] = ld_xchg_u32(ghist + threadIdx.x * per + j, xg);
     loc += c[j];
   }
   unsigned int incl = loc;
@@ -1076,21 +1104,27 @@ __device__ __noinline__ void final_match(const Grid* gp, const IcpProblem* Pp, c
 }
 
 // CTA-wide: fold the warps' sums (drain_pairs) into the problem's accumulators (L2 atomics).
-__device__ __forceinline__ void flush_slabs(unsigned long long (*acc_w)[28], unsigned long long* gacc) {
+__device__ __forceinline__ void flush_slabs(unsigned long long (*acc_w)[28], unsigned long long* gacc, bool xg = false) {
   __syncthreads();
   if (threadIdx.x < 28) {
     unsigned long long t = 0ull;
 #pragma unroll
     for (int w = 0; w < kIcpThreads / 32; ++w) t += acc_w[w][threadIdx.x];
-    if (t != 0ull) atomicAdd(&gacc[threadIdx.x], t);
+    if (t != 0ull) {
+      if (xg) atomicAdd_system(&gacc[threadIdx.x], t);
+      else atomicAdd(&gacc[threadIdx.x], t);
+    }
   }
   __syncthreads();  // the slabs may be rewritten
 }
 
-__device__ __forceinline__ void flush_hist(const unsigned int* hs, int nbins, unsigned int* gh) {
+__device__ __forceinline__ void flush_hist(const unsigned int* hs, int nbins, unsigned int* gh, bool xg = false) {
   for (int k = threadIdx.x; k < nbins; k += kIcpThreads) {
     const unsigned int v = hs[k];
-    if (v) atomicAdd(&gh[k], v);
+    if (v) {
+      if (xg) atomicAdd_system(&gh[k], v);
+      else atomicAdd(&gh[k], v);
+    }
   }
 }
 
@@ -1111,8 +1145,12 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
   const int pi = blockIdx.x / ctas_per_problem;
   const int cta = blockIdx.x - pi * ctas_per_problem;
   const IcpProblem& P = probs[pi];
-  IcpWork* W = P.work;
-  const unsigned int G = (unsigned int)ctas_per_problem;
+  IcpWork* W = P.work;                 // local: work counters, results
+  const bool xg = P.shard_count > 1;   // query-sharded: the exchange scratch is shared by several GPUs
+  IcpWork* X = xg ? P.xwork : W;       // histograms, normal-equation sums, barrier
+  const bool lead = cta == 0 && (!xg || P.shard_rank == 0);  // the one CTA that clears the exchange scratch
+  const unsigned int G = (unsigned int)ctas_per_problem;     // this GPU's CTAs on the problem (query chunks)
+  const unsigned int GB = xg ? P.barrier_ctas : G;           // barrier participants
   const int tid = threadIdx.x, lane = tid & 31;
 
   __shared__ Grid g;
@@ -1160,10 +1198,18 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
   // the cap are counted in the +inf histogram bin, and if the quantile lands in that bin the queries that found
   // nothing -- only those: a match found inside a smaller cap is the nearest neighbour under any cap -- are
   // searched again with a 4x larger cap (`redo` counts these rounds).
+  if (xg && P.shard_rank == 0) {
+    // Three exchange scratches rotate over successive registrations.  The one cleared here served the registration
+    // before the previous one: this kernel runs, so every shard has entered the previous registration's kernel and
+    // therefore finished the one before it.  It is used next by the registration after this one, which no shard starts
+    // before it has been through this kernel's barriers, i.e. after these stores.
+    unsigned int* z = reinterpret_cast<unsigned int*>(P.xwork_clear);
+    for (int k = cta * kIcpThreads + tid; k < (int)(sizeof(IcpWork) / 4); k += (int)G * kIcpThreads) z[k] = 0u;
+  }
   float cap = 0.04f;
   int redo = 0;
   unsigned int epoch = 0;
-  problem_barrier(&W->barrier, G, epoch);  // the state initialised above is read by other CTAs
+  problem_barrier(&X->barrier, GB, epoch, xg);  // the state initialised above is read by other CTAs
   int hist_count = 1;  // entries in qh/th
   int iter = 0, converged = 0, max_reached = 0, last_kept = 0;
   float last_limit = 0.f;
@@ -1243,17 +1289,17 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
       }
     }
     drain_pairs(Q, acc_w[tid >> 5]);
-    flush_slabs(acc_w, W->acc[par]);  // (starts with a __syncthreads: every warp is done with phase A)
-    flush_hist(hs.h1, 1024, W->hist[par][0]);
+    flush_slabs(acc_w, X->acc[par], xg);  // (starts with a __syncthreads: every warp is done with phase A)
+    flush_hist(hs.h1, 1024, X->hist[par][0], xg);
     if (pred_bin1 != kNoPrediction) {
-      flush_hist(hs.h2, 2048, W->hist[par][3]);
-      flush_hist(hs.h3, 1024, W->hist[par][4]);
+      flush_hist(hs.h2, 2048, X->hist[par][3], xg);
+      flush_hist(hs.h3, 1024, X->hist[par][4], xg);
     }
-    problem_barrier(&W->barrier, G, epoch);
+    problem_barrier(&X->barrier, GB, epoch, xg);
     LS_STAMP(1);
 
     // ---------------- select, level 1 ----------------
-    block_select(W->hist[par][0], 1024, 0u, true, prm.trim_ratio, &sel, ws);
+    block_select(X->hist[par][0], 1024, 0u, true, prm.trim_ratio, &sel, ws, xg);
     if (sel.total == 0u) {  // no point at all -> ConvergenceError
       if (tid == 0) { flag_status = 1; if (cta == 0) W->fail_code = 1; }
       __syncthreads();
@@ -1268,21 +1314,19 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
       }
       cap = cap < 64.0f ? cap * 4.0f : INFINITY;
       ++redo;
-      problem_barrier(&W->barrier, G, epoch);  // everyone has read the histogram
-      if (cta == 0 && tid == 0) {
-        W->hist[par][0][1020] = 0u;  // the unmatched queries are counted again; everything else stands
-        W->qctr[par] = 0u;
-      }
-      problem_barrier(&W->barrier, G, epoch);
+      problem_barrier(&X->barrier, GB, epoch, xg);  // everyone has read the histogram
+      if (lead && tid == 0) X->hist[par][0][1020] = 0u;  // the unmatched queries are counted again; everything else stands
+      if (cta == 0 && tid == 0) W->qctr[par] = 0u;
+      problem_barrier(&X->barrier, GB, epoch, xg);
       continue;  // phase A again, for the queries without a match, with the larger cap
     }
     const unsigned int bin1 = sel.bin, rem1 = sel.rem;
-    if (cta == 0) {  // clear the other parity's scratch for the next iteration (nobody touches it before the next barrier)
-      unsigned int* h = &W->hist[par ^ 1][0][0];
+    if (lead) {  // clear the other parity's scratch for the next iteration (nobody touches it before the next barrier)
+      unsigned int* h = &X->hist[par ^ 1][0][0];
       for (int k = tid; k < 5 * 2048; k += kIcpThreads) h[k] = 0u;
-      if (tid < 32) W->acc[par ^ 1][tid] = 0ull;
-      if (tid == 0) W->qctr[par ^ 1] = 0u;
+      if (tid < 32) X->acc[par ^ 1][tid] = 0ull;
     }
+    if (cta == 0 && tid == 0) W->qctr[par ^ 1] = 0u;
     // ---------------- level 2: from the speculative histogram, or a pass over d2 + barrier ----------------
     const bool spec2 = bin1 == pred_bin1;
     if (!spec2) {
@@ -1293,11 +1337,11 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
         if (key < 0x7f800000u && (key >> 21) == bin1) atomicAdd(&hs.h2[(key >> 10) & 2047u], 1u);
       }
       __syncthreads();
-      flush_hist(hs.h2, 2048, W->hist[par][1]);
-      problem_barrier(&W->barrier, G, epoch);
+      flush_hist(hs.h2, 2048, X->hist[par][1], xg);
+      problem_barrier(&X->barrier, GB, epoch, xg);
     }
     LS_STAMP(2);
-    block_select(W->hist[par][spec2 ? 3 : 1], 2048, rem1, false, 0.f, &sel, ws);
+    block_select(X->hist[par][spec2 ? 3 : 1], 2048, rem1, false, 0.f, &sel, ws, xg);
     const unsigned int bin2 = sel.bin, rem2 = sel.rem;
     const unsigned int prefix12 = (bin1 << 11) | bin2;
     // ---------------- level 3 ----------------
@@ -1310,11 +1354,11 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
         if (key < 0x7f800000u && (key >> 10) == prefix12) atomicAdd(&hs.h3[key & 1023u], 1u);
       }
       __syncthreads();
-      flush_hist(hs.h3, 1024, W->hist[par][2]);
-      problem_barrier(&W->barrier, G, epoch);
+      flush_hist(hs.h3, 1024, X->hist[par][2], xg);
+      problem_barrier(&X->barrier, GB, epoch, xg);
     }
     LS_STAMP(3);
-    block_select(W->hist[par][spec3 ? 4 : 2], 1024, rem2, false, 0.f, &sel, ws);
+    block_select(X->hist[par][spec3 ? 4 : 2], 1024, rem2, false, 0.f, &sel, ws, xg);
     const float limit = __uint_as_float((prefix12 << 10) | sel.bin);
     // guess for the next iteration (verified there): the first step removes most of the initial misalignment, so the
     // limit drops sharply once and then settles -- a guess that turns out too small costs one more round for the
@@ -1343,8 +1387,8 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
       push_pairs<3>(P, Q, sign, sx, sy, sz, q, pos);
     }
     drain_pairs(Q, acc_w[tid >> 5]);
-    flush_slabs(acc_w, W->acc[par]);
-    problem_barrier(&W->barrier, G, epoch);
+    flush_slabs(acc_w, X->acc[par], xg);
+    problem_barrier(&X->barrier, GB, epoch, xg);
     LS_STAMP(4);
 
     // ---------------- phase E: solve, update, checkers (every CTA, identically) ----------------
@@ -1353,12 +1397,12 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
       int k = 0;
       for (int rr = 0; rr < 6; ++rr)
         for (int cc = rr; cc < 6; ++cc, ++k) {
-          const double v = (double)(long long)__ldcg(&W->acc[par][k]) / 4194304.0;
+          const double v = (double)(long long)ld_xchg_u64(&X->acc[par][k], xg) / 4194304.0;
           A[rr * 6 + cc] = v;
           A[cc * 6 + rr] = v;
         }
-      for (int rr = 0; rr < 6; ++rr) b[rr] = -((double)(long long)__ldcg(&W->acc[par][21 + rr]) / 4194304.0);
-      last_kept = (int)__ldcg(&W->acc[par][27]);
+      for (int rr = 0; rr < 6; ++rr) b[rr] = -((double)(long long)ld_xchg_u64(&X->acc[par][21 + rr], xg) / 4194304.0);
+      last_kept = (int)ld_xchg_u64(&X->acc[par][27], xg);
       last_limit = limit;
       int status = 0, stop = 0;
       if (last_kept == 0) {
