@@ -7,8 +7,9 @@
 
 One track; every step registers the next scan of the drive against the rolling sub-map, one registration per launch
 (the latency case: a single dense sensor that has to be matched before the next scan arrives).  With N ranks every rank
-holds the whole map and 1/N of the reading's queries; the ranks meet, inside the persistent kernel, in one exchange
-scratch in rank 0's memory (ls_icp_register_submap_sharded, include/ls_b200.h).  The timed quantity is the latency of a
+holds the whole map and 1/N of the reading's queries; inside the persistent kernel every GPU stores its partial select
+histograms and normal-equation sums into the peers' exchange buffers over NVLink (ls_icp_register_submap_sharded,
+include/ls_b200.h).  The timed quantity is the latency of a
 registration with the scans resident (max over ranks, CUDA events of the launch + host wall clock), and its inverse.
 
 Parity, outside the clock: every timed registration's transform is compared BIT FOR BIT with the unsharded
@@ -114,13 +115,15 @@ def main():
                        "shards": world, "iterations": ITERS},
             "parity": {"bit_equal_to_unsharded_on_every_rank": bool(same_all), "registrations_compared": len(outs),
                        "first_bit_equal_to_oracle": oracle_equal},
-            "exchange": {"where": "rank 0 HBM, peer-mapped over NVLink (CUDA IPC)",
-                         "per_iteration_per_cta": "<= 4096 histogram reds + 28 u64 reds out, 4096 u32 + 28 u64 loads in, 2-3 barrier arrivals"},
+            "exchange": {"how": "each GPU stores its partial histograms / sums into a slot of every peer's buffer (CUDA IPC, NVLink) from inside the persistent kernel; readers sum local slots",
+                         "bytes_per_iteration_per_peer_pair": "16 KiB histograms + 256 B sums (steady state), 2 arrival signals"},
         }), flush=True)
-        if not same_all:
-            raise SystemExit("sharded registration differs from the unsharded one")
+    if reg is not None:
+        reg.close()
     if world > 1:
         dist.destroy_process_group()
+    if not same_all:
+        raise SystemExit("sharded registration differs from the unsharded one")
 
 
 if __name__ == "__main__":

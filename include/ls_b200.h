@@ -192,23 +192,24 @@ int ls_icp_register_submap_batch_end(ls_ctx* ctx, float* T_outs, ls_icp_stats* s
 
 /* ---- one registration sharded by queries over the GPUs of a node -------------------------
  * The scan-matching of LaserTrack::processPoseAndLaserScan (laser_slam/src/laser_track.cpp:196-292) for ONE scan,
- * with the reading split over `shard_count` GPUs (one process / context per GPU).  Every shard pushes the same scans
- * into its own map and makes the same call; the shards exchange the trimmed-select histograms and the normal-equation
- * sums through a small buffer in shard 0's memory that the others map over NVLink (CUDA IPC), from inside the
- * persistent kernel.  The result is bit-identical to ls_icp_register_submap on every shard.
+ * with the reading split over the GPUs of a node (one process / context per GPU, at most 8).  Every shard pushes the
+ * same scans into its own map and makes the same call; per iteration each GPU stores its partial trimmed-select
+ * histograms and normal-equation sums into a slot of every peer's exchange buffer over NVLink (CUDA IPC mapping), from
+ * inside the persistent kernel.  The result is bit-identical to ls_icp_register_submap on every shard.
  *
- * Setup, once: shard 0 calls ls_shard_exchange_create and passes the 64 handle bytes to the other processes by any
- * means (torch.distributed broadcast, a pipe ...); they call ls_shard_exchange_open.  After that
- * ls_icp_register_submap_sharded is a COLLECTIVE: every shard must make the same sequence of calls with the same
- * arguments (except shard_rank).  A shard that does not show up trips the kernel's barrier watchdog on the others
- * (the launch fails after 8 s; it does not hang).  Readings need at least 32 points per shard. */
+ * Setup, once: every shard calls ls_shard_exchange_create (allocates its buffer, returns 64 handle bytes); the handles
+ * are gathered in rank order by any means (torch.distributed all_gather, a pipe ...) and passed to
+ * ls_shard_exchange_connect on every shard.  After that ls_icp_register_submap_sharded is a COLLECTIVE: every shard
+ * makes the same sequence of calls with the same arguments.  A shard that does not show up trips the kernel's watchdog
+ * on the others (the launch fails after 8 s; it does not hang).  Close only after every shard is done (the peers store
+ * into the buffer). */
 #define LS_IPC_HANDLE_BYTES 64
-int ls_shard_exchange_create(ls_ctx* ctx, unsigned char handle[LS_IPC_HANDLE_BYTES]);
-int ls_shard_exchange_open(ls_ctx* ctx, const unsigned char handle[LS_IPC_HANDLE_BYTES]);
+int ls_shard_exchange_create(ls_ctx* ctx, int shard_rank, int shard_count, unsigned char handle[LS_IPC_HANDLE_BYTES]);
+int ls_shard_exchange_connect(ls_ctx* ctx, const unsigned char* handles /* shard_count x LS_IPC_HANDLE_BYTES, rank order */);
 void ls_shard_exchange_close(ls_ctx* ctx);
 int ls_icp_register_submap_sharded(ls_ctx* ctx, const ls_icp_params* prm, const ls_map* map, uint64_t reading_id,
                                    int n_parts, const uint64_t* part_ids, const float* T_parts, const float T0[16],
-                                   int shard_rank, int shard_count, float T_out[16], ls_icp_stats* stats);
+                                   float T_out[16], ls_icp_stats* stats);
 
 /* Sub-map <-> sub-map registration on resident data: the loop-closure ICP of
  * IncrementalEstimator::processLoopClosure (laser_slam/src/incremental_estimator.cpp:90-115) without the two

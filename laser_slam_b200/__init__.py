@@ -101,11 +101,11 @@ def lib():
         L.ls_map_scan_size.argtypes = [vp, u64]
         L.ls_icp_register_submap.argtypes = [vp, PP, vp, u64, ci, vp, vp, vp, vp, PS, vp, vp, vp]
         L.ls_map_assemble.argtypes = [vp, vp, ci, vp, vp, vp, vp, ctypes.POINTER(ci)]
-        L.ls_shard_exchange_create.argtypes = [vp, vp]
-        L.ls_shard_exchange_open.argtypes = [vp, vp]
+        L.ls_shard_exchange_create.argtypes = [vp, ci, ci, vp]
+        L.ls_shard_exchange_connect.argtypes = [vp, vp]
         L.ls_shard_exchange_close.argtypes = [vp]
         L.ls_shard_exchange_close.restype = None
-        L.ls_icp_register_submap_sharded.argtypes = [vp, PP, vp, u64, ci, vp, vp, vp, ci, ci, vp, PS]
+        L.ls_icp_register_submap_sharded.argtypes = [vp, PP, vp, u64, ci, vp, vp, vp, vp, PS]
         L.ls_icp_register_submaps.argtypes = [vp, PP, vp, ci, vp, vp, vp, ci, vp, vp, vp, vp, PS]
         L.ls_estimate_normals.argtypes = [vp, vp, ci, ci, vp]
         L.ls_map_push_scan_estimate_normals.argtypes = [vp, vp, ci, ci, ctypes.POINTER(u64)]
@@ -267,17 +267,17 @@ class Context:
         self._check(lib().ls_b200_set_icp_cta_budget(self._h, int(ctas)))
         return int(lib().ls_b200_icp_cta_budget(self._h))
 
-    def shard_exchange_create(self):
-        """Shard 0 of a query-sharded registration: allocate the exchange buffer, return its 64 IPC handle bytes."""
+    def shard_exchange_create(self, shard_rank, shard_count):
+        """Query-sharded registration, step 1 on every shard: allocate this GPU's exchange buffer; returns its 64 IPC
+        handle bytes (ls_shard_exchange_create)."""
         h = np.zeros(64, np.uint8)
-        self._check(lib().ls_shard_exchange_create(self._h, h.ctypes.data))
+        self._check(lib().ls_shard_exchange_create(self._h, int(shard_rank), int(shard_count), h.ctypes.data))
         return h.tobytes()
 
-    def shard_exchange_open(self, handle):
-        """Every other shard: map shard 0's exchange buffer (peer memory over NVLink)."""
-        h = np.frombuffer(bytes(handle), np.uint8).copy()
-        assert h.size == 64
-        self._check(lib().ls_shard_exchange_open(self._h, h.ctypes.data))
+    def shard_exchange_connect(self, handles):
+        """Step 2 on every shard: map the peers' buffers; `handles` = every shard's handle bytes in rank order."""
+        h = np.frombuffer(b"".join(bytes(x) for x in handles), np.uint8).copy()
+        self._check(lib().ls_shard_exchange_connect(self._h, h.ctypes.data))
 
     def icp_register(self, reading4, ref4, ref_normals3, T0, params=None, want_ids=False, want_hist=False,
                      raise_on_convergence=True):
@@ -421,11 +421,10 @@ class Map:
             out["T_iter_hist"] = hist[:st.iterations].reshape(-1, 4, 4).transpose(0, 2, 1).copy()
         return out
 
-    def register_sharded(self, reading_id, part_ids, T_parts, T0, shard_rank, shard_count, params=None,
-                         raise_on_convergence=True):
-        """This process's share of ONE registration sharded by queries over `shard_count` GPUs
+    def register_sharded(self, reading_id, part_ids, T_parts, T0, params=None, raise_on_convergence=True):
+        """This process's share of ONE registration sharded by queries over the GPUs of the node
         (ls_icp_register_submap_sharded): a collective -- every shard makes the same call on its own copy of the map.
-        The context needs its exchange buffer first (Context.shard_exchange_create / _open, or dist.ShardedRegistrar)."""
+        The context needs its exchange first (Context.shard_exchange_create + _connect, or dist.ShardedRegistrar)."""
         p = params or default_params()
         ids_arr = np.ascontiguousarray(part_ids, np.uint64)
         tp = np.ascontiguousarray(np.stack([colmajor(T) for T in T_parts]), np.float32)
@@ -433,8 +432,8 @@ class Map:
         tout = np.empty(16, np.float32)
         st = IcpStats()
         rc = lib().ls_icp_register_submap_sharded(self.ctx._h, ctypes.byref(p), self._h, reading_id, len(ids_arr),
-                                                  ids_arr.ctypes.data, tp.ctypes.data, t0.ctypes.data, int(shard_rank),
-                                                  int(shard_count), tout.ctypes.data, ctypes.byref(st))
+                                                  ids_arr.ctypes.data, tp.ctypes.data, t0.ctypes.data, tout.ctypes.data,
+                                                  ctypes.byref(st))
         if rc != LS_ERR_CONVERGENCE or raise_on_convergence:
             self.ctx._check(rc)
         return dict(T=from_colmajor(tout), stats=st, rc=rc)

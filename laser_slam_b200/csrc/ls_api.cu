@@ -58,10 +58,12 @@ struct ls_ctx {
   BuildJob* jobs_dev = nullptr;      // [kMaxBatch]: workspace b stages its build in slot b
   BuildJob* jobs_host = nullptr;     // pinned
   IcpWork* work_pool = nullptr;      // [kMaxBatch] contiguous, so one memset clears a whole batch
-  // query-sharded registration: three rotating exchange scratches in the hosting rank's memory (peer-mapped elsewhere)
-  IcpWork* xwork = nullptr;
-  bool xwork_owner = false;
-  uint64_t xseq = 0;  // sharded registrations issued so far (every shard counts the same calls)
+  // query-sharded registration: this GPU's exchange buffer (shard_count slots + the arrival counter) and the peers'
+  unsigned char* xbuf = nullptr;
+  unsigned char* xpeer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int shard_rank = 0, shard_count = 1;
+  bool xconnected = false;
+  unsigned int xflag_base = 0;  // arrivals the earlier registrations consumed from the counter
   // a batch between ls_icp_register_submap_batch_begin and _end: the workspaces are busy
   bool pending = false;
   int pending_batch = 0;
@@ -351,11 +353,9 @@ int fill_problem(ls_ctx* ctx, Workspace* w, const ls_icp_params* prm, int n, con
   hp.lists.vpts = w->vpts;
   hp.lists.n = n;
   hp.work = w->work;
-  hp.xwork = nullptr;
-  hp.xwork_clear = nullptr;
   hp.shard_rank = 0;
   hp.shard_count = 1;
-  hp.barrier_ctas = 0u;
+  std::memset(&hp.link, 0, sizeof(hp.link));
   hp.T_hist = want_hist ? w->T_hist : nullptr;
   if (want_hist) {  // entries past the executed iterations read as zeros, not as stale device memory
     CU(cudaMemsetAsync(w->T_hist, 0, (size_t)prm->max_iterations * 16 * sizeof(float), w->stream));
@@ -391,7 +391,7 @@ int prep_icp(ls_ctx* ctx, Workspace* w, const ls_icp_params* prm, const float4* 
 // One cooperative launch over `batch` staged problems (workspaces 0..batch-1): the grid is partitioned into
 // `batch` groups of CTAs, each with its own barrier.  Runs on workspace 0's stream after every workspace's
 // staging has finished; on return the results are on the host (pinned mirrors).
-int launch_icp(ls_ctx* ctx, const ls_icp_params* prm, int batch, int n_max) {
+int launch_icp(ls_ctx* ctx, const ls_icp_params* prm, int batch, int n_max, bool sharded = false) {
   Workspace* w0 = ctx->ws[0];
   for (int b = 0; b < batch; ++b) ctx->probs_host[b] = ctx->ws[b]->hp;
   CU(cudaMemcpyAsync(ctx->probs_dev, ctx->probs_host, sizeof(IcpProblem) * (size_t)batch, cudaMemcpyHostToDevice, w0->stream));
@@ -409,6 +409,10 @@ int launch_icp(ls_ctx* ctx, const ls_icp_params* prm, int batch, int n_max) {
   const IcpProblem* probs = ctx->probs_dev;
   int dynamic = batch > 1 ? 1 : 0;  // several problems: warps pull work from per-problem counters
   void* args[] = {(void*)&probs, (void*)&ctas, (void*)&dp, (void*)&dynamic};
+  if (sharded) {  // narrow the staged problem to this shard's queries (cuts at cell starts, computed on the device)
+    shard_slice_kernel<<<1, 32, 0, w0->stream>>>(ctx->probs_dev, w0->job_dev, w0->hp.shard_rank, w0->hp.shard_count);
+    LAUNCH_CHECK();
+  }
   CU(cudaEventRecord(w0->ev_launch, w0->stream));
   CU(cudaLaunchCooperativeKernel((void*)icp_kernel, dim3(ctas * batch), dim3(kIcpThreads), args, kIcpPairBytes, w0->stream));
   ++ctx->launches;
@@ -1005,62 +1009,78 @@ int ls_icp_register_submap(ls_ctx* ctx, const ls_icp_params* prm, const ls_map* 
 
 // ---- query-sharded registration -------------------------------------------------------------
 // ONE registration whose reading is split over the GPUs of a node.  Every shard holds the whole map (the build is
-// replicated: it is 54 us) and a contiguous range of the cell-sorted reading; per iteration the shards meet in the select
-// histograms, the 28 normal-equation sums and the barrier counter of one exchange scratch that lives in shard 0's
-// memory and is peer-mapped (CUDA IPC, NVLink) by the others -- system-scope atomics and loads issued from inside the
-// persistent kernel, no collective call and no host involvement per iteration.  All the sums are integers, so the
-// result is bit-identical to the unsharded registration whatever the number of shards.
-int ls_shard_exchange_create(ls_ctx* ctx, unsigned char handle[LS_IPC_HANDLE_BYTES]) {
+// replicated: it costs ~54 us) and a contiguous range of the cell-sorted reading.  Per iteration the shards exchange
+// their partial select histograms and their 28 partial normal-equation sums: each GPU pushes its sections into a slot
+// of every peer's exchange buffer (peer-mapped with CUDA IPC, plain stores over NVLink) from inside the persistent
+// kernel and bumps the peer's arrival counter; readers sum the slots, all local (ShardLink, shard_exchange in
+// ls_kernels.cuh).  No collective call, no host involvement per iteration, nothing polled across NVLink.  All the sums
+// are integers, so the result is bit-identical to the unsharded registration whatever the number of shards.
+namespace {
+size_t xbuf_bytes(int shards) { return sizeof(IcpWork) * (size_t)shards + 128; }
+}
+
+int ls_shard_exchange_create(ls_ctx* ctx, int shard_rank, int shard_count, unsigned char handle[LS_IPC_HANDLE_BYTES]) {
   if (!ctx || !handle) return LS_ERR_ARG;
   BUSY_CHECK(ctx);
   static_assert(sizeof(cudaIpcMemHandle_t) <= LS_IPC_HANDLE_BYTES, "handle size");
+  if (shard_count < 1 || shard_count > kMaxShards || shard_rank < 0 || shard_rank >= shard_count)
+    return fail(ctx, LS_ERR_ARG, "shard %d of %d (at most %d shards)", shard_rank, shard_count, kMaxShards);
   CU(cudaSetDevice(ctx->device));
   ls_shard_exchange_close(ctx);
-  CU(cudaMalloc((void**)&ctx->xwork, 3 * sizeof(IcpWork)));
-  ctx->xwork_owner = true;
-  ctx->xseq = 0;
-  CU(cudaMemset(ctx->xwork, 0, 3 * sizeof(IcpWork)));
+  CU(cudaMalloc((void**)&ctx->xbuf, xbuf_bytes(shard_count)));
+  CU(cudaMemset(ctx->xbuf, 0, xbuf_bytes(shard_count)));
   CU(cudaDeviceSynchronize());
+  ctx->shard_rank = shard_rank;
+  ctx->shard_count = shard_count;
+  ctx->xflag_base = 0;
+  ctx->xconnected = shard_count == 1;
   cudaIpcMemHandle_t h;
-  CU(cudaIpcGetMemHandle(&h, ctx->xwork));
+  CU(cudaIpcGetMemHandle(&h, ctx->xbuf));
   std::memset(handle, 0, LS_IPC_HANDLE_BYTES);
   std::memcpy(handle, &h, sizeof(h));
   return LS_OK;
 }
 
-int ls_shard_exchange_open(ls_ctx* ctx, const unsigned char handle[LS_IPC_HANDLE_BYTES]) {
-  if (!ctx || !handle) return LS_ERR_ARG;
+int ls_shard_exchange_connect(ls_ctx* ctx, const unsigned char* handles) {
+  if (!ctx || !handles) return LS_ERR_ARG;
   BUSY_CHECK(ctx);
+  if (!ctx->xbuf) return fail(ctx, LS_ERR_STATE, "ls_shard_exchange_create first");
   CU(cudaSetDevice(ctx->device));
-  ls_shard_exchange_close(ctx);
-  cudaIpcMemHandle_t h;
-  std::memcpy(&h, handle, sizeof(h));
-  void* p = nullptr;
-  CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-  ctx->xwork = static_cast<IcpWork*>(p);
-  ctx->xwork_owner = false;
-  ctx->xseq = 0;
+  for (int g = 0; g < ctx->shard_count; ++g) {
+    if (g == ctx->shard_rank || ctx->xpeer[g]) continue;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handles + (size_t)g * LS_IPC_HANDLE_BYTES, sizeof(h));
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->xpeer[g] = static_cast<unsigned char*>(p);
+  }
+  ctx->xconnected = true;
   return LS_OK;
 }
 
 void ls_shard_exchange_close(ls_ctx* ctx) {
-  if (!ctx || !ctx->xwork) return;
+  if (!ctx) return;
   cudaSetDevice(ctx->device);
-  if (ctx->xwork_owner) cudaFree(ctx->xwork);
-  else cudaIpcCloseMemHandle(ctx->xwork);
-  ctx->xwork = nullptr;
+  for (int g = 0; g < kMaxShards; ++g) {
+    if (ctx->xpeer[g]) cudaIpcCloseMemHandle(ctx->xpeer[g]);
+    ctx->xpeer[g] = nullptr;
+  }
+  if (ctx->xbuf) cudaFree(ctx->xbuf);
+  ctx->xbuf = nullptr;
+  ctx->xconnected = false;
+  ctx->shard_count = 1;
+  ctx->shard_rank = 0;
 }
 
 int ls_icp_register_submap_sharded(ls_ctx* ctx, const ls_icp_params* prm, const ls_map* map, uint64_t reading_id, int n_parts,
-                                   const uint64_t* part_ids, const float* T_parts, const float T0[16], int shard_rank,
-                                   int shard_count, float T_out[16], ls_icp_stats* stats) {
+                                   const uint64_t* part_ids, const float* T_parts, const float T0[16], float T_out[16],
+                                   ls_icp_stats* stats) {
   if (!ctx) return LS_ERR_ARG;
   BUSY_CHECK(ctx);
   if (!map || map->ctx != ctx || !part_ids || !T_parts || !T0 || !T_out) return fail(ctx, LS_ERR_ARG, "bad argument");
-  if (shard_count < 1 || shard_count > 64 || shard_rank < 0 || shard_rank >= shard_count)
-    return fail(ctx, LS_ERR_ARG, "shard %d of %d", shard_rank, shard_count);
-  if (!ctx->xwork) return fail(ctx, LS_ERR_STATE, "no exchange buffer: ls_shard_exchange_create / _open first");
-  if ((shard_rank == 0) != ctx->xwork_owner) return fail(ctx, LS_ERR_STATE, "the exchange buffer lives on shard 0");
+  if (!ctx->xbuf || !ctx->xconnected)
+    return fail(ctx, LS_ERR_STATE, "no exchange buffer: ls_shard_exchange_create + ls_shard_exchange_connect first");
+  const int shard_rank = ctx->shard_rank, shard_count = ctx->shard_count;
   int rc = check_params(ctx, prm);
   if (rc) return rc;
   std::memcpy(T_out, T0, 16 * sizeof(float));
@@ -1074,36 +1094,31 @@ int ls_icp_register_submap_sharded(ls_ctx* ctx, const ls_icp_params* prm, const 
   if (wait_slot(rs, w->stream) != LS_OK) return fail(ctx, LS_ERR_CUDA, "cudaStreamWaitEvent failed");
   const int n = rs->n, m = parts.offset[n_parts];
   if (n == 0 || m == 0) return fail(ctx, LS_ERR_CONVERGENCE, "empty reading or reference");
-  if (n < 32 * shard_count) return fail(ctx, LS_ERR_ARG, "reading of %d points is too small for %d shards", n, shard_count);
   const Resolved r = resolve(prm);
   if ((rc = ensure_capacity(ctx, w, n, m, r.max_cells, prm->max_iterations))) return rc;
   CU(cudaEventRecord(w->ev0, w->stream));
   if ((rc = enqueue_build(ctx, w, parts, r, T0))) return rc;
   if ((rc = prep_icp(ctx, w, prm, rs->pts, n, T0, false, false))) return rc;
-  // this shard's range of the cell-sorted reading (whole warps), and everybody's CTA counts for the barrier
-  auto cut = [&](int s) { return (int)(((long long)n * s / shard_count) & ~31ll); };
-  unsigned int total_ctas = 0;
-  for (int s = 0; s < shard_count; ++s) {
-    const int ns = (s + 1 == shard_count ? n : cut(s + 1)) - cut(s);
-    total_ctas += (unsigned int)std::min(ctx->icp_ctas, (ns + 31) / 32);
-  }
-  const int q0 = cut(shard_rank), q1 = shard_rank + 1 == shard_count ? n : cut(shard_rank + 1);
   IcpProblem& hp = w->hp;
-  hp.rd += q0;
-  hp.qperm += q0;
-  hp.pos += q0;
-  hp.d2 += q0;
-  hp.lists.vq += q0;
-  hp.lists.vpts += q0;  // the candidate slots keep their stride (lists.n = n)
-  hp.n = q1 - q0;
-  hp.xwork = ctx->xwork + (ctx->xseq % 3);
-  hp.xwork_clear = ctx->xwork + ((ctx->xseq + 1) % 3);
   hp.shard_rank = shard_rank;
   hp.shard_count = shard_count;
-  hp.barrier_ctas = total_ctas;
-  ++ctx->xseq;
-  if ((rc = launch_icp(ctx, prm, 1, q1 - q0))) return rc;
+  if (shard_count > 1) {
+    IcpWork* slots = reinterpret_cast<IcpWork*>(ctx->xbuf);
+    // this shard's own slot starts from zero; the peers' slots are overwritten section by section before they are read
+    CU(cudaMemsetAsync(slots + shard_rank, 0, sizeof(IcpWork), w->stream));
+    hp.link.slots = slots;
+    hp.link.flag = reinterpret_cast<unsigned int*>(ctx->xbuf + sizeof(IcpWork) * (size_t)shard_count);
+    hp.link.flag_base = ctx->xflag_base;
+    for (int g = 0; g < kMaxShards; ++g) {
+      unsigned char* pb = g < shard_count ? ctx->xpeer[g] : nullptr;
+      hp.link.peer_slots[g] = reinterpret_cast<IcpWork*>(pb);
+      hp.link.peer_flag[g] = pb ? reinterpret_cast<unsigned int*>(pb + sizeof(IcpWork) * (size_t)shard_count) : nullptr;
+    }
+  }
+  // every shard runs the full co-resident grid (the exchange needs a CTA per peer, and all shards the same shape)
+  if ((rc = launch_icp(ctx, prm, 1, 1 << 30, shard_count > 1))) return rc;
   CU(cudaStreamSynchronize(w->stream));
+  ctx->xflag_base += w->h_work->xsignals;
   return fetch_icp(ctx, w, prm, n, T0, T_out, stats);
 }
 

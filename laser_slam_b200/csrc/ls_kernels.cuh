@@ -92,7 +92,7 @@ struct IcpParamsDev {
   int smooth_length;
 };
 
-struct IcpWork {
+struct alignas(16) IcpWork {
   unsigned int barrier;
   unsigned int pad0[31];
   unsigned int hist[2][5][2048];  // per parity: radix levels 1-3, then the speculative copies of levels 2 and 3
@@ -102,8 +102,22 @@ struct IcpWork {
   int status, iterations, converged, max_iter_reached, last_kept;
   float last_limit;
   int fail_code;       // 1 no finite match, 2 nothing kept, 3 non-finite solve, 4 NaN in checker, 5 non-finite T
+  unsigned int xsignals;  // query-sharded: arrivals this registration consumed from the local exchange flag
   unsigned int dbg_total, dbg_bin[3], dbg_rem[3];
   double dbg_A[6], dbg_x[6];
+};
+
+// Query-sharded registration: how one GPU reaches the others.  Every GPU owns an array of `shard_count` IcpWork
+// "slots" plus an arrival counter.  Slot [self] is where the GPU's own CTAs accumulate (L2 atomics, as in the unsharded
+// kernel); slot [r] receives, by plain stores over NVLink, the sections of shard r's slot [r] that the next step reads.
+// A reader sums the slots -- all of them local memory.  Nothing is ever LOADED or polled across NVLink.
+constexpr int kMaxShards = 8;
+struct ShardLink {
+  IcpWork* slots;                       // this GPU's slots [shard_count]
+  IcpWork* peer_slots[kMaxShards];      // peer g's slot array, mapped into this GPU's address space (CUDA IPC)
+  unsigned int* flag;                   // this GPU's arrival counter; never reset while the buffer lives
+  unsigned int* peer_flag[kMaxShards];
+  unsigned int flag_base;               // arrivals consumed by earlier registrations
 };
 
 struct IcpProblem {
@@ -119,14 +133,9 @@ struct IcpProblem {
   const uint32_t* qperm;  // rank -> original query index
   VLists lists;           // certified candidate lists (ls_grid.cuh), rank order
   IcpWork* work;
-  // Query-sharded registration (one registration, its queries split over several GPUs): the select histograms, the
-  // normal-equation sums and the barrier live in ONE IcpWork that every GPU's CTAs reach over NVLink (peer-mapped
-  // memory of the hosting rank); everything else -- per-query state, work counters, results -- stays local.
-  // null: not sharded, `work` serves both purposes.
-  IcpWork* xwork;
-  IcpWork* xwork_clear;          // shard 0 zeroes this one (the exchange scratch of the registration after this) on entry
-  int shard_rank, shard_count;   // shard_count <= 1: not sharded
-  unsigned int barrier_ctas;     // CTAs of ALL shards taking part in the barrier (sharded only)
+  // Query-sharded registration (one registration, its queries split over several GPUs; shard_count <= 1: not sharded)
+  int shard_rank, shard_count;
+  ShardLink link;
   float* T_hist;  // max_iterations*16 floats or null
   int want_matches;  // 1: finish with an uncapped NN pass so ids/d2 hold every point's true match
   unsigned long long* phase_ns;  // debug: max_iterations*6 globaltimer stamps (CTA 0) or null
@@ -679,6 +688,36 @@ __global__ void __launch_bounds__(256) q_scatter_kernel(const BuildJob* __restri
   }
 }
 
+// Query-sharded registration: narrow a staged problem to this shard's range of the cell-sorted reading.  The order
+// of the queries INSIDE a cell depends on the scatter's atomics and differs from GPU to GPU; where a cell starts does not
+// (it is a prefix sum of counts).  So the cuts are moved to the next cell start: every shard computes the same cuts and
+// every query belongs to exactly one shard.  One thread; qtop_start is non-decreasing over the level-0 cells.
+__global__ void shard_slice_kernel(IcpProblem* P, const BuildJob* __restrict__ job, int shard_rank, int shard_count) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const BuildArrays A = job->A;
+  const int n_cells = job->bs->grid.n_cells0, n = job->n;
+  auto cut = [&](int s) -> int {
+    if (s <= 0) return 0;
+    if (s >= shard_count) return n;
+    const unsigned int target = (unsigned int)((long long)n * s / shard_count);
+    int lo = 0, hi = n_cells;  // first cell whose start is >= target
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (A.qtop_start[mid] < target) lo = mid + 1;
+      else hi = mid;
+    }
+    return lo < n_cells ? (int)A.qtop_start[lo] : n;
+  };
+  const int q0 = cut(shard_rank), q1 = cut(shard_rank + 1);
+  P->rd += q0;
+  P->qperm += q0;
+  P->pos += q0;
+  P->d2 += q0;
+  P->lists.vq += q0;
+  P->lists.vpts += q0;  // the candidate slots keep their stride (lists.n = the whole reading)
+  P->n = q1 - q0;
+}
+
 // ---- reading pre-transform: R' = T_refMean_dataIn * R ----------------------------------------------
 __global__ void __launch_bounds__(256) reading_kernel(const BuildJob* __restrict__ jobs) {
   const BuildState* __restrict__ bs = jobs[blockIdx.y].bs;
@@ -832,11 +871,6 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned 
 __device__ __forceinline__ void red_release_sys_inc(unsigned int* p) {
   asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
 }
-// reads of the exchange scratch: L2 of this GPU, or the hosting GPU's memory when sharded
-__device__ __forceinline__ unsigned int ld_xchg_u32(const unsigned int* p, bool xg) { return xg ? ld_relaxed_sys_u32(p) : __ldcg(p); }
-__device__ __forceinline__ unsigned long long ld_xchg_u64(const unsigned long long* p, bool xg) {
-  return xg ? ld_relaxed_sys_u64(p) : __ldcg(p);
-}
 
 // All CTAs of one problem.  `epoch` is the number of arrivals expected so far (kept in a register).
 //
@@ -846,15 +880,14 @@ __device__ __forceinline__ unsigned long long ld_xchg_u64(const unsigned long lo
 // atomic or read back with ld.global.cg, i.e. served by L2, the point of coherence; per-query state
 // (pos/d2/ids) is only ever touched by its owning thread.  So the arrive is a release (prior writes are
 // performed at L2 before the counter moves) and the wait is a relaxed poll: L1 keeps the read-only map.
-__device__ __forceinline__ void problem_barrier(unsigned int* ctr, unsigned int n_ctas, unsigned int& epoch, bool xg = false) {
+__device__ __forceinline__ void problem_barrier(unsigned int* ctr, unsigned int n_ctas, unsigned int& epoch) {
   __syncthreads();
   if (threadIdx.x == 0) {
     epoch += n_ctas;
-    if (xg) red_release_sys_inc(ctr);
-    else red_release_inc(ctr);
+    red_release_inc(ctr);
     unsigned int polls = 0;
     unsigned long long t0 = 0ull;
-    while ((xg ? ld_relaxed_sys_u32(ctr) : ld_relaxed_u32(ctr)) < epoch) {
+    while (ld_relaxed_u32(ctr) < epoch) {
       __nanosleep(64);  // the polling thread shares its SM's issue slots with a CTA that is still working
       // watchdog: a barrier that does not complete within seconds is a bug (or a launch that was not co-resident);
       // fail the launch loudly instead of hanging the device
@@ -874,16 +907,73 @@ __device__ __forceinline__ void problem_barrier(unsigned int* ctr, unsigned int 
 struct SelectOut {
   unsigned int bin, rem, total;
 };
+constexpr size_t kWorkWords = sizeof(IcpWork) / 4;
+static_assert(sizeof(IcpWork) % 16 == 0 && offsetof(IcpWork, hist) % 16 == 0 && offsetof(IcpWork, acc) % 16 == 0, "sections move as uint4");
+
+// Query-sharded registration: the cross-GPU step that takes the place of problem_barrier.
+//   1. local barrier: this GPU's contribution to the sections is complete (in L2)
+//   2. CTA c < shard_count-1 pushes the sections to peer c's slot for this shard (16-byte stores over NVLink), then
+//      bumps that peer's arrival counter with a system-scope release
+//   3. every CTA waits until all peers have bumped THIS GPU's counter (a local poll), after which the peers' sections
+//      are in this GPU's memory
+// A section is rewritten by a peer two iterations later at the earliest (the buffers alternate with the iteration's
+// parity), and the peer gets there only through exchanges this GPU feeds after all its CTAs have read -- so no reader is
+// ever overtaken.  Sections are word offsets into IcpWork, multiples of 4.
+__device__ __forceinline__ void shard_exchange(const IcpProblem& P, IcpWork* X, int cta, unsigned int G, unsigned int& epoch,
+                                               unsigned int& xepoch, int off0, int n0, int off1, int n1, int off2, int n2) {
+  problem_barrier(&X->barrier, G, epoch);
+  const int peers = P.shard_count - 1;
+  if (cta < peers) {
+    const int g = cta + (cta >= P.shard_rank ? 1 : 0);
+    const uint4* src = reinterpret_cast<const uint4*>(X);
+    uint4* dst = reinterpret_cast<uint4*>(P.link.peer_slots[g] + P.shard_rank);
+    for (int k = threadIdx.x; k < n0 / 4; k += kIcpThreads) __stcg(dst + off0 / 4 + k, __ldcg(src + off0 / 4 + k));
+    for (int k = threadIdx.x; k < n1 / 4; k += kIcpThreads) __stcg(dst + off1 / 4 + k, __ldcg(src + off1 / 4 + k));
+    for (int k = threadIdx.x; k < n2 / 4; k += kIcpThreads) __stcg(dst + off2 / 4 + k, __ldcg(src + off2 / 4 + k));
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      red_release_sys_inc(P.link.peer_flag[g]);
+    }
+  }
+  xepoch += (unsigned int)peers;
+  if (threadIdx.x == 0) {
+    const unsigned int target = P.link.flag_base + xepoch;
+    unsigned int polls = 0;
+    unsigned long long t0 = 0ull;
+    while ((int)(ld_relaxed_sys_u32(P.link.flag) - target) < 0) {
+      __nanosleep(64);
+      if ((++polls & 0x3fffu) == 0u) {
+        const unsigned long long now = globaltimer_ns();
+        if (t0 == 0ull) t0 = now;
+        else if (now - t0 > 8000000000ull) {
+          printf("[ls] icp_kernel shard %d: a peer did not arrive (block %d waits for %u, counter %u)\n", P.shard_rank, (int)blockIdx.x,
+                 target, ld_relaxed_sys_u32(P.link.flag));
+          __trap();
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ unsigned long long sum_slots_u64(const unsigned long long* p, int n_slots) {
+  unsigned long long v = 0ull;
+  for (int g = 0; g < n_slots; ++g) v += __ldcg(p + (size_t)g * (kWorkWords / 2));
+  return v;
+}
 
 // Block-wide: find the histogram bin holding the element of 0-based rank k.
 // If `first` the rank is derived from the total: k = (unsigned)((float)total * ratio), clamped.
 __device__ __forceinline__ void block_select(const unsigned int* ghist, int nbins, unsigned int k, bool first,
-                                             float ratio, SelectOut* out, unsigned int* ws, bool xg = false) {
+                                             float ratio, SelectOut* out, unsigned int* ws, int n_slots = 1) {
   const int per = nbins / kIcpThreads;
   unsigned int c[2048 / kIcpThreads], loc = 0;
   for (int j = 0; j < per; ++j) {
-    c[j] = ld_xchg_u32(ghist + threadIdx.x * per + j, xg);
-    loc += c[j];
+    unsigned int v = 0;  // sharded: the histogram is the sum of the shards' (slot g sits kWorkWords after slot g-1)
+    for (int g = 0; g < n_slots; ++g) v += __ldcg(ghist + (size_t)g * kWorkWords + threadIdx.x * per + j);
+    c[j] = v;
+    loc += v;
   }
   unsigned int incl = loc;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1104,27 +1194,21 @@ __device__ __noinline__ void final_match(const Grid* gp, const IcpProblem* Pp, c
 }
 
 // CTA-wide: fold the warps' sums (drain_pairs) into the problem's accumulators (L2 atomics).
-__device__ __forceinline__ void flush_slabs(unsigned long long (*acc_w)[28], unsigned long long* gacc, bool xg = false) {
+__device__ __forceinline__ void flush_slabs(unsigned long long (*acc_w)[28], unsigned long long* gacc) {
   __syncthreads();
   if (threadIdx.x < 28) {
     unsigned long long t = 0ull;
 #pragma unroll
     for (int w = 0; w < kIcpThreads / 32; ++w) t += acc_w[w][threadIdx.x];
-    if (t != 0ull) {
-      if (xg) atomicAdd_system(&gacc[threadIdx.x], t);
-      else atomicAdd(&gacc[threadIdx.x], t);
-    }
+    if (t != 0ull) atomicAdd(&gacc[threadIdx.x], t);
   }
   __syncthreads();  // the slabs may be rewritten
 }
 
-__device__ __forceinline__ void flush_hist(const unsigned int* hs, int nbins, unsigned int* gh, bool xg = false) {
+__device__ __forceinline__ void flush_hist(const unsigned int* hs, int nbins, unsigned int* gh) {
   for (int k = threadIdx.x; k < nbins; k += kIcpThreads) {
     const unsigned int v = hs[k];
-    if (v) {
-      if (xg) atomicAdd_system(&gh[k], v);
-      else atomicAdd(&gh[k], v);
-    }
+    if (v) atomicAdd(&gh[k], v);
   }
 }
 
@@ -1145,12 +1229,13 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
   const int pi = blockIdx.x / ctas_per_problem;
   const int cta = blockIdx.x - pi * ctas_per_problem;
   const IcpProblem& P = probs[pi];
-  IcpWork* W = P.work;                 // local: work counters, results
-  const bool xg = P.shard_count > 1;   // query-sharded: the exchange scratch is shared by several GPUs
-  IcpWork* X = xg ? P.xwork : W;       // histograms, normal-equation sums, barrier
-  const bool lead = cta == 0 && (!xg || P.shard_rank == 0);  // the one CTA that clears the exchange scratch
-  const unsigned int G = (unsigned int)ctas_per_problem;     // this GPU's CTAs on the problem (query chunks)
-  const unsigned int GB = xg ? P.barrier_ctas : G;           // barrier participants
+  IcpWork* W = P.work;                 // work counters, results
+  const bool xg = P.shard_count > 1;   // query-sharded over several GPUs (ShardLink)
+  IcpWork* X = xg ? P.link.slots + P.shard_rank : W;   // where this GPU's CTAs accumulate histograms and sums
+  const IcpWork* S0 = xg ? P.link.slots : W;           // first of the n_slots slots a reader sums
+  const int n_slots = xg ? P.shard_count : 1;
+  const unsigned int G = (unsigned int)ctas_per_problem;
+  unsigned int xepoch = 0;             // arrivals expected from the peers so far
   const int tid = threadIdx.x, lane = tid & 31;
 
   __shared__ Grid g;
@@ -1198,18 +1283,16 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
   // the cap are counted in the +inf histogram bin, and if the quantile lands in that bin the queries that found
   // nothing -- only those: a match found inside a smaller cap is the nearest neighbour under any cap -- are
   // searched again with a 4x larger cap (`redo` counts these rounds).
-  if (xg && P.shard_rank == 0) {
-    // Three exchange scratches rotate over successive registrations.  The one cleared here served the registration
-    // before the previous one: this kernel runs, so every shard has entered the previous registration's kernel and
-    // therefore finished the one before it.  It is used next by the registration after this one, which no shard starts
-    // before it has been through this kernel's barriers, i.e. after these stores.
-    unsigned int* z = reinterpret_cast<unsigned int*>(P.xwork_clear);
-    for (int k = cta * kIcpThreads + tid; k < (int)(sizeof(IcpWork) / 4); k += (int)G * kIcpThreads) z[k] = 0u;
-  }
   float cap = 0.04f;
   int redo = 0;
   unsigned int epoch = 0;
-  problem_barrier(&X->barrier, GB, epoch, xg);  // the state initialised above is read by other CTAs
+  // grid-wide step: a barrier, or -- sharded -- a barrier + the exchange of up to three sections of the scratch
+  constexpr int kHistOff = (int)(offsetof(IcpWork, hist) / 4), kAccOff = (int)(offsetof(IcpWork, acc) / 4);
+  auto meet = [&](int off0, int n0, int off1, int n1, int off2, int n2) {
+    if (xg) shard_exchange(P, X, cta, G, epoch, xepoch, off0, n0, off1, n1, off2, n2);
+    else problem_barrier(&X->barrier, G, epoch);
+  };
+  problem_barrier(&X->barrier, G, epoch);  // the state initialised above is read by other CTAs
   int hist_count = 1;  // entries in qh/th
   int iter = 0, converged = 0, max_reached = 0, last_kept = 0;
   float last_limit = 0.f;
@@ -1289,17 +1372,21 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
       }
     }
     drain_pairs(Q, acc_w[tid >> 5]);
-    flush_slabs(acc_w, X->acc[par], xg);  // (starts with a __syncthreads: every warp is done with phase A)
-    flush_hist(hs.h1, 1024, X->hist[par][0], xg);
+    flush_slabs(acc_w, X->acc[par]);  // (starts with a __syncthreads: every warp is done with phase A)
+    flush_hist(hs.h1, 1024, X->hist[par][0]);
     if (pred_bin1 != kNoPrediction) {
-      flush_hist(hs.h2, 2048, X->hist[par][3], xg);
-      flush_hist(hs.h3, 1024, X->hist[par][4], xg);
+      flush_hist(hs.h2, 2048, X->hist[par][3]);
+      flush_hist(hs.h3, 1024, X->hist[par][4]);
     }
-    problem_barrier(&X->barrier, GB, epoch, xg);
+    {
+      const int hb = kHistOff + par * 5 * 2048;
+      const bool pr = pred_bin1 != kNoPrediction;
+      meet(hb, 1024, hb + 3 * 2048, pr ? 2048 : 0, hb + 4 * 2048, pr ? 1024 : 0);
+    }
     LS_STAMP(1);
 
     // ---------------- select, level 1 ----------------
-    block_select(X->hist[par][0], 1024, 0u, true, prm.trim_ratio, &sel, ws, xg);
+    block_select(S0->hist[par][0], 1024, 0u, true, prm.trim_ratio, &sel, ws, n_slots);
     if (sel.total == 0u) {  // no point at all -> ConvergenceError
       if (tid == 0) { flag_status = 1; if (cta == 0) W->fail_code = 1; }
       __syncthreads();
@@ -1314,14 +1401,16 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
       }
       cap = cap < 64.0f ? cap * 4.0f : INFINITY;
       ++redo;
-      problem_barrier(&X->barrier, GB, epoch, xg);  // everyone has read the histogram
-      if (lead && tid == 0) X->hist[par][0][1020] = 0u;  // the unmatched queries are counted again; everything else stands
-      if (cta == 0 && tid == 0) W->qctr[par] = 0u;
-      problem_barrier(&X->barrier, GB, epoch, xg);
+      meet(0, 0, 0, 0, 0, 0);  // everyone, on every shard, has read the histogram
+      if (cta == 0 && tid == 0) {
+        X->hist[par][0][1020] = 0u;  // the unmatched queries are counted again; everything else stands
+        W->qctr[par] = 0u;
+      }
+      problem_barrier(&X->barrier, G, epoch);
       continue;  // phase A again, for the queries without a match, with the larger cap
     }
     const unsigned int bin1 = sel.bin, rem1 = sel.rem;
-    if (lead) {  // clear the other parity's scratch for the next iteration (nobody touches it before the next barrier)
+    if (cta == 0) {  // clear the other parity's scratch for the next iteration (nobody touches it before the next barrier)
       unsigned int* h = &X->hist[par ^ 1][0][0];
       for (int k = tid; k < 5 * 2048; k += kIcpThreads) h[k] = 0u;
       if (tid < 32) X->acc[par ^ 1][tid] = 0ull;
@@ -1337,11 +1426,11 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
         if (key < 0x7f800000u && (key >> 21) == bin1) atomicAdd(&hs.h2[(key >> 10) & 2047u], 1u);
       }
       __syncthreads();
-      flush_hist(hs.h2, 2048, X->hist[par][1], xg);
-      problem_barrier(&X->barrier, GB, epoch, xg);
+      flush_hist(hs.h2, 2048, X->hist[par][1]);
+      meet(kHistOff + (par * 5 + 1) * 2048, 2048, 0, 0, 0, 0);
     }
     LS_STAMP(2);
-    block_select(X->hist[par][spec2 ? 3 : 1], 2048, rem1, false, 0.f, &sel, ws, xg);
+    block_select(S0->hist[par][spec2 ? 3 : 1], 2048, rem1, false, 0.f, &sel, ws, n_slots);
     const unsigned int bin2 = sel.bin, rem2 = sel.rem;
     const unsigned int prefix12 = (bin1 << 11) | bin2;
     // ---------------- level 3 ----------------
@@ -1354,11 +1443,11 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
         if (key < 0x7f800000u && (key >> 10) == prefix12) atomicAdd(&hs.h3[key & 1023u], 1u);
       }
       __syncthreads();
-      flush_hist(hs.h3, 1024, X->hist[par][2], xg);
-      problem_barrier(&X->barrier, GB, epoch, xg);
+      flush_hist(hs.h3, 1024, X->hist[par][2]);
+      meet(kHistOff + (par * 5 + 2) * 2048, 1024, 0, 0, 0, 0);
     }
     LS_STAMP(3);
-    block_select(X->hist[par][spec3 ? 4 : 2], 1024, rem2, false, 0.f, &sel, ws, xg);
+    block_select(S0->hist[par][spec3 ? 4 : 2], 1024, rem2, false, 0.f, &sel, ws, n_slots);
     const float limit = __uint_as_float((prefix12 << 10) | sel.bin);
     // guess for the next iteration (verified there): the first step removes most of the initial misalignment, so the
     // limit drops sharply once and then settles -- a guess that turns out too small costs one more round for the
@@ -1387,8 +1476,8 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
       push_pairs<3>(P, Q, sign, sx, sy, sz, q, pos);
     }
     drain_pairs(Q, acc_w[tid >> 5]);
-    flush_slabs(acc_w, X->acc[par], xg);
-    problem_barrier(&X->barrier, GB, epoch, xg);
+    flush_slabs(acc_w, X->acc[par]);
+    meet(kAccOff + par * 64, 64, 0, 0, 0, 0);
     LS_STAMP(4);
 
     // ---------------- phase E: solve, update, checkers (every CTA, identically) ----------------
@@ -1397,12 +1486,12 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
       int k = 0;
       for (int rr = 0; rr < 6; ++rr)
         for (int cc = rr; cc < 6; ++cc, ++k) {
-          const double v = (double)(long long)ld_xchg_u64(&X->acc[par][k], xg) / 4194304.0;
+          const double v = (double)(long long)sum_slots_u64(&S0->acc[par][k], n_slots) / 4194304.0;
           A[rr * 6 + cc] = v;
           A[cc * 6 + rr] = v;
         }
-      for (int rr = 0; rr < 6; ++rr) b[rr] = -((double)(long long)ld_xchg_u64(&X->acc[par][21 + rr], xg) / 4194304.0);
-      last_kept = (int)ld_xchg_u64(&X->acc[par][27], xg);
+      for (int rr = 0; rr < 6; ++rr) b[rr] = -((double)(long long)sum_slots_u64(&S0->acc[par][21 + rr], n_slots) / 4194304.0);
+      last_kept = (int)sum_slots_u64(&S0->acc[par][27], n_slots);
       last_limit = limit;
       int status = 0, stop = 0;
       if (last_kept == 0) {
@@ -1492,6 +1581,7 @@ icp_kernel(const IcpProblem* __restrict__ probs, int ctas_per_problem, IcpParams
     W->max_iter_reached = max_reached;
     W->last_kept = last_kept;
     W->last_limit = last_limit;
+    W->xsignals = xepoch;
   }
 }
 

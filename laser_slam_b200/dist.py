@@ -214,19 +214,28 @@ class ShardedRegistrar:
     """One registration sharded by queries over the ranks of a node (ls_icp_register_submap_sharded).
 
     Every rank owns a Context + Map on its GPU and pushes the same scans; `register` is a collective that returns the
-    same bits on every rank.  The only thing that travels through torch.distributed is the 64-byte IPC handle of the
-    exchange buffer at construction; per iteration the shards meet inside the persistent kernel (system-scope atomics
-    on rank 0's memory over NVLink)."""
+    same bits on every rank.  The only thing that travels through torch.distributed is the 64-byte IPC handle of every
+    rank's exchange buffer, once, at construction; per iteration the shards meet inside the persistent kernel (stores
+    into each other's buffers over NVLink)."""
 
     def __init__(self, ctx, rank, world):
         import torch.distributed as dist
         self.ctx, self.rank, self.world = ctx, rank, world
-        box = [ctx.shard_exchange_create() if rank == 0 else None]
+        mine = ctx.shard_exchange_create(rank, world)
+        handles = [None] * world
         if world > 1:
-            dist.broadcast_object_list(box, src=0)
-            if rank != 0:
-                ctx.shard_exchange_open(box[0])
-            dist.barrier()  # nobody launches before every rank has the buffer mapped
+            dist.all_gather_object(handles, mine)
+        else:
+            handles[0] = mine
+        ctx.shard_exchange_connect(handles)
 
     def register(self, map_, reading_id, part_ids, T_parts, T0, params=None, raise_on_convergence=True):
-        return map_.register_sharded(reading_id, part_ids, T_parts, T0, self.rank, self.world, params, raise_on_convergence)
+        return map_.register_sharded(reading_id, part_ids, T_parts, T0, params, raise_on_convergence)
+
+    def close(self):
+        """Collective: nobody frees its buffer while a peer may still store into it."""
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.barrier()
+        from . import lib
+        lib().ls_shard_exchange_close(self.ctx._h)
