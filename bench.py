@@ -496,7 +496,7 @@ def main():
             idxs = [walk(s) for _ in range(B)]
             return est.step_batch(list(range(B)), [s * 100_000_000] * B, [pose7(tracks[t][1][idxs[t]]) for t in range(B)],
                                   [feats[t][idxs[t]].data_ptr() for t in range(B)], [nrms[t][idxs[t]].data_ptr() for t in range(B)],
-                                  [N_SCAN] * B, with_estimator=False)
+                                  [N_SCAN] * B, with_estimator=False, views=True)
 
         n_host = max(3, min(args.steps, 10))
         w_host = K_MAP + 2
@@ -510,8 +510,9 @@ def main():
         t_host = time.perf_counter() - t0
         t_host, = lsd.max_over_ranks([t_host], device=local)
         host_arm = {"value": world * B * n_host / t_host, "unit": "registrations/s", "steps": n_host,
-                    "api": "laser_slam::IncrementalEstimator::processPosesAndLaserScans over libls_host.so: DataPoints in, "
-                           "RelativePose out; uploads are synchronous copies from pageable DataPoints storage inside the call",
+                    "api": "laser_slam::IncrementalEstimator::processPosesAndLaserScans over libls_host.so: DataPoints in "
+                           "(views of the same pinned host buffers the C-ABI arm reads, no copy), RelativePose out; every "
+                           "step's uploads are issued inside the call, before its batched launch (no cross-step pipelining)",
                     "iterations": int(hstats[0].iterations)}
         est.close()
         os.unlink(yaml_path)

@@ -167,22 +167,60 @@ struct PointMatcher {
     std::string text;
     size_t span;
   };
-  // column-major dynamic matrix with the few Eigen members laser_slam touches (rows(), cols(), data(), (r,c))
+  // column-major dynamic matrix with the few Eigen members laser_slam touches (rows(), cols(), data(), (r,c)).
+  // Copies share their storage until one of them is written (copy-on-write): LaserTrack keeps every scan it is handed
+  // and a LaserScan travels by value through the reference's interfaces, so a copy must not move 3.6 MB.  view() borrows
+  // caller-owned memory without copying (e.g. a pinned staging buffer the driver fills): it is read-only until the
+  // first write, which copies.
   struct Matrix {
-    std::vector<T> v;
-    size_t nrows = 0;
+    std::shared_ptr<std::vector<T>> own;  // null while empty or borrowed
+    const T* ext = nullptr;               // borrowed storage
+    size_t nrows = 0, count = 0;
     Matrix() {}
-    Matrix(size_t r, size_t c) : v(r * c), nrows(r) {}
+    Matrix(size_t r, size_t c) : own(std::make_shared<std::vector<T>>(r * c)), nrows(r), count(r * c) {}
+    static Matrix view(const T* p, size_t r, size_t c) {
+      Matrix m;
+      m.ext = p;
+      m.nrows = r;
+      m.count = r * c;
+      return m;
+    }
     size_t rows() const { return nrows; }
-    size_t cols() const { return nrows ? v.size() / nrows : 0; }
-    size_t size() const { return v.size(); }
-    T* data() { return v.data(); }
-    const T* data() const { return v.data(); }
-    T& operator()(size_t r, size_t c) { return v[c * nrows + r]; }
-    T operator()(size_t r, size_t c) const { return v[c * nrows + r]; }
-    void resize(size_t r, size_t c) { nrows = r; v.resize(r * c); }
-    void assign(size_t r, const T* first, const T* last) { nrows = r; v.assign(first, last); }
-    void append(const Matrix& o) { v.insert(v.end(), o.v.begin(), o.v.end()); }
+    size_t cols() const { return nrows ? count / nrows : 0; }
+    size_t size() const { return count; }
+    const T* data() const { return ext ? ext : (own ? own->data() : nullptr); }
+    T* data() { detach(); return own ? own->data() : nullptr; }
+    T& operator()(size_t r, size_t c) { detach(); return (*own)[c * nrows + r]; }
+    T operator()(size_t r, size_t c) const { return data()[c * nrows + r]; }
+    void resize(size_t r, size_t c) { detach(); if (!own) own = std::make_shared<std::vector<T>>(); nrows = r; count = r * c; own->resize(count); }
+    void assign(size_t r, const T* first, const T* last) {
+      own = std::make_shared<std::vector<T>>(first, last);
+      ext = nullptr;
+      nrows = r;
+      count = own->size();
+    }
+    void append(const Matrix& o) {
+      detach();
+      if (!own) own = std::make_shared<std::vector<T>>();
+      own->insert(own->end(), o.data(), o.data() + o.count);
+      count = own->size();
+    }
+    void push_back(T x) {
+      detach();
+      if (!own) own = std::make_shared<std::vector<T>>();
+      own->push_back(x);
+      count = own->size();
+    }
+    void reserve(size_t n) { detach(); if (!own) own = std::make_shared<std::vector<T>>(); own->reserve(n); }
+   private:
+    void detach() {
+      if (ext) {
+        own = std::make_shared<std::vector<T>>(ext, ext + count);
+        ext = nullptr;
+      } else if (own && own.use_count() > 1) {
+        own = std::make_shared<std::vector<T>>(*own);
+      }
+    }
   };
   struct DataPoints {
     Matrix features;     // 4 x N, column-major: x,y,z,1 per point
@@ -235,6 +273,18 @@ struct PointMatcher {
       d.featureLabels = {{"x", 1}, {"y", 1}, {"z", 1}, {"pad", 1}};
       if (normals3) {
         d.descriptors.assign(3, normals3, normals3 + 3 * n);
+        d.descriptorLabels = {{"normals", 3}};
+        d.descriptorDim = 3;
+      }
+      return d;
+    }
+    // the same cloud as a VIEW of caller-owned arrays (no copy; the arrays must outlive every copy of the DataPoints)
+    static DataPoints viewOfArrays(const T* feat4, const T* normals3, size_t n) {
+      DataPoints d;
+      d.features = Matrix::view(feat4, 4, n);
+      d.featureLabels = {{"x", 1}, {"y", 1}, {"z", 1}, {"pad", 1}};
+      if (normals3) {
+        d.descriptors = Matrix::view(normals3, 3, n);
         d.descriptorLabels = {{"normals", 3}};
         d.descriptorDim = 3;
       }
@@ -316,7 +366,7 @@ struct PointMatcher {
         if (f.name == "SurfaceNormalDataPointsFilter" || f.name == "SamplingSurfaceNormalDataPointsFilter") {
           const size_t n = cloud.getNbPoints();
           std::vector<T> nrm(3 * (n ? n : 1));
-          const int rc = ls_estimate_normals(sharedContext(), cloud.features.data(), (int)n, f.knn < 3 ? 3 : (f.knn > 16 ? 16 : f.knn), nrm.data());
+          const int rc = ls_estimate_normals(sharedContext(), static_cast<const DataPoints&>(cloud).features.data(), (int)n, f.knn < 3 ? 3 : (f.knn > 16 ? 16 : f.knn), nrm.data());
           if (rc != LS_OK) throw std::runtime_error(std::string("ls_estimate_normals: ") + ls_b200_last_error(sharedContext()));
           cloud.setDescriptor("normals", 3, nrm.data());
           if (f.name == "SamplingSurfaceNormalDataPointsFilter" && f.prob < 1.0) subsample(cloud, f.prob, 0x5a17u);
@@ -333,8 +383,8 @@ struct PointMatcher {
       Matrix f(4, 0), d(D, 0);
       for (size_t i = 0; i < n; ++i) {
         if (!ls_keep_point((uint32_t)i, salt, (float)prob)) continue;
-        for (size_t r = 0; r < 4; ++r) f.v.push_back(cloud.features(r, i));
-        for (size_t r = 0; r < D; ++r) d.v.push_back(cloud.descriptors(r, i));
+        for (size_t r = 0; r < 4; ++r) f.push_back(cloud.features(r, i));
+        for (size_t r = 0; r < D; ++r) d.push_back(cloud.descriptors(r, i));
       }
       cloud.features = f;
       cloud.descriptors = d;

@@ -150,6 +150,9 @@ int ls_map_push_scan(ls_map* map, const float* features4, const float* normals, 
  * laser_track.cpp:143,197).  3 <= normals_stride <= 8. */
 int ls_map_push_scan_async(ls_map* map, const float* features4, const float* normals, int normals_stride, int n,
                            uint64_t* scan_id);
+/* 1 if `p` points into page-locked (pinned) host memory known to the CUDA driver, 0 if not, < 0 on error.  The host
+ * layer uses it to pick ls_map_push_scan_async (no staging copy) for DataPoints whose storage is pinned. */
+int ls_host_is_pinned(const void* p);
 int ls_map_sync(ls_map* map); /* wait for every asynchronous upload of this map */
 int ls_map_scan_size(const ls_map* map, uint64_t scan_id); /* points, or <0 if evicted/unknown */
 

@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("LS_B200_LIB") or os.path.join(_HERE, "_build", "libls
 _lib = None
 
 LS_OK, LS_ERR_CONVERGENCE = 0, 1
+LS_ERR_ARG = -1
 
 
 class ConvergenceError(RuntimeError):
@@ -98,6 +99,7 @@ def lib():
         L.ls_map_push_scan.argtypes = [vp, vp, vp, ci, ci, ctypes.POINTER(u64)]
         L.ls_map_push_scan_async.argtypes = [vp, vp, vp, ci, ci, ctypes.POINTER(u64)]
         L.ls_map_sync.argtypes = [vp]
+        L.ls_host_is_pinned.argtypes = [vp]
         L.ls_map_scan_size.argtypes = [vp, u64]
         L.ls_icp_register_submap.argtypes = [vp, PP, vp, u64, ci, vp, vp, vp, vp, PS, vp, vp, vp]
         L.ls_map_assemble.argtypes = [vp, vp, ci, vp, vp, vp, vp, ctypes.POINTER(ci)]

@@ -408,6 +408,7 @@ int launch_icp(ls_ctx* ctx, const ls_icp_params* prm, int batch, int n_max, bool
   if (ctas < 1) ctas = 1;
   const IcpProblem* probs = ctx->probs_dev;
   int dynamic = batch > 1 ? 1 : 0;  // several problems: warps pull work from per-problem counters
+  if (const char* e = getenv("LS_DYNAMIC")) dynamic = atoi(e);  // experiment
   void* args[] = {(void*)&probs, (void*)&ctas, (void*)&dp, (void*)&dynamic};
   if (sharded) {  // narrow the staged problem to this shard's queries (cuts at cell starts, computed on the device)
     shard_slice_kernel<<<1, 32, 0, w0->stream>>>(ctx->probs_dev, w0->job_dev, w0->hp.shard_rank, w0->hp.shard_count);
@@ -894,6 +895,16 @@ int ls_map_push_scan_async(ls_map* map, const float* features4, const float* nor
   s.used = true;
   *scan_id = id;
   return LS_OK;
+}
+
+int ls_host_is_pinned(const void* p) {
+  if (!p) return LS_ERR_ARG;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return a.type == cudaMemoryTypeHost ? 1 : 0;
 }
 
 int ls_map_sync(ls_map* map) {

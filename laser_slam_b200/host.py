@@ -77,10 +77,12 @@ class Estimator:
                                    out.ctypes.data, ctypes.byref(st)))
         return out, st
 
-    def step_batch(self, workers, times_ns, poses7, feat_ptrs, nrm_ptrs, ns, with_estimator=True):
+    def step_batch(self, workers, times_ns, poses7, feat_ptrs, nrm_ptrs, ns, with_estimator=True, views=False):
         """The scan callbacks of several workers at once: one batched launch registers them all
         (IncrementalEstimator::processPosesAndLaserScans).  feat_ptrs / nrm_ptrs: host addresses of each worker's
-        4xN features and 3xN normals.  Returns (icp T_a_b (len,7), list of IcpStats)."""
+        4xN features and 3xN normals.  views=True hands the tracks DataPoints that BORROW those arrays (no copy; they
+        must stay valid while the estimator lives; pinned arrays are then uploaded asynchronously, in place).
+        Returns (icp T_a_b (len,7), list of IcpStats)."""
         k = len(workers)
         w = np.ascontiguousarray(workers, np.int32)
         t = np.ascontiguousarray(times_ns, np.int64)
@@ -91,7 +93,7 @@ class Estimator:
         out = np.zeros((k, 7), np.float64)
         st = (IcpStats * k)()
         self._check(lib().lsh_step_batch(self._h, k, w.ctypes.data, t.ctypes.data, p.ctypes.data, ctypes.cast(fp, ctypes.c_void_p),
-                                         ctypes.cast(npp, ctypes.c_void_p), nn.ctypes.data, int(with_estimator), out.ctypes.data,
+                                         ctypes.cast(npp, ctypes.c_void_p), nn.ctypes.data, int(bool(with_estimator)) | (2 if views else 0), out.ctypes.data,
                                          ctypes.cast(st, ctypes.c_void_p)))
         return out, list(st)
 

@@ -91,6 +91,10 @@ int lsh_step(void* hv, int worker, int64_t time_ns, const double* pose7, const f
 // out_icp7 (may be NULL): 7 doubles per worker.  with_estimator == 0 skips the pose-graph update (odometry only).
 int lsh_step_batch(void* hv, int n_workers, const int* workers, const int64_t* times_ns, const double* pose7, const float* const* feat4,
                    const float* const* normals3, const int* n, int with_estimator, double* out_icp7, ls_icp_stats* out_stats) {
+  // with_estimator bit 1 (value 2): the DataPoints are VIEWS of the caller's arrays (DataPoints::viewOfArrays), which
+  // must then stay valid for the life of the estimator -- the tracks keep every scan.  Otherwise they are copies.
+  const bool views = (with_estimator & 2) != 0;
+  with_estimator &= 1;
   Handle* h = static_cast<Handle*>(hv);
   return guarded(h, [&]() {
     std::vector<unsigned int> ids;
@@ -100,7 +104,7 @@ int lsh_step_batch(void* hv, int n_workers, const int* workers, const int64_t* t
       ids.push_back((unsigned int)workers[i]);
       poses[i].T_w = SE3::fromArray7(pose7 + 7 * (size_t)i);
       poses[i].time_ns = times_ns[i];
-      scans[i].scan = DataPoints::fromArrays(feat4[i], normals3[i], (size_t)n[i]);
+      scans[i].scan = views ? DataPoints::viewOfArrays(feat4[i], normals3[i], (size_t)n[i]) : DataPoints::fromArrays(feat4[i], normals3[i], (size_t)n[i]);
       scans[i].time_ns = times_ns[i];
     }
     std::vector<gtsam::NonlinearFactorGraph> nf;

@@ -386,7 +386,13 @@ uint64_t LaserTrack::residentScan(size_t index) const {
   const int off = c.descriptorOffset("normals");
   LS_CHECK(off >= 0, "scan without normals");
   uint64_t id = 0;
-  const int rc = ls_map_push_scan(*map_p_, c.features.data(), c.descriptors.data() + off, (int)c.descriptorDim, (int)c.getNbPoints(), &id);
+  // A scan whose storage is pinned goes up asynchronously straight from where it lies (the track keeps the scan, so the
+  // memory outlives the upload; the registration orders itself behind it); any other is staged by ls_map_push_scan.
+  const float* fp = c.features.data();
+  const float* np = c.descriptors.data() + off;
+  const bool direct = c.descriptorDim >= 3 && c.descriptorDim <= 8 && ls_host_is_pinned(fp) == 1 && ls_host_is_pinned(np) == 1;
+  const int rc = direct ? ls_map_push_scan_async(*map_p_, fp, np, (int)c.descriptorDim, (int)c.getNbPoints(), &id)
+                        : ls_map_push_scan(*map_p_, fp, np, (int)c.descriptorDim, (int)c.getNbPoints(), &id);
   throwOnError(ctx_, rc, "ls_map_push_scan");
   resident_[index] = id;
   return id;

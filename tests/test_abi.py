@@ -149,3 +149,16 @@ def test_reference_call_sites_compile_against_the_headers():
     r = subprocess.run([cxx, "-std=c++17", "-fsyntax-only", "-I" + os.path.join(ROOT, "include"),
                         os.path.join(ROOT, "tests", "compile", "reference_call_sites.cpp")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_datapoints_copy_on_write_and_views(tmp_path):
+    """The compat DataPoints: copies share storage until written, views borrow caller memory (tests/compile)."""
+    import subprocess
+    exe = str(tmp_path / "dp_storage")
+    build = os.path.join(ROOT, "laser_slam_b200", "_build")
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "compile", "datapoints_storage.cpp"), "-o", exe,
+                        "-L", build, "-lls_b200", f"-Wl,-rpath,{build}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
