@@ -492,27 +492,38 @@ def main():
             q[1:] = np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]]) / (4.0 * q[0])
             return np.concatenate([q / np.linalg.norm(q), T[:3, 3]])
 
-        def step_host(s):
+        def host_args(s):
             idxs = [walk(s) for _ in range(B)]
-            return est.step_batch(list(range(B)), [s * 100_000_000] * B, [pose7(tracks[t][1][idxs[t]]) for t in range(B)],
-                                  [feats[t][idxs[t]].data_ptr() for t in range(B)], [nrms[t][idxs[t]].data_ptr() for t in range(B)],
-                                  [N_SCAN] * B, with_estimator=False, views=True)
+            return (list(range(B)), [s * 100_000_000] * B, [feats[t][idxs[t]].data_ptr() for t in range(B)],
+                    [nrms[t][idxs[t]].data_ptr() for t in range(B)], [N_SCAN] * B), [pose7(tracks[t][1][idxs[t]]) for t in range(B)]
 
         n_host = max(3, min(args.steps, 10))
         w_host = K_MAP + 2
-        for s in range(w_host):
-            step_host(s)
+        hargs = [host_args(s) for s in range(w_host + n_host + 1)]   # marshalled before the clock, like the C-ABI arm's
+
+        def run_host(s0, n):
+            """Step s: begin (stage + launch), prefetch step s+1's scans while it runs, end."""
+            out = None
+            for s in range(s0, s0 + n):
+                (wk, tm, fp, npp, ns), poses = hargs[s]
+                est.begin_batch(wk, tm, poses, fp, npp, ns, views=True)
+                (wk2, tm2, fp2, np2, ns2), _ = hargs[s + 1]
+                est.prefetch(wk2, tm2, fp2, np2, ns2, views=True)
+                out = est.end_batch(with_estimator=False)
+            return out
+
+        run_host(0, w_host)
         barrier()
         t0 = time.perf_counter()
-        for s in range(w_host, w_host + n_host):
-            icp7, hstats = step_host(s)
+        icp7, hstats = run_host(w_host, n_host)
         barrier()
         t_host = time.perf_counter() - t0
         t_host, = lsd.max_over_ranks([t_host], device=local)
         host_arm = {"value": world * B * n_host / t_host, "unit": "registrations/s", "steps": n_host,
                     "api": "laser_slam::IncrementalEstimator::processPosesAndLaserScans over libls_host.so: DataPoints in "
-                           "(views of the same pinned host buffers the C-ABI arm reads, no copy), RelativePose out; every "
-                           "step's uploads are issued inside the call, before its batched launch (no cross-step pipelining)",
+                           "(views of the same pinned host buffers the C-ABI arm reads, no copy), RelativePose out; "
+                           "beginPosesAndLaserScans / prefetchLaserScans(next step) / endPosesAndLaserScans, so the next "
+                           "step's uploads overlap this step's launch, as in the C-ABI arm",
                     "iterations": int(hstats[0].iterations)}
         est.close()
         os.unlink(yaml_path)

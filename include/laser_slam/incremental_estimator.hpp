@@ -44,6 +44,15 @@ class IncrementalEstimator {
   void processPosesAndLaserScans(const std::vector<unsigned int>& worker_ids, const std::vector<Pose>& poses,
                                  const std::vector<LaserScan>& scans, std::vector<gtsam::NonlinearFactorGraph>* new_factors,
                                  std::vector<gtsam::Values>* new_values, std::vector<bool>* is_prior);
+  // (new) The same in two halves, for callers that have something to do while the GPU registers: begin() stages every
+  // track's registration and launches, end() waits and finishes the callbacks.  In between only prefetchLaserScans may be
+  // called: it uploads scans that a later begin() will be handed (recognised by their time stamps), so the next step's
+  // host-to-device copies overlap this step's ICP iterations.  Purely an overlap device: results never change.
+  void beginPosesAndLaserScans(const std::vector<unsigned int>& worker_ids, const std::vector<Pose>& poses,
+                               const std::vector<LaserScan>& scans);
+  void endPosesAndLaserScans(std::vector<gtsam::NonlinearFactorGraph>* new_factors, std::vector<gtsam::Values>* new_values,
+                             std::vector<bool>* is_prior);
+  void prefetchLaserScans(const std::vector<unsigned int>& worker_ids, const std::vector<LaserScan>& scans);
   ls_ctx* trackContext() const { return track_ctx_; }
 
   const ls_pg_stats& getLastSolveStats() const { return last_stats_; }
@@ -53,6 +62,16 @@ class IncrementalEstimator {
                             const std::vector<uint64_t>& remove, std::vector<uint64_t>* new_indices);
   unsigned int n_laser_slam_workers_ = 0u;
   mutable std::recursive_mutex full_class_mutex_;
+  // a step between beginPosesAndLaserScans and endPosesAndLaserScans
+  struct PendingStep {
+    bool open = false, inflight = false;
+    std::vector<unsigned int> worker_ids;
+    std::vector<LaserTrack::PendingIcp> pending;
+    std::vector<size_t> active;
+    std::vector<float> T_outs;
+    std::vector<ls_icp_stats> stats;
+    std::vector<int> statuses;
+  } step_;
   std::vector<std::shared_ptr<LaserTrack> > laser_tracks_;
   ls_pg* graph_ = nullptr;
   // device side of the lidar odometry, shared by all tracks so that one launch can serve them all

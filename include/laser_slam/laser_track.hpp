@@ -94,6 +94,10 @@ class LaserTrack {
     double t_start_ms = 0.0;
   };
   void beginPoseAndLaserScan(const Pose& pose, const LaserScan& in_scan, PendingIcp* pending);
+  // (new) A hint: upload a scan that WILL be passed to processPoseAndLaserScan / beginPoseAndLaserScan (recognised by its
+  // time stamp) now, e.g. while the previous scan is still being registered.  Without it the upload happens inside the
+  // scan's own call.  Never changes a result.
+  void prefetchLaserScan(const LaserScan& scan);
   void endPoseAndLaserScan(PendingIcp* pending, int rc, const float* T_out16, const ls_icp_stats* stats,
                            gtsam::NonlinearFactorGraph* newFactors, gtsam::Values* newValues, bool* is_prior);
   const ls_icp_params& icpParams() const { return icp_params_; }
@@ -118,6 +122,7 @@ class LaserTrack {
   Key extendTrajectory(const Time& timestamp_ns, const SE3& value);
   size_t scanIndexAtTime(const curves::Time& time_ns) const;
   uint64_t residentScan(size_t index) const;  // device id of laser_scans_[index], uploading it if it was evicted
+  uint64_t uploadScan(const DataPoints& cloud) const;
   void describeSubMapAroundTime(const curves::Time& time_ns, const unsigned int sub_maps_radius, std::vector<size_t>* scan_indices,
                                 std::vector<PointMatcher::TransformationParameters>* Ts) const;
   void assembleSubMap(const std::vector<size_t>& scan_indices, const std::vector<PointMatcher::TransformationParameters>& Ts,
@@ -146,6 +151,7 @@ class LaserTrack {
   int* map_max_pts_p_ = &own_max_pts_;
   int ring_slots_per_track_ = 0;  // shared ring: slots every track may count on
   mutable std::map<size_t, uint64_t> resident_;  // scan index -> device scan id
+  std::map<Time, std::pair<uint64_t, LaserScan> > prefetched_;  // time stamp -> (device scan id, the scan: keeps its storage alive)
   static constexpr double kDistanceBetweenPriorPoses_m = 100.0;
 };
 

@@ -29,6 +29,9 @@ def lib():
         L.lsh_step.argtypes = [vp, ci, i64, vp, vp, vp, ci, vp, ctypes.POINTER(IcpStats)]
         L.lsh_loop_closure.argtypes = [vp, ci, i64, ci, i64, vp]
         L.lsh_step_batch.argtypes = [vp, ci, vp, vp, vp, vp, vp, vp, ci, vp, vp]
+        L.lsh_begin_batch.argtypes = [vp, ci, vp, vp, vp, vp, vp, vp, ci]
+        L.lsh_prefetch.argtypes = [vp, ci, vp, vp, vp, vp, vp, ci]
+        L.lsh_end_batch.argtypes = [vp, ci, vp, vp]
         L.lsh_trajectory.argtypes = [vp, ci, vp, vp, ci]
         L.lsh_num_scans.argtypes = [vp, ci]
         L.lsh_build_submap.argtypes = [vp, ci, i64, ci, vp, vp, ci]
@@ -95,6 +98,34 @@ class Estimator:
         self._check(lib().lsh_step_batch(self._h, k, w.ctypes.data, t.ctypes.data, p.ctypes.data, ctypes.cast(fp, ctypes.c_void_p),
                                          ctypes.cast(npp, ctypes.c_void_p), nn.ctypes.data, int(bool(with_estimator)) | (2 if views else 0), out.ctypes.data,
                                          ctypes.cast(st, ctypes.c_void_p)))
+        return out, list(st)
+
+    def _ptr_arrays(self, workers, times_ns, feat_ptrs, nrm_ptrs, ns):
+        k = len(workers)
+        return (k, np.ascontiguousarray(workers, np.int32), np.ascontiguousarray(times_ns, np.int64),
+                (ctypes.c_void_p * k)(*[int(a) for a in feat_ptrs]), (ctypes.c_void_p * k)(*[int(a) for a in nrm_ptrs]),
+                np.ascontiguousarray(ns, np.int32))
+
+    def begin_batch(self, workers, times_ns, poses7, feat_ptrs, nrm_ptrs, ns, views=False):
+        """First half of step_batch (IncrementalEstimator::beginPosesAndLaserScans): stage and launch, return at once."""
+        k, w, t, fp, npp, nn = self._ptr_arrays(workers, times_ns, feat_ptrs, nrm_ptrs, ns)
+        p = np.ascontiguousarray(poses7, np.float64).reshape(k, 7)
+        self._pending_k = k
+        self._check(lib().lsh_begin_batch(self._h, k, w.ctypes.data, t.ctypes.data, p.ctypes.data, ctypes.cast(fp, ctypes.c_void_p),
+                                          ctypes.cast(npp, ctypes.c_void_p), nn.ctypes.data, 2 if views else 0))
+
+    def prefetch(self, workers, times_ns, feat_ptrs, nrm_ptrs, ns, views=False):
+        """Hint (IncrementalEstimator::prefetchLaserScans): upload scans a later begin_batch will be handed."""
+        k, w, t, fp, npp, nn = self._ptr_arrays(workers, times_ns, feat_ptrs, nrm_ptrs, ns)
+        self._check(lib().lsh_prefetch(self._h, k, w.ctypes.data, t.ctypes.data, ctypes.cast(fp, ctypes.c_void_p),
+                                       ctypes.cast(npp, ctypes.c_void_p), nn.ctypes.data, 2 if views else 0))
+
+    def end_batch(self, with_estimator=True):
+        """Second half of step_batch.  Returns (icp T_a_b (len,7), list of IcpStats)."""
+        k = self._pending_k
+        out = np.zeros((k, 7), np.float64)
+        st = (IcpStats * k)()
+        self._check(lib().lsh_end_batch(self._h, int(bool(with_estimator)), out.ctypes.data, ctypes.cast(st, ctypes.c_void_p)))
         return out, list(st)
 
     def loop_closure(self, track_a, time_a, track_b, time_b, w_T_a_b7):

@@ -14,7 +14,15 @@ namespace {
 struct Handle {
   std::unique_ptr<IncrementalEstimator> est;
   std::string err;
+  std::vector<unsigned int> step_ids;   // the step between lsh_begin_batch and lsh_end_batch
+  std::vector<int64_t> step_times;
 };
+LaserScan make_scan(const float* feat4, const float* normals3, int n, int64_t time_ns, bool view) {
+  LaserScan s;
+  s.scan = view ? DataPoints::viewOfArrays(feat4, normals3, (size_t)n) : DataPoints::fromArrays(feat4, normals3, (size_t)n);
+  s.time_ns = time_ns;
+  return s;
+}
 template <typename F>
 int guarded(Handle* h, F f) {
   try {
@@ -121,6 +129,66 @@ int lsh_step_batch(void* hv, int n_workers, const int* workers, const int64_t* t
         SE3 T;
         if (!track->getIcpTransformations().empty() && !prior[i]) T = track->getIcpTransformations().back().T_a_b;
         T.toArray7(out_icp7 + 7 * (size_t)i);
+      }
+      if (out_stats) out_stats[i] = track->getLastIcpStats();
+    }
+    return LS_OK;
+  });
+}
+
+// lsh_step_batch in two halves (IncrementalEstimator::beginPosesAndLaserScans / endPosesAndLaserScans) with the prefetch
+// hint in between.  flags bit 1 (value 2): DataPoints are views of the caller's arrays.
+int lsh_begin_batch(void* hv, int n_workers, const int* workers, const int64_t* times_ns, const double* pose7, const float* const* feat4,
+                    const float* const* normals3, const int* n, int flags) {
+  Handle* h = static_cast<Handle*>(hv);
+  return guarded(h, [&]() {
+    std::vector<Pose> poses((size_t)n_workers);
+    std::vector<LaserScan> scans((size_t)n_workers);
+    h->step_ids.clear();
+    h->step_times.assign(times_ns, times_ns + n_workers);
+    for (int i = 0; i < n_workers; ++i) {
+      h->step_ids.push_back((unsigned int)workers[i]);
+      poses[i].T_w = SE3::fromArray7(pose7 + 7 * (size_t)i);
+      poses[i].time_ns = times_ns[i];
+      scans[i] = make_scan(feat4[i], normals3[i], n[i], times_ns[i], (flags & 2) != 0);
+    }
+    h->est->beginPosesAndLaserScans(h->step_ids, poses, scans);
+    return LS_OK;
+  });
+}
+
+int lsh_prefetch(void* hv, int n_workers, const int* workers, const int64_t* times_ns, const float* const* feat4,
+                 const float* const* normals3, const int* n, int flags) {
+  Handle* h = static_cast<Handle*>(hv);
+  return guarded(h, [&]() {
+    std::vector<unsigned int> ids;
+    std::vector<LaserScan> scans((size_t)n_workers);
+    for (int i = 0; i < n_workers; ++i) {
+      ids.push_back((unsigned int)workers[i]);
+      scans[i] = make_scan(feat4[i], normals3[i], n[i], times_ns[i], (flags & 2) != 0);
+    }
+    h->est->prefetchLaserScans(ids, scans);
+    return LS_OK;
+  });
+}
+
+int lsh_end_batch(void* hv, int with_estimator, double* out_icp7, ls_icp_stats* out_stats) {
+  Handle* h = static_cast<Handle*>(hv);
+  return guarded(h, [&]() {
+    std::vector<gtsam::NonlinearFactorGraph> nf;
+    std::vector<gtsam::Values> nv;
+    std::vector<bool> prior;
+    h->est->endPosesAndLaserScans(&nf, &nv, &prior);
+    for (size_t i = 0; i < h->step_ids.size(); ++i) {
+      std::shared_ptr<LaserTrack> track = h->est->getLaserTrack(h->step_ids[i]);
+      if (with_estimator & 1) {
+        gtsam::Values result = prior[i] ? h->est->registerPrior(nf[i], nv[i], h->step_ids[i]) : h->est->estimate(nf[i], nv[i], h->step_times[i]);
+        track->updateFromGTSAMValues(result);
+      }
+      if (out_icp7) {
+        SE3 T;
+        if (!track->getIcpTransformations().empty() && !prior[i]) T = track->getIcpTransformations().back().T_a_b;
+        T.toArray7(out_icp7 + 7 * i);
       }
       if (out_stats) out_stats[i] = track->getLastIcpStats();
     }

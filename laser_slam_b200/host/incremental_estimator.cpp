@@ -66,25 +66,33 @@ void IncrementalEstimator::processPosesAndLaserScans(const std::vector<unsigned 
                                                      std::vector<gtsam::NonlinearFactorGraph>* new_factors,
                                                      std::vector<gtsam::Values>* new_values, std::vector<bool>* is_prior) {
   std::lock_guard<std::recursive_mutex> lock(full_class_mutex_);
+  LS_CHECK(new_factors != NULL && new_values != NULL && is_prior != NULL, "null output");
+  beginPosesAndLaserScans(worker_ids, poses, scans);
+  endPosesAndLaserScans(new_factors, new_values, is_prior);
+}
+
+void IncrementalEstimator::beginPosesAndLaserScans(const std::vector<unsigned int>& worker_ids, const std::vector<Pose>& poses,
+                                                   const std::vector<LaserScan>& scans) {
+  std::lock_guard<std::recursive_mutex> lock(full_class_mutex_);
+  LS_CHECK(!step_.open, "beginPosesAndLaserScans: the previous step has not been ended");
   const size_t n = worker_ids.size();
   LS_CHECK(poses.size() == n && scans.size() == n, "one pose and one scan per worker");
-  LS_CHECK(new_factors != NULL && new_values != NULL && is_prior != NULL, "null output");
-  new_factors->assign(n, gtsam::NonlinearFactorGraph());
-  new_values->assign(n, gtsam::Values());
-  is_prior->assign(n, false);
-  std::vector<LaserTrack::PendingIcp> pending(n);
-  std::vector<size_t> active;
+  step_ = PendingStep();
+  step_.worker_ids = worker_ids;
+  step_.pending.resize(n);
   for (size_t i = 0; i < n; ++i) {
     LS_CHECK(worker_ids[i] < laser_tracks_.size(), "bad worker id");
     for (size_t j = 0; j < i; ++j) LS_CHECK(worker_ids[j] != worker_ids[i], "a worker may appear once per step");
-    laser_tracks_[worker_ids[i]]->beginPoseAndLaserScan(poses[i], scans[i], &pending[i]);
-    if (pending[i].active) active.push_back(i);
+    laser_tracks_[worker_ids[i]]->beginPoseAndLaserScan(poses[i], scans[i], &step_.pending[i]);
+    if (step_.pending[i].active) step_.active.push_back(i);
   }
+  step_.open = true;
   // a scan uploaded by a later track may have evicted an earlier track's scan from the shared ring only if the ring
   // were too small for one step: it holds nscan_in_sub_map + 4 slots per track
-  std::vector<float> T_outs(16 * std::max<size_t>(active.size(), 1));
-  std::vector<ls_icp_stats> stats(std::max<size_t>(active.size(), 1));
-  std::vector<int> statuses(std::max<size_t>(active.size(), 1), LS_OK);
+  const std::vector<size_t>& active = step_.active;
+  step_.T_outs.assign(16 * std::max<size_t>(active.size(), 1), 0.f);
+  step_.stats.assign(std::max<size_t>(active.size(), 1), ls_icp_stats());
+  step_.statuses.assign(std::max<size_t>(active.size(), 1), LS_OK);
   constexpr size_t kMaxBatch = 80;  // ls_icp_register_submap_batch's limit
   for (size_t b0 = 0; b0 < active.size(); b0 += kMaxBatch) {
     const size_t nb = std::min(kMaxBatch, active.size() - b0);
@@ -92,7 +100,7 @@ void IncrementalEstimator::processPosesAndLaserScans(const std::vector<unsigned 
     std::vector<int> n_parts;
     std::vector<float> T_parts, T0s;
     for (size_t k = 0; k < nb; ++k) {
-      const LaserTrack::PendingIcp& p = pending[active[b0 + k]];
+      const LaserTrack::PendingIcp& p = step_.pending[active[b0 + k]];
       reading_ids.push_back(p.reading_id);
       n_parts.push_back((int)p.part_ids.size());
       part_ids.insert(part_ids.end(), p.part_ids.begin(), p.part_ids.end());
@@ -100,22 +108,60 @@ void IncrementalEstimator::processPosesAndLaserScans(const std::vector<unsigned 
       T0s.insert(T0s.end(), p.T0.data(), p.T0.data() + 16);
     }
     const ls_icp_params& prm = laser_tracks_[worker_ids[active[b0]]]->icpParams();
-    const int rc = ls_icp_register_submap_batch(track_ctx_, &prm, track_ring_, (int)nb, reading_ids.data(), n_parts.data(),
-                                                part_ids.data(), T_parts.data(), T0s.data(), T_outs.data() + 16 * b0,
-                                                stats.data() + b0, statuses.data() + b0);
-    if (rc < 0) throw std::runtime_error(std::string("ls_icp_register_submap_batch: ") + ls_b200_last_error(track_ctx_));
+    int rc;
+    if (active.size() <= kMaxBatch) {  // the usual case: one launch, left in flight until endPosesAndLaserScans
+      std::memcpy(step_.T_outs.data(), T0s.data(), sizeof(float) * T0s.size());
+      rc = ls_icp_register_submap_batch_begin(track_ctx_, &prm, track_ring_, (int)nb, reading_ids.data(), n_parts.data(),
+                                              part_ids.data(), T_parts.data(), T0s.data());
+      step_.inflight = rc == LS_OK;
+    } else {
+      rc = ls_icp_register_submap_batch(track_ctx_, &prm, track_ring_, (int)nb, reading_ids.data(), n_parts.data(), part_ids.data(),
+                                        T_parts.data(), T0s.data(), step_.T_outs.data() + 16 * b0, step_.stats.data() + b0,
+                                        step_.statuses.data() + b0);
+    }
+    if (rc < 0) {
+      step_.open = false;
+      throw std::runtime_error(std::string("ls_icp_register_submap_batch: ") + ls_b200_last_error(track_ctx_));
+    }
   }
+}
+
+void IncrementalEstimator::endPosesAndLaserScans(std::vector<gtsam::NonlinearFactorGraph>* new_factors,
+                                                 std::vector<gtsam::Values>* new_values, std::vector<bool>* is_prior) {
+  std::lock_guard<std::recursive_mutex> lock(full_class_mutex_);
+  LS_CHECK(step_.open, "endPosesAndLaserScans without beginPosesAndLaserScans");
+  LS_CHECK(new_factors != NULL && new_values != NULL && is_prior != NULL, "null output");
+  step_.open = false;
+  if (step_.inflight) {
+    step_.inflight = false;
+    const int rc = ls_icp_register_submap_batch_end(track_ctx_, step_.T_outs.data(), step_.stats.data(), step_.statuses.data());
+    if (rc < 0) throw std::runtime_error(std::string("ls_icp_register_submap_batch_end: ") + ls_b200_last_error(track_ctx_));
+  }
+  const size_t n = step_.worker_ids.size();
+  new_factors->assign(n, gtsam::NonlinearFactorGraph());
+  new_values->assign(n, gtsam::Values());
+  is_prior->assign(n, false);
   size_t a = 0;
   for (size_t i = 0; i < n; ++i) {
     bool prior = false;
-    if (pending[i].active) {
-      laser_tracks_[worker_ids[i]]->endPoseAndLaserScan(&pending[i], statuses[a], T_outs.data() + 16 * a, &stats[a],
-                                                        &(*new_factors)[i], &(*new_values)[i], &prior);
+    LaserTrack& track = *laser_tracks_[step_.worker_ids[i]];
+    if (step_.pending[i].active) {
+      track.endPoseAndLaserScan(&step_.pending[i], step_.statuses[a], step_.T_outs.data() + 16 * a, &step_.stats[a],
+                                &(*new_factors)[i], &(*new_values)[i], &prior);
       ++a;
     } else {
-      laser_tracks_[worker_ids[i]]->endPoseAndLaserScan(&pending[i], LS_OK, NULL, NULL, &(*new_factors)[i], &(*new_values)[i], &prior);
+      track.endPoseAndLaserScan(&step_.pending[i], LS_OK, NULL, NULL, &(*new_factors)[i], &(*new_values)[i], &prior);
     }
     (*is_prior)[i] = prior;
+  }
+}
+
+void IncrementalEstimator::prefetchLaserScans(const std::vector<unsigned int>& worker_ids, const std::vector<LaserScan>& scans) {
+  std::lock_guard<std::recursive_mutex> lock(full_class_mutex_);
+  LS_CHECK(worker_ids.size() == scans.size(), "one scan per worker");
+  for (size_t i = 0; i < worker_ids.size(); ++i) {
+    LS_CHECK(worker_ids[i] < laser_tracks_.size(), "bad worker id");
+    laser_tracks_[worker_ids[i]]->prefetchLaserScan(scans[i]);
   }
 }
 

@@ -135,6 +135,14 @@ void LaserTrack::beginPoseAndLaserScan(const Pose& pose, const LaserScan& in_sca
   laser_scans_.push_back(in_scan);  // the one copy the track keeps (the reference copies twice, :143 and :197)
   LaserScan& scan = laser_scans_.back();
   pose_measurements_.push_back(pose);
+  auto pf = prefetched_.find(scan.time_ns);
+  if (pf != prefetched_.end()) {  // already on the device (prefetchLaserScan); share the storage that upload reads from
+    if (*map_p_ && ls_map_scan_size(*map_p_, pf->second.first) >= 0) {
+      scan.scan = pf->second.second.scan;
+      resident_[laser_scans_.size() - 1u] = pf->second.first;
+    }
+    prefetched_.erase(pf);
+  }
 
   if (trajectory_.empty()) {
     pending->first = true;
@@ -382,7 +390,12 @@ gtsam::ExpressionFactor<SE3> LaserTrack::makeMeasurementFactor(const Pose& pose_
 uint64_t LaserTrack::residentScan(size_t index) const {
   auto it = resident_.find(index);
   if (it != resident_.end() && ls_map_scan_size(*map_p_, it->second) >= 0) return it->second;
-  const DataPoints& c = laser_scans_[index].scan;
+  const uint64_t id = uploadScan(laser_scans_[index].scan);
+  resident_[index] = id;
+  return id;
+}
+
+uint64_t LaserTrack::uploadScan(const DataPoints& c) const {
   const int off = c.descriptorOffset("normals");
   LS_CHECK(off >= 0, "scan without normals");
   uint64_t id = 0;
@@ -394,8 +407,21 @@ uint64_t LaserTrack::residentScan(size_t index) const {
   const int rc = direct ? ls_map_push_scan_async(*map_p_, fp, np, (int)c.descriptorDim, (int)c.getNbPoints(), &id)
                         : ls_map_push_scan(*map_p_, fp, np, (int)c.descriptorDim, (int)c.getNbPoints(), &id);
   throwOnError(ctx_, rc, "ls_map_push_scan");
-  resident_[index] = id;
   return id;
+}
+
+void LaserTrack::prefetchLaserScan(const LaserScan& scan) {
+  std::lock_guard<std::recursive_mutex> lock(full_laser_track_mutex_);
+  if (!params_.use_icp_factors || scan.scan.getNbPoints() == 0 || !scan.scan.descriptorExists("normals")) return;
+  if (prefetched_.count(scan.time_ns)) return;
+  if (!*map_p_ || (int)scan.scan.getNbPoints() > *map_max_pts_p_) return;  // no ring yet, or it would have to grow: not now
+  if (prefetched_.size() >= 2) {  // hints that were never followed up
+    ls_map_sync(*map_p_);         // their uploads may still be reading the storage about to be released
+    prefetched_.erase(prefetched_.begin());
+  }
+  std::pair<uint64_t, LaserScan>& slot = prefetched_[scan.time_ns];
+  slot.second = scan;  // shares the storage (copy-on-write)
+  slot.first = uploadScan(slot.second.scan);
 }
 
 // device ring large enough for the sub-map + the reading; (re)created when a larger scan shows up.  A track of its own

@@ -163,3 +163,49 @@ def test_batched_scan_callbacks_equal_one_callback_per_worker(synth_mod):
         assert np.array_equal(t1, t2) and np.abs(p1 - p2).max() < 1e-9       # same factors -> same estimate
     one.close()
     bat.close()
+
+
+@pytest.mark.gpu
+def test_split_step_with_prefetch_and_views_equals_step_batch(synth_mod):
+    """beginPosesAndLaserScans / prefetchLaserScans(next scans) / endPosesAndLaserScans over DataPoints that borrow pinned
+    caller memory (uploaded in place, asynchronously) gives the same bits as processPosesAndLaserScans over copies."""
+    import torch
+    from laser_slam_b200 import host
+    W, n_scans = 3, 7
+    data = []
+    for w in range(W):
+        truth, odom = synth_mod.trajectory(10 + w, n_scans)
+        sc = [synth_mod.subsample(*synth_mod.scan(truth[k], 10 + w, k), 8) for k in range(n_scans)]
+        data.append((pg.se3_from_matrix(odom), sc))
+    # pinned staging the views borrow; kept alive for the life of the estimator
+    pin_f = [[torch.from_numpy(np.ascontiguousarray(data[w][1][k][0])).pin_memory() for k in range(n_scans)] for w in range(W)]
+    pin_n = [[torch.from_numpy(np.ascontiguousarray(data[w][1][k][1])).pin_memory() for k in range(n_scans)] for w in range(W)]
+    ref = host.Estimator(n_workers=W, nscan_in_sub_map=3)
+    spl = host.Estimator(n_workers=W, nscan_in_sub_map=3)
+    ws = list(range(W))
+
+    def ptrs(k, pinned):
+        if pinned:
+            return [pin_f[w][k].data_ptr() for w in ws], [pin_n[w][k].data_ptr() for w in ws]
+        return [data[w][1][k][0].ctypes.data for w in ws], [data[w][1][k][1].ctypes.data for w in ws]
+
+    for k in range(n_scans):
+        ns = [len(data[w][1][k][0]) for w in ws]
+        poses = [data[w][0][k] for w in ws]
+        fp, npp = ptrs(k, False)
+        icp_r, st_r = ref.step_batch(ws, [k * 100] * W, poses, fp, npp, ns)
+        fp, npp = ptrs(k, True)
+        spl.begin_batch(ws, [k * 100] * W, poses, fp, npp, ns, views=True)
+        if k + 1 < n_scans and k != 3:          # one step goes without the hint: the upload then happens in its own begin
+            fq, nq = ptrs(k + 1, True)
+            spl.prefetch(ws, [(k + 1) * 100] * W, fq, nq, [len(data[w][1][k + 1][0]) for w in ws], views=True)
+        icp_s, st_s = spl.end_batch()
+        assert np.array_equal(icp_r, icp_s), k
+        assert [s.iterations for s in st_r] == [s.iterations for s in st_s]
+        assert [s.last_kept for s in st_r] == [s.last_kept for s in st_s]
+    for w in ws:
+        t1, p1 = ref.trajectory(w)
+        t2, p2 = spl.trajectory(w)
+        assert np.array_equal(t1, t2) and np.abs(p1 - p2).max() < 1e-9
+    ref.close()
+    spl.close()
