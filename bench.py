@@ -497,8 +497,9 @@ def main():
             return (list(range(B)), [s * 100_000_000] * B, [feats[t][idxs[t]].data_ptr() for t in range(B)],
                     [nrms[t][idxs[t]].data_ptr() for t in range(B)], [N_SCAN] * B), [pose7(tracks[t][1][idxs[t]]) for t in range(B)]
 
-        n_host = max(3, min(args.steps, 10))
-        w_host = K_MAP + 2
+        # the same scans as the C-ABI arm's timed steps: its step s registers scan walk(s + K_MAP + 1)
+        n_host = max(3, min(args.steps, 60))
+        w_host = args.warmup + K_MAP + 1
         hargs = [host_args(s) for s in range(w_host + n_host + 1)]   # marshalled before the clock, like the C-ABI arm's
 
         def run_host(s0, n):
