@@ -568,7 +568,7 @@ def main():
             "kernel_ms": t_icp * 1e3,
             "registration": {"algorithmic_bytes": ALG_BYTES_REG, "device_ms_per_batch": t_dev * 1e3,
                              "achieved": B * ALG_BYTES_REG / t_step / 1e9, "frac": B * ALG_BYTES_REG / t_step / 1e9 / peak}}
-    cpu = cpu_baseline_sample() if args.gpus == 1 else None
+    cpu = cpu_baseline_sample() if args.gpus == 1 and not os.environ.get('LS_BENCH_NO_CPU') else None
     out = {
         "metric": wl["metric"],
         "value": world * B * args.steps / t_res, "unit": "registrations/s", "n_gpus": args.gpus, "steps": args.steps,

@@ -180,7 +180,7 @@ int ls_icp_register_submap(ls_ctx* ctx, const ls_icp_params* prm, const ls_map* 
  * GPU: the reference's n_laser_slam_workers tracks, laser_slam/src/incremental_estimator.cpp:22-26).  Problem b
  * uses reading_ids[b], its n_parts[b] parts follow each other in part_ids / T_parts (16 floats per part),
  * T0s / T_outs hold 16 floats per problem, statuses[b] is LS_OK or LS_ERR_CONVERGENCE (then T_out == T0).
- * Results are bit-identical to separate ls_icp_register_submap calls.  1 <= batch <= 80. */
+ * Results are bit-identical to separate ls_icp_register_submap calls.  1 <= batch <= 160. */
 int ls_icp_register_submap_batch(ls_ctx* ctx, const ls_icp_params* prm, const ls_map* map, int batch,
                                  const uint64_t* reading_ids, const int* n_parts, const uint64_t* part_ids,
                                  const float* T_parts, const float* T0s, float* T_outs, ls_icp_stats* stats,

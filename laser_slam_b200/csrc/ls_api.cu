@@ -73,7 +73,7 @@ struct ls_ctx {
   // ring slots (map, slot index) the in-flight batch reads: an asynchronous upload must not overwrite them
   std::vector<std::pair<const ls_map*, int>> pending_slots;
 };
-constexpr int kMaxBatch = 80;
+constexpr int kMaxBatch = 160;
 
 struct ls_scan_slot {
   float4* pts = nullptr;

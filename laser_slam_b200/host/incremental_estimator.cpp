@@ -93,7 +93,7 @@ void IncrementalEstimator::beginPosesAndLaserScans(const std::vector<unsigned in
   step_.T_outs.assign(16 * std::max<size_t>(active.size(), 1), 0.f);
   step_.stats.assign(std::max<size_t>(active.size(), 1), ls_icp_stats());
   step_.statuses.assign(std::max<size_t>(active.size(), 1), LS_OK);
-  constexpr size_t kMaxBatch = 80;  // ls_icp_register_submap_batch's limit
+  constexpr size_t kMaxBatch = 160;  // ls_icp_register_submap_batch's limit
   for (size_t b0 = 0; b0 < active.size(); b0 += kMaxBatch) {
     const size_t nb = std::min(kMaxBatch, active.size() - b0);
     std::vector<uint64_t> reading_ids, part_ids;
