@@ -543,14 +543,28 @@ def main():
     # ncu DRAM bytes of one launch of the same shape (8 registrations per launch has its own capture: eight maps do
     # not fit L2 together, one does)
     traffic, traffic_note = None, None
-    for fname, regs in ((f"r2_icp_kernel_cfg{args.config}_batch{B // G}_summary.json", B // G),):
-        prof = os.path.join(ROOT, "profiles", fname)
-        if os.path.exists(prof):
-            try:
-                traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+    import glob
+    import re
+    caps = {}
+    for prof in glob.glob(os.path.join(ROOT, "profiles", f"r2_icp_kernel_cfg{args.config}_batch*_summary.json")):
+        m = re.search(r"_batch(\d+)_summary", prof)
+        if m:
+            caps[int(m.group(1))] = prof
+    if caps:
+        regs = min(caps, key=lambda r: (abs(r - B // G), -r))   # the capture closest in shape to what was timed
+        try:
+            per_launch = float(json.load(open(caps[regs])).get("dram_bytes_per_launch"))
+            fname = os.path.basename(caps[regs])
+            if regs == B // G:
+                traffic = per_launch
                 traffic_note = f"ncu dram__bytes_read+write of one launch with {regs} registration(s) (profiles/{fname})"
-            except Exception:
-                traffic = None
+            else:
+                traffic = per_launch * (B // G) / regs
+                traffic_note = (f"no ncu capture with {B // G} registrations per launch: scaled per registration from the capture with "
+                                f"{regs} per launch (profiles/{fname}: {per_launch / 1e9:.2f} GB for {regs}); the working sets "
+                                "of > 3 registrations already exceed L2, so DRAM bytes per registration are flat from there on")
+        except Exception:
+            traffic, traffic_note = None, None
     Bg = B / G   # registrations per launch
     t_step = t_res / args.steps
     # G launches (one per context, B/G registrations and 1/G of the co-resident CTAs each) run side by side, so the device-level
