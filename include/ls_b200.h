@@ -243,11 +243,21 @@ int ls_map_assemble(ls_ctx* ctx, const ls_map* map, int n_parts, const uint64_t*
  *                           cylinder, in input order; out4 holds up to n points, *n_out the number kept
  *   ls_voxel_grid           pcl::VoxelGrid as getFilteredMap uses it (laser_slam_worker.cpp:434-441): one centroid per
  *                           occupied voxel of edge leaf_size, voxels in ascending cell-index order (x fastest); the
- *                           centroid is the exact mean of the voxel's points (fixed-point sums), rounded once */
+ *                           centroid is the exact mean of the voxel's points (fixed-point sums), rounded once
+ *   ls_deskew_revolution    the point arithmetic of the Velodyne assembler
+ *                           (sensor_drivers/velodyne_assembler/src/velodyne_assembler_ros.cpp:57-143): the packets of one
+ *                           revolution, concatenated (packet k = points [packet_offsets[k], packet_offsets[k+1])), each
+ *                           transformed by its T_packets[k] (column-major 4x4: sensor at the packet's time -> sensor at the
+ *                           revolution's start, :124-130) and then all by T_final (start -> last packet, :107-108), as two
+ *                           float32 transforms like the reference; an exact identity copies verbatim.  The wrap detection
+ *                           and the composition of the transforms stay on the host:
+ *                           include/laser_slam/velodyne_assembler.hpp */
 int ls_ingest_pointcloud2(int device, const void* data, int point_step, int off_x, int off_y, int off_z, int n, float* out4);
 int ls_filter_cylinder(int device, const float* in4, int n, const double center[3], double radius_m, double height_m,
                        int remove_points_inside, float* out4, int* n_out);
 int ls_voxel_grid(int device, const float* in4, int n, const float leaf_size[3], float* out4, int* n_out);
+int ls_deskew_revolution(int device, const float* points4, const int* packet_offsets, int n_packets, const float* T_packets,
+                         const float T_final[16], float* out4);
 
 /* ---- pose graph ------------------------------------------------------------------------------------
  * Replaces gtsam::ISAM2 as IncrementalEstimator uses it (laser_slam/src/incremental_estimator.cpp:17-20,

@@ -134,6 +134,7 @@ def lib():
         L.ls_ingest_pointcloud2.argtypes = [ci, vp, ci, ci, ci, ci, ci, vp]
         L.ls_filter_cylinder.argtypes = [ci, vp, ci, vp, ctypes.c_double, ctypes.c_double, ci, vp, ctypes.POINTER(ci)]
         L.ls_voxel_grid.argtypes = [ci, vp, ci, vp, vp, ctypes.POINTER(ci)]
+        L.ls_deskew_revolution.argtypes = [ci, vp, vp, ci, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -195,6 +196,21 @@ def voxel_grid(pts4, leaf_size, device=0):
     n = ctypes.c_int(0)
     _rc(lib().ls_voxel_grid(device, p.ctypes.data, len(p), leaf.ctypes.data, out.ctypes.data, ctypes.byref(n)), "ls_voxel_grid")
     return out[:n.value].copy()
+
+
+def deskew_revolution(points4, packet_offsets, T_packets, T_final, device=0):
+    """The point arithmetic of the Velodyne assembler (reference sensor_drivers/velodyne_assembler/src/
+    velodyne_assembler_ros.cpp:57-143) on the device: packet k = points[packet_offsets[k]:packet_offsets[k+1]] is moved by
+    T_packets[k] and then everything by T_final (4x4 row-major numpy matrices here; ls_deskew_revolution)."""
+    p = np.ascontiguousarray(points4, np.float32)
+    offs = np.ascontiguousarray(packet_offsets, np.int32)
+    K = len(offs) - 1
+    tp = np.ascontiguousarray(np.stack([colmajor(T) for T in T_packets]), np.float32) if K > 0 else np.zeros((1, 16), np.float32)
+    tf = colmajor(T_final)
+    out = np.empty((max(len(p), 1), 4), np.float32)
+    _rc(lib().ls_deskew_revolution(device, p.ctypes.data, offs.ctypes.data, K, tp.ctypes.data, tf.ctypes.data, out.ctypes.data),
+        "ls_deskew_revolution")
+    return out[:len(p)].copy()
 
 
 def apply_chain_filters(ctx, reading4, ref4, ref_normals3, params):

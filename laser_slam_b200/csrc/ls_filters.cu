@@ -4,6 +4,8 @@
 //   applyCylindricalFilter           reference laser_slam_ros/include/laser_slam_ros/common.hpp:194-223 (used by
 //                                    LaserSlamWorker::getFilteredMap, laser_slam_worker.cpp:415-488)
 //   pcl::VoxelGrid                   laser_slam_worker.cpp:434-441 (voxel_filter_, leaf from params)
+//   velodyne assembler de-skew       reference sensor_drivers/velodyne_assembler/src/velodyne_assembler_ros.cpp:57-143: the
+//                                    packets of one revolution, each moved into the frame of the revolution's last packet
 // as device kernels behind the C ABI.  Not the hot path: the radix sort and the scans are CUB (library code), the
 // kernels around them are ours.  Order of the outputs is defined so that results are reproducible: the cylinder filter
 // keeps the input order (as the reference's sequential push_back), the voxel grid emits voxels by ascending cell index
@@ -49,6 +51,48 @@ __global__ void compact_kernel(const float4* __restrict__ in, const int* __restr
                                float4* __restrict__ out) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     if (keep[i]) out[pos[i]] = in[i];
+}
+
+// ---- de-skew of one revolution: out = T_final (x) (T_packet (x) p), two float32 transforms in the reference's order
+// (velodyne_assembler_ros.cpp:129-133 transforms a packet into the frame of the revolution's start when it arrives,
+// :107-108 moves the assembled cloud to the frame of its last packet before publishing).  An exact identity matrix copies
+// the point verbatim -- the reference does not transform the first packet at all.  Same arithmetic as ls_transform_cloud.
+__device__ __forceinline__ void xform3(const float* T, float x, float y, float z, float& ox, float& oy, float& oz) {
+  float a, b, c, s;
+  a = T[0] * x; b = T[4] * y; c = T[8] * z; s = a + b; s = s + c; ox = s + T[12];
+  a = T[1] * x; b = T[5] * y; c = T[9] * z; s = a + b; s = s + c; oy = s + T[13];
+  a = T[2] * x; b = T[6] * y; c = T[10] * z; s = a + b; s = s + c; oz = s + T[14];
+}
+__device__ __forceinline__ bool is_identity(const float* T) {
+  bool id = true;
+  for (int k = 0; k < 16; ++k) id = id && T[k] == ((k % 5 == 0) ? 1.0f : 0.0f);
+  return id;
+}
+__global__ void deskew_kernel(const float4* __restrict__ in, int m, const int* __restrict__ offs, int n_packets,
+                              const float* __restrict__ T_packets, const float* __restrict__ T_final, float4* __restrict__ out) {
+  __shared__ float Tf[16];
+  __shared__ int final_identity;
+  if (threadIdx.x < 16) Tf[threadIdx.x] = T_final[threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x == 0) final_identity = is_identity(Tf) ? 1 : 0;
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+    int lo = 0, hi = n_packets - 1;  // last packet whose first point is <= i (empty packets share an offset: skipped)
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (offs[mid] <= i) lo = mid;
+      else hi = mid - 1;
+    }
+    const float* Tk = T_packets + 16 * (size_t)lo;
+    const float4 p = in[i];
+    float x = p.x, y = p.y, z = p.z;
+    if (!is_identity(Tk)) xform3(Tk, p.x, p.y, p.z, x, y, z);
+    if (!final_identity) {
+      const float a = x, b = y, c = z;
+      xform3(Tf, a, b, c, x, y, z);
+    }
+    out[i] = make_float4(x, y, z, p.w);
+  }
 }
 
 // ---- voxel grid
@@ -186,6 +230,36 @@ int ls_filter_cylinder(int device, const float* in4, int n, const double center[
   FCU(cudaMemcpy(&last_keep, d_keep + (n - 1), sizeof(int), cudaMemcpyDeviceToHost));
   *n_out = last_pos + last_keep;
   FCU(cudaMemcpy(out4, d_out, (size_t)*n_out * sizeof(float4), cudaMemcpyDeviceToHost));
+  return LS_OK;
+}
+
+int ls_deskew_revolution(int device, const float* points4, const int* packet_offsets, int n_packets, const float* T_packets,
+                         const float T_final[16], float* out4) {
+  if (!packet_offsets || n_packets < 1 || !T_packets || !T_final) return LS_ERR_ARG;
+  const int m = packet_offsets[n_packets];
+  if (packet_offsets[0] != 0 || m < 0) return LS_ERR_ARG;
+  for (int k = 0; k < n_packets; ++k)
+    if (packet_offsets[k + 1] < packet_offsets[k]) return LS_ERR_ARG;
+  if (m == 0) return LS_OK;
+  if (!points4 || !out4) return LS_ERR_ARG;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return LS_ERR_CUDA;
+  FCU(cudaSetDevice(device));
+  Scratch s;
+  float4 *d_in, *d_out;
+  int* d_offs;
+  float* d_T;
+  FCU(s.alloc(&d_in, (size_t)m));
+  FCU(s.alloc(&d_out, (size_t)m));
+  FCU(s.alloc(&d_offs, (size_t)n_packets + 1));
+  FCU(s.alloc(&d_T, 16 * ((size_t)n_packets + 1)));
+  FCU(cudaMemcpy(d_in, points4, (size_t)m * sizeof(float4), cudaMemcpyHostToDevice));
+  FCU(cudaMemcpy(d_offs, packet_offsets, ((size_t)n_packets + 1) * sizeof(int), cudaMemcpyHostToDevice));
+  FCU(cudaMemcpy(d_T, T_packets, 16 * (size_t)n_packets * sizeof(float), cudaMemcpyHostToDevice));
+  FCU(cudaMemcpy(d_T + 16 * (size_t)n_packets, T_final, 16 * sizeof(float), cudaMemcpyHostToDevice));
+  deskew_kernel<<<blocks(m), 256>>>(d_in, m, d_offs, n_packets, d_T, d_T + 16 * (size_t)n_packets, d_out);
+  FCU(cudaGetLastError());
+  FCU(cudaMemcpy(out4, d_out, (size_t)m * sizeof(float4), cudaMemcpyDeviceToHost));
   return LS_OK;
 }
 

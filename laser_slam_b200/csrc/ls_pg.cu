@@ -12,7 +12,8 @@
 // and the update solves H d = -g exactly through the Woodbury identity:
 //   y = H_c^-1 (-g),  Z = H_c^-1 U^T,  (I + U Z) w = U y,  d = y - Z w,
 // with H_c^-1 applied to all 6 #LC + 1 right-hand sides at once by block cyclic reduction (log2 P parallel levels).
-// All arithmetic is float64; every sum has a fixed order (deterministic).  Not HBM-bound (a few MB per iteration,
+// All arithmetic is float64; every sum that enters the solve has a fixed order (deterministic); only the reported cost
+// statistic is an atomic sum.  Not HBM-bound (a few MB per iteration,
 // SURVEY.md §8d): the cost is latency -- kernel launches and dependent levels -- not bandwidth.
 #include <cmath>
 #include <cstdio>

@@ -147,3 +147,37 @@ class Estimator:
         nr = np.zeros((cap_points, 3), np.float32)
         m = self._check(lib().lsh_build_submap(self._h, worker, int(time_ns), radius, f.ctypes.data, nr.ctypes.data, cap_points))
         return f[:m], nr[:m]
+
+
+class Assembler:
+    """laser_slam::VelodyneAssembler (include/laser_slam/velodyne_assembler.hpp): packets in, de-skewed revolutions out."""
+
+    def __init__(self, T_sensor_base=None, naive=False, device=0):
+        L = lib()
+        L.lsh_assembler_create.restype = ctypes.c_void_p
+        L.lsh_assembler_create.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        L.lsh_assembler_destroy.argtypes = [ctypes.c_void_p]
+        L.lsh_assembler_destroy.restype = None
+        L.lsh_assembler_add_packet.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
+                                               ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
+                                               ctypes.POINTER(ctypes.c_int64)]
+        t = None if T_sensor_base is None else np.ascontiguousarray(np.asarray(T_sensor_base, np.float32).T).reshape(16)
+        self._h = ctypes.c_void_p(L.lsh_assembler_create(None if t is None else t.ctypes.data, int(naive), device))
+        self._cap = 1 << 20
+        self._out = np.empty((self._cap, 4), np.float32)
+
+    def add_packet(self, points4, T_fixed_base, stamp_ns):
+        """None, or (revolution points (m,4), stamp of its last packet)."""
+        p = np.ascontiguousarray(points4, np.float32)
+        t = np.ascontiguousarray(np.asarray(T_fixed_base, np.float32).T).reshape(16)   # column-major
+        m, st = ctypes.c_int(0), ctypes.c_int64(0)
+        rc = lib().lsh_assembler_add_packet(self._h, p.ctypes.data, len(p), t.ctypes.data, int(stamp_ns), self._out.ctypes.data,
+                                            self._cap, ctypes.byref(m), ctypes.byref(st))
+        if rc < 0:
+            raise RuntimeError(f"lsh_assembler_add_packet failed with {rc}")
+        return (self._out[:m.value].copy(), int(st.value)) if rc == 1 else None
+
+    def close(self):
+        if self._h:
+            lib().lsh_assembler_destroy(self._h)
+            self._h = None

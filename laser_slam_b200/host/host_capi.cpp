@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "laser_slam/incremental_estimator.hpp"
+#include "laser_slam/velodyne_assembler.hpp"
 
 using namespace laser_slam;
 
@@ -248,4 +249,32 @@ int lsh_build_submap(void* hv, int worker, int64_t time_ns, int radius, float* f
   });
 }
 
+
+// ---- laser_slam::VelodyneAssembler (include/laser_slam/velodyne_assembler.hpp) for the tests
+void* lsh_assembler_create(const float* T_sensor_base16, int naive, int device) {
+  VelodyneAssembler::Matrix4 T;
+  if (T_sensor_base16) std::memcpy(T.data(), T_sensor_base16, 16 * sizeof(float));
+  return new VelodyneAssembler(T, naive != 0, device);
+}
+void lsh_assembler_destroy(void* a) { delete static_cast<VelodyneAssembler*>(a); }
+// returns 1 when a revolution was completed by this packet (out4 then holds *m_out points, at most cap), 0 if not, < 0 on error
+int lsh_assembler_add_packet(void* av, const float* pts4, int n, const float* T_fixed_base16, int64_t stamp_ns, float* out4, int cap,
+                             int* m_out, int64_t* stamp_out) {
+  try {
+    VelodyneAssembler* a = static_cast<VelodyneAssembler*>(av);
+    VelodyneAssembler::Matrix4 T;
+    std::memcpy(T.data(), T_fixed_base16, 16 * sizeof(float));
+    DataPoints in = DataPoints::viewOfArrays(pts4, NULL, (size_t)n), rev;
+    Time st = 0;
+    if (!a->addPacket(in, T, (Time)stamp_ns, &rev, &st)) return 0;
+    const int m = (int)rev.getNbPoints();
+    if (m > cap) return LS_ERR_ARG;
+    std::memcpy(out4, static_cast<const DataPoints&>(rev).features.data(), sizeof(float) * 4 * (size_t)m);
+    *m_out = m;
+    if (stamp_out) *stamp_out = (int64_t)st;
+    return 1;
+  } catch (const std::exception&) {
+    return LS_ERR_STATE;
+  }
+}
 }  // extern "C"

@@ -273,3 +273,101 @@ def icp(reading4, ref4, ref_normals3, T0, params=None, want_hist=False):
                 ids_hist=ids_hist[:st.iterations, :n] if want_hist else None, d2_last=d2_last[:n],
                 T_iter_hist=(t_hist[:st.iterations].reshape(-1, 4, 4).transpose(0, 2, 1).copy()
                              if want_hist else None))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Velodyne assembler (reference sensor_drivers/velodyne_assembler/src/velodyne_assembler_ros.cpp)
+def _is_identity(T):
+    return bool(np.array_equal(np.asarray(T, np.float32), np.eye(4, dtype=np.float32)))
+
+
+def _xform_points(T, pts4):
+    """float32 point transform with the operation order of lso_transform_cloud; an exact identity copies verbatim."""
+    p = np.ascontiguousarray(pts4, np.float32)
+    if len(p) == 0 or _is_identity(T):
+        return p.copy()
+    out, _ = transform_cloud(T, p, np.zeros((len(p), 3), np.float32))
+    return out
+
+
+def deskew_revolution(points4, packet_offsets, T_packets, T_final):
+    """out = T_final (x) (T_packets[k] (x) p) for the points of packet k: the two float32 transforms the reference applies
+    to a packet (velodyne_assembler_ros.cpp:129-133 on arrival, :107-108 before publishing)."""
+    p = np.ascontiguousarray(points4, np.float32)
+    out = np.empty_like(p)
+    for k in range(len(packet_offsets) - 1):
+        a, b = int(packet_offsets[k]), int(packet_offsets[k + 1])
+        out[a:b] = _xform_points(T_packets[k], p[a:b])
+    return _xform_points(T_final, out)
+
+
+def rigid_inverse_f32(T):
+    """[DEFINED] inverse of a rigid 4x4 in float32: [R^T, -(R^T t)], every product and sum rounded to float32 in a fixed
+    order (the reference calls Eigen's general 4x4 inverse, velodyne_assembler_ros.cpp:95,107)."""
+    T = np.asarray(T, np.float32)
+    out = np.eye(4, dtype=np.float32)
+    for i in range(3):
+        for j in range(3):
+            out[i, j] = T[j, i]
+    for i in range(3):
+        a = np.float32(T[0, i] * T[0, 3])
+        b = np.float32(T[1, i] * T[1, 3])
+        c = np.float32(T[2, i] * T[2, 3])
+        s = np.float32(np.float32(a + b) + c)
+        out[i, 3] = -s
+    return out
+
+
+def matmul_f32(A, B):
+    """4x4 float32 product, c_ij = ((a_i0 b_0j + a_i1 b_1j) + a_i2 b_2j) + a_i3 b_3j, each operation rounded."""
+    A, B = np.asarray(A, np.float32), np.asarray(B, np.float32)
+    C = np.empty((4, 4), np.float32)
+    for i in range(4):
+        for j in range(4):
+            s = np.float32(np.float32(A[i, 0] * B[0, j]) + np.float32(A[i, 1] * B[1, j]))
+            s = np.float32(s + np.float32(A[i, 2] * B[2, j]))
+            C[i, j] = np.float32(s + np.float32(A[i, 3] * B[3, j]))
+    return C
+
+
+class VelodyneAssembler:
+    """Restatement of VelodyneAssemblerRos::pclCallback (velodyne_assembler_ros.cpp:57-143) without ROS: packets in
+    (points in the sensor frame + the vehicle pose T_fixed_base at the packet's stamp), one de-skewed revolution out
+    whenever the azimuth of a packet's first point wraps past +pi/2 (:99-103)."""
+    START_ANGLE = np.pi / 2.0
+
+    def __init__(self, T_sensor_base=None, naive=False):
+        self.T_sensor_base = np.eye(4, dtype=np.float32) if T_sensor_base is None else np.asarray(T_sensor_base, np.float32)
+        self.T_base_sensor = rigid_inverse_f32(self.T_sensor_base)
+        self.naive = naive
+        self.T_fixed_base_prev = np.eye(4, dtype=np.float32)
+        self.T_start_cur = np.eye(4, dtype=np.float32)
+        self.initialized = False
+        self.last_az = 0.0
+        self.last_stamp = 0
+        self.parts = []      # points of the revolution being assembled, already in the start frame
+
+    def add_packet(self, points4, T_fixed_base, stamp):
+        """Returns None, or (revolution points, stamp of its last packet) when this packet starts a new revolution."""
+        p = np.ascontiguousarray(points4, np.float32)
+        if len(p) == 0:
+            return None
+        T_cur = np.eye(4, dtype=np.float32) if self.naive else np.asarray(T_fixed_base, np.float32)
+        T_prev_cur = matmul_f32(rigid_inverse_f32(self.T_fixed_base_prev), T_cur)
+        self.T_fixed_base_prev = T_cur
+        az = float(np.arctan2(np.float64(p[0, 1]), np.float64(p[0, 0])))
+        out = None
+        if (self.last_az > self.START_ANGLE and az <= self.START_ANGLE) or not self.initialized:
+            if self.initialized:
+                cloud = np.concatenate(self.parts)
+                out = (_xform_points(rigid_inverse_f32(self.T_start_cur), cloud), self.last_stamp)
+            self.parts = [p.copy()]
+            self.initialized = True
+            self.T_start_cur = np.eye(4, dtype=np.float32)
+        else:
+            T_sp_sc = matmul_f32(matmul_f32(self.T_sensor_base, T_prev_cur), self.T_base_sensor)
+            self.T_start_cur = matmul_f32(self.T_start_cur, T_sp_sc)
+            self.parts.append(_xform_points(self.T_start_cur, p))
+        self.last_az = az
+        self.last_stamp = stamp
+        return out
