@@ -1,5 +1,5 @@
 """Workload for compute-sanitizer (memcheck / racecheck / synccheck): the smoke registration plus one batched launch of four
-small scan-to-sub-map problems, a normals estimate and a pose-graph solve with marginals -- every kernel family of the
+small scan-to-sub-map problems, a normals estimate, a pose-graph solve with marginals and the input-side kernels -- every kernel family of the
 library on inputs small enough for the tool's ~100x slow-down.  Results are still checked against the oracle."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -35,4 +35,15 @@ G.add_factors(factors)
 G.optimize(3)
 cov = G.marginals(keys[:10])
 assert np.isfinite(cov).all()
+# input side (ls_filters.cu): ingest, cylinder, voxel grid, de-skew
+pts = sc[0][0][:4096]
+rec = np.zeros((len(pts), 8), np.float32)
+rec[:, :3] = pts[:, :3]
+assert np.array_equal(ls.ingest_pointcloud2(rec.tobytes(), 32, 0, 4, 8, len(pts)), pts)
+assert np.array_equal(ls.filter_cylinder(pts, [0, 0, 0], 15.0, 6.0, False), oracle.filter_cylinder(pts, [0, 0, 0], 15.0, 6.0, False))
+assert np.array_equal(ls.voxel_grid(pts, 0.5), oracle.voxel_grid(pts, 0.5))
+offs = [0, 100, 100, 1500, 4096]
+Tp = [np.eye(4, dtype=np.float32)] + [(np.linalg.inv(truth[0]) @ truth[k]).astype(np.float32) for k in (1, 2, 3)]
+Tf = oracle.rigid_inverse_f32(Tp[3])
+assert np.array_equal(ls.deskew_revolution(pts, offs, Tp, Tf), oracle.deskew_revolution(pts, offs, Tp, Tf))
 print("sanitize workload ok:", g["stats"].iterations, "iterations;", len(batch), "batched problems;", ctx.launch_count, "launches")
